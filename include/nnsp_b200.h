@@ -1,0 +1,201 @@
+/*
+ * nnsp_b200.h -- C ABI of libnnsp_b200.so: the ns-nnsp streaming-inference hot path
+ * (FeatureClass -> NeuralNetClass -> NNSPClass post-processing, and the VAD->KWS->S2I
+ * cascade of nnCntrlClass) batched over thousands of independent 16 kHz streams on one
+ * NVIDIA B200 (sm_100a).
+ *
+ * Plain C types only. All device work runs in hand-written CUDA kernels; there is NO CPU
+ * fallback: every entry point that computes returns NNSP_B200_ERR_CUDA when no usable
+ * device is present.
+ *
+ * What each entry point replaces in the reference (AmbiqAI/nnsp, file:line):
+ *   nnsp_b200_model_from_net ........ reading a linked model table, e.g. evb/src/def_nn1_vad.c:8-110
+ *                                     (mean/stdR arrays + the `NeuralNetClass net_*` literal)
+ *   nnsp_b200_batch_create .......... NNSPClass_init            ns-nnsp/src/nn_speech.c:23-55
+ *                                     (+ FeatureClass_construct  ns-nnsp/src/feature_module.c:12-24)
+ *   nnsp_b200_batch_reset ........... NNSPClass_reset           ns-nnsp/src/nn_speech.c:57-72
+ *   nnsp_b200_batch_exec[_host] ..... NNSPClass_exec            ns-nnsp/src/nn_speech.c:74-127
+ *                                     called n_frames times for each of n_streams instances
+ *   nnsp_b200_cascade_create ........ nnCntrlClass_init         evb/src/nnCntrlClass.c:56-128
+ *   nnsp_b200_cascade_reset ......... nnCntrlClass_reset        evb/src/nnCntrlClass.c:130-150
+ *   nnsp_b200_cascade_exec[_host] ... nnCntrlClass_exec         evb/src/nnCntrlClass.c:152-272
+ *   nnsp_b200_feature_stages ........ stftModule_analyze/spec2pspec/melSpecProc/log10_vec
+ *                                     ns-nnsp/src/spectrogram_module.c:33-77, melSpecProc.c:6-27,
+ *                                     fixlog10.c:53-61 (debug tap of every intermediate)
+ * The nine legacy single-instance symbols themselves (NNSPClass_*, FeatureClass_*,
+ * NeuralNetClass_*) are also exported, see include/nnsp_compat/nnsp_legacy_api.h.
+ */
+#ifndef NNSP_B200_H
+#define NNSP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNSP_B200_OK             0
+#define NNSP_B200_ERR_ARG       (-1)   /* bad argument / malformed model            */
+#define NNSP_B200_ERR_CUDA      (-2)   /* CUDA runtime failure or no device         */
+#define NNSP_B200_ERR_NOMEM     (-3)
+#define NNSP_B200_ERR_UNSUPPORTED (-4) /* model shape outside the engine's limits   */
+
+#define NNSP_B200_FRAME          160   /* samples per hop  (ambiq_nnsp_const.h:5)   */
+#define NNSP_B200_NMEL           40    /* mel bands        (ambiq_nnsp_const.h:6)   */
+#define NNSP_B200_NCTX           6     /* context frames   (ambiq_nnsp_const.h:7)   */
+#define NNSP_B200_MAX_LAYERS     10    /* neural_nets.h:18-30                       */
+#define NNSP_B200_MAX_WIDTH      128   /* widest hidden layer / LSTM state the kernels support */
+#define NNSP_B200_MAX_OUT        64    /* widest final (linear) layer               */
+
+/* post-processing flavour, keyed like NNSP_ID (nnsp_identification.h:3-9) */
+#define NNSP_B200_ID_S2I         0
+#define NNSP_B200_ID_VAD         1
+#define NNSP_B200_ID_KWS         2
+
+const char *nnsp_b200_version(void);
+const char *nnsp_b200_strerror(int code);
+/* text of the last error raised on the calling thread ("" if none) */
+const char *nnsp_b200_last_error(void);
+/* number of CUDA kernels launched by this library since load (all handles) */
+long long nnsp_b200_kernel_launches(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Models                                                                               */
+/* ------------------------------------------------------------------------------------ */
+typedef struct nnsp_b200_model nnsp_b200_model;
+
+/* Read a live reference model table (`NeuralNetClass`, ARM 4-row weight interleave as
+ * written by python/nnsp_pack/c_weight_man.py) plus its normalisation stats.
+ * Accumulator width per layer is taken from layer_func[] (== &fc_8x16_acc32b etc.). */
+int nnsp_b200_model_from_net(const void *neural_net_class, const int32_t *feature_mean,
+                             const int32_t *feature_stdR, int nn_id, nnsp_b200_model **out);
+/* Same model from / to the flat little-endian container described in DESIGN.md ("NNSPM1"). */
+int nnsp_b200_model_from_blob(const void *blob, size_t nbytes, nnsp_b200_model **out);
+int nnsp_b200_model_to_blob(const nnsp_b200_model *m, void *buf, size_t cap, size_t *nbytes);
+/* Force accumulator semantics: 0 = 64-bit saturating (affine.c), 1 = wrapping 32-bit
+ * (affine_acc32b.c, what -DDEF_ACC32BIT_OPT selects in def_nn*.c:68-84). */
+int nnsp_b200_model_set_acc32(nnsp_b200_model *m, int acc32);
+int nnsp_b200_model_info(const nnsp_b200_model *m, int *nn_id, int *numlayers,
+                         int16_t size_layer[NNSP_B200_MAX_LAYERS + 1], int *acc32);
+void nnsp_b200_model_free(nnsp_b200_model *m);
+
+/* ------------------------------------------------------------------------------------ */
+/* Per-stream-frame result record                                                       */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    int16_t trigger;      /* return value of NNSPClass_exec for this frame (nn_speech.c:126) */
+    int16_t outputs[3];   /* NNSPClass.outputs after this frame: intent, slot0, slot1        */
+} nnsp_b200_result;       /* 8 bytes */
+
+/* Optional debug taps (device pointers, any may be NULL). Index [s][t] = stream s, frame t
+ * of the current exec call; rows are dense, stream-major. Frames on which the network did
+ * not run (NNSPClass.slides == 0) get zero-filled act/logits rows.                      */
+typedef struct {
+    int32_t *logmel;      /* [S][T][40]  FeatureClass.feature after log10_vec            */
+    int16_t *feat;        /* [S][T][40]  newest normFeatContext row                      */
+    int16_t *act;         /* [S][T][act_stride] outputs of layers 0..L-2 back to back    */
+    int32_t *logits;      /* [S][T][n_out]  final linear layer (Q15)                     */
+    int16_t *hstate;      /* [S][T][h_stride] LSTM h after the frame (all LSTM layers)   */
+    int32_t *cstate;      /* [S][T][h_stride] LSTM c after the frame                     */
+    int16_t *post;        /* [S][T][16]: trigger, outputs[3], counts_category[8],
+                                         argmax_last, slides(after), ran_nn, stage      */
+} nnsp_b200_taps;
+
+/* ------------------------------------------------------------------------------------ */
+/* Batched NNSPClass: n_streams independent instances of one model                      */
+/* ------------------------------------------------------------------------------------ */
+typedef struct nnsp_b200_batch nnsp_b200_batch;
+
+int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device,
+                           int16_t thresh_prob, int16_t th_count_trigger,
+                           nnsp_b200_batch **out);
+int nnsp_b200_batch_reset(nnsp_b200_batch *b);
+/* Advance every stream by n_frames hops.
+ *   pcm      device pointer; sample i of frame t of stream s at pcm[s*stream_stride + t*160 + i]
+ *   results  device pointer [n_streams][n_frames] (may be NULL)
+ * Asynchronous on the handle's stream; call nnsp_b200_batch_sync to wait.               */
+int nnsp_b200_batch_exec(nnsp_b200_batch *b, const int16_t *pcm_dev, long long stream_stride,
+                         int n_frames, nnsp_b200_result *results_dev,
+                         const nnsp_b200_taps *taps);
+/* Same with HOST buffers (pageable or pinned): H2D of the PCM, kernels, D2H of the results,
+ * pipelined over stream slices; returns after the results are in `results`.             */
+int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long stream_stride,
+                              int n_frames, nnsp_b200_result *results);
+int nnsp_b200_batch_sync(nnsp_b200_batch *b);
+/* Device time (ms) spent in the kernels of the most recent exec call, per kernel:
+ * [0] feature kernel, [1] network/post-processing kernel, [2] everything else.          */
+int nnsp_b200_batch_last_kernel_ms(nnsp_b200_batch *b, float ms[3]);
+int nnsp_b200_batch_dims(const nnsp_b200_batch *b, int *n_streams, int *act_stride,
+                         int *h_stride, int *n_out);
+/* CUDA stream the handle launches on (cudaStream_t as void*), for callers that time it. */
+void *nnsp_b200_batch_stream(nnsp_b200_batch *b);
+void nnsp_b200_batch_destroy(nnsp_b200_batch *b);
+
+/* ------------------------------------------------------------------------------------ */
+/* Batched nnCntrlClass: VAD -> KWS -> S2I gated cascade per stream                     */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    int16_t thresh_prob_vad,  thresh_cnts_vad;                         /* ParamsNNCntrl.h:8-9   */
+    int16_t frs_vbufBk_s2i,   thresh_timeout_s2i, thresh_prob_s2i, thresh_cnts_s2i; /* :12-15 */
+    int16_t frs_vbufBk_kws,   thresh_timeout_kws, thresh_prob_kws, thresh_cnts_kws; /* :18-21 */
+} nnsp_b200_cascade_params;   /* same fields, same order as ParamCntrlClass (nnCntrlClass.h:12-29) */
+
+typedef struct {
+    int8_t  stage_id;     /* NNSP id that executed this frame (seq[current_pos_seq] on entry) */
+    int8_t  pos_after;    /* current_pos_seq on return                                     */
+    int16_t detected;     /* NNSPClass_exec return value for the instance that ran         */
+    int16_t outputs[3];   /* that instance's outputs[] right after exec (before any reset)  */
+    uint16_t cnt_timeout; /* cnt_timeout_kws / _s2i on return (0 for VAD frames)            */
+} nnsp_b200_cascade_result;   /* 12 bytes */
+
+typedef struct nnsp_b200_cascade nnsp_b200_cascade;
+
+void nnsp_b200_cascade_default_params(nnsp_b200_cascade_params *p);
+/* models[id] indexed by NNSP id (0 s2i, 1 vad, 2 kws); seq = ids in cascade order,
+ * e.g. {1,2,0} (evb/src/main_nnsp.cc:109). */
+int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *seq, int len_seq,
+                             const nnsp_b200_cascade_params *params, int n_streams, int device,
+                             nnsp_b200_cascade **out);
+int nnsp_b200_cascade_reset(nnsp_b200_cascade *c);
+int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long long stream_stride,
+                           int n_frames, nnsp_b200_cascade_result *results_dev,
+                           const nnsp_b200_taps *taps);
+int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long long stream_stride,
+                                int n_frames, nnsp_b200_cascade_result *results);
+int nnsp_b200_cascade_sync(nnsp_b200_cascade *c);
+int nnsp_b200_cascade_last_kernel_ms(nnsp_b200_cascade *c, float ms[3]);
+void *nnsp_b200_cascade_stream(nnsp_b200_cascade *c);
+void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c);
+
+/* ------------------------------------------------------------------------------------ */
+/* Stage-by-stage tap of the feature front end (parity tool)                            */
+/* ------------------------------------------------------------------------------------ */
+/* For n windows of 480 int16 samples each (host pointers), computes on `device`:
+ *   fft_in [n][512] int32   windowed, zero-padded frame      spectrogram_module.c:62-71
+ *   spec   [n][514] int32   257 complex bins, re/im pairs    fft.c:27-126
+ *   pspec  [n][257] int32   power spectrum                   spectrogram_module.c:33-45
+ *   mel    [n][40]  int32   mel energies                     melSpecProc.c:6-27
+ *   logmel [n][40]  int32   log10 Q15                        fixlog10.c:53-61
+ * Any output pointer may be NULL. */
+int nnsp_b200_feature_stages(int device, const int16_t *windows, int n, int32_t *fft_in,
+                             int32_t *spec, int32_t *pspec, int32_t *mel, int32_t *logmel);
+
+/* Constant tables the engine generates at load time (host copies; see nnsp_tables.c).
+ * name: "stft_win" int16[480], "fft_tw" int32[256], "rfft_tw" int32[256], "bitrev" int16[256],
+ *       "mel" int16[534], "log_lut" int16[256], "tanh_lut" int16[384].
+ * Returns element count or a negative error. */
+int nnsp_b200_table(const char *name, const void **data, int *elem_bytes);
+
+/* Device utilities so that C callers need no CUDA headers. */
+int nnsp_b200_device_count(void);
+int nnsp_b200_dev_alloc(int device, size_t nbytes, void **ptr);
+int nnsp_b200_dev_free(int device, void *ptr);
+int nnsp_b200_host_alloc_pinned(size_t nbytes, void **ptr);
+int nnsp_b200_host_free_pinned(void *ptr);
+int nnsp_b200_memcpy_h2d(int device, void *dst, const void *src, size_t nbytes);
+int nnsp_b200_memcpy_d2h(int device, void *dst, const void *src, size_t nbytes);
+int nnsp_b200_memset(int device, void *dst, int value, size_t nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNSP_B200_H */
