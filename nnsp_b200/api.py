@@ -1,0 +1,305 @@
+"""Host-side mirror of the reference interface, batched.
+
+Reference (single instance, C)                      here (n_streams instances, CUDA behind the C ABI)
+  NNSPClass_init / _reset / _exec                    NNSPBatch(model, n_streams, ...) / .reset() / .exec()
+  nnCntrlClass_init / _reset / _exec                 Cascade(models, seq, ...)        / .reset() / .exec()
+  a linked def_nn*.c table                           Model.from_blob() / Model.from_net()
+Same argument meaning (thresholds, frame = 160 int16 samples, trigger / outputs[3] results) and
+the same error behaviour for the legacy calls (they cannot fail); the batched calls raise
+NnspError on CUDA failure -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+from .capi import CASCADE_RESULT_DT, RESULT_DT, NnspError, check, lib
+
+FRAME = 160
+S2I, VAD, KWS = 0, 1, 2
+
+
+class Model:
+    def __init__(self, handle):
+        self.h = handle
+        L = lib()
+        nid, nl, acc = C.c_int(), C.c_int(), C.c_int()
+        sizes = (C.c_int16 * 11)()
+        check(L.nnsp_b200_model_info(self.h, C.byref(nid), C.byref(nl), sizes, C.byref(acc)), "model_info")
+        self.nn_id, self.numlayers, self.acc32 = nid.value, nl.value, bool(acc.value)
+        self.size_layer = list(sizes)[: nl.value + 1]
+
+    @classmethod
+    def from_blob(cls, blob, acc32=None):
+        if isinstance(blob, (str, os.PathLike)):
+            with open(blob, "rb") as f:
+                blob = f.read()
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(blob), len(blob))
+        check(lib().nnsp_b200_model_from_blob(buf, len(blob), C.byref(h)), "model_from_blob")
+        m = cls(h)
+        if acc32 is not None:
+            m.set_acc32(acc32)
+        return m
+
+    @classmethod
+    def from_net(cls, net_ptr, mean_ptr, stdr_ptr, nn_id):
+        h = C.c_void_p()
+        check(lib().nnsp_b200_model_from_net(net_ptr, mean_ptr, stdr_ptr, nn_id, C.byref(h)), "model_from_net")
+        return cls(h)
+
+    def set_acc32(self, acc32):
+        check(lib().nnsp_b200_model_set_acc32(self.h, int(bool(acc32))), "model_set_acc32")
+        self.acc32 = bool(acc32)
+
+    def to_blob(self):
+        n = C.c_size_t()
+        check(lib().nnsp_b200_model_to_blob(self.h, None, 0, C.byref(n)), "model_to_blob")
+        buf = C.create_string_buffer(n.value)
+        check(lib().nnsp_b200_model_to_blob(self.h, buf, n.value, C.byref(n)), "model_to_blob")
+        return buf.raw[: n.value]
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().nnsp_b200_model_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class DeviceArray:
+    """A dense array in HBM owned by the library's allocator (cudaMalloc)."""
+
+    def __init__(self, shape, dtype, device=0, zero=True):
+        self.shape, self.dtype, self.device = tuple(shape), np.dtype(dtype), device
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = C.c_void_p()
+        check(lib().nnsp_b200_dev_alloc(device, max(self.nbytes, 16), C.byref(self.ptr)), "dev_alloc")
+        if zero:
+            check(lib().nnsp_b200_memset(device, self.ptr, 0, max(self.nbytes, 16)), "memset")
+
+    @classmethod
+    def from_host(cls, a, device=0):
+        a = np.ascontiguousarray(a)
+        d = cls(a.shape, a.dtype, device, zero=False)
+        check(lib().nnsp_b200_memcpy_h2d(device, d.ptr, a.ctypes.data_as(C.c_void_p), a.nbytes), "h2d")
+        return d
+
+    def to_host(self):
+        out = np.empty(self.shape, self.dtype)
+        check(lib().nnsp_b200_memcpy_d2h(self.device, out.ctypes.data_as(C.c_void_p), self.ptr, self.nbytes), "d2h")
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().nnsp_b200_dev_free(self.device, self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedArray:
+    """Page-locked host array (cudaMallocHost) exposed as numpy."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = C.c_void_p()
+        check(lib().nnsp_b200_host_alloc_pinned(max(self.nbytes, 16), C.byref(self.ptr)), "host_alloc_pinned")
+        buf = (C.c_char * self.nbytes).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().nnsp_b200_host_free_pinned(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def _make_taps(S, T, act_stride, h_stride, n_out, device):
+    arrs = dict(
+        logmel=DeviceArray((S, T, 40), np.int32, device), feat=DeviceArray((S, T, 40), np.int16, device),
+        act=DeviceArray((S, T, max(act_stride, 1)), np.int16, device), logits=DeviceArray((S, T, max(n_out, 1)), np.int32, device),
+        hstate=DeviceArray((S, T, max(h_stride, 1)), np.int16, device), cstate=DeviceArray((S, T, max(h_stride, 1)), np.int32, device),
+        post=DeviceArray((S, T, 16), np.int16, device))
+    t = capi.Taps(**{k: v.ptr for k, v in arrs.items()})
+    return t, arrs
+
+
+class NNSPBatch:
+    """n_streams independent NNSPClass instances of one model on one GPU."""
+
+    def __init__(self, model, n_streams, device=0, thresh_prob=16383, th_count=4):
+        self.model, self.S, self.device = model, int(n_streams), device
+        self.h = C.c_void_p()
+        check(lib().nnsp_b200_batch_create(model.h, self.S, device, thresh_prob, th_count, C.byref(self.h)), "batch_create")
+        a, hs, no = C.c_int(), C.c_int(), C.c_int()
+        check(lib().nnsp_b200_batch_dims(self.h, None, C.byref(a), C.byref(hs), C.byref(no)), "batch_dims")
+        self.act_stride, self.h_stride, self.n_out = a.value, hs.value, no.value
+
+    def reset(self):
+        check(lib().nnsp_b200_batch_reset(self.h), "batch_reset")
+
+    def sync(self):
+        check(lib().nnsp_b200_batch_sync(self.h), "batch_sync")
+
+    def exec_device(self, pcm_dev, stride, n_frames, results_dev=None, taps=None):
+        """Asynchronous; pcm_dev / results_dev are DeviceArray (or raw pointers)."""
+        p = pcm_dev.ptr if isinstance(pcm_dev, DeviceArray) else pcm_dev
+        r = results_dev.ptr if isinstance(results_dev, DeviceArray) else results_dev
+        check(lib().nnsp_b200_batch_exec(self.h, p, stride, n_frames, r, C.byref(taps) if taps is not None else None), "batch_exec")
+
+    def exec(self, pcm, taps=False):
+        """pcm: int16 [S, T*160] numpy. Returns results [S, T] (and a dict of tap arrays)."""
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        assert pcm.ndim == 2 and pcm.shape[0] == self.S and pcm.shape[1] % FRAME == 0
+        T = pcm.shape[1] // FRAME
+        d_pcm = DeviceArray.from_host(pcm, self.device)
+        d_res = DeviceArray((self.S, T), RESULT_DT, self.device)
+        tp, arrs = (None, None)
+        if taps:
+            tp, arrs = _make_taps(self.S, T, self.act_stride, self.h_stride, self.n_out, self.device)
+        self.exec_device(d_pcm, pcm.shape[1], T, d_res, tp)
+        self.sync()
+        res = d_res.to_host()
+        out = {k: v.to_host() for k, v in arrs.items()} if taps else None
+        d_pcm.free(); d_res.free()
+        if arrs:
+            for v in arrs.values():
+                v.free()
+        return (res, out) if taps else res
+
+    def exec_host(self, pcm, results=None):
+        """End-to-end call with host buffers (H2D + kernels + D2H inside)."""
+        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and pcm.shape[0] == self.S
+        T = pcm.shape[1] // FRAME
+        if results is None:
+            results = np.empty((self.S, T), RESULT_DT)
+        check(lib().nnsp_b200_batch_exec_host(self.h, pcm.ctypes.data_as(C.c_void_p), pcm.shape[1], T,
+                                              results.ctypes.data_as(C.c_void_p)), "batch_exec_host")
+        return results
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 3)()
+        check(lib().nnsp_b200_batch_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")
+        return list(ms)
+
+    def close(self):
+        if self.h:
+            lib().nnsp_b200_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Cascade:
+    """n_streams independent nnCntrlClass controllers (VAD -> KWS -> S2I by default)."""
+
+    def __init__(self, models, n_streams, seq=(VAD, KWS, S2I), params=None, device=0):
+        L = lib()
+        self.models, self.S, self.device = models, int(n_streams), device
+        arr = (C.c_void_p * 3)(*[m.h if m is not None else None for m in models])
+        seq_a = (C.c_int * len(seq))(*seq)
+        p = capi.CascadeParams()
+        L.nnsp_b200_cascade_default_params(C.byref(p))
+        if params:
+            for k, v in params.items():
+                setattr(p, k, v)
+        self.params = p
+        self.h = C.c_void_p()
+        check(L.nnsp_b200_cascade_create(arr, seq_a, len(seq), C.byref(p), self.S, device, C.byref(self.h)), "cascade_create")
+
+    def params_array(self):
+        return np.array([getattr(self.params, n) for n, _ in capi.CascadeParams._fields_], np.int16)
+
+    def reset(self):
+        check(lib().nnsp_b200_cascade_reset(self.h), "cascade_reset")
+
+    def sync(self):
+        check(lib().nnsp_b200_cascade_sync(self.h), "cascade_sync")
+
+    def exec_device(self, pcm_dev, stride, n_frames, results_dev=None, taps=None):
+        p = pcm_dev.ptr if isinstance(pcm_dev, DeviceArray) else pcm_dev
+        r = results_dev.ptr if isinstance(results_dev, DeviceArray) else results_dev
+        check(lib().nnsp_b200_cascade_exec(self.h, p, stride, n_frames, r, C.byref(taps) if taps is not None else None), "cascade_exec")
+
+    def exec(self, pcm, taps=False):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        T = pcm.shape[1] // FRAME
+        d_pcm = DeviceArray.from_host(pcm, self.device)
+        d_res = DeviceArray((self.S, T), CASCADE_RESULT_DT, self.device)
+        tp, arrs = (None, None)
+        if taps:
+            tp, arrs = _make_taps(self.S, T, 1, 128, 1, self.device)
+        self.exec_device(d_pcm, pcm.shape[1], T, d_res, tp)
+        self.sync()
+        res = d_res.to_host()
+        out = {k: v.to_host() for k, v in arrs.items()} if taps else None
+        d_pcm.free(); d_res.free()
+        if arrs:
+            for v in arrs.values():
+                v.free()
+        return (res, out) if taps else res
+
+    def exec_host(self, pcm, results=None):
+        T = pcm.shape[1] // FRAME
+        if results is None:
+            results = np.empty((self.S, T), CASCADE_RESULT_DT)
+        check(lib().nnsp_b200_cascade_exec_host(self.h, pcm.ctypes.data_as(C.c_void_p), pcm.shape[1], T,
+                                                results.ctypes.data_as(C.c_void_p)), "cascade_exec_host")
+        return results
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 3)()
+        check(lib().nnsp_b200_cascade_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")
+        return list(ms)
+
+    def close(self):
+        if self.h:
+            lib().nnsp_b200_cascade_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def feature_stages(windows, device=0):
+    """windows: int16 [n, 480]. Every intermediate of the front end, computed on the GPU."""
+    w = np.ascontiguousarray(windows, np.int16)
+    n = w.shape[0]
+    out = dict(fft_in=np.zeros((n, 512), np.int32), spec=np.zeros((n, 514), np.int32), pspec=np.zeros((n, 257), np.int32),
+               mel=np.zeros((n, 40), np.int32), logmel=np.zeros((n, 40), np.int32))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().nnsp_b200_feature_stages(device, p(w), n, p(out["fft_in"]), p(out["spec"]), p(out["pspec"]),
+                                         p(out["mel"]), p(out["logmel"])), "feature_stages")
+    return out
+
+
+def table(name):
+    p, eb = C.c_void_p(), C.c_int()
+    n = lib().nnsp_b200_table(name.encode(), C.byref(p), C.byref(eb))
+    if n < 0:
+        raise NnspError("unknown table %r" % name)
+    ct = C.c_int16 if eb.value == 2 else C.c_int32
+    return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), (n,)).copy()
+
+
+def device_count():
+    return lib().nnsp_b200_device_count()
+
+
+def kernel_launches():
+    return lib().nnsp_b200_kernel_launches()

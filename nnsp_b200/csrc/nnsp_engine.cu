@@ -1,0 +1,763 @@
+/* nnsp_engine.cu -- kernels and host driver of the batched NNSPClass path.
+ *
+ * Two kernels per exec call:
+ *   feat_kernel : log-mel of every (stream, frame) of the call; frames are independent, so the
+ *                 grid covers S*T frames with one half-warp each (nnsp_feat.cuh)
+ *   nn_kernel   : per stream (one warp), the T frames in order: standardise the new row into
+ *                 the 6x40 context, every 2nd frame run the network and the post-processing,
+ *                 update the NNSPClass scalars and LSTM state (nnsp_net.cuh)
+ * plus a tiny hist_kernel that keeps the last two PCM frames for the next call's windows.
+ * sm_100a only; no CPU path exists. */
+#include <cuda_runtime.h>
+#include <mutex>
+#include <new>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nnsp_feat.cuh"
+#include "nnsp_host.h"
+#include "nnsp_net.cuh"
+
+namespace nnsp {
+
+std::atomic<long long> g_launches{0};
+
+/* ======================================================================================== */
+/* device bookkeeping                                                                         */
+/* ======================================================================================== */
+static std::mutex g_mu;
+static DevTables *g_dev_tables[64] = { nullptr };
+static int g_sm_count[64] = { 0 };
+
+int select_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        nnsp_set_error("no CUDA device available (%s); nnsp-b200 has no CPU fallback", cudaGetErrorString(e));
+        return NNSP_B200_ERR_CUDA;
+    }
+    if (device < 0 || device >= n || device >= 64) { nnsp_set_error("device %d out of range (have %d)", device, n); return NNSP_B200_ERR_ARG; }
+    NNSP_CUDA(cudaSetDevice(device));
+    if (!g_sm_count[device]) {
+        cudaDeviceProp p;
+        NNSP_CUDA(cudaGetDeviceProperties(&p, device));
+        if (p.major < 10) {
+            nnsp_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+            return NNSP_B200_ERR_CUDA;
+        }
+        g_sm_count[device] = p.multiProcessorCount;
+    }
+    return NNSP_B200_OK;
+}
+int sm_count(int device) { return g_sm_count[device] ? g_sm_count[device] : 148; }
+
+static void fill_dev_tables(const nnsp_tables *t, DevTables *d)
+{
+    memset(d, 0, sizeof *d);
+    for (int p = 0; p < 240; p++)
+        d->win2[p] = (uint32_t)(uint16_t)t->stft_win[2 * p] | ((uint32_t)(uint16_t)t->stft_win[2 * p + 1] << 16);
+    memcpy(d->fft_tw, t->fft_tw, sizeof d->fft_tw);
+    memcpy(d->rfft_tw, t->rfft_tw, sizeof d->rfft_tw);
+    memcpy(d->mel_taps, t->mel_taps, sizeof t->mel_taps);
+    memcpy(d->mel_start, t->mel_start, sizeof d->mel_start);
+    memcpy(d->mel_end, t->mel_end, sizeof d->mel_end);
+    memcpy(d->mel_off, t->mel_off, sizeof d->mel_off);
+    memcpy(d->log_lut, t->log_lut, sizeof d->log_lut);
+    memcpy(d->tanh_lut, t->tanh_lut, sizeof d->tanh_lut);
+}
+
+int get_device_tables(int device, const DevTables **out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_dev_tables[device]) {
+        const nnsp_tables *t = nnsp_tables_get();
+        if (!t) { nnsp_set_error("constant-table self check failed (fingerprint mismatch)"); return NNSP_B200_ERR_ARG; }
+        DevTables h;
+        fill_dev_tables(t, &h);
+        DevTables *d = nullptr;
+        NNSP_CUDA(cudaMalloc(&d, sizeof h));
+        NNSP_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
+        g_dev_tables[device] = d;
+    }
+    *out = g_dev_tables[device];
+    return NNSP_B200_OK;
+}
+
+/* ---- model upload: canonical row-major int8 -> K-major packed words ----------------------- */
+static void pack_matrix(uint32_t *dst, const int8_t *w, int nrows, int nrows_pad, int cols, int k4)
+{
+    for (int k = 0; k < k4; k++)
+        for (int r = 0; r < nrows_pad; r++) {
+            uint32_t word = 0;
+            for (int b = 0; b < 4; b++) {
+                const int c = 4 * k + b;
+                const uint8_t v = (r < nrows && c < cols) ? (uint8_t)w[(size_t)r * cols + c] : 0;
+                word |= (uint32_t)v << (8 * b);
+            }
+            dst[(size_t)k * nrows_pad + r] = word;
+        }
+}
+
+int upload_model(const nnsp_b200_model *m, DeviceModel *out)
+{
+    DevModel &D = out->h;
+    memset(&D, 0, sizeof D);
+    D.nn_id = m->nn_id;
+    D.numlayers = m->numlayers;
+    D.n_out = m->size_layer[m->numlayers];
+    D.feat_rshift = 30 - m->layer[0].qi;
+    memcpy(D.mean, m->mean, sizeof D.mean);
+    memcpy(D.stdR, m->stdR, sizeof D.stdR);
+    for (int i = 0; i < 40; i++) {          /* feature_module.c:32-37, LOG10_2POW_N15_Q15 = -147963 (:9) */
+        int64_t t = ((int64_t)-147963 - (int64_t)m->mean[i]) * (int64_t)m->stdR[i];
+        t >>= D.feat_rshift;
+        t = t > 32767 ? 32767 : (t < -32768 ? -32768 : t);
+        D.silence[i] = (int16_t)t;
+    }
+    int woff = 0, boff = 0;
+    for (int i = 0; i < m->numlayers; i++) {
+        const nnsp_layer &L = m->layer[i];
+        DevLayer &G = D.layer[i];
+        G.type = L.type; G.act = L.act; G.rows = L.rows; G.cols = L.cols; G.acc32 = L.acc32;
+        G.nrows = (L.type == NNSP_LAYER_LSTM) ? 4 * L.rows : L.rows;
+        G.nrows_pad = (G.nrows + 31) & ~31;
+        G.k4 = (L.cols + 3) / 4;
+        G.k4rec = (L.type == NNSP_LAYER_LSTM) ? (L.rows + 3) / 4 : 0;
+        /* the affine that produces the output: for lstm it is the recurrent half, whose input
+         * Q-format is qbit_input_rec (affine.c:387-393) */
+        const int qi_out = (L.type == NNSP_LAYER_LSTM) ? L.qi_next : L.qi;
+        const int qs = (qi_out + L.qk) > 15 ? (qi_out + L.qk) : 15;     /* affine.c:69-72 (bias present) */
+        G.sh_x = (L.type == NNSP_LAYER_LSTM) ? (L.qi_next - L.qi) : 0;
+        G.sh_bias = qs - L.qb;
+        G.sh_out = 15 - qs;
+        G.w_off = woff; woff += G.k4 * G.nrows_pad;
+        G.wrec_off = woff; woff += G.k4rec * G.nrows_pad;
+        G.bias_off = boff; boff += G.nrows_pad;
+        if (i < m->numlayers - 1) D.act_stride += L.rows;
+        if (L.type == NNSP_LAYER_LSTM) D.h_stride += L.rows;
+        if (L.cols > 480) { nnsp_set_error("layer %d: %d inputs exceed the exact-int32 dot-product bound (480)", i, L.cols); return NNSP_B200_ERR_UNSUPPORTED; }
+    }
+    if (D.h_stride > NNSP_B200_MAX_WIDTH) { nnsp_set_error("total LSTM state %d exceeds %d", D.h_stride, NNSP_B200_MAX_WIDTH); return NNSP_B200_ERR_UNSUPPORTED; }
+    D.weight_words = (woff + 3) & ~3;      /* 16-byte multiple for the bulk copy */
+    D.bias_count = (boff + 7) & ~7;
+    uint32_t *hw = (uint32_t *)calloc((size_t)D.weight_words + 4, 4);
+    int16_t *hb = (int16_t *)calloc((size_t)D.bias_count + 8, 2);
+    if (!hw || !hb) { free(hw); free(hb); return NNSP_B200_ERR_NOMEM; }
+    for (int i = 0; i < m->numlayers; i++) {
+        const nnsp_layer &L = m->layer[i];
+        const DevLayer &G = D.layer[i];
+        pack_matrix(hw + G.w_off, L.w, G.nrows, G.nrows_pad, L.cols, G.k4);
+        if (L.type == NNSP_LAYER_LSTM) pack_matrix(hw + G.wrec_off, L.wrec, G.nrows, G.nrows_pad, L.rows, G.k4rec);
+        memcpy(hb + G.bias_off, L.bias, (size_t)G.nrows * 2);
+    }
+    cudaError_t e1 = cudaMalloc(&out->wimg, (size_t)D.weight_words * 4);
+    cudaError_t e2 = cudaMalloc(&out->bimg, (size_t)D.bias_count * 2);
+    cudaError_t e3 = cudaMalloc(&out->d, sizeof D);
+    if (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
+        e1 = cudaMemcpy(out->wimg, hw, (size_t)D.weight_words * 4, cudaMemcpyHostToDevice);
+        e2 = cudaMemcpy(out->bimg, hb, (size_t)D.bias_count * 2, cudaMemcpyHostToDevice);
+        e3 = cudaMemcpy(out->d, &D, sizeof D, cudaMemcpyHostToDevice);
+    }
+    free(hw);
+    free(hb);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        nnsp_set_error("model upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+        free_model(out);
+        return NNSP_B200_ERR_CUDA;
+    }
+    return NNSP_B200_OK;
+}
+
+void free_model(DeviceModel *dm)
+{
+    if (dm->wimg) cudaFree(dm->wimg);
+    if (dm->bimg) cudaFree(dm->bimg);
+    if (dm->d) cudaFree(dm->d);
+    dm->wimg = nullptr; dm->bimg = nullptr; dm->d = nullptr;
+}
+
+/* ======================================================================================== */
+/* feature kernel                                                                             */
+/* ======================================================================================== */
+constexpr int FEAT_WARPS = 8;                 /* 16 frames in flight per CTA */
+constexpr int FEAT_THREADS = FEAT_WARPS * 32;
+
+struct FeatSmem {
+    FeatSmemTables tb;
+    FrameScratch fs[FEAT_WARPS * 2];
+};
+
+__global__ void __launch_bounds__(FEAT_THREADS)
+feat_kernel(const DevTables *__restrict__ tables, const int16_t *__restrict__ pcm, long long stride,
+            const int16_t *__restrict__ hist, int hist_frames, int s0, int ns, int T,
+            int32_t *__restrict__ logmel)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FeatSmem &sm = *reinterpret_cast<FeatSmem *>(smem_raw);
+    load_feat_tables(&sm.tb, tables, threadIdx.x, FEAT_THREADS);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, L = lane & 15;
+    FrameScratch &fs = sm.fs[warp * 2 + half];
+    const long long F = (long long)ns * T;
+    const int hist_len = hist_frames * NNSP_B200_FRAME;
+    for (long long f0 = ((long long)blockIdx.x * FEAT_WARPS + warp) * 2; f0 < F; f0 += (long long)gridDim.x * FEAT_WARPS * 2) {
+        const long long f = f0 + half;
+        const bool valid = f < F;
+        const long long fc = valid ? f : 0;
+        const int s = s0 + (int)(fc / T), t = (int)(fc % T);
+        const int16_t *ps = pcm + (long long)s * stride;
+        const int16_t *hs = hist + (long long)s * hist_len + hist_len;     /* hs[g], g < 0: samples before this call */
+        const int base = (t - 2) * NNSP_B200_FRAME;                        /* first sample of the 480-sample window */
+        auto load_pair = [&](int p) -> uint32_t {
+            const int g = base + 2 * p;
+            const int16_t *q = (g < 0) ? (hs + g) : (ps + g);
+            return __ldg(reinterpret_cast<const unsigned int *>(q));
+        };
+        frame_logmel<false>(sm.tb, fs, L, load_pair, logmel + ((long long)s * T + t) * NNSP_B200_NMEL, valid, FeatDump{});
+    }
+}
+
+int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStream_t st)
+{
+    static bool attr_set[64] = { false };
+    if (!attr_set[device]) {
+        NNSP_CUDA(cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem)));
+        attr_set[device] = true;
+    }
+    const long long F = (long long)a.ns * a.T;
+    if (F <= 0) return NNSP_B200_OK;
+    long long blocks = (F + FEAT_WARPS * 2 - 1) / (FEAT_WARPS * 2);
+    const long long cap = (long long)sm_count(device) * 4;          /* persistent: 4 CTAs (32 warps) per SM */
+    if (blocks > cap) blocks = cap;
+    feat_kernel<<<(unsigned)blocks, FEAT_THREADS, sizeof(FeatSmem), st>>>(tb, a.pcm, a.stride, a.hist, a.hist_frames,
+                                                                            a.s0, a.ns, a.T, a.logmel);
+    NNSP_LAUNCH_CHECK();
+    return NNSP_B200_OK;
+}
+
+/* keep the newest hist_frames PCM frames of (previous history ++ this call) for the next call */
+__global__ void hist_kernel(const int16_t *__restrict__ pcm, long long stride, int16_t *__restrict__ hist,
+                            int hist_frames, int s0, int ns, int T)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= ns) return;
+    const int s = s0 + warp;
+    const int words = hist_frames * (NNSP_B200_FRAME / 2);
+    const int keep = hist_frames - T;                                  /* frames of old history that survive (T < hist_frames) */
+    unsigned int *h = reinterpret_cast<unsigned int *>(hist + (long long)s * hist_frames * NNSP_B200_FRAME);
+    const unsigned int *p = reinterpret_cast<const unsigned int *>(pcm + (long long)s * stride);
+    if (keep <= 0) {
+        const unsigned int *src = p + (long long)(T - hist_frames) * (NNSP_B200_FRAME / 2);
+        for (int i = lane; i < words; i += 32) h[i] = src[i];
+    } else {
+        /* shift old frames down by T, append the T new ones; chunked so reads precede overlapping writes */
+        const int kw = keep * (NNSP_B200_FRAME / 2), tw = T * (NNSP_B200_FRAME / 2);
+        for (int i0 = 0; i0 < kw; i0 += 32) {
+            const int i = i0 + lane;
+            unsigned int v = 0;
+            if (i < kw) v = h[i + tw];
+            __syncwarp();
+            if (i < kw) h[i] = v;
+            __syncwarp();
+        }
+        for (int i = lane; i < tw; i += 32) h[kw + i] = p[i];
+    }
+}
+
+int launch_hist_update(const int16_t *pcm, long long stride, int16_t *hist, int hist_frames,
+                       int s0, int ns, int T, cudaStream_t st)
+{
+    if (ns <= 0 || T <= 0) return NNSP_B200_OK;
+    const int threads = 256, blocks = (ns * 32 + threads - 1) / threads;
+    hist_kernel<<<blocks, threads, 0, st>>>(pcm, stride, hist, hist_frames, s0, ns, T);
+    NNSP_LAUNCH_CHECK();
+    return NNSP_B200_OK;
+}
+
+/* ======================================================================================== */
+/* network + post-processing kernel                                                           */
+/* ======================================================================================== */
+constexpr int NN_WARPS = 16;
+constexpr int NN_THREADS = NN_WARPS * 32;
+
+struct NNArgs {
+    const DevModel *model;
+    const uint32_t *wimg;
+    const int16_t  *bimg;
+    const DevTables *tables;
+    StreamState st;
+    const int32_t *logmel;          /* [S][T][40] */
+    int s0, ns, T;
+    nnsp_b200_result *results;      /* [S][T] or null */
+    nnsp_b200_taps taps;
+    int16_t thresh_prob, th_count;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+/* Stage `bytes` (multiple of 16) from global to shared with one TMA bulk copy tracked by an
+ * mbarrier; every thread of the CTA waits on the barrier's phase 0. */
+__device__ __forceinline__ void tma_stage_weights(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        uint32_t off = 0;
+        while (off < bytes) {
+            const uint32_t n = (bytes - off) > 32768u ? 32768u : (bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32((char *)dst + off)), "l"((const char *)src + off), "r"(n), "r"(smem_u32(bar)) : "memory");
+            off += n;
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+    }
+}
+
+struct NNSmemLayout { size_t bar, w, b, lut, model, scratch, total; };
+static inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+static NNSmemLayout nn_layout(const DevModel &D)
+{
+    NNSmemLayout l;
+    l.bar = 0;
+    l.w = 16;
+    l.b = l.w + (size_t)D.weight_words * 4;
+    l.lut = align16(l.b + (size_t)D.bias_count * 2);
+    l.model = align16(l.lut + 384 * 2);
+    l.scratch = align16(l.model + sizeof(DevModel));
+    l.total = l.scratch + sizeof(WarpScratch) * NN_WARPS;
+    return l;
+}
+
+__global__ void __launch_bounds__(NN_THREADS, 1)
+nn_kernel(NNArgs a, int off_b, int off_lut, int off_model, int off_scratch)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *wimg = reinterpret_cast<uint32_t *>(smem_raw + 16);
+    int16_t *bimg = reinterpret_cast<int16_t *>(smem_raw + off_b);
+    int16_t *lut = reinterpret_cast<int16_t *>(smem_raw + off_lut);
+    DevModel &M = *reinterpret_cast<DevModel *>(smem_raw + off_model);
+    WarpScratch *wsa = reinterpret_cast<WarpScratch *>(smem_raw + off_scratch);
+
+    {   /* descriptor, bias, LUT by plain loads; the weight image by TMA */
+        const int *src = reinterpret_cast<const int *>(a.model);
+        int *dst = reinterpret_cast<int *>(&M);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += NN_THREADS) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 384; i += NN_THREADS) lut[i] = a.tables->tanh_lut[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < M.bias_count; i += NN_THREADS) bimg[i] = a.bimg[i];
+    tma_stage_weights(wimg, a.wimg, (uint32_t)M.weight_words * 4u, bar);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch *ws = &wsa[warp];
+    const int T = a.T, HS = M.h_stride, AS = M.act_stride, NO = M.n_out;
+
+    for (int si = blockIdx.x * NN_WARPS + warp; si < a.ns; si += gridDim.x * NN_WARPS) {
+        const int s = a.s0 + si;
+        /* load the stream's state */
+        for (int i = lane; i < 240; i += 32) ws->ctx[i] = a.st.ctx[(long long)s * 240 + i];
+        for (int i = lane; i < HS; i += 32) { ws->h[i] = a.st.h[(long long)s * HS + i]; ws->c[i] = a.st.c[(long long)s * HS + i]; }
+        if (lane < SC_N) ws->scal[lane] = a.st.scal[(long long)s * SC_N + lane];
+        __syncwarp();
+        const int32_t *lm = a.logmel + (long long)s * T * NNSP_B200_NMEL;
+        int32_t lm0 = lm[lane], lm1 = (lane < 8) ? lm[32 + lane] : 0;
+        for (int t = 0; t < T; t++) {
+            const long long ft = (long long)s * T + t;
+            /* FeatureClass_execute tail: slide the context (feature_module.c:54-57), standardise (:67-73) */
+            int16_t mv[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) { const int i = lane + 32 * j; mv[j] = (i < 200) ? ws->ctx[i + 40] : (int16_t)0; }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 7; j++) { const int i = lane + 32 * j; if (i < 200) ws->ctx[i] = mv[j]; }
+            const int16_t f0 = standardise(lm0, M.mean[lane], M.stdR[lane], M.feat_rshift);
+            ws->ctx[200 + lane] = f0;
+            int16_t f1 = 0;
+            if (lane < 8) { f1 = standardise(lm1, M.mean[32 + lane], M.stdR[32 + lane], M.feat_rshift); ws->ctx[232 + lane] = f1; }
+            if (a.taps.logmel) { a.taps.logmel[ft * 40 + lane] = lm0; if (lane < 8) a.taps.logmel[ft * 40 + 32 + lane] = lm1; }
+            if (a.taps.feat) { a.taps.feat[ft * 40 + lane] = f0; if (lane < 8) a.taps.feat[ft * 40 + 32 + lane] = f1; }
+            if (t + 1 < T) { lm0 = lm[(t + 1) * 40 + lane]; lm1 = (lane < 8) ? lm[(t + 1) * 40 + 32 + lane] : 0; }   /* prefetch */
+            __syncwarp();
+            const bool ran = (ws->scal[SC_SLIDES] == 1);                                  /* nn_speech.c:84 */
+            if (ran) {
+                net_forward(M, wimg, bimg, lut, ws, lane,
+                            a.taps.act ? a.taps.act + ft * AS : nullptr,
+                            a.taps.logits ? a.taps.logits + ft * NO : nullptr);
+                if (lane == 0) {
+                    if (M.nn_id == NNSP_B200_ID_S2I) post_s2i(ws->scal, ws->logits, a.th_count);   /* nn_speech.c:97-119 */
+                    else post_binary(ws->scal, ws->logits, a.thresh_prob, a.th_count);
+                }
+            } else {
+                if (a.taps.act) for (int i = lane; i < AS; i += 32) a.taps.act[ft * AS + i] = 0;
+                if (a.taps.logits) for (int i = lane; i < NO; i += 32) a.taps.logits[ft * NO + i] = 0;
+            }
+            if (lane == 0) {
+                ws->scal[SC_SLIDES] = (int16_t)((ws->scal[SC_SLIDES] + 1) % 2);            /* nn_speech.c:125 */
+                if (a.results) {
+                    nnsp_b200_result r;
+                    r.trigger = ws->scal[SC_TRIGGER];
+                    r.outputs[0] = ws->scal[SC_OUT0]; r.outputs[1] = ws->scal[SC_OUT0 + 1]; r.outputs[2] = ws->scal[SC_OUT0 + 2];
+                    a.results[ft] = r;
+                }
+            }
+            __syncwarp();
+            if (a.taps.hstate) for (int i = lane; i < HS; i += 32) a.taps.hstate[ft * HS + i] = ws->h[i];
+            if (a.taps.cstate) for (int i = lane; i < HS; i += 32) a.taps.cstate[ft * HS + i] = ws->c[i];
+            if (a.taps.post && lane < SC_N) {
+                int16_t v = ws->scal[lane];
+                if (lane == SC_RAN) v = ran ? 1 : 0;
+                if (lane == SC_STAGE) v = (int16_t)M.nn_id;
+                a.taps.post[ft * SC_N + lane] = v;
+            }
+        }
+        /* store the stream's state */
+        __syncwarp();
+        for (int i = lane; i < 240; i += 32) a.st.ctx[(long long)s * 240 + i] = ws->ctx[i];
+        for (int i = lane; i < HS; i += 32) { a.st.h[(long long)s * HS + i] = ws->h[i]; a.st.c[(long long)s * HS + i] = ws->c[i]; }
+        if (lane < SC_N) a.st.scal[(long long)s * SC_N + lane] = ws->scal[lane];
+        __syncwarp();
+    }
+}
+
+/* NNSPClass_reset for every stream (nn_speech.c:57-72, feature_module.c:26-45, neural_nets.c:27-42) */
+__global__ void reset_kernel(const DevModel *__restrict__ M, StreamState st, int S, int hist_words)
+{
+    const int s = blockIdx.x;
+    if (s >= S) return;
+    const int HS = M->h_stride;
+    /* FeatureClass_setDefault pre-fills rows 0..4 only (feature_module.c:39-42); row 5 keeps whatever the
+     * previous activation left there and is shifted into row 4 by the first execute -- reproduced */
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) st.ctx[(long long)s * 240 + i] = M->silence[i % 40];
+    for (int i = threadIdx.x; i < HS; i += blockDim.x) { st.h[(long long)s * HS + i] = 0; st.c[(long long)s * HS + i] = 0; }
+    for (int i = threadIdx.x; i < SC_N; i += blockDim.x) st.scal[(long long)s * SC_N + i] = (i == SC_SLIDES) ? 1 : 0;
+    unsigned int *h = reinterpret_cast<unsigned int *>(st.hist) + (long long)s * hist_words;
+    for (int i = threadIdx.x; i < hist_words; i += blockDim.x) h[i] = 0;                  /* spectrogram_module.c:25-31 */
+}
+
+/* stage-by-stage tap of the front end (parity tool, nnsp_b200_feature_stages) */
+__global__ void __launch_bounds__(FEAT_THREADS)
+feat_stages_kernel(const DevTables *__restrict__ tables, const int16_t *__restrict__ windows, int n,
+                   int32_t *fft_in, int32_t *spec, int32_t *pspec, int32_t *mel, int32_t *logmel)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FeatSmem &sm = *reinterpret_cast<FeatSmem *>(smem_raw);
+    load_feat_tables(&sm.tb, tables, threadIdx.x, FEAT_THREADS);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, L = lane & 15;
+    FrameScratch &fs = sm.fs[warp * 2 + half];
+    for (int f0 = (blockIdx.x * FEAT_WARPS + warp) * 2; f0 < n; f0 += gridDim.x * FEAT_WARPS * 2) {
+        const int f = f0 + half;
+        const bool valid = f < n;
+        const int fc = valid ? f : 0;
+        const int16_t *w = windows + (long long)fc * 480;
+        auto load_pair = [&](int p) -> uint32_t { return *reinterpret_cast<const unsigned int *>(w + 2 * p); };
+        FeatDump d;
+        d.fft_in = fft_in ? fft_in + (long long)fc * 512 : nullptr;
+        d.spec = spec ? spec + (long long)fc * 514 : nullptr;
+        d.pspec = pspec ? pspec + (long long)fc * 257 : nullptr;
+        d.mel = mel ? mel + (long long)fc * 40 : nullptr;
+        frame_logmel<true>(sm.tb, fs, L, load_pair, logmel + (long long)fc * 40, valid, d);
+    }
+}
+
+}  // namespace nnsp
+
+/* ======================================================================================== */
+/* C ABI: batched NNSPClass                                                                   */
+/* ======================================================================================== */
+using namespace nnsp;
+
+struct nnsp_b200_batch {
+    int device = 0, S = 0;
+    cudaStream_t stream = nullptr;          /* device-buffer API */
+    cudaStream_t xs[3] = { nullptr, nullptr, nullptr };   /* host-buffer API pipeline */
+    const DevTables *tables = nullptr;
+    DeviceModel dm;
+    StreamState st{};
+    int16_t thresh_prob = 0, th_count = 0;
+    int32_t *logmel = nullptr; long long logmel_frames = 0;       /* capacity in frames per stream */
+    int16_t *d_pcm = nullptr; long long d_pcm_frames = 0;
+    nnsp_b200_result *d_res = nullptr; long long d_res_frames = 0;
+    NNSmemLayout lay{};
+    int nn_ctas_per_sm = 1;
+    cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+    bool ev_valid = false;
+};
+
+static int batch_ensure_logmel(nnsp_b200_batch *b, int T)
+{
+    if (T <= b->logmel_frames) return NNSP_B200_OK;
+    if (b->logmel) { NNSP_CUDA(cudaStreamSynchronize(b->stream)); for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s)); cudaFree(b->logmel); b->logmel = nullptr; }
+    NNSP_CUDA(cudaMalloc(&b->logmel, (size_t)b->S * T * NNSP_B200_NMEL * sizeof(int32_t)));
+    b->logmel_frames = T;
+    return NNSP_B200_OK;
+}
+
+static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride, int T, int s0, int ns,
+                        nnsp_b200_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed)
+{
+    FeatLaunch fl{ pcm, stride, b->st.hist, 2, s0, ns, T, b->logmel };
+    if (timed) NNSP_CUDA(cudaEventRecord(b->ev[0], st));
+    int rc = launch_feature(b->tables, fl, b->device, st);
+    if (rc) return rc;
+    if (timed) NNSP_CUDA(cudaEventRecord(b->ev[1], st));
+    NNArgs a{};
+    a.model = b->dm.d; a.wimg = b->dm.wimg; a.bimg = b->dm.bimg; a.tables = b->tables; a.st = b->st;
+    a.logmel = b->logmel; a.s0 = s0; a.ns = ns; a.T = T; a.results = results;
+    if (taps) a.taps = *taps;
+    a.thresh_prob = b->thresh_prob; a.th_count = b->th_count;
+    int blocks = (ns + NN_WARPS - 1) / NN_WARPS;
+    const int cap = sm_count(b->device) * b->nn_ctas_per_sm;
+    if (blocks > cap) blocks = cap;
+    nn_kernel<<<blocks, NN_THREADS, b->lay.total, st>>>(a, (int)b->lay.b, (int)b->lay.lut, (int)b->lay.model, (int)b->lay.scratch);
+    NNSP_LAUNCH_CHECK();
+    if (timed) NNSP_CUDA(cudaEventRecord(b->ev[2], st));
+    rc = launch_hist_update(pcm, stride, b->st.hist, 2, s0, ns, T, st);
+    if (timed) b->ev_valid = true;
+    return rc;
+}
+
+extern "C" {
+
+const char *nnsp_b200_version(void) { return "nnsp-b200 0.1 (sm_100a)"; }
+long long nnsp_b200_kernel_launches(void) { return g_launches.load(); }
+
+int nnsp_b200_device_count(void)
+{
+    int n = 0;
+    return (cudaGetDeviceCount(&n) == cudaSuccess) ? n : 0;
+}
+
+int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device, int16_t thresh_prob,
+                           int16_t th_count_trigger, nnsp_b200_batch **out)
+{
+    if (!m || !out || n_streams <= 0) return NNSP_B200_ERR_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    nnsp_b200_batch *b = new (std::nothrow) nnsp_b200_batch();
+    if (!b) return NNSP_B200_ERR_NOMEM;
+    b->device = device; b->S = n_streams; b->thresh_prob = thresh_prob; b->th_count = th_count_trigger;
+    auto fail = [&](int code) { nnsp_b200_batch_destroy(b); return code; };
+    if ((rc = get_device_tables(device, &b->tables))) return fail(rc);
+    if ((rc = upload_model(m, &b->dm))) return fail(rc);
+    b->lay = nn_layout(b->dm.h);
+    if (b->lay.total > 227 * 1024) { nnsp_set_error("model needs %zu bytes of shared memory (> 227 KB)", b->lay.total); return fail(NNSP_B200_ERR_UNSUPPORTED); }
+    b->nn_ctas_per_sm = (int)((227 * 1024) / b->lay.total);
+    if (b->nn_ctas_per_sm > 4) b->nn_ctas_per_sm = 4;
+    if (b->nn_ctas_per_sm < 1) b->nn_ctas_per_sm = 1;
+    const int HS = b->dm.h.h_stride > 0 ? b->dm.h.h_stride : 1;
+    const size_t S = (size_t)n_streams;
+#define TRY(x) do { if ((x) != cudaSuccess) { nnsp_set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); return fail(NNSP_B200_ERR_CUDA); } } while (0)
+    TRY(cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lay.total > 48 * 1024 ? 227 * 1024 : 48 * 1024));
+    TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    for (auto &s : b->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &e : b->ev) TRY(cudaEventCreate(&e));
+    TRY(cudaMalloc(&b->st.ctx, S * 240 * sizeof(int16_t)));
+    TRY(cudaMemset(b->st.ctx, 0, S * 240 * sizeof(int16_t)));
+    TRY(cudaMalloc(&b->st.h, S * HS * sizeof(int16_t)));
+    TRY(cudaMalloc(&b->st.c, S * HS * sizeof(int32_t)));
+    TRY(cudaMalloc(&b->st.scal, S * SC_N * sizeof(int16_t)));
+    TRY(cudaMalloc(&b->st.hist, S * 2 * NNSP_B200_FRAME * sizeof(int16_t)));
+#undef TRY
+    if ((rc = nnsp_b200_batch_reset(b))) return fail(rc);
+    *out = b;
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_batch_reset(nnsp_b200_batch *b)
+{
+    if (!b) return NNSP_B200_ERR_ARG;
+    NNSP_CUDA(cudaSetDevice(b->device));
+    for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    reset_kernel<<<b->S, 128, 0, b->stream>>>(b->dm.d, b->st, b->S, NNSP_B200_FRAME);
+    NNSP_LAUNCH_CHECK();
+    NNSP_CUDA(cudaStreamSynchronize(b->stream));
+    return NNSP_B200_OK;
+}
+
+static int check_pcm_args(const void *pcm, long long stride, int T)
+{
+    if (!pcm || T <= 0) { nnsp_set_error("null PCM pointer or n_frames <= 0"); return NNSP_B200_ERR_ARG; }
+    if ((stride & 1) || ((uintptr_t)pcm & 3) || stride < (long long)T * NNSP_B200_FRAME) {
+        nnsp_set_error("PCM must be 4-byte aligned with an even stream_stride >= n_frames*160");
+        return NNSP_B200_ERR_ARG;
+    }
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_batch_exec(nnsp_b200_batch *b, const int16_t *pcm_dev, long long stream_stride, int n_frames,
+                         nnsp_b200_result *results_dev, const nnsp_b200_taps *taps)
+{
+    if (!b) return NNSP_B200_ERR_ARG;
+    int rc = check_pcm_args(pcm_dev, stream_stride, n_frames);
+    if (rc) return rc;
+    NNSP_CUDA(cudaSetDevice(b->device));
+    if ((rc = batch_ensure_logmel(b, n_frames))) return rc;
+    return batch_launch(b, pcm_dev, stream_stride, n_frames, 0, b->S, results_dev, taps, b->stream, true);
+}
+
+int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long stream_stride, int n_frames,
+                              nnsp_b200_result *results)
+{
+    if (!b) return NNSP_B200_ERR_ARG;
+    int rc = check_pcm_args(pcm, stream_stride, n_frames);
+    if (rc) return rc;
+    NNSP_CUDA(cudaSetDevice(b->device));
+    const int T = n_frames;
+    if ((rc = batch_ensure_logmel(b, T))) return rc;
+    if (T > b->d_pcm_frames) {
+        NNSP_CUDA(cudaDeviceSynchronize());
+        if (b->d_pcm) cudaFree(b->d_pcm);
+        if (b->d_res) cudaFree(b->d_res);
+        b->d_pcm = nullptr; b->d_res = nullptr;
+        NNSP_CUDA(cudaMalloc(&b->d_pcm, (size_t)b->S * T * NNSP_B200_FRAME * sizeof(int16_t)));
+        NNSP_CUDA(cudaMalloc(&b->d_res, (size_t)b->S * T * sizeof(nnsp_b200_result)));
+        b->d_pcm_frames = T; b->d_res_frames = T;
+    }
+    NNSP_CUDA(cudaStreamSynchronize(b->stream));
+    /* slices of streams pipelined over three CUDA streams: H2D(k+1) overlaps kernels(k) overlaps D2H(k-1) */
+    const long long dstride = (long long)T * NNSP_B200_FRAME;
+    int nsl = b->S >= 4096 ? 8 : (b->S >= 256 ? 4 : 1);
+    for (int k = 0; k < nsl; k++) {
+        const int s0 = (int)((long long)b->S * k / nsl), s1 = (int)((long long)b->S * (k + 1) / nsl);
+        if (s1 <= s0) continue;
+        cudaStream_t st = b->xs[k % 3];
+        if (stream_stride == dstride) {
+            NNSP_CUDA(cudaMemcpyAsync(b->d_pcm + (size_t)s0 * dstride, pcm + (size_t)s0 * stream_stride,
+                                      (size_t)(s1 - s0) * dstride * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        } else {
+            NNSP_CUDA(cudaMemcpy2DAsync(b->d_pcm + (size_t)s0 * dstride, dstride * sizeof(int16_t),
+                                        pcm + (size_t)s0 * stream_stride, stream_stride * sizeof(int16_t),
+                                        dstride * sizeof(int16_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
+        }
+        rc = batch_launch(b, b->d_pcm, dstride, T, s0, s1 - s0, results ? b->d_res : nullptr, nullptr, st, false);
+        if (rc) return rc;
+        if (results)
+            NNSP_CUDA(cudaMemcpyAsync(results + (size_t)s0 * T, b->d_res + (size_t)s0 * T,
+                                      (size_t)(s1 - s0) * T * sizeof(nnsp_b200_result), cudaMemcpyDeviceToHost, st));
+    }
+    for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_batch_sync(nnsp_b200_batch *b)
+{
+    if (!b) return NNSP_B200_ERR_ARG;
+    NNSP_CUDA(cudaSetDevice(b->device));
+    NNSP_CUDA(cudaStreamSynchronize(b->stream));
+    for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_batch_last_kernel_ms(nnsp_b200_batch *b, float ms[3])
+{
+    if (!b || !ms) return NNSP_B200_ERR_ARG;
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (!b->ev_valid) return NNSP_B200_OK;
+    NNSP_CUDA(cudaSetDevice(b->device));
+    NNSP_CUDA(cudaEventSynchronize(b->ev[2]));
+    NNSP_CUDA(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[1]));
+    NNSP_CUDA(cudaEventElapsedTime(&ms[1], b->ev[1], b->ev[2]));
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_batch_dims(const nnsp_b200_batch *b, int *n_streams, int *act_stride, int *h_stride, int *n_out)
+{
+    if (!b) return NNSP_B200_ERR_ARG;
+    if (n_streams) *n_streams = b->S;
+    if (act_stride) *act_stride = b->dm.h.act_stride;
+    if (h_stride) *h_stride = b->dm.h.h_stride;
+    if (n_out) *n_out = b->dm.h.n_out;
+    return NNSP_B200_OK;
+}
+
+void *nnsp_b200_batch_stream(nnsp_b200_batch *b) { return b ? (void *)b->stream : nullptr; }
+
+void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaDeviceSynchronize();
+    free_model(&b->dm);
+    cudaFree(b->st.ctx); cudaFree(b->st.h); cudaFree(b->st.c); cudaFree(b->st.scal); cudaFree(b->st.hist);
+    cudaFree(b->logmel); cudaFree(b->d_pcm); cudaFree(b->d_res);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    for (auto s : b->xs) if (s) cudaStreamDestroy(s);
+    for (auto e : b->ev) if (e) cudaEventDestroy(e);
+    delete b;
+}
+
+/* ---- stage-by-stage front-end tap -------------------------------------------------------- */
+
+int nnsp_b200_feature_stages(int device, const int16_t *windows, int n, int32_t *fft_in, int32_t *spec,
+                             int32_t *pspec, int32_t *mel, int32_t *logmel)
+{
+    if (!windows || n <= 0) return NNSP_B200_ERR_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    const DevTables *tb;
+    if ((rc = get_device_tables(device, &tb))) return rc;
+    int16_t *dw = nullptr;
+    int32_t *dbuf = nullptr;
+    const size_t per = 512 + 514 + 257 + 40 + 40;
+    NNSP_CUDA(cudaMalloc(&dw, (size_t)n * 480 * 2));
+    NNSP_CUDA(cudaMalloc(&dbuf, (size_t)n * per * 4));
+    NNSP_CUDA(cudaMemcpy(dw, windows, (size_t)n * 480 * 2, cudaMemcpyHostToDevice));
+    int32_t *d_fi = dbuf, *d_sp = d_fi + (size_t)n * 512, *d_ps = d_sp + (size_t)n * 514, *d_me = d_ps + (size_t)n * 257, *d_lm = d_me + (size_t)n * 40;
+    NNSP_CUDA(cudaFuncSetAttribute(feat_stages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem)));
+    int blocks = (n + FEAT_WARPS * 2 - 1) / (FEAT_WARPS * 2);
+    if (blocks > 1024) blocks = 1024;
+    feat_stages_kernel<<<blocks, FEAT_THREADS, sizeof(FeatSmem)>>>(tb, dw, n, d_fi, d_sp, d_ps, d_me, d_lm);
+    NNSP_LAUNCH_CHECK();
+    NNSP_CUDA(cudaDeviceSynchronize());
+    if (fft_in) NNSP_CUDA(cudaMemcpy(fft_in, d_fi, (size_t)n * 512 * 4, cudaMemcpyDeviceToHost));
+    if (spec) NNSP_CUDA(cudaMemcpy(spec, d_sp, (size_t)n * 514 * 4, cudaMemcpyDeviceToHost));
+    if (pspec) NNSP_CUDA(cudaMemcpy(pspec, d_ps, (size_t)n * 257 * 4, cudaMemcpyDeviceToHost));
+    if (mel) NNSP_CUDA(cudaMemcpy(mel, d_me, (size_t)n * 40 * 4, cudaMemcpyDeviceToHost));
+    if (logmel) NNSP_CUDA(cudaMemcpy(logmel, d_lm, (size_t)n * 40 * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dw);
+    cudaFree(dbuf);
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_table(const char *name, const void **data, int *elem_bytes)
+{
+    const nnsp_tables *t = nnsp_tables_get();
+    if (!t || !name || !data || !elem_bytes) return NNSP_B200_ERR_ARG;
+    struct { const char *n; const void *p; int eb, cnt; } tab[] = {
+        { "stft_win", t->stft_win, 2, 480 }, { "fft_tw", t->fft_tw, 4, 256 }, { "rfft_tw", t->rfft_tw, 4, 256 },
+        { "bitrev", t->bitrev, 2, 256 }, { "mel", t->mel, 2, 534 }, { "log_lut", t->log_lut, 2, 256 },
+        { "tanh_lut", t->tanh_lut, 2, 384 },
+    };
+    for (auto &e : tab)
+        if (!strcmp(e.n, name)) { *data = e.p; *elem_bytes = e.eb; return e.cnt; }
+    return NNSP_B200_ERR_ARG;
+}
+
+/* ---- device utilities ---------------------------------------------------------------------- */
+int nnsp_b200_dev_alloc(int device, size_t nbytes, void **ptr)
+{
+    int rc = select_device(device);
+    if (rc) return rc;
+    NNSP_CUDA(cudaMalloc(ptr, nbytes));
+    return NNSP_B200_OK;
+}
+int nnsp_b200_dev_free(int device, void *ptr) { NNSP_CUDA(cudaSetDevice(device)); NNSP_CUDA(cudaFree(ptr)); return NNSP_B200_OK; }
+int nnsp_b200_host_alloc_pinned(size_t nbytes, void **ptr) { NNSP_CUDA(cudaMallocHost(ptr, nbytes)); return NNSP_B200_OK; }
+int nnsp_b200_host_free_pinned(void *ptr) { NNSP_CUDA(cudaFreeHost(ptr)); return NNSP_B200_OK; }
+int nnsp_b200_memcpy_h2d(int device, void *dst, const void *src, size_t n) { NNSP_CUDA(cudaSetDevice(device)); NNSP_CUDA(cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice)); return NNSP_B200_OK; }
+int nnsp_b200_memcpy_d2h(int device, void *dst, const void *src, size_t n) { NNSP_CUDA(cudaSetDevice(device)); NNSP_CUDA(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost)); return NNSP_B200_OK; }
+int nnsp_b200_memset(int device, void *dst, int value, size_t n) { NNSP_CUDA(cudaSetDevice(device)); NNSP_CUDA(cudaMemset(dst, value, n)); return NNSP_B200_OK; }
+
+}  /* extern "C" */

@@ -1,0 +1,64 @@
+/* nnsp_engine.cuh -- device-visible data structures of the nnsp-b200 engine. */
+#pragma once
+#include <stdint.h>
+#include "nnsp_b200.h"
+
+namespace nnsp {
+
+/* ---- constant tables as the kernels see them (global memory, copied to SMEM per CTA) ---- */
+struct DevTables {
+    uint32_t win2[240];        /* stft window, two Q15 coefficients per word (sample 2p, 2p+1)   */
+    int32_t  fft_tw[256];      /* packed complex16, [k][tw^0, tw^2, tw^1, tw^3]                  */
+    int32_t  rfft_tw[256];
+    int16_t  mel_taps[456];    /* 454 taps (+2 pad)                                              */
+    int16_t  mel_start[40], mel_end[40], mel_off[40];
+    int16_t  log_lut[256];
+    int16_t  tanh_lut[384];
+};
+
+/* ---- one layer, GPU layout -------------------------------------------------------------
+ * Weights are stored K-major in 32-bit words: word (k4, r) holds W[r][4*k4 .. 4*k4+3]
+ * (int8, little endian), rows padded to a multiple of 32 with zero rows, K padded to a
+ * multiple of 4 with zero columns. lstm rows are ordered gate*H + unit (i, j, f, o). */
+struct DevLayer {
+    int type, act;
+    int rows;            /* units out (H for lstm)                 */
+    int nrows;           /* rows of W: rows (fc) or 4*rows (lstm)  */
+    int nrows_pad;       /* nrows rounded up to 32                 */
+    int cols, k4;        /* inputs, ceil(cols/4)                   */
+    int k4rec;           /* lstm: ceil(rows/4)                     */
+    int acc32;
+    int sh_x;            /* lstm: qi_next - qi          (affine.c:371)         */
+    int sh_bias;         /* qs - qbit_bias              (affine.c:192)         */
+    int sh_out;          /* 15 - qs                     (affine.c:244)         */
+    int w_off, wrec_off; /* word offsets into the weight image                 */
+    int bias_off;        /* int16 offset into the bias image                   */
+};
+
+struct DevModel {
+    int      nn_id, numlayers;
+    int      act_stride, h_stride, n_out;
+    int      feat_rshift;                   /* 30 - qbit_input[0] (feature_module.c:70) */
+    int      weight_words, bias_count;      /* sizes of the two images                  */
+    int32_t  mean[40], stdR[40];
+    int16_t  silence[40];                   /* standardised log10(2^-15) row (feature_module.c:32-43) */
+    DevLayer layer[NNSP_B200_MAX_LAYERS];
+};
+
+/* per-stream NNSPClass scalars, same order as the `post` tap */
+enum { SC_TRIGGER = 0, SC_OUT0 = 1, SC_CNT0 = 4, SC_ARGMAX_LAST = 12, SC_SLIDES = 13, SC_RAN = 14, SC_STAGE = 15, SC_N = 16 };
+
+/* cascade-only per-stream scalars */
+enum { CS_POS = 0, CS_CNT_KWS = 1, CS_CNT_S2I = 2, CS_AGE = 3, CS_N = 4 };
+
+struct StreamState {           /* all arrays stream-major, dense */
+    int16_t *ctx;              /* [S][240]  normFeatContext, 6 rows x 40 (row 5 survives a reset) */
+    int16_t *h;                /* [S][h_stride]                                        */
+    int32_t *c;                /* [S][h_stride]                                        */
+    int16_t *scal;             /* [S][16]                                              */
+    int16_t *hist;             /* [S][hist_frames*160] newest PCM frames of the previous exec call */
+    int32_t *lmhist;           /* cascade: [S][lm_hist][40] newest log-mel rows of previous calls  */
+    uint16_t *casc;            /* cascade: [S][4]                                      */
+};
+
+}  // namespace nnsp

@@ -1,0 +1,201 @@
+/* nnsp_feat.cuh -- the FeatureClass front end for one frame, computed by one half-warp.
+ *
+ * Reference path (per frame, per stream): FeatureClass_execute (feature_module.c:47-75) ->
+ * stftModule_analyze (spectrogram_module.c:47-77) -> rfft/fft (fft.c:27-221, complex.c:14-72)
+ * -> spec2pspec (spectrogram_module.c:33-45) -> melSpecProc (melSpecProc.c:6-27) ->
+ * log10_vec (fixlog10.c:53-61).
+ *
+ * Mapping: 16 lanes own the 256 complex points of the packed real FFT, 16 points each, in
+ * registers. Radix-4 DIF stages 0 and 1 touch points {L + 16a}; one padded 16x16 transpose
+ * through shared memory; stages 2 and 3 touch points {16L + b}. The bit-reversed result is
+ * scattered to shared memory, each lane then forms the real-FFT bins i and 256-i from the
+ * pair (Z[i], Z[256-i]), squares them into the power spectrum, and finally 40 mel bands and
+ * their log10 are produced (up to three bands per lane).
+ * All arithmetic is integer and identical to the reference's; see nnsp_device.cuh for why the
+ * reference's int32 clamps inside the FFT are unreachable and therefore not emitted. */
+#pragma once
+#include "nnsp_device.cuh"
+#include "nnsp_engine.cuh"
+
+namespace nnsp {
+
+struct FeatSmemTables {
+    uint32_t win2[240];
+    int32_t  fft_tw[256];
+    int32_t  rfft_tw[256];
+    int16_t  mel_taps[456];
+    int16_t  mel_start[40], mel_end[40], mel_off[40];
+    int16_t  log_lut[256];
+};
+
+struct FrameScratch {              /* per half-warp */
+    int2    x[272];                /* 256 complex points, one pad slot per 16 */
+    int32_t ps[260];               /* power spectrum, bins 0..256             */
+};
+
+struct FeatDump {                  /* optional stage taps (global memory), all may be null */
+    int32_t *fft_in, *spec, *pspec, *mel;
+};
+
+__device__ __forceinline__ void load_feat_tables(FeatSmemTables *dst, const DevTables *__restrict__ src,
+                                                 int tid, int nthreads)
+{
+    for (int i = tid; i < 240; i += nthreads) dst->win2[i] = src->win2[i];
+    for (int i = tid; i < 256; i += nthreads) { dst->fft_tw[i] = src->fft_tw[i]; dst->rfft_tw[i] = src->rfft_tw[i]; dst->log_lut[i] = src->log_lut[i]; }
+    for (int i = tid; i < 456; i += nthreads) dst->mel_taps[i] = src->mel_taps[i];
+    for (int i = tid; i < 40; i += nthreads) { dst->mel_start[i] = src->mel_start[i]; dst->mel_end[i] = src->mel_end[i]; dst->mel_off[i] = src->mel_off[i]; }
+}
+
+#define NNSP_TW_RE(w) ((int32_t)(int16_t)((w) & 0xffff))
+#define NNSP_TW_IM(w) ((int32_t)(w) >> 16)
+
+/* radix-4 DIF butterfly on register slots A,C,B,D = x[i0], x[i0+q], x[i0+2q], x[i0+3q]
+ * (fft.c:171-193 with M4_ of fft.c:12-15 written out), outputs times tw[0..3] (complex.c:54-72).
+ * W0 is always the Q15 "one"; ALLONE marks the last stage where every twiddle is. */
+template <bool ALLONE>
+__device__ __forceinline__ void bfly4(int32_t &ar, int32_t &ai, int32_t &cr, int32_t &ci,
+                                      int32_t &br, int32_t &bi, int32_t &dr, int32_t &di,
+                                      int32_t w1, int32_t w2, int32_t w3)
+{
+    const int32_t s0r = ar + br, s0i = ai + bi, d0r = ar - br, d0i = ai - bi;
+    const int32_t s1r = cr + dr, s1i = ci + di, d1r = cr - dr, d1i = ci - di;
+    const int32_t o0r = s0r + s1r, o0i = s0i + s1i;
+    const int32_t o1r = s0r - s1r, o1i = s0i - s1i;
+    const int32_t o2r = d0r + d1i, o2i = d0i - d1r;
+    const int32_t o3r = d0r - d1i, o3i = d0i + d1r;
+    ar = mul_one_q15(o0r);
+    ai = mul_one_q15(o0i);
+    if (ALLONE) {
+        cr = mul_one_q15(o1r); ci = mul_one_q15(o1i);
+        br = mul_one_q15(o2r); bi = mul_one_q15(o2i);
+        dr = mul_one_q15(o3r); di = mul_one_q15(o3i);
+    } else {
+        const int32_t w1r = NNSP_TW_RE(w1), w1i = NNSP_TW_IM(w1);
+        const int32_t w2r = NNSP_TW_RE(w2), w2i = NNSP_TW_IM(w2);
+        const int32_t w3r = NNSP_TW_RE(w3), w3i = NNSP_TW_IM(w3);
+        cr = msub_q15(o1r, w1r, o1i, w1i); ci = madd_q15(o1r, w1i, o1i, w1r);
+        br = msub_q15(o2r, w2r, o2i, w2i); bi = madd_q15(o2r, w2i, o2i, w2r);
+        dr = msub_q15(o3r, w3r, o3i, w3i); di = madd_q15(o3r, w3i, o3i, w3r);
+    }
+}
+
+__device__ __forceinline__ int xpad(int p) { return p + (p >> 4); }
+
+/* One frame by the 16 lanes of a half-warp (L = lane & 15). `load_pair(p)` returns PCM samples
+ * 2p and 2p+1 of the 480-sample analysis window packed in one word (p = 0..239).
+ * Every lane of the WARP must call this together (full-warp __syncwarp inside). */
+template <bool DUMP, typename LoadPair>
+__device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScratch &fs, int L,
+                                             LoadPair load_pair, int32_t *__restrict__ out_logmel,
+                                             bool store, FeatDump dump)
+{
+    int32_t xr[16], xi[16];
+    /* window, Q15 x Q15 >> 15 (spectrogram_module.c:62-66); zero padding 480..511 (:68-71) */
+#pragma unroll
+    for (int a = 0; a < 15; a++) {
+        const int p = L + 16 * a;
+        const uint32_t s = load_pair(p), w = tb.win2[p];
+        xr[a] = ((int32_t)(int16_t)(w & 0xffff) * (int32_t)(int16_t)(s & 0xffff)) >> 15;
+        xi[a] = ((int32_t)(int16_t)(w >> 16) * (int32_t)(int16_t)(s >> 16)) >> 15;
+    }
+    xr[15] = 0; xi[15] = 0;
+    if (DUMP && dump.fft_in && store) {
+#pragma unroll
+        for (int a = 0; a < 16; a++) { dump.fft_in[2 * (L + 16 * a)] = xr[a]; dump.fft_in[2 * (L + 16 * a) + 1] = xi[a]; }
+    }
+    /* stage 0: Nf = 256, q = 64, butterflies m = L + 16a', twiddle index k = m (fft.c:162-200) */
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int k = L + 16 * a;
+        bfly4<false>(xr[a], xi[a], xr[a + 4], xi[a + 4], xr[a + 8], xi[a + 8], xr[a + 12], xi[a + 12],
+                     tb.fft_tw[4 * k + 1], tb.fft_tw[4 * k + 2], tb.fft_tw[4 * k + 3]);
+    }
+    /* stage 1: Nf = 64, q = 16, group g, m = L, k = 4L */
+    {
+        const int32_t w1 = tb.fft_tw[16 * L + 1], w2 = tb.fft_tw[16 * L + 2], w3 = tb.fft_tw[16 * L + 3];
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            bfly4<false>(xr[4 * g], xi[4 * g], xr[4 * g + 1], xi[4 * g + 1], xr[4 * g + 2], xi[4 * g + 2],
+                         xr[4 * g + 3], xi[4 * g + 3], w1, w2, w3);
+    }
+    /* 16x16 transpose: point L + 16a -> lane a, slot L */
+#pragma unroll
+    for (int a = 0; a < 16; a++) fs.x[xpad(L + 16 * a)] = make_int2(xr[a], xi[a]);
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 16; b++) { const int2 v = fs.x[xpad(16 * L + b)]; xr[b] = v.x; xi[b] = v.y; }
+    __syncwarp();
+    /* stage 2: Nf = 16, q = 4, group g = L, m = 0..3, k = 16m (same for every lane) */
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+        bfly4<false>(xr[m], xi[m], xr[m + 4], xi[m + 4], xr[m + 8], xi[m + 8], xr[m + 12], xi[m + 12],
+                     tb.fft_tw[64 * m + 1], tb.fft_tw[64 * m + 2], tb.fft_tw[64 * m + 3]);
+    /* stage 3: Nf = 4, q = 1, k = 0: every twiddle is 0x7fff + 0j */
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+        bfly4<true>(xr[4 * g], xi[4 * g], xr[4 * g + 1], xi[4 * g + 1], xr[4 * g + 2], xi[4 * g + 2],
+                    xr[4 * g + 3], xi[4 * g + 3], 0, 0, 0);
+    /* bit-reversed read-out (fft.c:217-220): Z[brev8(p)] = x[p]; store at index m = brev8(16L + b) */
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        const int m = (int)(__brev((unsigned)(16 * L + b)) >> 24);
+        fs.x[m] = make_int2(xr[b], xi[b]);
+    }
+    __syncwarp();
+    /* real-FFT split (fft.c:66-124) and power spectrum (spectrogram_module.c:33-45) */
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        const int i = L + 16 * j;
+        if (j < 8 || L == 0) {
+            const int2 zi = fs.x[i], zr = fs.x[(256 - i) & 255];
+            const int32_t w = tb.rfft_tw[i & 255];
+            const int32_t wr = NNSP_TW_RE(w), wi = NNSP_TW_IM(w);
+            const int32_t er = (zi.x + zr.x) >> 1, ei = (zi.y - zr.y) >> 1;
+            const int32_t orr = (zi.y + zr.y) >> 1, oi = (zr.x - zi.x) >> 1;
+            if (i == 128 && j == 8) {
+                /* lane 0's extra turn: Nyquist bin X[256] = Xe[0] - Xo[0] (fft.c:123-124) */
+                const int2 z0 = fs.x[0];
+                const int32_t re = z0.x - z0.y, im = 0;
+                if (DUMP && dump.spec && store) { dump.spec[512] = re; dump.spec[513] = im; }
+                fs.ps[256] = (int32_t)(((int64_t)re * re + (int64_t)im * im) >> 15);
+                /* and the centre bin 128, whose mirror is itself */
+                const int32_t cr = er + msub_q15(orr, wr, oi, wi), ci = ei + madd_q15(orr, wi, oi, wr);
+                if (DUMP && dump.spec && store) { dump.spec[256] = cr; dump.spec[257] = ci; }
+                fs.ps[128] = (int32_t)(((int64_t)cr * cr + (int64_t)ci * ci) >> 15);
+            } else {
+                const int32_t xr0 = er + msub_q15(orr, wr, oi, wi), xi0 = ei + madd_q15(orr, wi, oi, wr);
+                if (DUMP && dump.spec && store) { dump.spec[2 * i] = xr0; dump.spec[2 * i + 1] = xi0; }
+                fs.ps[i] = (int32_t)(((int64_t)xr0 * xr0 + (int64_t)xi0 * xi0) >> 15);
+                if (i != 0) {
+                    /* mirrored bin 256 - i from the same pair, roles of Z[i] and Z[256-i] swapped */
+                    const int32_t v = tb.rfft_tw[256 - i];
+                    const int32_t vr = NNSP_TW_RE(v), vi = NNSP_TW_IM(v);
+                    const int32_t fi = (zr.y - zi.y) >> 1, pi = (zi.x - zr.x) >> 1;
+                    const int32_t xr1 = er + msub_q15(orr, vr, pi, vi), xi1 = fi + madd_q15(orr, vi, pi, vr);
+                    if (DUMP && dump.spec && store) { dump.spec[2 * (256 - i)] = xr1; dump.spec[2 * (256 - i) + 1] = xi1; }
+                    fs.ps[256 - i] = (int32_t)(((int64_t)xr1 * xr1 + (int64_t)xi1 * xi1) >> 15);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (DUMP && dump.pspec && store)
+        for (int i = L; i < 257; i += 16) dump.pspec[i] = fs.ps[i];
+    /* mel filterbank (melSpecProc.c:6-27) + log10 (fixlog10.c:53-61) */
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const int b = L + 16 * r;
+        if (b < 40) {
+            const int s = tb.mel_start[b], e = tb.mel_end[b];
+            const int16_t *tap = &tb.mel_taps[tb.mel_off[b]];
+            int64_t mac = 0;
+            for (int j = s; j <= e; j++) mac += (int64_t)(*tap++) * (int64_t)fs.ps[j];
+            const int32_t mel = sat32_dev(mac >> 15);
+            if (DUMP && dump.mel && store) dump.mel[b] = mel;
+            if (store) out_logmel[b] = log10_q15(mel, tb.log_lut);
+        }
+    }
+    __syncwarp();
+}
+
+}  // namespace nnsp

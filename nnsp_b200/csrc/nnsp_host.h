@@ -1,0 +1,59 @@
+/* nnsp_host.h -- host-side internals shared by the engine translation units. */
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <stdint.h>
+#include "nnsp_b200.h"
+#include "nnsp_engine.cuh"
+#include "nnsp_model.h"
+#include "nnsp_tables.h"
+
+namespace nnsp {
+
+extern std::atomic<long long> g_launches;
+
+#define NNSP_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            nnsp_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return NNSP_B200_ERR_CUDA;                                                        \
+        }                                                                                     \
+    } while (0)
+
+#define NNSP_LAUNCH_CHECK()                                                                   \
+    do {                                                                                      \
+        ::nnsp::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) {                                                             \
+            nnsp_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return NNSP_B200_ERR_CUDA;                                                        \
+        }                                                                                     \
+    } while (0)
+
+/* device-resident copies of one model: descriptor + weight image + bias image */
+struct DeviceModel {
+    DevModel  h;              /* host copy of the descriptor */
+    DevModel *d = nullptr;
+    uint32_t *wimg = nullptr;
+    int16_t  *bimg = nullptr;
+};
+
+int select_device(int device);                         /* cudaSetDevice + sm_100 check */
+int get_device_tables(int device, const DevTables **out);
+int upload_model(const nnsp_b200_model *m, DeviceModel *out);
+void free_model(DeviceModel *dm);
+int sm_count(int device);
+
+/* kernel launchers (nnsp_engine.cu) */
+struct FeatLaunch {
+    const int16_t *pcm; long long stride;
+    const int16_t *hist; int hist_frames;    /* [S][hist_frames*160], newest frames last */
+    int s0, ns, T;
+    int32_t *logmel;                          /* [S][T][40] */
+};
+int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStream_t st);
+int launch_hist_update(const int16_t *pcm, long long stride, int16_t *hist, int hist_frames,
+                       int s0, int ns, int T, cudaStream_t st);
+
+}  // namespace nnsp

@@ -486,7 +486,8 @@ int nnsp_oracle_nnsp_run(const nnsp_b200_model *m, nnsp_oracle_stream *s, int do
     const nnsp_tables *T = nnsp_tables_get();
     if (!T || !m || !s) return -1;
     const int as = model_act_stride(m), hs = model_h_stride(m), no = m->size_layer[m->numlayers];
-    if (do_reset) { memset(s, 0, sizeof *s); stream_reset(s, m); }
+    if (do_reset == 1) { memset(s, 0, sizeof *s); stream_reset(s, m); }   /* brand-new instance */
+    else if (do_reset == 2) stream_reset(s, m);                           /* NNSPClass_reset of a live instance: context row 5 survives */
     for (int t = 0; t < n_frames; t++) {
         int16_t act[O_MAXW];
         int32_t logits[O_MAXW];

@@ -131,7 +131,7 @@ class Oracle:
         res = np.zeros(T, RESULT_DT)
         tp = Taps(T, act_stride, h_stride, n_out) if taps else None
         a = [_p(getattr(tp, n)) for n in tp.names()] if taps else [None] * 7
-        rc = self.lib.nnsp_oracle_nnsp_run(m, st, int(reset), _p(pcm), T, thresh_prob, th_count, _p(res), *a)
+        rc = self.lib.nnsp_oracle_nnsp_run(m, st, int(reset), _p(pcm), T, thresh_prob, th_count, _p(res), *a)   # reset: 0 continue, 1 new instance, 2 NNSPClass_reset
         if own:
             self.lib.nnsp_oracle_stream_free(st)
         if rc:

@@ -183,10 +183,12 @@ int ref_nnsp_run(int nn_id, int do_reset, const int16_t *pcm, int n_frames,
     if (ref_model(nn_id, &netv, &mean, &stdR)) return -1;
     NeuralNetClass *net = (NeuralNetClass *)netv;
     const int as = act_stride(net), hs = h_stride(net), no = net->size_layer[net->numlayers];
-    if (do_reset) {
+    if (do_reset == 1) {            /* brand-new instance: zeroed structs, init, reset */
         g_thresh_prob = thresh_prob; g_th_count = th_count;
         memset(&g_inst, 0, sizeof g_inst); memset(&g_feat, 0, sizeof g_feat);
         NNSPClass_init(&g_inst, net, &g_feat, (char)nn_id, mean, stdR, &g_thresh_prob, &g_th_count);
+        NNSPClass_reset(&g_inst);
+    } else if (do_reset == 2) {     /* NNSPClass_reset of the live instance (what the controllers do) */
         NNSPClass_reset(&g_inst);
     }
     for (t = 0; t < n_frames; t++) {
