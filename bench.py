@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ns-nnsp streaming hot path on B200, next to the reference's CPU path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): the VAD model (def_nn1_vad, 64-bit accumulators) over 4,096
+independent synthetic 16 kHz streams per GPU; one step = 100 frames (1.0 s of audio) of every stream
+through FeatureClass -> NeuralNetClass -> NNSPClass post-processing.
+
+One JSON line on stdout (rank 0):
+  value    audio-seconds per second, PCM already resident in HBM, CUDA-event timed on the engine's stream
+  e2e      the same metric through the C ABI call with HOST (pinned) buffers: H2D + kernels + D2H inside
+  roofline dominant kernel (feat_kernel): algorithmic bytes per launch / CUDA-event duration vs measured HBM peak
+  cpu_baseline  the reference's own C (oracle/_ref, unmodified sources, gcc -O2) on this host's cores
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME = 160
+STREAMS_PER_GPU = 4096
+FRAMES_PER_STEP = 100
+MODEL_ID = 1                                     # VAD
+ALGO_BYTES_PER_STREAM_FRAME = 2608               # SURVEY.md section 8(d), VAD, one-frame-per-launch design
+ALGO_INTOPS_PER_FRAME_FEATURE = 17700            # SURVEY.md section 8(d), feature stage
+AUDIO_S_PER_FRAME = FRAME / 16000.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self._stop_evt = device, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own C implementation on the host cores
+# ---------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    kind, nn_id, pcm, T = args
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle
+    t0 = time.perf_counter()
+    if kind == "reference":
+        R = pyoracle.RefLib(False)
+        for row in pcm:                                   # single-instance library: stream after stream
+            R.nnsp_run(nn_id, row, taps=False)
+    else:
+        O = pyoracle.Oracle()
+        O.batch_run(O.model(nn_id, False), pcm, n_threads=1)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_throughput(pcm, T, cores, pool):
+    """audio-s/s of the reference C over `pcm` ([n, T*160]) split across `cores` forked processes
+    (processes, not threads: the reference keeps global scratch)."""
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.RefLib.available(False) else "port"
+    n = pcm.shape[0]
+    chunks = [pcm[n * k // cores: n * (k + 1) // cores] for k in range(cores)]
+    chunks = [c for c in chunks if len(c)]
+    t0 = time.perf_counter()
+    pool.map(_ref_worker, [(kind, MODEL_ID, c, T) for c in chunks])
+    dt = time.perf_counter() - t0
+    return n * T * AUDIO_S_PER_FRAME / dt, kind, dt
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    from nnsp_b200.synth import synth_pcm
+    cores = os.cpu_count() or 1
+    T = FRAMES_PER_STEP
+    n = min(STREAMS_PER_GPU, max(cores * 24, 64))
+    pcm = synth_pcm(n, T)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_reference_throughput(pcm, T, cores, pool)
+        t0 = time.perf_counter()
+        kind = "port"
+        for _ in range(args.steps):
+            _, kind, _ = cpu_reference_throughput(pcm, T, cores, pool)
+        dt = time.perf_counter() - t0
+    value = args.steps * n * T * AUDIO_S_PER_FRAME / dt
+    sample = "%d of the %d streams x %d frames per step, %d forked processes, oracle/%s" % (
+        n, STREAMS_PER_GPU, T, cores, "_ref (unmodified reference C, gcc -O2)" if kind == "reference" else "nnsp_oracle.c port")
+    line = {"impl": "reference", "metric": "audio-sec/sec (16 kHz streams, VAD, FeatureClass+NeuralNetClass+NNSPClass)",
+            "value": value, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16 activations x int8 weights, int64 accumulate", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "VAD model (def_nn1_vad, acc64) x %d streams per GPU x %d frames (%.1f s audio) per step; "
+                        "FeatureClass -> NeuralNetClass -> NNSPClass post-proc, bit-exact vs reference C" %
+                        (STREAMS_PER_GPU, FRAMES_PER_STEP, FRAMES_PER_STEP * AUDIO_S_PER_FRAME),
+            "streams_per_gpu": STREAMS_PER_GPU, "frames_per_step": FRAMES_PER_STEP, "total_streams": STREAMS_PER_GPU * n_gpus,
+            "partition": "streams block-partitioned over GPUs, no data-path collective",
+            "cache": "two alternating %d MB PCM buffers per GPU (larger than the 126 MB L2)" %
+                     (STREAMS_PER_GPU * FRAMES_PER_STEP * FRAME * 2 // 1000000)}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import nnsp_b200 as nb
+    from nnsp_b200.synth import synth_pcm
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    S, T = STREAMS_PER_GPU, FRAMES_PER_STEP
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU context makes fork() unsafe
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = min(S, max(cores * 24, 64))
+        sample_pcm = synth_pcm(n, T)
+        with mp.get_context("fork").Pool(cores) as pool:
+            cpu_reference_throughput(sample_pcm[: max(cores, 8)], T, cores, pool)       # warm the processes
+            reps, t_total, val, kind = 0, 0.0, 0.0, "port"
+            while t_total < 10.0 and reps < 8:
+                v, kind, dt = cpu_reference_throughput(sample_pcm, T, cores, pool)
+                val, t_total, reps = max(val, v), t_total + dt, reps + 1
+        cpu_baseline = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                        "sample": "%d of the %d streams x %d frames, best of %d passes, %d forked processes, %s" % (
+                            n, S, T, reps, cores, "oracle/_ref = unmodified reference C (gcc -O2)" if kind == "reference" else "oracle/nnsp_oracle.c port")}
+
+    model = nb.Model.from_blob(os.path.join(nb.MODEL_DIR, "vad.nnspm"), acc32=False)
+    batch = nb.NNSPBatch(model, S, device=device)
+    # two distinct PCM sets so consecutive steps never re-read L2-resident input
+    host_pcm = [synth_pcm(S, T, first_stream=rank * S + k * 1000003) for k in range(2)]
+    dev_pcm = [nb.DeviceArray.from_host(p, device) for p in host_pcm]
+    dev_res = nb.DeviceArray((S, T), nb.RESULT_DT, device)
+    ev0, ev1 = nb.Event(device), nb.Event(device)
+
+    def barrier():
+        batch.sync()
+        if dist is not None:
+            dist.barrier()
+        batch.sync()
+
+    def step(i):
+        batch.exec_device(dev_pcm[i & 1], T * FRAME, T, dev_res)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(device)
+    sampler.start()
+    n0 = nb.kernel_launches()
+    feat_ms = nn_ms = 0.0
+    ev0.record(batch.stream)
+    for i in range(args.steps):
+        step(i)
+    ev1.record(batch.stream)
+    batch.sync()
+    ms_total = ev0.elapsed_ms_to(ev1)
+    launches = nb.kernel_launches() - n0
+    clocks = sampler.stop()
+    # per-kernel durations (CUDA events the engine records around its own launches on the same stream)
+    km = []
+    for i in range(min(args.steps, 5)):
+        step(i)
+        batch.sync()
+        km.append(batch.last_kernel_ms())
+    feat_ms = float(np.mean([k[0] for k in km]))
+    nn_ms = float(np.mean([k[1] for k in km]))
+    barrier()
+
+    # end to end through the host-buffer entry point (pinned host memory -> H2D -> kernels -> D2H)
+    pin = [nb.PinnedArray((S, T * FRAME), np.int16) for _ in range(2)]
+    for k in range(2):
+        pin[k].array[...] = host_pcm[k]
+    pin_res = nb.PinnedArray((S, T), nb.RESULT_DT)
+    for i in range(2):
+        batch.exec_host(pin[i & 1].array, pin_res.array)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        batch.exec_host(pin[i & 1].array, pin_res.array)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        audio_s = world * S * T * AUDIO_S_PER_FRAME * args.steps
+        value = audio_s / (ms_total * 1e-3)
+        peak, peak_src = measured_peaks()
+        frames_per_launch = S * T
+        ach = ALGO_BYTES_PER_STREAM_FRAME * frames_per_launch / (feat_ms * 1e-3) / 1e9
+        imad, mixed = nb.int_peak(device)
+        int_ach = ALGO_INTOPS_PER_FRAME_FEATURE * frames_per_launch / (feat_ms * 1e-3) / 1e9
+        line = {
+            "metric": "audio-sec/sec (16 kHz streams, VAD, FeatureClass+NeuralNetClass+NNSPClass)",
+            "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16 activations x int8 weights, int32/int64 accumulate (bit-exact integer path)",
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": S * T * FRAME * 2,
+                    "d2h_bytes_per_step": S * T * 8, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "feat_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STREAM_FRAME * frames_per_launch,
+                         "launch_ms": feat_ms,
+                         "note": "the path is integer-issue bound, not HBM bound (SURVEY.md 8d); see int_alu"},
+            "int_alu": {"kernel": "feat_kernel", "achieved_gops": int_ach, "peak_gops_imad": imad,
+                        "peak_gops_mixed": mixed, "frac_of_mixed_peak": int_ach / mixed if mixed else None,
+                        "algorithmic_int_ops_per_frame": ALGO_INTOPS_PER_FRAME_FEATURE,
+                        "peak_source": "self-measured nnsp_b200_int_peak (register-resident IMAD / IMAD+ALU chains)"},
+            "kernel_ms": {"feat_kernel": feat_ms, "nn_kernel": nn_ms},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

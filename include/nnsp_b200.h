@@ -185,6 +185,17 @@ int nnsp_b200_feature_stages(int device, const int16_t *windows, int n, int32_t 
  * Returns element count or a negative error. */
 int nnsp_b200_table(const char *name, const void **data, int *elem_bytes);
 
+/* CUDA-event timing on a handle's stream (so callers can time exactly what the engine runs,
+ * on the stream it runs on, without CUDA headers). stream = nnsp_b200_*_stream() or NULL. */
+int nnsp_b200_event_create(int device, void **event);
+int nnsp_b200_event_record(void *event, void *stream);
+int nnsp_b200_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchronises on `stop` */
+int nnsp_b200_event_destroy(void *event);
+/* Self-measured integer-pipe peak of the device: a register-resident chain of 32-bit
+ * multiply-adds (IMAD) interleaved with adds/shifts, in giga integer-ops per second.
+ * MEASURED_PEAKS.json has no integer figure, so the int-ALU roofline uses this one. */
+int nnsp_b200_int_peak(int device, double *imad_gops, double *mixed_gops);
+
 /* Device utilities so that C callers need no CUDA headers. */
 int nnsp_b200_device_count(void);
 int nnsp_b200_dev_alloc(int device, size_t nbytes, void **ptr);

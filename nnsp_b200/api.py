@@ -190,6 +190,10 @@ class NNSPBatch:
         check(lib().nnsp_b200_batch_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")
         return list(ms)
 
+    @property
+    def stream(self):
+        return lib().nnsp_b200_batch_stream(self.h)
+
     def close(self):
         if self.h:
             lib().nnsp_b200_batch_destroy(self.h)
@@ -264,6 +268,10 @@ class Cascade:
         check(lib().nnsp_b200_cascade_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")
         return list(ms)
 
+    @property
+    def stream(self):
+        return lib().nnsp_b200_cascade_stream(self.h)
+
     def close(self):
         if self.h:
             lib().nnsp_b200_cascade_destroy(self.h)
@@ -295,6 +303,28 @@ def table(name):
         raise NnspError("unknown table %r" % name)
     ct = C.c_int16 if eb.value == 2 else C.c_int32
     return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), (n,)).copy()
+
+
+class Event:
+    """CUDA event recorded on an engine handle's stream (nnsp_b200_event_*)."""
+
+    def __init__(self, device=0):
+        self.ptr = C.c_void_p()
+        check(lib().nnsp_b200_event_create(device, C.byref(self.ptr)), "event_create")
+
+    def record(self, stream):
+        check(lib().nnsp_b200_event_record(self.ptr, stream), "event_record")
+
+    def elapsed_ms_to(self, stop):
+        ms = C.c_float()
+        check(lib().nnsp_b200_event_elapsed_ms(self.ptr, stop.ptr, C.byref(ms)), "event_elapsed_ms")
+        return ms.value
+
+
+def int_peak(device=0):
+    a, b = C.c_double(), C.c_double()
+    check(lib().nnsp_b200_int_peak(device, C.byref(a), C.byref(b)), "int_peak")
+    return a.value, b.value
 
 
 def device_count():

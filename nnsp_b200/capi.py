@@ -42,7 +42,8 @@ nnsp_b200_batch_stream nnsp_b200_batch_destroy nnsp_b200_cascade_default_params 
 nnsp_b200_cascade_reset nnsp_b200_cascade_exec nnsp_b200_cascade_exec_host nnsp_b200_cascade_sync
 nnsp_b200_cascade_last_kernel_ms nnsp_b200_cascade_stream nnsp_b200_cascade_destroy nnsp_b200_feature_stages
 nnsp_b200_table nnsp_b200_device_count nnsp_b200_dev_alloc nnsp_b200_dev_free nnsp_b200_host_alloc_pinned
-nnsp_b200_host_free_pinned nnsp_b200_memcpy_h2d nnsp_b200_memcpy_d2h nnsp_b200_memset""".split()
+nnsp_b200_host_free_pinned nnsp_b200_memcpy_h2d nnsp_b200_memcpy_d2h nnsp_b200_memset nnsp_b200_event_create
+nnsp_b200_event_record nnsp_b200_event_elapsed_ms nnsp_b200_event_destroy nnsp_b200_int_peak""".split()
 
 
 def lib():
@@ -100,6 +101,11 @@ def lib():
     L.nnsp_b200_memcpy_h2d.argtypes = [ci, vp, vp, C.c_size_t]
     L.nnsp_b200_memcpy_d2h.argtypes = [ci, vp, vp, C.c_size_t]
     L.nnsp_b200_memset.argtypes = [ci, vp, ci, C.c_size_t]
+    L.nnsp_b200_event_create.argtypes = [ci, C.POINTER(vp)]
+    L.nnsp_b200_event_record.argtypes = [vp, vp]
+    L.nnsp_b200_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.nnsp_b200_event_destroy.argtypes = [vp]
+    L.nnsp_b200_int_peak.argtypes = [ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -1,0 +1,546 @@
+/* nnsp_cascade.cu -- batched nnCntrlClass: the VAD -> KWS -> S2I gated cascade, one controller per
+ * stream (evb/src/nnCntrlClass.c:56-272, PcmBufClass.c:10-85, ParamsNNCntrl.h:8-21).
+ *
+ * What the reference keeps per stream: three NNSPClass instances (own FeatureClass, own LSTM state),
+ * a 100-frame PCM ring with look-back, two timeout counters and the sequence position. Exactly one
+ * instance runs per frame, and an instance is always reset when the controller leaves it, so the
+ * engine keeps ONE live instance state per stream plus what survives a reset in the reference:
+ * context row 5 of every instance (feature_module.c:39-42 refills rows 0..4 only).
+ *
+ * Per exec call:
+ *   feat_kernel    : log-mel of every raw (undelayed) frame of the call, full 3-frame window
+ *   cascade_kernel : per stream (one warp), frame by frame: pick the active model and its look-back d,
+ *                    take the log-mel row of frame t-d (this call or the log-mel history), or -- for the
+ *                    first two frames after an activation, whose window is partly the zeroed
+ *                    dataBuffer -- recompute it on the spot; standardise, network, post-processing,
+ *                    controller transition, reset-on-exit
+ *   hist kernels   : newest d_max+2 PCM frames and d_max log-mel rows for the next call */
+#include <cuda_runtime.h>
+#include <new>
+#include <string.h>
+
+#include "nnsp_feat.cuh"
+#include "nnsp_host.h"
+#include "nnsp_net.cuh"
+#include "nnsp_tma.cuh"
+
+namespace nnsp {
+
+constexpr int CS_WARPS = 8;
+constexpr int CS_THREADS = CS_WARPS * 32;
+constexpr int CS_MAXSEQ = 3;
+constexpr int LOGMEL_OF_ZERO = 0x2688 * -15;     /* log10_q15(0): fixlog10.c:39-47 with x -> 1 */
+
+struct CascadeDev {                   /* small, by value in kernel params */
+    int seq[CS_MAXSEQ], len_seq;
+    nnsp_b200_cascade_params P;
+    int dmax;                         /* max look-back frames over the ids in seq */
+    int wbytes[3], woff_words[3], boff[3];   /* per id: weight bytes, word offset of its image in smem, bias offset */
+};
+
+struct CascadeArgs {
+    const DevModel *model[3];
+    const uint32_t *wimg[3];
+    const int16_t *bimg[3];
+    const DevTables *tables;
+    StreamState st;                   /* ctx/h/c/scal of the live instance, hist, lmhist, casc */
+    int16_t *stale;                   /* [S][3][40] context row 5 left behind by each instance */
+    const int16_t *pcm; long long stride;
+    const int32_t *logmel;            /* [S][T][40] of this call */
+    int s0, ns, T;
+    nnsp_b200_cascade_result *results;
+    nnsp_b200_taps taps;
+    CascadeDev cd;
+};
+
+struct CascadeSmem {
+    FeatSmemTables ft;
+    int16_t tanh_lut[384];
+    DevModel model[3];
+    FrameScratch fs[CS_WARPS];
+    WarpScratch ws[CS_WARPS];
+};
+
+__global__ void __launch_bounds__(CS_THREADS, 1)
+cascade_kernel(CascadeArgs a, int off_w, int off_b)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    CascadeSmem &sm = *reinterpret_cast<CascadeSmem *>(smem_raw + 16);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *wimg = reinterpret_cast<uint32_t *>(smem_raw + off_w);
+    int16_t *bimg = reinterpret_cast<int16_t *>(smem_raw + off_b);
+    const CascadeDev &cd = a.cd;
+
+    load_feat_tables(&sm.ft, a.tables, threadIdx.x, CS_THREADS);
+    for (int i = threadIdx.x; i < 384; i += CS_THREADS) sm.tanh_lut[i] = a.tables->tanh_lut[i];
+    for (int k = 0; k < cd.len_seq; k++) {
+        const int id = cd.seq[k];
+        const int *src = reinterpret_cast<const int *>(a.model[id]);
+        int *dst = reinterpret_cast<int *>(&sm.model[id]);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += CS_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    for (int k = 0; k < cd.len_seq; k++) {
+        const int id = cd.seq[k];
+        for (int i = threadIdx.x; i < sm.model[id].bias_count; i += CS_THREADS) bimg[cd.boff[id] + i] = a.bimg[id][i];
+    }
+    /* all weight images by TMA bulk copies on one mbarrier */
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int k = 0; k < cd.len_seq; k++) total += (uint32_t)cd.wbytes[cd.seq[k]];
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
+        for (int k = 0; k < cd.len_seq; k++) {
+            const int id = cd.seq[k];
+            uint32_t off = 0;
+            const uint32_t bytes = (uint32_t)cd.wbytes[id];
+            while (off < bytes) {
+                const uint32_t n = (bytes - off) > 32768u ? 32768u : (bytes - off);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32((char *)(wimg + cd.woff_words[id]) + off)), "l"((const char *)a.wimg[id] + off), "r"(n), "r"(smem_u32(bar)) : "memory");
+                off += n;
+            }
+        }
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, L16 = lane & 15;
+    WarpScratch *ws = &sm.ws[warp];
+    FrameScratch &fs = sm.fs[warp];
+    const int T = a.T, HS = NNSP_B200_MAX_WIDTH;
+    const int hist_frames = cd.dmax + 2, hist_len = hist_frames * NNSP_B200_FRAME;
+
+    for (int si = blockIdx.x * CS_WARPS + warp; si < a.ns; si += gridDim.x * CS_WARPS) {
+        const int s = a.s0 + si;
+        for (int i = lane; i < 240; i += 32) ws->ctx[i] = a.st.ctx[(long long)s * 240 + i];
+        for (int i = lane; i < HS; i += 32) { ws->h[i] = a.st.h[(long long)s * HS + i]; ws->c[i] = a.st.c[(long long)s * HS + i]; }
+        if (lane < SC_N) ws->scal[lane] = a.st.scal[(long long)s * SC_N + lane];
+        int pos = a.st.casc[(long long)s * CS_N + CS_POS];
+        int cnt_kws = a.st.casc[(long long)s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[(long long)s * CS_N + CS_CNT_S2I];
+        int age = a.st.casc[(long long)s * CS_N + CS_AGE];
+        __syncwarp();
+        const int16_t *ps = a.pcm + (long long)s * a.stride;
+        const int16_t *hs = a.st.hist + (long long)s * hist_len + hist_len;                 /* hs[g], g < 0 */
+        const int32_t *lm_now = a.logmel + (long long)s * T * NNSP_B200_NMEL;
+        const int32_t *lm_old = a.st.lmhist + ((long long)s * cd.dmax + cd.dmax) * NNSP_B200_NMEL;   /* lm_old[r*40], r < 0 */
+
+        for (int t = 0; t < T; t++) {
+            const long long ft = (long long)s * T + t;
+            const int id = cd.seq[pos];
+            const DevModel &M = sm.model[id];
+            const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
+            const int tf = t - d;                                        /* raw frame fed to the instance (PcmBufClass_getData look-back) */
+            /* ---- FeatureClass_execute of the live instance ------------------------------------------ */
+            int32_t lm0, lm1;
+            if (age >= 2) {
+                const int32_t *row = (tf >= 0) ? (lm_now + (long long)tf * NNSP_B200_NMEL) : (lm_old + (long long)tf * NNSP_B200_NMEL);
+                lm0 = row[lane];
+                lm1 = (lane < 8) ? row[32 + lane] : 0;
+            } else {
+                /* the instance's dataBuffer still holds zeros from its reset (spectrogram_module.c:25-31):
+                 * window = [0, (age ? frame tf-1 : 0), frame tf]; both half-warps compute the same frame */
+                const int base = (tf - 2) * NNSP_B200_FRAME;
+                const int first_live = (2 - age) * NNSP_B200_FRAME;
+                auto load_pair = [&](int p) -> uint32_t {
+                    if (2 * p < first_live) return 0u;
+                    const int g = base + 2 * p;
+                    const int16_t *q = (g < 0) ? (hs + g) : (ps + g);
+                    return *reinterpret_cast<const unsigned int *>(q);
+                };
+                frame_logmel<false>(sm.ft, fs, L16, load_pair, ws->logits, lane < 16, FeatDump{});   /* logits[] doubles as a 40-int scratch row */
+                __syncwarp();
+                lm0 = ws->logits[lane];
+                lm1 = (lane < 8) ? ws->logits[32 + lane] : 0;
+                __syncwarp();
+            }
+            int16_t mv[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) { const int i = lane + 32 * j; mv[j] = (i < 200) ? ws->ctx[i + 40] : (int16_t)0; }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 7; j++) { const int i = lane + 32 * j; if (i < 200) ws->ctx[i] = mv[j]; }
+            const int16_t f0 = standardise(lm0, M.mean[lane], M.stdR[lane], M.feat_rshift);
+            ws->ctx[200 + lane] = f0;
+            if (lane < 8) ws->ctx[232 + lane] = standardise(lm1, M.mean[32 + lane], M.stdR[32 + lane], M.feat_rshift);
+            if (a.taps.logmel) { a.taps.logmel[ft * 40 + lane] = lm0; if (lane < 8) a.taps.logmel[ft * 40 + 32 + lane] = lm1; }
+            __syncwarp();
+            /* ---- NNSPClass_exec tail ------------------------------------------------------------------ */
+            const bool ran = (ws->scal[SC_SLIDES] == 1);
+            const int16_t th_prob = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_prob_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_prob_kws : cd.P.thresh_prob_s2i);
+            const int16_t th_cnt = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_cnts_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_cnts_kws : cd.P.thresh_cnts_s2i);
+            if (ran) {
+                net_forward(M, wimg + cd.woff_words[id], bimg + cd.boff[id], sm.tanh_lut, ws, lane, nullptr, nullptr);
+                if (lane == 0) {
+                    if (id == NNSP_B200_ID_S2I) post_s2i(ws->scal, ws->logits, th_cnt);
+                    else post_binary(ws->scal, ws->logits, th_prob, th_cnt);
+                }
+            }
+            if (lane == 0) ws->scal[SC_SLIDES] = (int16_t)((ws->scal[SC_SLIDES] + 1) % 2);
+            __syncwarp();
+            /* ---- controller (nnCntrlClass.c:172-269), evaluated redundantly by every lane ------------- */
+            const int detected = ws->scal[SC_TRIGGER];
+            int next_pos = pos, do_reset = 0, cnt_out = 0;
+            if (id == NNSP_B200_ID_S2I) {
+                cnt_s2i = (cnt_s2i + 1) % cd.P.thresh_timeout_s2i;
+                if (detected || cnt_s2i == cd.P.thresh_timeout_s2i - 1) {
+                    next_pos = (pos + 1) % cd.len_seq;
+                    if (detected || cd.seq[next_pos] != id) { cnt_s2i = 0; do_reset = 1; }
+                }
+                cnt_out = cnt_s2i;
+            } else if (id == NNSP_B200_ID_KWS) {
+                cnt_kws = (cnt_kws + 1) % cd.P.thresh_timeout_kws;
+                if (detected || cnt_kws == cd.P.thresh_timeout_kws - 1) {
+                    if (detected) next_pos = (pos + 1) % cd.len_seq;
+                    else { next_pos = (pos - 1) % cd.len_seq; if (next_pos < 0) next_pos += cd.len_seq; }
+                    if (detected || cd.seq[next_pos] != id) { cnt_kws = 0; do_reset = 1; }
+                }
+                cnt_out = cnt_kws;
+            } else if (detected) {
+                next_pos = (pos + 1) % cd.len_seq;
+                do_reset = 1;
+            }
+            if (lane == 0 && a.results) {
+                nnsp_b200_cascade_result r;
+                r.stage_id = (int8_t)id; r.pos_after = (int8_t)next_pos; r.detected = (int16_t)detected;
+                r.outputs[0] = ws->scal[SC_OUT0]; r.outputs[1] = ws->scal[SC_OUT0 + 1]; r.outputs[2] = ws->scal[SC_OUT0 + 2];
+                r.cnt_timeout = (uint16_t)cnt_out;
+                a.results[ft] = r;
+            }
+            /* taps of the instance that ran; zero-filled when the controller reset it this frame */
+            if (a.taps.feat) { a.taps.feat[ft * 40 + lane] = do_reset ? (int16_t)0 : ws->ctx[200 + lane]; if (lane < 8) a.taps.feat[ft * 40 + 32 + lane] = do_reset ? (int16_t)0 : ws->ctx[232 + lane]; }
+            if (a.taps.hstate) for (int i = lane; i < HS; i += 32) a.taps.hstate[ft * HS + i] = (do_reset || i >= M.h_stride) ? (int16_t)0 : ws->h[i];
+            if (a.taps.cstate) for (int i = lane; i < HS; i += 32) a.taps.cstate[ft * HS + i] = (do_reset || i >= M.h_stride) ? 0 : ws->c[i];
+            if (a.taps.post && lane < SC_N) {
+                int16_t v = do_reset ? (int16_t)0 : ws->scal[lane];
+                if (lane == SC_RAN) v = do_reset ? (int16_t)0 : (int16_t)(ran ? 1 : 0);
+                if (lane == SC_STAGE) v = (int16_t)id;
+                a.taps.post[ft * SC_N + lane] = v;
+            }
+            __syncwarp();
+            if (do_reset) {
+                /* NNSPClass_reset of the instance we leave: its context row 5 stays behind ... */
+                int16_t *stale = a.stale + ((long long)s * 3 + id) * 40;
+                stale[lane] = ws->ctx[200 + lane];
+                if (lane < 8) stale[32 + lane] = ws->ctx[232 + lane];
+                __syncwarp();
+                /* ... and the instance we enter starts from ITS reset state plus ITS stale row 5 */
+                const int nid = cd.seq[next_pos];
+                reset_stream_scratch(sm.model[nid], ws, lane);
+                const int16_t *st2 = a.stale + ((long long)s * 3 + nid) * 40;
+                ws->ctx[200 + lane] = st2[lane];
+                if (lane < 8) ws->ctx[232 + lane] = st2[32 + lane];
+                age = 0;
+            } else {
+                age = age < 2 ? age + 1 : 2;
+            }
+            pos = next_pos;
+            __syncwarp();
+        }
+        __syncwarp();
+        for (int i = lane; i < 240; i += 32) a.st.ctx[(long long)s * 240 + i] = ws->ctx[i];
+        for (int i = lane; i < HS; i += 32) { a.st.h[(long long)s * HS + i] = ws->h[i]; a.st.c[(long long)s * HS + i] = ws->c[i]; }
+        if (lane < SC_N) a.st.scal[(long long)s * SC_N + lane] = ws->scal[lane];
+        if (lane == 0) {
+            a.st.casc[(long long)s * CS_N + CS_POS] = (uint16_t)pos;
+            a.st.casc[(long long)s * CS_N + CS_CNT_KWS] = (uint16_t)cnt_kws;
+            a.st.casc[(long long)s * CS_N + CS_CNT_S2I] = (uint16_t)cnt_s2i;
+            a.st.casc[(long long)s * CS_N + CS_AGE] = (uint16_t)age;
+        }
+        __syncwarp();
+    }
+}
+
+struct ResetModels { const DevModel *m[3]; int seq[CS_MAXSEQ]; };
+
+/* nnCntrlClass_reset (nnCntrlClass.c:130-150): every instance reset, ring cleared, timeout counters
+ * zeroed; current_pos_seq is NOT rewound (only nnCntrlClass_init sets it, :125) and every instance keeps
+ * its context row 5. fresh != 0 (create = init + reset on zeroed structs) also rewinds and clears those. */
+__global__ void cascade_reset_kernel(ResetModels rm, StreamState st, int16_t *stale, int S,
+                                     int hist_words, int lm_words, int fresh)
+{
+    const int s = blockIdx.x;
+    if (s >= S) return;
+    const int HS = NNSP_B200_MAX_WIDTH;
+    const int pos = fresh ? 0 : st.casc[(long long)s * CS_N + CS_POS];
+    const DevModel *M = rm.m[rm.seq[pos]];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) st.ctx[(long long)s * 240 + i] = M->silence[i % 40];
+    if (fresh) {
+        for (int i = threadIdx.x; i < 40; i += blockDim.x) st.ctx[(long long)s * 240 + 200 + i] = 0;
+        for (int i = threadIdx.x; i < 120; i += blockDim.x) stale[(long long)s * 120 + i] = 0;
+    }
+    for (int i = threadIdx.x; i < HS; i += blockDim.x) { st.h[(long long)s * HS + i] = 0; st.c[(long long)s * HS + i] = 0; }
+    for (int i = threadIdx.x; i < SC_N; i += blockDim.x) st.scal[(long long)s * SC_N + i] = (i == SC_SLIDES) ? 1 : 0;
+    for (int i = threadIdx.x; i < CS_N; i += blockDim.x) st.casc[(long long)s * CS_N + i] = (i == CS_POS) ? (uint16_t)pos : (uint16_t)0;
+    unsigned int *h = reinterpret_cast<unsigned int *>(st.hist) + (long long)s * hist_words;
+    for (int i = threadIdx.x; i < hist_words; i += blockDim.x) h[i] = 0;                       /* PcmBufClass_reset, PcmBufClass.c:19-28 */
+    int32_t *lm = st.lmhist + (long long)s * lm_words;
+    for (int i = threadIdx.x; i < lm_words; i += blockDim.x) lm[i] = LOGMEL_OF_ZERO;           /* log-mel of an all-zero window */
+}
+
+}  // namespace nnsp
+
+using namespace nnsp;
+
+struct nnsp_b200_cascade {
+    int device = 0, S = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t xs[3] = { nullptr, nullptr, nullptr };
+    const DevTables *tables = nullptr;
+    DeviceModel dm[3];
+    bool have[3] = { false, false, false };
+    CascadeDev cd{};
+    StreamState st{};
+    int16_t *stale = nullptr;
+    int32_t *logmel = nullptr; long long logmel_frames = 0;
+    int16_t *d_pcm = nullptr; long long d_pcm_frames = 0;
+    nnsp_b200_cascade_result *d_res = nullptr;
+    size_t smem_total = 0; int off_w = 0, off_b = 0;
+    cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+    bool ev_valid = false;
+};
+
+static int cascade_ensure_logmel(nnsp_b200_cascade *c, int T)
+{
+    if (T <= c->logmel_frames) return NNSP_B200_OK;
+    NNSP_CUDA(cudaDeviceSynchronize());
+    if (c->logmel) cudaFree(c->logmel);
+    c->logmel = nullptr;
+    NNSP_CUDA(cudaMalloc(&c->logmel, (size_t)c->S * T * NNSP_B200_NMEL * sizeof(int32_t)));
+    c->logmel_frames = T;
+    return NNSP_B200_OK;
+}
+
+static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long stride, int T, int s0, int ns,
+                          nnsp_b200_cascade_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed)
+{
+    const int hist_frames = c->cd.dmax + 2;
+    FeatLaunch fl{ pcm, stride, c->st.hist, hist_frames, s0, ns, T, c->logmel };
+    if (timed) NNSP_CUDA(cudaEventRecord(c->ev[0], st));
+    int rc = launch_feature(c->tables, fl, c->device, st);
+    if (rc) return rc;
+    if (timed) NNSP_CUDA(cudaEventRecord(c->ev[1], st));
+    CascadeArgs a{};
+    for (int i = 0; i < 3; i++) { a.model[i] = c->dm[i].d; a.wimg[i] = c->dm[i].wimg; a.bimg[i] = c->dm[i].bimg; }
+    a.tables = c->tables; a.st = c->st; a.stale = c->stale; a.pcm = pcm; a.stride = stride; a.logmel = c->logmel;
+    a.s0 = s0; a.ns = ns; a.T = T; a.results = results; a.cd = c->cd;
+    if (taps) a.taps = *taps;
+    int blocks = (ns + CS_WARPS - 1) / CS_WARPS;
+    const int cap = sm_count(c->device);
+    if (blocks > cap) blocks = cap;
+    cascade_kernel<<<blocks, CS_THREADS, c->smem_total, st>>>(a, c->off_w, c->off_b);
+    NNSP_LAUNCH_CHECK();
+    if (timed) { NNSP_CUDA(cudaEventRecord(c->ev[2], st)); c->ev_valid = true; }
+    if ((rc = launch_hist_update(pcm, stride / 2, c->st.hist, hist_frames, NNSP_B200_FRAME / 2, s0, ns, T, st))) return rc;
+    if (c->cd.dmax > 0)
+        rc = launch_hist_update(c->logmel, (long long)T * NNSP_B200_NMEL, c->st.lmhist, c->cd.dmax, NNSP_B200_NMEL, s0, ns, T, st);
+    return rc;
+}
+
+extern "C" {
+
+void nnsp_b200_cascade_default_params(nnsp_b200_cascade_params *p)     /* ParamsNNCntrl.h:8-21 */
+{
+    if (!p) return;
+    p->thresh_prob_vad = 32767 >> 1; p->thresh_cnts_vad = 4;
+    p->frs_vbufBk_s2i = 80; p->thresh_timeout_s2i = 1000; p->thresh_prob_s2i = 32767 >> 1; p->thresh_cnts_s2i = 4;
+    p->frs_vbufBk_kws = 80; p->thresh_timeout_kws = 1000; p->thresh_prob_kws = 32767 >> 1; p->thresh_cnts_kws = 4;
+}
+
+int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *seq, int len_seq,
+                             const nnsp_b200_cascade_params *params, int n_streams, int device,
+                             nnsp_b200_cascade **out)
+{
+    if (!models || !seq || !out || n_streams <= 0 || len_seq < 1 || len_seq > CS_MAXSEQ) {
+        nnsp_set_error("cascade_create: bad arguments (sequence length must be 1..%d)", CS_MAXSEQ);
+        return NNSP_B200_ERR_ARG;
+    }
+    bool seen[3] = { false, false, false };
+    for (int i = 0; i < len_seq; i++) {
+        if (seq[i] < 0 || seq[i] > 2 || !models[seq[i]]) { nnsp_set_error("cascade_create: seq[%d]=%d has no model", i, seq[i]); return NNSP_B200_ERR_ARG; }
+        if (seen[seq[i]]) { nnsp_set_error("cascade_create: id %d appears twice in the sequence (unsupported)", seq[i]); return NNSP_B200_ERR_UNSUPPORTED; }
+        if (models[seq[i]]->nn_id != seq[i]) { nnsp_set_error("cascade_create: models[%d] carries nn_id %d", seq[i], models[seq[i]]->nn_id); return NNSP_B200_ERR_ARG; }
+        seen[seq[i]] = true;
+    }
+    int rc = select_device(device);
+    if (rc) return rc;
+    nnsp_b200_cascade *c = new (std::nothrow) nnsp_b200_cascade();
+    if (!c) return NNSP_B200_ERR_NOMEM;
+    c->device = device; c->S = n_streams;
+    auto fail = [&](int code) { nnsp_b200_cascade_destroy(c); return code; };
+    if (params) c->cd.P = *params; else nnsp_b200_cascade_default_params(&c->cd.P);
+    const nnsp_b200_cascade_params &P = c->cd.P;
+    if (P.thresh_timeout_kws < 1 || P.thresh_timeout_s2i < 1 || P.frs_vbufBk_kws < 0 || P.frs_vbufBk_s2i < 0 ||
+        P.frs_vbufBk_kws > 99 || P.frs_vbufBk_s2i > 99) {      /* PcmBufClass ring holds NUM_FRS_VBUF = 100 frames (PcmBufClass.c:6) */
+        nnsp_set_error("cascade_create: look-back must be 0..99 frames and timeouts >= 1");
+        return fail(NNSP_B200_ERR_ARG);
+    }
+    c->cd.len_seq = len_seq;
+    for (int i = 0; i < len_seq; i++) c->cd.seq[i] = seq[i];
+    c->cd.dmax = 0;
+    if (seen[NNSP_B200_ID_KWS] && P.frs_vbufBk_kws > c->cd.dmax) c->cd.dmax = P.frs_vbufBk_kws;
+    if (seen[NNSP_B200_ID_S2I] && P.frs_vbufBk_s2i > c->cd.dmax) c->cd.dmax = P.frs_vbufBk_s2i;
+    if ((rc = get_device_tables(device, &c->tables))) return fail(rc);
+    size_t wtot = 0, btot = 0;
+    for (int id = 0; id < 3; id++) {
+        if (!seen[id]) continue;
+        if ((rc = upload_model(models[id], &c->dm[id]))) return fail(rc);
+        c->have[id] = true;
+        c->cd.woff_words[id] = (int)(wtot / 4); c->cd.wbytes[id] = c->dm[id].h.weight_words * 4; wtot += (size_t)c->cd.wbytes[id];
+        c->cd.boff[id] = (int)btot; btot += (size_t)c->dm[id].h.bias_count;
+    }
+    c->off_w = (int)((16 + sizeof(CascadeSmem) + 127) & ~(size_t)127);
+    c->off_b = (int)(c->off_w + wtot);
+    c->smem_total = (size_t)c->off_b + btot * 2 + 16;
+    if (c->smem_total > 227 * 1024) { nnsp_set_error("cascade needs %zu bytes of shared memory (> 227 KB)", c->smem_total); return fail(NNSP_B200_ERR_UNSUPPORTED); }
+    const size_t S = (size_t)n_streams, HS = NNSP_B200_MAX_WIDTH;
+    const int hist_frames = c->cd.dmax + 2, lm_rows = c->cd.dmax > 0 ? c->cd.dmax : 1;
+#define TRY(x) do { if ((x) != cudaSuccess) { nnsp_set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); return fail(NNSP_B200_ERR_CUDA); } } while (0)
+    TRY(cudaFuncSetAttribute(cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &e : c->ev) TRY(cudaEventCreate(&e));
+    TRY(cudaMalloc(&c->st.ctx, S * 240 * sizeof(int16_t)));
+    TRY(cudaMalloc(&c->st.h, S * HS * sizeof(int16_t)));
+    TRY(cudaMalloc(&c->st.c, S * HS * sizeof(int32_t)));
+    TRY(cudaMalloc(&c->st.scal, S * SC_N * sizeof(int16_t)));
+    TRY(cudaMalloc(&c->st.casc, S * CS_N * sizeof(uint16_t)));
+    TRY(cudaMalloc(&c->st.hist, S * hist_frames * NNSP_B200_FRAME * sizeof(int16_t)));
+    TRY(cudaMalloc(&c->st.lmhist, S * lm_rows * NNSP_B200_NMEL * sizeof(int32_t)));
+    TRY(cudaMalloc(&c->stale, S * 120 * sizeof(int16_t)));
+#undef TRY
+    ResetModels rm{};
+    for (int i = 0; i < 3; i++) rm.m[i] = c->dm[i].d;
+    for (int i = 0; i < len_seq; i++) rm.seq[i] = seq[i];
+    cascade_reset_kernel<<<c->S, 128, 0, c->stream>>>(rm, c->st, c->stale, c->S, hist_frames * (NNSP_B200_FRAME / 2),
+                                                      lm_rows * NNSP_B200_NMEL, 1);
+    g_launches.fetch_add(1);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { nnsp_set_error("cascade reset kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(NNSP_B200_ERR_CUDA); }
+    *out = c;
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_cascade_reset(nnsp_b200_cascade *c)
+{
+    if (!c) return NNSP_B200_ERR_ARG;
+    NNSP_CUDA(cudaSetDevice(c->device));
+    NNSP_CUDA(cudaDeviceSynchronize());
+    const int hist_frames = c->cd.dmax + 2, lm_rows = c->cd.dmax > 0 ? c->cd.dmax : 1;
+    ResetModels rm{};
+    for (int i = 0; i < 3; i++) rm.m[i] = c->dm[i].d;
+    for (int i = 0; i < c->cd.len_seq; i++) rm.seq[i] = c->cd.seq[i];
+    cascade_reset_kernel<<<c->S, 128, 0, c->stream>>>(rm, c->st, c->stale, c->S,
+                                                      hist_frames * (NNSP_B200_FRAME / 2), lm_rows * NNSP_B200_NMEL, 0);
+    NNSP_LAUNCH_CHECK();
+    NNSP_CUDA(cudaStreamSynchronize(c->stream));
+    return NNSP_B200_OK;
+}
+
+static int cascade_check_pcm(const void *pcm, long long stride, int T)
+{
+    if (!pcm || T <= 0) { nnsp_set_error("null PCM pointer or n_frames <= 0"); return NNSP_B200_ERR_ARG; }
+    if ((stride & 1) || ((uintptr_t)pcm & 3) || stride < (long long)T * NNSP_B200_FRAME) {
+        nnsp_set_error("PCM must be 4-byte aligned with an even stream_stride >= n_frames*160");
+        return NNSP_B200_ERR_ARG;
+    }
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long long stream_stride, int n_frames,
+                           nnsp_b200_cascade_result *results_dev, const nnsp_b200_taps *taps)
+{
+    if (!c) return NNSP_B200_ERR_ARG;
+    int rc = cascade_check_pcm(pcm_dev, stream_stride, n_frames);
+    if (rc) return rc;
+    NNSP_CUDA(cudaSetDevice(c->device));
+    if ((rc = cascade_ensure_logmel(c, n_frames))) return rc;
+    return cascade_launch(c, pcm_dev, stream_stride, n_frames, 0, c->S, results_dev, taps, c->stream, true);
+}
+
+int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long long stream_stride, int n_frames,
+                                nnsp_b200_cascade_result *results)
+{
+    if (!c) return NNSP_B200_ERR_ARG;
+    int rc = cascade_check_pcm(pcm, stream_stride, n_frames);
+    if (rc) return rc;
+    NNSP_CUDA(cudaSetDevice(c->device));
+    const int T = n_frames;
+    if ((rc = cascade_ensure_logmel(c, T))) return rc;
+    if (T > c->d_pcm_frames) {
+        NNSP_CUDA(cudaDeviceSynchronize());
+        if (c->d_pcm) cudaFree(c->d_pcm);
+        if (c->d_res) cudaFree(c->d_res);
+        c->d_pcm = nullptr; c->d_res = nullptr;
+        NNSP_CUDA(cudaMalloc(&c->d_pcm, (size_t)c->S * T * NNSP_B200_FRAME * sizeof(int16_t)));
+        NNSP_CUDA(cudaMalloc(&c->d_res, (size_t)c->S * T * sizeof(nnsp_b200_cascade_result)));
+        c->d_pcm_frames = T;
+    }
+    NNSP_CUDA(cudaStreamSynchronize(c->stream));
+    const long long dstride = (long long)T * NNSP_B200_FRAME;
+    const int nsl = c->S >= 4096 ? 8 : (c->S >= 256 ? 4 : 1);
+    for (int k = 0; k < nsl; k++) {
+        const int s0 = (int)((long long)c->S * k / nsl), s1 = (int)((long long)c->S * (k + 1) / nsl);
+        if (s1 <= s0) continue;
+        cudaStream_t st = c->xs[k % 3];
+        NNSP_CUDA(cudaMemcpy2DAsync(c->d_pcm + (size_t)s0 * dstride, dstride * sizeof(int16_t),
+                                    pcm + (size_t)s0 * stream_stride, stream_stride * sizeof(int16_t),
+                                    dstride * sizeof(int16_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
+        rc = cascade_launch(c, c->d_pcm, dstride, T, s0, s1 - s0, results ? c->d_res : nullptr, nullptr, st, false);
+        if (rc) return rc;
+        if (results)
+            NNSP_CUDA(cudaMemcpyAsync(results + (size_t)s0 * T, c->d_res + (size_t)s0 * T,
+                                      (size_t)(s1 - s0) * T * sizeof(nnsp_b200_cascade_result), cudaMemcpyDeviceToHost, st));
+    }
+    for (auto s : c->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_cascade_sync(nnsp_b200_cascade *c)
+{
+    if (!c) return NNSP_B200_ERR_ARG;
+    NNSP_CUDA(cudaSetDevice(c->device));
+    NNSP_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto s : c->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_cascade_last_kernel_ms(nnsp_b200_cascade *c, float ms[3])
+{
+    if (!c || !ms) return NNSP_B200_ERR_ARG;
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (!c->ev_valid) return NNSP_B200_OK;
+    NNSP_CUDA(cudaSetDevice(c->device));
+    NNSP_CUDA(cudaEventSynchronize(c->ev[2]));
+    NNSP_CUDA(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
+    NNSP_CUDA(cudaEventElapsedTime(&ms[1], c->ev[1], c->ev[2]));
+    return NNSP_B200_OK;
+}
+
+void *nnsp_b200_cascade_stream(nnsp_b200_cascade *c) { return c ? (void *)c->stream : nullptr; }
+
+void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 3; i++) if (c->have[i]) free_model(&c->dm[i]);
+    cudaFree(c->st.ctx); cudaFree(c->st.h); cudaFree(c->st.c); cudaFree(c->st.scal); cudaFree(c->st.casc);
+    cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale);
+    cudaFree(c->logmel); cudaFree(c->d_pcm); cudaFree(c->d_res);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto s : c->xs) if (s) cudaStreamDestroy(s);
+    for (auto e : c->ev) if (e) cudaEventDestroy(e);
+    delete c;
+}
+
+}  /* extern "C" */

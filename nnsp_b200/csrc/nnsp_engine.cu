@@ -17,6 +17,7 @@
 #include "nnsp_feat.cuh"
 #include "nnsp_host.h"
 #include "nnsp_net.cuh"
+#include "nnsp_tma.cuh"
 
 namespace nnsp {
 
@@ -236,23 +237,24 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
     return NNSP_B200_OK;
 }
 
-/* keep the newest hist_frames PCM frames of (previous history ++ this call) for the next call */
-__global__ void hist_kernel(const int16_t *__restrict__ pcm, long long stride, int16_t *__restrict__ hist,
-                            int hist_frames, int s0, int ns, int T)
+/* keep the newest hist_frames frames of (previous history ++ this call) for the next call; a "frame" is
+ * wpf 32-bit words (80 for PCM, 40 for log-mel rows) */
+__global__ void hist_kernel(const unsigned int *__restrict__ src, long long stride_words, unsigned int *__restrict__ hist,
+                            int hist_frames, int wpf, int s0, int ns, int T)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= ns) return;
     const int s = s0 + warp;
-    const int words = hist_frames * (NNSP_B200_FRAME / 2);
+    const int words = hist_frames * wpf;
     const int keep = hist_frames - T;                                  /* frames of old history that survive (T < hist_frames) */
-    unsigned int *h = reinterpret_cast<unsigned int *>(hist + (long long)s * hist_frames * NNSP_B200_FRAME);
-    const unsigned int *p = reinterpret_cast<const unsigned int *>(pcm + (long long)s * stride);
+    unsigned int *h = hist + (long long)s * words;
+    const unsigned int *p = src + (long long)s * stride_words;
     if (keep <= 0) {
-        const unsigned int *src = p + (long long)(T - hist_frames) * (NNSP_B200_FRAME / 2);
-        for (int i = lane; i < words; i += 32) h[i] = src[i];
+        const unsigned int *q = p + (long long)(T - hist_frames) * wpf;
+        for (int i = lane; i < words; i += 32) h[i] = q[i];
     } else {
         /* shift old frames down by T, append the T new ones; chunked so reads precede overlapping writes */
-        const int kw = keep * (NNSP_B200_FRAME / 2), tw = T * (NNSP_B200_FRAME / 2);
+        const int kw = keep * wpf, tw = T * wpf;
         for (int i0 = 0; i0 < kw; i0 += 32) {
             const int i = i0 + lane;
             unsigned int v = 0;
@@ -265,12 +267,13 @@ __global__ void hist_kernel(const int16_t *__restrict__ pcm, long long stride, i
     }
 }
 
-int launch_hist_update(const int16_t *pcm, long long stride, int16_t *hist, int hist_frames,
+int launch_hist_update(const void *src, long long stride_words, void *hist, int hist_frames, int words_per_frame,
                        int s0, int ns, int T, cudaStream_t st)
 {
-    if (ns <= 0 || T <= 0) return NNSP_B200_OK;
+    if (ns <= 0 || T <= 0 || hist_frames <= 0) return NNSP_B200_OK;
     const int threads = 256, blocks = (ns * 32 + threads - 1) / threads;
-    hist_kernel<<<blocks, threads, 0, st>>>(pcm, stride, hist, hist_frames, s0, ns, T);
+    hist_kernel<<<blocks, threads, 0, st>>>((const unsigned int *)src, stride_words, (unsigned int *)hist, hist_frames,
+                                            words_per_frame, s0, ns, T);
     NNSP_LAUNCH_CHECK();
     return NNSP_B200_OK;
 }
@@ -293,34 +296,6 @@ struct NNArgs {
     nnsp_b200_taps taps;
     int16_t thresh_prob, th_count;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-/* Stage `bytes` (multiple of 16) from global to shared with one TMA bulk copy tracked by an
- * mbarrier; every thread of the CTA waits on the barrier's phase 0. */
-__device__ __forceinline__ void tma_stage_weights(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-        uint32_t off = 0;
-        while (off < bytes) {
-            const uint32_t n = (bytes - off) > 32768u ? 32768u : (bytes - off);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32((char *)dst + off)), "l"((const char *)src + off), "r"(n), "r"(smem_u32(bar)) : "memory");
-            off += n;
-        }
-    }
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)) : "memory");
-    }
-}
 
 struct NNSmemLayout { size_t bar, w, b, lut, model, scratch, total; };
 static inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -445,6 +420,30 @@ __global__ void reset_kernel(const DevModel *__restrict__ M, StreamState st, int
     for (int i = threadIdx.x; i < hist_words; i += blockDim.x) h[i] = 0;                  /* spectrogram_module.c:25-31 */
 }
 
+/* integer-pipe peak: 8 independent chains per thread; mode 0 = 16 IMAD, mode 1 = 8 IMAD + 8 add/shift/xor */
+__global__ void __launch_bounds__(256) int_peak_kernel(int *sink, int iters, int mode)
+{
+    int a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 7 + i * 13 + blockIdx.x;
+    const int m = (int)threadIdx.x | 1, c = blockIdx.x + 3;
+    if (mode == 0) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a[i] = a[i] * m + c; a[i] = a[i] * c + m; }
+        }
+    } else {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a[i] = a[i] * m + c; a[i] = (a[i] >> 3) ^ (a[i] + it); }
+        }
+    }
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= a[i];
+    if (r == 0x7fffffff) sink[threadIdx.x] = r;      /* keeps the chains alive, (almost) never stores */
+}
+
 /* stage-by-stage tap of the front end (parity tool, nnsp_b200_feature_stages) */
 __global__ void __launch_bounds__(FEAT_THREADS)
 feat_stages_kernel(const DevTables *__restrict__ tables, const int16_t *__restrict__ windows, int n,
@@ -523,7 +522,7 @@ static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride
     nn_kernel<<<blocks, NN_THREADS, b->lay.total, st>>>(a, (int)b->lay.b, (int)b->lay.lut, (int)b->lay.model, (int)b->lay.scratch);
     NNSP_LAUNCH_CHECK();
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[2], st));
-    rc = launch_hist_update(pcm, stride, b->st.hist, 2, s0, ns, T, st);
+    rc = launch_hist_update(pcm, stride / 2, b->st.hist, 2, NNSP_B200_FRAME / 2, s0, ns, T, st);
     if (timed) b->ev_valid = true;
     return rc;
 }
@@ -743,6 +742,57 @@ int nnsp_b200_table(const char *name, const void **data, int *elem_bytes)
     for (auto &e : tab)
         if (!strcmp(e.n, name)) { *data = e.p; *elem_bytes = e.eb; return e.cnt; }
     return NNSP_B200_ERR_ARG;
+}
+
+/* ---- events and the integer-pipe microbenchmark --------------------------------------------- */
+int nnsp_b200_event_create(int device, void **event)
+{
+    int rc = select_device(device);
+    if (rc) return rc;
+    cudaEvent_t e;
+    NNSP_CUDA(cudaEventCreate(&e));
+    *event = (void *)e;
+    return NNSP_B200_OK;
+}
+int nnsp_b200_event_record(void *event, void *stream) { NNSP_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream)); return NNSP_B200_OK; }
+int nnsp_b200_event_elapsed_ms(void *start, void *stop, float *ms)
+{
+    NNSP_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+    NNSP_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return NNSP_B200_OK;
+}
+int nnsp_b200_event_destroy(void *event) { NNSP_CUDA(cudaEventDestroy((cudaEvent_t)event)); return NNSP_B200_OK; }
+
+int nnsp_b200_int_peak(int device, double *imad_gops, double *mixed_gops)
+{
+    int rc = select_device(device);
+    if (rc) return rc;
+    int *sink = nullptr;
+    NNSP_CUDA(cudaMalloc(&sink, 1 << 20));
+    const int blocks = sm_count(device) * 8, threads = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    NNSP_CUDA(cudaEventCreate(&e0));
+    NNSP_CUDA(cudaEventCreate(&e1));
+    double out[2] = { 0, 0 };
+    for (int mode = 0; mode < 2; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            NNSP_CUDA(cudaEventRecord(e0));
+            int_peak_kernel<<<blocks, threads>>>(sink, iters, mode);
+            NNSP_LAUNCH_CHECK();
+            NNSP_CUDA(cudaEventRecord(e1));
+            NNSP_CUDA(cudaEventSynchronize(e1));
+            float ms;
+            NNSP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        /* 16 integer ops per thread per iteration in both modes */
+        out[mode] = (double)blocks * threads * (double)iters * 16.0 / (best * 1e-3) * 1e-9;
+    }
+    if (imad_gops) *imad_gops = out[0];
+    if (mixed_gops) *mixed_gops = out[1];
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return NNSP_B200_OK;
 }
 
 /* ---- device utilities ---------------------------------------------------------------------- */

@@ -53,7 +53,8 @@ struct FeatLaunch {
     int32_t *logmel;                          /* [S][T][40] */
 };
 int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStream_t st);
-int launch_hist_update(const int16_t *pcm, long long stride, int16_t *hist, int hist_frames,
+/* hist <- newest hist_frames frames of (hist ++ src[0..T)); frames are words_per_frame 32-bit words */
+int launch_hist_update(const void *src, long long stride_words, void *hist, int hist_frames, int words_per_frame,
                        int s0, int ns, int T, cudaStream_t st);
 
 }  // namespace nnsp

@@ -620,7 +620,13 @@ int nnsp_oracle_cascade_run(const nnsp_b200_model *const models[3], nnsp_oracle_
 {
     const nnsp_tables *T = nnsp_tables_get();
     if (!T || !c) return -1;
-    if (do_reset) cascade_reset(c, models, seq, len_seq, params);
+    if (do_reset == 2) {            /* nnCntrlClass_reset of a live controller, nnCntrlClass.c:130-150: position kept */
+        c->cnt_kws = c->cnt_s2i = 0;
+        for (int i = 0; i < 3; i++) if (models[i]) stream_reset(&c->inst[i], models[i]);
+        memset(c->ring, 0, sizeof c->ring);
+        c->idx_set = 0;
+        c->idx_latest = RING_FRAMES - 1;
+    } else if (do_reset) cascade_reset(c, models, seq, len_seq, params);
     for (int t = 0; t < n_frames; t++) {
         int ran = 0, was_reset = 0;
         const int id = cascade_step(c, models, pcm + (size_t)t * 160, results ? &results[t] : NULL, T, &ran, &was_reset);

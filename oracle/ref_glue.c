@@ -258,7 +258,9 @@ int ref_cascade_run(int do_reset, const int *seq, int len_seq, const int16_t *pa
 {
     static int16_t frame[160], chunk[160], hbuf[1024]; static int32_t cbuf[1024];
     int t, i;
-    if (do_reset) {
+    if (do_reset == 2) {             /* nnCntrlClass_reset of the live controller (position kept) */
+        nnCntrlClass_reset(&g_cntrl);
+    } else if (do_reset) {
         for (i = 0; i < len_seq; i++) g_seq[i] = (NNSP_ID)seq[i];
         nnCntrlClass_init(&g_cntrl, (void *)g_seq, (int8_t)len_seq);
         if (params10) memcpy(&g_cntrl.Params, params10, sizeof(ParamCntrlClass));

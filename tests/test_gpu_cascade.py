@@ -1,0 +1,115 @@
+"""GPU parity of the batched nnCntrlClass cascade (evb/src/nnCntrlClass.c:152-272) against the oracle:
+stage id, position, detection, outputs and timeout counter of every frame, plus the live instance's
+feature row / LSTM state / NNSPClass scalars, through stage changes, look-back and timeouts."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+MODEL_FILE = {0: "s2i.nnspm", 1: "vad.nnspm", 2: "kws_galaxy.nnspm"}
+
+
+def _models(nb, acc32=False):
+    return [nb.Model.from_blob(nb.MODEL_DIR + "/" + MODEL_FILE[i], acc32=acc32) for i in range(3)]
+
+
+def _oracle_models(oracle, acc32=False):
+    return [oracle.model(i, acc32) for i in range(3)]
+
+
+def _check(res_gpu, taps_gpu, s, res_or, taps_or, valid):
+    for f in ("stage_id", "pos_after", "detected", "outputs", "cnt_timeout"):
+        if not (res_gpu[s][f] == res_or[f]).all():
+            t = int(np.nonzero((res_gpu[s][f] != res_or[f]).reshape(len(res_or), -1).any(axis=1))[0][0])
+            raise AssertionError("stream %d frame %d: %s gpu %s oracle %s (stage %d)" % (s, t, f, res_gpu[s][f][t], res_or[f][t], res_or["stage_id"][t]))
+    if taps_gpu is None:
+        return
+    for g, o in (("logmel", "logmel"), ("feat", "feat"), ("hstate", "h"), ("cstate", "c"), ("post", "post")):
+        a, b = taps_gpu[g][s], getattr(taps_or, o)
+        if not (a == b).all():
+            t = int(np.nonzero((a != b).any(axis=1))[0][0])
+            raise AssertionError("stream %d frame %d: tap %s differs (stage %d valid %d): gpu %s oracle %s" %
+                                 (s, t, g, res_or["stage_id"][t], valid[t], a[t][:6], b[t][:6]))
+
+
+def test_cascade_default_sequence_every_frame(nb, oracle):
+    S, T = 20, 2600                 # long enough for detections, look-back and the 999-frame timeouts
+    pcm = nb.synth_pcm(S, T, first_stream=4)
+    c = nb.Cascade(_models(nb), S)
+    res, taps = c.exec(pcm, taps=True)
+    om = _oracle_models(oracle)
+    stages, transitions = set(), 0
+    for s in range(S):
+        r, tp, valid = oracle.cascade_run(om, pcm[s])
+        _check(res, taps, s, r, tp, valid)
+        stages |= set(np.unique(r["stage_id"]).tolist())
+        transitions += int((np.diff(r["pos_after"].astype(int)) != 0).sum())
+    assert stages == {0, 1, 2} and transitions > 10      # the workload really exercises the controller
+    c.close()
+
+
+def test_cascade_chunked_equals_one_shot(nb, oracle):
+    S, T = 12, 700
+    pcm = nb.synth_pcm(S, T, first_stream=20)
+    models = _models(nb)
+    c = nb.Cascade(models, S)
+    full = c.exec(pcm)
+    c.close()
+    c = nb.Cascade(models, S)
+    parts, t = [], 0
+    for n in (1, 1, 3, 80, 1, 2, 79, 200, 33, 300):
+        parts.append(c.exec(pcm[:, t * 160:(t + n) * 160]))
+        t += n
+    assert t == T
+    chunked = np.concatenate(parts, axis=1)
+    for f in full.dtype.names:
+        assert (chunked[f] == full[f]).all(), f
+    c.close()
+
+
+@pytest.mark.parametrize("seq,params", [
+    ((1, 0), dict(frs_vbufBk_s2i=5, thresh_timeout_s2i=60, thresh_cnts_vad=2)),
+    ((0,), dict(frs_vbufBk_s2i=0, thresh_timeout_s2i=37, thresh_cnts_s2i=1)),
+    ((1, 2, 0), dict(frs_vbufBk_kws=99, frs_vbufBk_s2i=1, thresh_timeout_kws=45, thresh_timeout_s2i=30, thresh_prob_kws=100, thresh_cnts_kws=2)),
+])
+def test_cascade_other_sequences_and_params(nb, oracle, seq, params):
+    S, T = 16, 600
+    pcm = nb.synth_pcm(S, T, first_stream=64)
+    c = nb.Cascade(_models(nb), S, seq=seq, params=params)
+    res, taps = c.exec(pcm, taps=True)
+    om = _oracle_models(oracle)
+    par = c.params_array()
+    for s in range(S):
+        r, tp, valid = oracle.cascade_run(om, pcm[s], seq=seq, params=par)
+        _check(res, taps, s, r, tp, valid)
+    c.close()
+
+
+def test_cascade_reset_midstream_and_acc32(nb, oracle):
+    S, T = 10, 500
+    pcm = nb.synth_pcm(S, 2 * T, first_stream=128)
+    c = nb.Cascade(_models(nb, acc32=True), S)
+    c.exec(pcm[:, :T * 160])
+    c.reset()                                       # nnCntrlClass_reset: position kept, stale context rows kept
+    res, taps = c.exec(pcm[:, T * 160:], taps=True)
+    om = _oracle_models(oracle, acc32=True)
+    for s in range(S):
+        st = oracle.lib.nnsp_oracle_cascade_new()
+        oracle.cascade_run(om, pcm[s, :T * 160], state=st, reset=1, taps=False)
+        r, tp, valid = oracle.cascade_run(om, pcm[s, T * 160:], state=st, reset=2)
+        oracle.lib.nnsp_oracle_cascade_free(st)
+        _check(res, taps, s, r, tp, valid)
+    c.close()
+
+
+def test_cascade_exec_host(nb):
+    S, T = 260, 120
+    pcm = nb.synth_pcm(S, T, first_stream=3)
+    models = _models(nb)
+    c = nb.Cascade(models, S)
+    dev = c.exec(pcm)
+    c.close()
+    c = nb.Cascade(models, S)
+    host = c.exec_host(pcm)
+    for f in dev.dtype.names:
+        assert (dev[f] == host[f]).all(), f
+    c.close()
