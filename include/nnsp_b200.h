@@ -44,7 +44,7 @@ extern "C" {
 #define NNSP_B200_NCTX           6     /* context frames   (ambiq_nnsp_const.h:7)   */
 #define NNSP_B200_MAX_LAYERS     10    /* neural_nets.h:18-30                       */
 #define NNSP_B200_MAX_WIDTH      128   /* widest hidden layer / LSTM state the kernels support */
-#define NNSP_B200_MAX_OUT        64    /* widest final (linear) layer               */
+#define NNSP_B200_MAX_OUT        128   /* widest final layer                        */
 
 /* post-processing flavour, keyed like NNSP_ID (nnsp_identification.h:3-9) */
 #define NNSP_B200_ID_S2I         0

@@ -37,6 +37,21 @@ extern "C" {
 #define DIM_INTENTS           7
 #define DIM_SLOTS             17
 
+/* helper macros some callers pick up from the library's public headers (minmax.h, ambiq_stdint.h) */
+#ifndef MAX
+#define MAX(x, y) (((x) > (y)) ? (x) : (y))
+#endif
+#ifndef MIN
+#define MIN(x, y) (((x) < (y)) ? (x) : (y))
+#endif
+#ifndef MAX_INT32_T
+#define MAX_INT32_T ((int32_t)0x7fffffff)
+#define MIN_INT32_T ((int32_t)0x80000000)
+#define MAX_INT16_T ((int16_t)0x7fff)
+#define MIN_INT16_T ((int16_t)0x8000)
+#define ONE_N32_Q15 ((int32_t)32768)
+#endif
+
 typedef enum { s2i_id = 0, vad_id = 1, kws_galaxy_id = 2, num_NNSP_IDS = 3 } NNSP_ID;
 
 /* ---- neural net description (what def_nn*.c instantiates) ------------------------- */

@@ -201,23 +201,31 @@ class Oracle:
 
 
 class RefLib:
-    """The compiled, unmodified reference. NOT re-entrant: one stream at a time per process."""
+    """The compiled, unmodified reference. NOT re-entrant: one stream at a time per process.
 
-    def __init__(self, acc32=False):
-        path = os.path.join(HERE, "_ref", "libnnsp_ref_acc%d.so" % (32 if acc32 else 64))
+    dropin=True loads oracle/_ref/libnnsp_dropin.so instead: the reference's controller and model tables
+    compiled against include/nnsp_compat and linked to libnnsp_b200.so, i.e. the same driver code on top of
+    the CUDA engine's legacy entry points (needs a GPU to run)."""
+
+    def __init__(self, acc32=False, dropin=False):
+        name = "libnnsp_dropin.so" if dropin else "libnnsp_ref_acc%d.so" % (32 if acc32 else 64)
+        path = os.path.join(HERE, "_ref", name)
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.lib = L = C.CDLL(path)
         self.acc32 = bool(acc32)
-        assert L.ref_is_acc32() == int(self.acc32)
+        self.dropin = dropin
+        assert dropin or L.ref_is_acc32() == int(self.acc32)
         L.ref_nnsp_run.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int16, C.c_int16] + [C.c_void_p] * 8
-        L.ref_feature_stages.argtypes = [C.c_void_p] * 6
+        if not dropin:
+            L.ref_feature_stages.argtypes = [C.c_void_p] * 6
+            L.ref_table.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
         L.ref_cascade_run.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
-        L.ref_table.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
 
     @staticmethod
-    def available(acc32=False):
-        return os.path.exists(os.path.join(HERE, "_ref", "libnnsp_ref_acc%d.so" % (32 if acc32 else 64)))
+    def available(acc32=False, dropin=False):
+        name = "libnnsp_dropin.so" if dropin else "libnnsp_ref_acc%d.so" % (32 if acc32 else 64)
+        return os.path.exists(os.path.join(HERE, "_ref", name))
 
     def strides(self, nn_id):
         a, h, n = C.c_int(), C.c_int(), C.c_int()

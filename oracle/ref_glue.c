@@ -17,10 +17,12 @@
 #include "feature_module.h"
 #include "neural_nets.h"
 #include "nnsp_identification.h"
+#ifndef GLUE_DROPIN          /* internals of the reference's front end: not part of the public interface */
 #include "spectrogram_module.h"
 #include "melSpecProc.h"
 #include "fixlog10.h"
 #include "fft.h"
+#endif
 #include "def_nn0_s2i.h"
 #include "def_nn1_vad.h"
 #include "def_nn2_kws_galaxy.h"
@@ -31,10 +33,13 @@ typedef struct { int16_t trigger; int16_t outputs[3]; } glue_result;            
 typedef struct { int8_t stage_id, pos_after; int16_t detected; int16_t outputs[3];
                  uint16_t cnt_timeout; } glue_cascade_result;                   /* == nnsp_b200_cascade_result */
 
+#ifndef GLUE_DROPIN
 extern const int16_t stft_win_coeff[];
 extern const int32_t fft_tw_coeff[], rfft_tw_coeff[];
 extern const int16_t br_coeff[], mfltrBank_coeff[], log_tayler_coeff[];
 extern int16_t coeffs_tanh[];
+
+#endif
 
 int ref_is_acc32(void)
 {
@@ -55,6 +60,7 @@ int ref_model(int nn_id, void **net, const int32_t **mean, const int32_t **stdR)
     return -1;
 }
 
+#ifndef GLUE_DROPIN
 /* the reference's constant tables, for tests/test_tables.py */
 int ref_table(const char *name, const void **p, int *elem_bytes)
 {
@@ -92,6 +98,8 @@ void ref_feature_stages(const int16_t *win480, int32_t *fft_in, int32_t *spec, i
     log10_vec(me, me, 40, 15);
     if (logmel) memcpy(logmel, me, 40 * sizeof(int32_t));
 }
+
+#endif /* !GLUE_DROPIN */
 
 /* ---- shared tap helpers ----------------------------------------------------------------- */
 static int act_stride(const NeuralNetClass *n)
@@ -262,6 +270,10 @@ int ref_cascade_run(int do_reset, const int *seq, int len_seq, const int16_t *pa
         nnCntrlClass_reset(&g_cntrl);
     } else if (do_reset) {
         for (i = 0; i < len_seq; i++) g_seq[i] = (NNSP_ID)seq[i];
+        /* a brand-new controller, as after program start: the reference keeps its instances in zero-
+         * initialised statics (nnCntrlClass.c:50-52) that neither _init nor _reset clears completely */
+        memset(NNSP_INSTS, 0, 3 * sizeof(NNSPClass));
+        memset(FEAT_INSTS, 0, 3 * sizeof(FeatureClass));
         nnCntrlClass_init(&g_cntrl, (void *)g_seq, (int8_t)len_seq);
         if (params10) memcpy(&g_cntrl.Params, params10, sizeof(ParamCntrlClass));
         nnCntrlClass_reset(&g_cntrl);
