@@ -1,0 +1,39 @@
+"""Multi-GPU host logic: streams are independent, so the path shards by a static block partition of stream
+ids over ranks (one process per GPU), with NO collective on the data path. Result records are gathered to
+every rank (or only used locally) over torch.distributed when a caller wants one global array
+(SURVEY.md section 8e)."""
+import numpy as np
+
+
+def stream_range(total_streams, world_size, rank):
+    """[first, last) stream ids owned by `rank`: contiguous blocks, sizes differ by at most one."""
+    if not (0 <= rank < world_size) or total_streams < 0:
+        raise ValueError("bad partition request")
+    first = total_streams * rank // world_size
+    last = total_streams * (rank + 1) // world_size
+    return first, last
+
+
+def gather_results(local, total_streams, group=None):
+    """All ranks contribute their [n_local, T] structured result block; every rank gets [total, T].
+
+    Blocks may differ in size by one stream, so they are padded to the largest block for all_gather."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    T = local.shape[1]
+    item = local.dtype.itemsize
+    sizes = [stream_range(total_streams, world, r) for r in range(world)]
+    nmax = max(b - a for a, b in sizes)
+    buf = np.zeros((nmax, T * item), np.uint8)
+    buf[: local.shape[0]] = np.frombuffer(np.ascontiguousarray(local).tobytes(), np.uint8).reshape(local.shape[0], T * item)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.from_numpy(buf).to(dev)
+    outs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(outs, mine, group=group)
+    full = np.empty((total_streams, T), local.dtype)
+    for r, (a, b) in enumerate(sizes):
+        blk = outs[r].cpu().numpy()[: b - a]
+        full[a:b] = np.frombuffer(blk.tobytes(), local.dtype).reshape(b - a, T)
+    return full

@@ -258,6 +258,19 @@ class RefLib:
             raise RuntimeError("ref_nnsp_run rc=%d" % rc)
         return res, tp
 
+    def net_eval(self, nn_id, x, h, c):
+        a_s, h_s, n_o = self.strides(nn_id)
+        x = np.ascontiguousarray(x, np.int16)
+        h = np.ascontiguousarray(h, np.int16).copy()
+        c = np.ascontiguousarray(c, np.int32).copy()
+        act = np.zeros(a_s, np.int16)
+        logits = np.zeros(n_o, np.int32)
+        self.lib.ref_net_eval.argtypes = [C.c_int] + [C.c_void_p] * 5
+        rc = self.lib.ref_net_eval(nn_id, _p(x), _p(h), _p(c), _p(act), _p(logits))
+        if rc:
+            raise RuntimeError("ref_net_eval rc=%d" % rc)
+        return act, logits, h, c
+
     def cascade_run(self, pcm, seq=(VAD, KWS, S2I), params=None, reset=True, taps=True):
         pcm = np.ascontiguousarray(pcm, np.int16)
         T = len(pcm) // 160

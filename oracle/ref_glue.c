@@ -174,6 +174,25 @@ static void fill_post(int16_t *post, const NNSPClass *p, int ran_nn, int stage)
     post[15] = (int16_t)stage;
 }
 
+/* ---- one network evaluation on an explicit input and explicit LSTM state ---------------------- */
+/* h/c hold the state of all lstm layers back to back (in/out); act = layers 0..L-2, logits = layer L-1 */
+int ref_net_eval(int nn_id, const int16_t *input, int16_t *h, int32_t *c, int16_t *act, int32_t *logits)
+{
+    void *netv; const int32_t *mean, *stdR;
+    static int16_t in[512], hl[1024]; static int32_t cl[1024];
+    static int32_t out[512];
+    if (ref_model(nn_id, &netv, &mean, &stdR)) return -1;
+    NeuralNetClass *net = (NeuralNetClass *)netv;
+    memcpy(in, input, net->size_layer[0] * sizeof(int16_t));
+    save_hc(net, hl, cl);
+    shadow_layers(net, in, h, c, act, logits);       /* per-layer taps via debug_layer, state restored */
+    load_hc(net, h, c);
+    NeuralNetClass_exe(net, in, out, -1);            /* the real evaluation advances the state */
+    save_hc(net, h, c);
+    load_hc(net, hl, cl);
+    return 0;
+}
+
 /* ---- one stream through NNSPClass (nn_speech.c:23-127) ----------------------------------- */
 static NNSPClass g_inst;
 static FeatureClass g_feat;

@@ -1,0 +1,91 @@
+"""Pin the oracle: restatement (oracle/nnsp_oracle.c) == unmodified reference (oracle/_ref) on the reference's
+own test wavs (where the reference tree exists), on synthetic streams and on adversarial input."""
+import os
+
+import numpy as np
+import pytest
+
+from common import TAP_NAMES, have_reference_tree
+from oracle.pyoracle import RefLib
+
+pytestmark = pytest.mark.skipif(not RefLib.available(False), reason="oracle/_ref not built (needs /root/reference)")
+WAVS = "/root/reference/python/test_wavs"
+
+
+def _same(tp_a, tp_b):
+    return [n for n in TAP_NAMES if not (getattr(tp_a, n) == getattr(tp_b, n)).all()]
+
+
+@pytest.mark.skipif(not have_reference_tree(), reason="reference wavs not on this machine")
+@pytest.mark.parametrize("acc32", [False, True])
+def test_full_reference_wavs_all_models(oracle, acc32):
+    R = RefLib(acc32)
+    for wname in ("speech", "galaxy", "galaxy_s2i"):
+        w = np.fromfile(os.path.join(WAVS, wname + ".wav"), dtype=np.int16, offset=44)
+        for nn_id in (0, 1, 2):
+            r1, t1 = oracle.nnsp_run(oracle.model(nn_id, acc32), w)
+            r2, t2 = R.nnsp_run(nn_id, w)
+            assert (r1 == r2).all() and not _same(t1, t2), (wname, nn_id)
+
+
+@pytest.mark.skipif(not have_reference_tree(), reason="reference wavs not on this machine")
+def test_cascade_over_the_three_wavs(oracle):
+    """config: nnCntrlClass {vad,kws,s2i} over speech+galaxy+galaxy_s2i; SURVEY.md 3.2 probe: 496/1562/942 frames."""
+    w = np.concatenate([np.fromfile(os.path.join(WAVS, n + ".wav"), dtype=np.int16, offset=44)
+                        for n in ("speech", "galaxy", "galaxy_s2i")])
+    r1, t1, v1 = oracle.cascade_run([oracle.model(i) for i in range(3)], w)
+    r2, t2, v2 = RefLib(False).cascade_run(w)
+    assert (r1 == r2).all() and (v1 == v2).all()
+    for n in ("logmel", "feat", "h", "c", "post"):
+        assert (getattr(t1, n) == getattr(t2, n)).all(), n
+    assert np.bincount(r1["stage_id"], minlength=3).tolist() == [942, 496, 1562]
+
+
+@pytest.mark.parametrize("acc32", [False, True])
+def test_synthetic_edge_streams(oracle, nb, acc32):
+    """noise at full scale, digital silence, square wave, DC: classes 0..3 of synth_pcm, plus speech-like ones."""
+    R = RefLib(acc32)
+    x = nb.synth_pcm(8, 150, first_stream=16)
+    for nn_id in (0, 1, 2):
+        for s in range(len(x)):
+            r1, t1 = oracle.nnsp_run(oracle.model(nn_id, acc32), x[s])
+            r2, t2 = R.nnsp_run(nn_id, x[s])
+            assert (r1 == r2).all() and not _same(t1, t2), (nn_id, s)
+
+
+def test_front_end_adversarial_windows(oracle, nb):
+    R = RefLib(False)
+    for w in nb.adversarial_windows():
+        a, b = oracle.feature_stages(w), R.feature_stages(w)
+        for k in a:
+            assert (a[k] == b[k]).all(), k
+
+
+@pytest.mark.parametrize("acc32", [False, True])
+def test_network_random_state_and_full_scale_input(oracle, acc32):
+    R = RefLib(acc32)
+    rng = np.random.default_rng(5)
+    for nn_id in (0, 1, 2):
+        _, h_s, _ = R.strides(nn_id)
+        m = oracle.model(nn_id, acc32)
+        for k in range(12):
+            x = rng.integers(-32768, 32768, 240).astype(np.int16) if k else np.full(240, -32768, np.int16)
+            h = rng.integers(-32768, 32768, h_s).astype(np.int16)
+            c = rng.integers(-2 ** 31, 2 ** 31, h_s).astype(np.int32)
+            a = oracle.net_eval(m, x, h, c)
+            b = R.net_eval(nn_id, x, h, c)
+            for u, v in zip(a, b):
+                assert (u == v).all(), (nn_id, k)
+
+
+def test_reset_of_a_live_instance(oracle, nb):
+    R = RefLib(False)
+    x = nb.synth_pcm(1, 100, first_stream=5)[0]
+    m = oracle.model(1, False)
+    st = oracle.lib.nnsp_oracle_stream_new()
+    oracle.nnsp_run(m, x[:50 * 160], state=st, reset=1, taps=False)
+    r1, t1 = oracle.nnsp_run(m, x[50 * 160:], state=st, reset=2)
+    oracle.lib.nnsp_oracle_stream_free(st)
+    R.nnsp_run(1, x[:50 * 160], reset=1, taps=False)
+    r2, t2 = R.nnsp_run(1, x[50 * 160:], reset=2)
+    assert (r1 == r2).all() and not _same(t1, t2)
