@@ -266,7 +266,8 @@ def main():
         peak, peak_src = measured_peaks()
         frames_per_launch = S * T
         ach = ALGO_BYTES_PER_STREAM_FRAME * frames_per_launch / (feat_ms * 1e-3) / 1e9
-        imad, mixed = nb.int_peak(device)
+        ipk = nb.int_peak(device)
+        imad, mixed = ipk["imad"], ipk["mixed"]
         int_ach = ALGO_INTOPS_PER_FRAME_FEATURE * frames_per_launch / (feat_ms * 1e-3) / 1e9
         line = {
             "metric": "audio-sec/sec (16 kHz streams, VAD, FeatureClass+NeuralNetClass+NNSPClass)",
@@ -284,7 +285,7 @@ def main():
                          "launch_ms": feat_ms,
                          "note": "the path is integer-issue bound, not HBM bound (SURVEY.md 8d); see int_alu"},
             "int_alu": {"kernel": "feat_kernel", "achieved_gops": int_ach, "peak_gops_imad": imad,
-                        "peak_gops_mixed": mixed, "frac_of_mixed_peak": int_ach / mixed if mixed else None,
+                        "peak_gops_mixed": mixed, "peak_gops_imad_wide": ipk["imad_wide"], "peak_gops_idp2a": ipk["idp2a"], "frac_of_mixed_peak": int_ach / mixed if mixed else None,
                         "algorithmic_int_ops_per_frame": ALGO_INTOPS_PER_FRAME_FEATURE,
                         "peak_source": "self-measured nnsp_b200_int_peak (register-resident IMAD / IMAD+ALU chains)"},
             "kernel_ms": {"feat_kernel": feat_ms, "nn_kernel": nn_ms},

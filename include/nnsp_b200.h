@@ -191,10 +191,11 @@ int nnsp_b200_event_create(int device, void **event);
 int nnsp_b200_event_record(void *event, void *stream);
 int nnsp_b200_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchronises on `stop` */
 int nnsp_b200_event_destroy(void *event);
-/* Self-measured integer-pipe peak of the device: a register-resident chain of 32-bit
- * multiply-adds (IMAD) interleaved with adds/shifts, in giga integer-ops per second.
- * MEASURED_PEAKS.json has no integer figure, so the int-ALU roofline uses this one. */
-int nnsp_b200_int_peak(int device, double *imad_gops, double *mixed_gops);
+/* Self-measured integer-pipe peaks of the device, in giga warp-lane instructions per second, from
+ * register-resident dependent chains (8 per thread): gops[0] IMAD, gops[1] IMAD + ALU interleaved 1:1
+ * (both pipes), gops[2] IMAD.WIDE, gops[3] IDP.2A. MEASURED_PEAKS.json has no integer figure, so the
+ * int-ALU roofline of bench.py uses gops[1]. */
+int nnsp_b200_int_peak(int device, double gops[4]);
 
 /* Device utilities so that C callers need no CUDA headers. */
 int nnsp_b200_device_count(void);

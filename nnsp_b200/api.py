@@ -322,9 +322,10 @@ class Event:
 
 
 def int_peak(device=0):
-    a, b = C.c_double(), C.c_double()
-    check(lib().nnsp_b200_int_peak(device, C.byref(a), C.byref(b)), "int_peak")
-    return a.value, b.value
+    """dict of self-measured integer-pipe peaks (giga lane-instructions/s): imad, mixed, imad_wide, idp2a."""
+    g = (C.c_double * 4)()
+    check(lib().nnsp_b200_int_peak(device, C.byref(g)), "int_peak")
+    return dict(imad=g[0], mixed=g[1], imad_wide=g[2], idp2a=g[3])
 
 
 def device_count():

@@ -105,7 +105,7 @@ def lib():
     L.nnsp_b200_event_record.argtypes = [vp, vp]
     L.nnsp_b200_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
     L.nnsp_b200_event_destroy.argtypes = [vp]
-    L.nnsp_b200_int_peak.argtypes = [ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.nnsp_b200_int_peak.argtypes = [ci, C.POINTER(C.c_double * 4)]
     _lib = L
     return L
 

@@ -420,27 +420,42 @@ __global__ void reset_kernel(const DevModel *__restrict__ M, StreamState st, int
     for (int i = threadIdx.x; i < hist_words; i += blockDim.x) h[i] = 0;                  /* spectrogram_module.c:25-31 */
 }
 
-/* integer-pipe peak: 8 independent chains per thread; mode 0 = 16 IMAD, mode 1 = 8 IMAD + 8 add/shift/xor */
+/* integer-pipe peaks: 8 independent register chains per thread, 16 operations per chain-iteration
+ *   mode 0: IMAD (32-bit multiply-add)          mode 1: IMAD + independent ALU ops (add / shift / xor), 1:1
+ *   mode 2: IMAD.WIDE (32x32 -> 64 accumulate)  mode 3: IDP.2A (two int16 x int8 MACs per instruction) */
 __global__ void __launch_bounds__(256) int_peak_kernel(int *sink, int iters, int mode)
 {
-    int a[8];
+    int a[8], b[8];
+    long long w[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 7 + i * 13 + blockIdx.x;
+    for (int i = 0; i < 8; i++) { a[i] = threadIdx.x * 7 + i * 13 + blockIdx.x; b[i] = a[i] ^ 0x55; w[i] = a[i]; }
     const int m = (int)threadIdx.x | 1, c = blockIdx.x + 3;
     if (mode == 0) {
         for (int it = 0; it < iters; it++) {
 #pragma unroll
             for (int i = 0; i < 8; i++) { a[i] = a[i] * m + c; a[i] = a[i] * c + m; }
         }
+    } else if (mode == 1) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a[i] = a[i] * m + c; b[i] = (b[i] >> 1) ^ it; }
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a[i] = a[i] * c + m; b[i] = b[i] + (it | c); }
+        }
+    } else if (mode == 2) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { w[i] += (long long)a[i] * m; w[i] += (long long)b[i] * c; }
+        }
     } else {
         for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) { a[i] = a[i] * m + c; a[i] = (a[i] >> 3) ^ (a[i] + it); }
+            for (int i = 0; i < 8; i++) { a[i] = __dp2a_lo(m, c, a[i]); a[i] = __dp2a_hi(c, m, a[i]); }
         }
     }
     int r = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r ^= a[i];
+    for (int i = 0; i < 8; i++) r ^= a[i] ^ b[i] ^ (int)w[i] ^ (int)(w[i] >> 32);
     if (r == 0x7fffffff) sink[threadIdx.x] = r;      /* keeps the chains alive, (almost) never stores */
 }
 
@@ -763,18 +778,18 @@ int nnsp_b200_event_elapsed_ms(void *start, void *stop, float *ms)
 }
 int nnsp_b200_event_destroy(void *event) { NNSP_CUDA(cudaEventDestroy((cudaEvent_t)event)); return NNSP_B200_OK; }
 
-int nnsp_b200_int_peak(int device, double *imad_gops, double *mixed_gops)
+int nnsp_b200_int_peak(int device, double gops[4])
 {
     int rc = select_device(device);
     if (rc) return rc;
+    if (!gops) return NNSP_B200_ERR_ARG;
     int *sink = nullptr;
     NNSP_CUDA(cudaMalloc(&sink, 1 << 20));
     const int blocks = sm_count(device) * 8, threads = 256, iters = 4096;
     cudaEvent_t e0, e1;
     NNSP_CUDA(cudaEventCreate(&e0));
     NNSP_CUDA(cudaEventCreate(&e1));
-    double out[2] = { 0, 0 };
-    for (int mode = 0; mode < 2; mode++) {
+    for (int mode = 0; mode < 4; mode++) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
             NNSP_CUDA(cudaEventRecord(e0));
@@ -786,11 +801,9 @@ int nnsp_b200_int_peak(int device, double *imad_gops, double *mixed_gops)
             NNSP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
             if (rep > 0 && ms < best) best = ms;
         }
-        /* 16 integer ops per thread per iteration in both modes */
-        out[mode] = (double)blocks * threads * (double)iters * 16.0 / (best * 1e-3) * 1e-9;
+        /* instructions per thread per iteration: 16 (modes 0, 2, 3) or 32 (mode 1) */
+        gops[mode] = (double)blocks * threads * (double)iters * (mode == 1 ? 32.0 : 16.0) / (best * 1e-3) * 1e-9;
     }
-    if (imad_gops) *imad_gops = out[0];
-    if (mixed_gops) *mixed_gops = out[1];
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return NNSP_B200_OK;
 }
