@@ -126,6 +126,9 @@ int nnsp_b200_batch_sync(nnsp_b200_batch *b);
 int nnsp_b200_batch_last_kernel_ms(nnsp_b200_batch *b, float ms[3]);
 int nnsp_b200_batch_dims(const nnsp_b200_batch *b, int *n_streams, int *act_stride,
                          int *h_stride, int *n_out);
+/* Which network kernel runs: 0 = automatic (tensor-core IMMA kernel when the model fits it), 1 = dp2a
+ * warp-per-stream kernel, 2 = IMMA kernel (error if the model does not fit). Both are bit-exact. */
+int nnsp_b200_batch_set_nn_path(nnsp_b200_batch *b, int path);
 /* CUDA stream the handle launches on (cudaStream_t as void*), for callers that time it. */
 void *nnsp_b200_batch_stream(nnsp_b200_batch *b);
 void nnsp_b200_batch_destroy(nnsp_b200_batch *b);

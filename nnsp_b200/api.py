@@ -135,10 +135,14 @@ def _make_taps(S, T, act_stride, h_stride, n_out, device):
 class NNSPBatch:
     """n_streams independent NNSPClass instances of one model on one GPU."""
 
-    def __init__(self, model, n_streams, device=0, thresh_prob=16383, th_count=4):
+    NN_PATH = {"auto": 0, "dp2a": 1, "imma": 2}
+
+    def __init__(self, model, n_streams, device=0, thresh_prob=16383, th_count=4, nn_path="auto"):
         self.model, self.S, self.device = model, int(n_streams), device
         self.h = C.c_void_p()
         check(lib().nnsp_b200_batch_create(model.h, self.S, device, thresh_prob, th_count, C.byref(self.h)), "batch_create")
+        if nn_path != "auto":
+            check(lib().nnsp_b200_batch_set_nn_path(self.h, self.NN_PATH[nn_path]), "batch_set_nn_path")
         a, hs, no = C.c_int(), C.c_int(), C.c_int()
         check(lib().nnsp_b200_batch_dims(self.h, None, C.byref(a), C.byref(hs), C.byref(no)), "batch_dims")
         self.act_stride, self.h_stride, self.n_out = a.value, hs.value, no.value

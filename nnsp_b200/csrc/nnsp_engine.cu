@@ -498,6 +498,9 @@ struct nnsp_b200_batch {
     cudaStream_t xs[3] = { nullptr, nullptr, nullptr };   /* host-buffer API pipeline */
     const DevTables *tables = nullptr;
     DeviceModel dm;
+    MmaDeviceModel mm;
+    bool mma_ok = false;
+    int nn_path = 0;                        /* 0 auto, 1 dp2a warp-per-stream, 2 IMMA 16-streams-per-warp */
     StreamState st{};
     int16_t thresh_prob = 0, th_count = 0;
     int32_t *logmel = nullptr; long long logmel_frames = 0;       /* capacity in frames per stream */
@@ -526,16 +529,26 @@ static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride
     int rc = launch_feature(b->tables, fl, b->device, st);
     if (rc) return rc;
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[1], st));
-    NNArgs a{};
-    a.model = b->dm.d; a.wimg = b->dm.wimg; a.bimg = b->dm.bimg; a.tables = b->tables; a.st = b->st;
-    a.logmel = b->logmel; a.s0 = s0; a.ns = ns; a.T = T; a.results = results;
-    if (taps) a.taps = *taps;
-    a.thresh_prob = b->thresh_prob; a.th_count = b->th_count;
-    int blocks = (ns + NN_WARPS - 1) / NN_WARPS;
-    const int cap = sm_count(b->device) * b->nn_ctas_per_sm;
-    if (blocks > cap) blocks = cap;
-    nn_kernel<<<blocks, NN_THREADS, b->lay.total, st>>>(a, (int)b->lay.b, (int)b->lay.lut, (int)b->lay.model, (int)b->lay.scratch);
-    NNSP_LAUNCH_CHECK();
+    const bool use_mma = (b->nn_path == 2) || (b->nn_path == 0 && b->mma_ok);
+    if (use_mma) {
+        if (!b->mma_ok) { nnsp_set_error("this model has no IMMA formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
+        NNLaunch l{};
+        l.tables = b->tables; l.st = b->st; l.logmel = b->logmel; l.s0 = s0; l.ns = ns; l.T = T; l.results = results;
+        if (taps) l.taps = *taps;
+        l.thresh_prob = b->thresh_prob; l.th_count = b->th_count;
+        if ((rc = launch_nn_mma(b->mm, l, b->device, st))) return rc;
+    } else {
+        NNArgs a{};
+        a.model = b->dm.d; a.wimg = b->dm.wimg; a.bimg = b->dm.bimg; a.tables = b->tables; a.st = b->st;
+        a.logmel = b->logmel; a.s0 = s0; a.ns = ns; a.T = T; a.results = results;
+        if (taps) a.taps = *taps;
+        a.thresh_prob = b->thresh_prob; a.th_count = b->th_count;
+        int blocks = (ns + NN_WARPS - 1) / NN_WARPS;
+        const int cap = sm_count(b->device) * b->nn_ctas_per_sm;
+        if (blocks > cap) blocks = cap;
+        nn_kernel<<<blocks, NN_THREADS, b->lay.total, st>>>(a, (int)b->lay.b, (int)b->lay.lut, (int)b->lay.model, (int)b->lay.scratch);
+        NNSP_LAUNCH_CHECK();
+    }
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[2], st));
     rc = launch_hist_update(pcm, stride / 2, b->st.hist, 2, NNSP_B200_FRAME / 2, s0, ns, T, st);
     if (timed) b->ev_valid = true;
@@ -565,6 +578,9 @@ int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device, 
     auto fail = [&](int code) { nnsp_b200_batch_destroy(b); return code; };
     if ((rc = get_device_tables(device, &b->tables))) return fail(rc);
     if ((rc = upload_model(m, &b->dm))) return fail(rc);
+    rc = upload_model_mma(m, &b->mm);
+    if (rc == NNSP_B200_OK) b->mma_ok = true;
+    else if (rc != NNSP_B200_ERR_UNSUPPORTED) return fail(rc);
     b->lay = nn_layout(b->dm.h);
     if (b->lay.total > 227 * 1024) { nnsp_set_error("model needs %zu bytes of shared memory (> 227 KB)", b->lay.total); return fail(NNSP_B200_ERR_UNSUPPORTED); }
     b->nn_ctas_per_sm = (int)((227 * 1024) / b->lay.total);
@@ -698,12 +714,21 @@ int nnsp_b200_batch_dims(const nnsp_b200_batch *b, int *n_streams, int *act_stri
 
 void *nnsp_b200_batch_stream(nnsp_b200_batch *b) { return b ? (void *)b->stream : nullptr; }
 
+int nnsp_b200_batch_set_nn_path(nnsp_b200_batch *b, int path)
+{
+    if (!b || path < 0 || path > 2) return NNSP_B200_ERR_ARG;
+    if (path == 2 && !b->mma_ok) { nnsp_set_error("this model has no IMMA formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
+    b->nn_path = path;
+    return NNSP_B200_OK;
+}
+
 void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
 {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaDeviceSynchronize();
     free_model(&b->dm);
+    free_model_mma(&b->mm);
     cudaFree(b->st.ctx); cudaFree(b->st.h); cudaFree(b->st.c); cudaFree(b->st.scal); cudaFree(b->st.hist);
     cudaFree(b->logmel); cudaFree(b->d_pcm); cudaFree(b->d_res);
     if (b->stream) cudaStreamDestroy(b->stream);

@@ -57,4 +57,24 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
 int launch_hist_update(const void *src, long long stride_words, void *hist, int hist_frames, int words_per_frame,
                        int s0, int ns, int T, cudaStream_t st);
 
+
+/* tensor-core (IMMA) network path, nnsp_mma.cu */
+struct MmaModel;
+struct MmaDeviceModel {
+    MmaModel *h = nullptr;        /* host copy (heap) */
+    MmaModel *d = nullptr;
+    void     *frag = nullptr;     /* uint2 fragment image */
+    int32_t  *bias32 = nullptr;
+    size_t    smem_base = 0, smem_warp = 0;
+    int       off_bias = 0, off_lut = 0, off_model = 0, off_warps = 0;
+};
+/* NNSP_B200_ERR_UNSUPPORTED when the model does not fit the IMMA formulation (the dp2a kernel then runs) */
+int upload_model_mma(const nnsp_b200_model *m, MmaDeviceModel *out);
+void free_model_mma(MmaDeviceModel *mm);
+struct NNLaunch {
+    const DevTables *tables; StreamState st; const int32_t *logmel;
+    int s0, ns, T; nnsp_b200_result *results; nnsp_b200_taps taps; int16_t thresh_prob, th_count;
+};
+int launch_nn_mma(const MmaDeviceModel &mm, const NNLaunch &a, int device, cudaStream_t st);
+
 }  // namespace nnsp

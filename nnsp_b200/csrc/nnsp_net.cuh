@@ -62,7 +62,8 @@ __device__ __forceinline__ void dot_rows_n(int nr, const uint32_t *W, int nrows_
 /* accumulator -> 32-bit pre-activation: bias alignment + add (affine.c:190-217), output shift
  * and saturation (affine.c:242-249); acc32: wrapping adds, no saturation (affine_acc32b.c:249).
  * Quirk Q1: the accumulator is NOT re-aligned to the bias Q-format (affine.c:186-187 is dead). */
-__device__ __forceinline__ int32_t finish_fc(const DevLayer &L, int32_t acc, int32_t bias)
+template <class LT>
+__device__ __forceinline__ int32_t finish_fc(const LT &L, int32_t acc, int32_t bias)
 {
     if (L.acc32) {
         const uint32_t b = (L.sh_bias >= 0) ? ((uint32_t)bias << L.sh_bias) : (uint32_t)(bias >> (-L.sh_bias));
@@ -73,7 +74,8 @@ __device__ __forceinline__ int32_t finish_fc(const DevLayer &L, int32_t acc, int
     return sat32_dev(shift64_dev(a, L.sh_out));
 }
 /* rc_Krows_8x16: input half, rescale by qbit_input_rec - qbit_input (affine.c:371,384), recurrent half */
-__device__ __forceinline__ int32_t finish_gate(const DevLayer &L, int32_t acc_x, int32_t acc_h, int32_t bias)
+template <class LT>
+__device__ __forceinline__ int32_t finish_gate(const LT &L, int32_t acc_x, int32_t acc_h, int32_t bias)
 {
     if (L.acc32) {
         const uint32_t a = (uint32_t)shift32_dev(acc_x, L.sh_x) + (uint32_t)acc_h;

@@ -39,12 +39,14 @@ def test_feature_stages_bit_exact(nb, oracle):
             assert (out[k][i] == ref[k]).all(), "stage %s differs for window %d" % (k, i)
 
 
+@pytest.mark.parametrize("path", ["imma", "dp2a"])
 @pytest.mark.parametrize("nn_id,acc32", [(1, False), (2, True), (0, False), (0, True), (1, True), (2, False)])
-def test_batch_matches_oracle_every_tap(nb, oracle, nn_id, acc32):
-    S, T = 48, 64
+def test_batch_matches_oracle_every_tap(nb, oracle, nn_id, acc32, path):
+    """Both network kernels: tensor-core IMMA (16 streams per warp) and dp2a (warp per stream)."""
+    S, T = 53, 64                      # 53: a partial 16-stream tile at the end
     pcm = nb.synth_pcm(S, T)
     m = _model(nb, nn_id, acc32)
-    b = nb.NNSPBatch(m, S)
+    b = nb.NNSPBatch(m, S, nn_path=path)
     res, taps = b.exec(pcm, taps=True)
     m_or = oracle.model(nn_id, acc32)
     for s in range(S):
