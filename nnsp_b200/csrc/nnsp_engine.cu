@@ -58,8 +58,16 @@ static void fill_dev_tables(const nnsp_tables *t, DevTables *d)
     memset(d, 0, sizeof *d);
     for (int p = 0; p < 240; p++)
         d->win2[p] = (uint32_t)(uint16_t)t->stft_win[2 * p] | ((uint32_t)(uint16_t)t->stft_win[2 * p + 1] << 16);
-    memcpy(d->fft_tw, t->fft_tw, sizeof d->fft_tw);
-    memcpy(d->rfft_tw, t->rfft_tw, sizeof d->rfft_tw);
+    auto unpack = [](int32_t w) { return make_int2((int)(int16_t)(w & 0xffff), (int)(w >> 16)); };   /* COMPLEX16: lo = re, hi = im */
+    for (int a = 0; a < 4; a++)
+        for (int n = 0; n < 3; n++)
+            for (int L = 0; L < 16; L++) d->tw0[a][n][L] = unpack(t->fft_tw[4 * (L + 16 * a) + 1 + n]);
+    for (int n = 0; n < 3; n++)
+        for (int L = 0; L < 16; L++) d->tw1[n][L] = unpack(t->fft_tw[16 * L + 1 + n]);
+    for (int m = 0; m < 4; m++)
+        for (int n = 0; n < 3; n++) d->tw2[m][n] = unpack(t->fft_tw[64 * m + 1 + n]);
+    for (int k = 0; k < 256; k++) d->rtw[k] = unpack(t->rfft_tw[k]);
+    d->rtw[256] = make_int2(0, 0);
     memcpy(d->mel_taps, t->mel_taps, sizeof t->mel_taps);
     memcpy(d->mel_start, t->mel_start, sizeof d->mel_start);
     memcpy(d->mel_end, t->mel_end, sizeof d->mel_end);
@@ -183,13 +191,16 @@ void free_model(DeviceModel *dm)
 /* ======================================================================================== */
 constexpr int FEAT_WARPS = 8;                 /* 16 frames in flight per CTA */
 constexpr int FEAT_THREADS = FEAT_WARPS * 32;
+#ifndef FEAT_CTAS_PER_SM
+#define FEAT_CTAS_PER_SM 3
+#endif
 
 struct FeatSmem {
     FeatSmemTables tb;
     FrameScratch fs[FEAT_WARPS * 2];
 };
 
-__global__ void __launch_bounds__(FEAT_THREADS)
+__global__ void __launch_bounds__(FEAT_THREADS, FEAT_CTAS_PER_SM)
 feat_kernel(const DevTables *__restrict__ tables, const int16_t *__restrict__ pcm, long long stride,
             const int16_t *__restrict__ hist, int hist_frames, int s0, int ns, int T,
             int32_t *__restrict__ logmel)
@@ -229,7 +240,7 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
     const long long F = (long long)a.ns * a.T;
     if (F <= 0) return NNSP_B200_OK;
     long long blocks = (F + FEAT_WARPS * 2 - 1) / (FEAT_WARPS * 2);
-    const long long cap = (long long)sm_count(device) * 4;          /* persistent: 4 CTAs (32 warps) per SM */
+    const long long cap = (long long)sm_count(device) * FEAT_CTAS_PER_SM;   /* persistent grid: every CTA resident */
     if (blocks > cap) blocks = cap;
     feat_kernel<<<(unsigned)blocks, FEAT_THREADS, sizeof(FeatSmem), st>>>(tb, a.pcm, a.stride, a.hist, a.hist_frames,
                                                                             a.s0, a.ns, a.T, a.logmel);

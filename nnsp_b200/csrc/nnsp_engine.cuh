@@ -8,8 +8,13 @@ namespace nnsp {
 /* ---- constant tables as the kernels see them (global memory, copied to SMEM per CTA) ---- */
 struct DevTables {
     uint32_t win2[240];        /* stft window, two Q15 coefficients per word (sample 2p, 2p+1)   */
-    int32_t  fft_tw[256];      /* packed complex16, [k][tw^0, tw^2, tw^1, tw^3]                  */
-    int32_t  rfft_tw[256];
+    /* radix-4 twiddles, sign-extended (re, im), laid out in the order the half-warp reads them:
+     *   tw0[a][n][L] = tw^(n+1 column) of butterfly k = L + 16a (stage 0), tw1[n][L] of k = 4L (stage 1),
+     *   tw2[m][n] of k = 16m (stage 2, same for every lane); column order tw^2, tw^1, tw^3 (fft.c:182) */
+    int2     tw0[4][3][16];
+    int2     tw1[3][16];
+    int2     tw2[4][3];
+    int2     rtw[257];         /* real-FFT split twiddles exp(-2 pi j k / 512), k = 0..256 (k = 256 unused) */
     int16_t  mel_taps[456];    /* 454 taps (+2 pad)                                              */
     int16_t  mel_start[40], mel_end[40], mel_off[40];
     int16_t  log_lut[256];

@@ -21,8 +21,10 @@ namespace nnsp {
 
 struct FeatSmemTables {
     uint32_t win2[240];
-    int32_t  fft_tw[256];
-    int32_t  rfft_tw[256];
+    int2     tw0[4][3][16];
+    int2     tw1[3][16];
+    int2     tw2[4][3];
+    int2     rtw[257];
     int16_t  mel_taps[456];
     int16_t  mel_start[40], mel_end[40], mel_off[40];
     int16_t  log_lut[256];
@@ -40,10 +42,10 @@ struct FeatDump {                  /* optional stage taps (global memory), all m
 __device__ __forceinline__ void load_feat_tables(FeatSmemTables *dst, const DevTables *__restrict__ src,
                                                  int tid, int nthreads)
 {
-    for (int i = tid; i < 240; i += nthreads) dst->win2[i] = src->win2[i];
-    for (int i = tid; i < 256; i += nthreads) { dst->fft_tw[i] = src->fft_tw[i]; dst->rfft_tw[i] = src->rfft_tw[i]; dst->log_lut[i] = src->log_lut[i]; }
-    for (int i = tid; i < 456; i += nthreads) dst->mel_taps[i] = src->mel_taps[i];
-    for (int i = tid; i < 40; i += nthreads) { dst->mel_start[i] = src->mel_start[i]; dst->mel_end[i] = src->mel_end[i]; dst->mel_off[i] = src->mel_off[i]; }
+    /* DevTables starts with the same members in the same order: copy the common prefix word by word */
+    const int *s = reinterpret_cast<const int *>(src);
+    int *d = reinterpret_cast<int *>(dst);
+    for (int i = tid; i < (int)(sizeof(FeatSmemTables) / 4); i += nthreads) d[i] = s[i];
 }
 
 #define NNSP_TW_RE(w) ((int32_t)(int16_t)((w) & 0xffff))
@@ -55,7 +57,7 @@ __device__ __forceinline__ void load_feat_tables(FeatSmemTables *dst, const DevT
 template <bool ALLONE>
 __device__ __forceinline__ void bfly4(int32_t &ar, int32_t &ai, int32_t &cr, int32_t &ci,
                                       int32_t &br, int32_t &bi, int32_t &dr, int32_t &di,
-                                      int32_t w1, int32_t w2, int32_t w3)
+                                      int2 w1, int2 w2, int2 w3)
 {
     const int32_t s0r = ar + br, s0i = ai + bi, d0r = ar - br, d0i = ai - bi;
     const int32_t s1r = cr + dr, s1i = ci + di, d1r = cr - dr, d1i = ci - di;
@@ -70,9 +72,7 @@ __device__ __forceinline__ void bfly4(int32_t &ar, int32_t &ai, int32_t &cr, int
         br = mul_one_q15(o2r); bi = mul_one_q15(o2i);
         dr = mul_one_q15(o3r); di = mul_one_q15(o3i);
     } else {
-        const int32_t w1r = NNSP_TW_RE(w1), w1i = NNSP_TW_IM(w1);
-        const int32_t w2r = NNSP_TW_RE(w2), w2i = NNSP_TW_IM(w2);
-        const int32_t w3r = NNSP_TW_RE(w3), w3i = NNSP_TW_IM(w3);
+        const int32_t w1r = w1.x, w1i = w1.y, w2r = w2.x, w2i = w2.y, w3r = w3.x, w3i = w3.y;
         cr = msub_q15(o1r, w1r, o1i, w1i); ci = madd_q15(o1r, w1i, o1i, w1r);
         br = msub_q15(o2r, w2r, o2i, w2i); bi = madd_q15(o2r, w2i, o2i, w2r);
         dr = msub_q15(o3r, w3r, o3i, w3i); di = madd_q15(o3r, w3i, o3i, w3r);
@@ -106,13 +106,12 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
     /* stage 0: Nf = 256, q = 64, butterflies m = L + 16a', twiddle index k = m (fft.c:162-200) */
 #pragma unroll
     for (int a = 0; a < 4; a++) {
-        const int k = L + 16 * a;
         bfly4<false>(xr[a], xi[a], xr[a + 4], xi[a + 4], xr[a + 8], xi[a + 8], xr[a + 12], xi[a + 12],
-                     tb.fft_tw[4 * k + 1], tb.fft_tw[4 * k + 2], tb.fft_tw[4 * k + 3]);
+                     tb.tw0[a][0][L], tb.tw0[a][1][L], tb.tw0[a][2][L]);
     }
     /* stage 1: Nf = 64, q = 16, group g, m = L, k = 4L */
     {
-        const int32_t w1 = tb.fft_tw[16 * L + 1], w2 = tb.fft_tw[16 * L + 2], w3 = tb.fft_tw[16 * L + 3];
+        const int2 w1 = tb.tw1[0][L], w2 = tb.tw1[1][L], w3 = tb.tw1[2][L];
 #pragma unroll
         for (int g = 0; g < 4; g++)
             bfly4<false>(xr[4 * g], xi[4 * g], xr[4 * g + 1], xi[4 * g + 1], xr[4 * g + 2], xi[4 * g + 2],
@@ -129,12 +128,12 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
 #pragma unroll
     for (int m = 0; m < 4; m++)
         bfly4<false>(xr[m], xi[m], xr[m + 4], xi[m + 4], xr[m + 8], xi[m + 8], xr[m + 12], xi[m + 12],
-                     tb.fft_tw[64 * m + 1], tb.fft_tw[64 * m + 2], tb.fft_tw[64 * m + 3]);
+                     tb.tw2[m][0], tb.tw2[m][1], tb.tw2[m][2]);
     /* stage 3: Nf = 4, q = 1, k = 0: every twiddle is 0x7fff + 0j */
 #pragma unroll
     for (int g = 0; g < 4; g++)
         bfly4<true>(xr[4 * g], xi[4 * g], xr[4 * g + 1], xi[4 * g + 1], xr[4 * g + 2], xi[4 * g + 2],
-                    xr[4 * g + 3], xi[4 * g + 3], 0, 0, 0);
+                    xr[4 * g + 3], xi[4 * g + 3], make_int2(0, 0), make_int2(0, 0), make_int2(0, 0));
     /* bit-reversed read-out (fft.c:217-220): Z[brev8(p)] = x[p]; store at index m = brev8(16L + b) */
 #pragma unroll
     for (int b = 0; b < 16; b++) {
@@ -148,8 +147,8 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
         const int i = L + 16 * j;
         if (j < 8 || L == 0) {
             const int2 zi = fs.x[i], zr = fs.x[(256 - i) & 255];
-            const int32_t w = tb.rfft_tw[i & 255];
-            const int32_t wr = NNSP_TW_RE(w), wi = NNSP_TW_IM(w);
+            const int2 w = tb.rtw[i & 255];
+            const int32_t wr = w.x, wi = w.y;
             const int32_t er = (zi.x + zr.x) >> 1, ei = (zi.y - zr.y) >> 1;
             const int32_t orr = (zi.y + zr.y) >> 1, oi = (zr.x - zi.x) >> 1;
             if (i == 128 && j == 8) {
@@ -168,8 +167,8 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
                 fs.ps[i] = (int32_t)(((int64_t)xr0 * xr0 + (int64_t)xi0 * xi0) >> 15);
                 if (i != 0) {
                     /* mirrored bin 256 - i from the same pair, roles of Z[i] and Z[256-i] swapped */
-                    const int32_t v = tb.rfft_tw[256 - i];
-                    const int32_t vr = NNSP_TW_RE(v), vi = NNSP_TW_IM(v);
+                    const int2 v = tb.rtw[256 - i];
+                    const int32_t vr = v.x, vi = v.y;
                     const int32_t fi = (zr.y - zi.y) >> 1, pi = (zi.x - zr.x) >> 1;
                     const int32_t xr1 = er + msub_q15(orr, vr, pi, vi), xi1 = fi + madd_q15(orr, vi, pi, vr);
                     if (DUMP && dump.spec && store) { dump.spec[2 * (256 - i)] = xr1; dump.spec[2 * (256 - i) + 1] = xi1; }
