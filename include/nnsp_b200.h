@@ -126,8 +126,10 @@ int nnsp_b200_batch_sync(nnsp_b200_batch *b);
 int nnsp_b200_batch_last_kernel_ms(nnsp_b200_batch *b, float ms[3]);
 int nnsp_b200_batch_dims(const nnsp_b200_batch *b, int *n_streams, int *act_stride,
                          int *h_stride, int *n_out);
-/* Which network kernel runs: 0 = automatic (tensor-core IMMA kernel when the model fits it), 1 = dp2a
- * warp-per-stream kernel, 2 = IMMA kernel (error if the model does not fit). Both are bit-exact. */
+/* Which network kernels run: 0 = automatic (3 when the model fits it, else 2, else 1), 1 = dp2a warp-per-stream
+ * kernel, 2 = tensor-core IMMA kernel with the whole network inside the time loop, 3 = scan-split (fc layers
+ * for all frames of the call at once, only the LSTM recurrence sequential; nnsp_split.cu). 2 and 3 return an
+ * error when the model does not fit them. All three are bit-exact. */
 int nnsp_b200_batch_set_nn_path(nnsp_b200_batch *b, int path);
 /* CUDA stream the handle launches on (cudaStream_t as void*), for callers that time it. */
 void *nnsp_b200_batch_stream(nnsp_b200_batch *b);

@@ -135,7 +135,7 @@ def _make_taps(S, T, act_stride, h_stride, n_out, device):
 class NNSPBatch:
     """n_streams independent NNSPClass instances of one model on one GPU."""
 
-    NN_PATH = {"auto": 0, "dp2a": 1, "imma": 2}
+    NN_PATH = {"auto": 0, "dp2a": 1, "imma": 2, "split": 3}
 
     def __init__(self, model, n_streams, device=0, thresh_prob=16383, th_count=4, nn_path="auto"):
         self.model, self.S, self.device = model, int(n_streams), device
@@ -146,6 +146,9 @@ class NNSPBatch:
         a, hs, no = C.c_int(), C.c_int(), C.c_int()
         check(lib().nnsp_b200_batch_dims(self.h, None, C.byref(a), C.byref(hs), C.byref(no)), "batch_dims")
         self.act_stride, self.h_stride, self.n_out = a.value, hs.value, no.value
+
+    def set_nn_path(self, nn_path):
+        check(lib().nnsp_b200_batch_set_nn_path(self.h, self.NN_PATH[nn_path]), "batch_set_nn_path")
 
     def reset(self):
         check(lib().nnsp_b200_batch_reset(self.h), "batch_reset")

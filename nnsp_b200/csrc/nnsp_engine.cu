@@ -510,8 +510,12 @@ struct nnsp_b200_batch {
     const DevTables *tables = nullptr;
     DeviceModel dm;
     MmaDeviceModel mm;
-    bool mma_ok = false;
-    int nn_path = 0;                        /* 0 auto, 1 dp2a warp-per-stream, 2 IMMA 16-streams-per-warp */
+    bool mma_ok = false, split_ok = false;
+    int nn_path = 0;                        /* 0 auto, 1 dp2a warp-per-stream, 2 IMMA 16-streams-per-warp, 3 scan-split */
+    int slides = 1;                         /* host mirror of NNSPClass.slides (nn_speech.c:62,125): uniform over the batch */
+    uint8_t *sp_planes[2] = { nullptr, nullptr };  /* scan-split activation planes [tile][inference][hi|lo][16][pa] */
+    int32_t *sp_dec = nullptr;              /* decision records [S][inference] */
+    long long sp_cap_inf = 0;
     StreamState st{};
     int16_t thresh_prob = 0, th_count = 0;
     int32_t *logmel = nullptr; long long logmel_frames = 0;       /* capacity in frames per stream */
@@ -532,6 +536,34 @@ static int batch_ensure_logmel(nnsp_b200_batch *b, int T)
     return NNSP_B200_OK;
 }
 
+static int batch_nn_path(const nnsp_b200_batch *b)
+{
+    if (b->nn_path) return b->nn_path;
+    return b->split_ok ? 3 : (b->mma_ok ? 2 : 1);
+}
+
+/* inference frames of a call of T frames that starts with NNSPClass.slides == slides0 (nn_speech.c:84,125) */
+static void inference_frames(int slides0, int T, int *first, int *n_inf)
+{
+    *first = (slides0 == 1) ? 0 : 1;
+    *n_inf = (T > *first) ? (T - *first + 1) / 2 : 0;
+}
+
+static int batch_ensure_split(nnsp_b200_batch *b, int n_inf)
+{
+    if (batch_nn_path(b) != 3 || n_inf <= b->sp_cap_inf) return NNSP_B200_OK;
+    NNSP_CUDA(cudaStreamSynchronize(b->stream));
+    for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    for (auto &p : b->sp_planes) { if (p) cudaFree(p); p = nullptr; }
+    if (b->sp_dec) { cudaFree(b->sp_dec); b->sp_dec = nullptr; }
+    b->sp_cap_inf = 0;
+    const size_t pb = split_plane_bytes(b->mm, b->S, n_inf);
+    for (auto &p : b->sp_planes) NNSP_CUDA(cudaMalloc(&p, pb));
+    NNSP_CUDA(cudaMalloc(&b->sp_dec, (size_t)((b->S + 15) & ~15) * n_inf * sizeof(int32_t)));
+    b->sp_cap_inf = n_inf;
+    return NNSP_B200_OK;
+}
+
 static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride, int T, int s0, int ns,
                         nnsp_b200_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed)
 {
@@ -540,8 +572,17 @@ static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride
     int rc = launch_feature(b->tables, fl, b->device, st);
     if (rc) return rc;
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[1], st));
-    const bool use_mma = (b->nn_path == 2) || (b->nn_path == 0 && b->mma_ok);
-    if (use_mma) {
+    const int path = batch_nn_path(b);
+    if (path == 3) {
+        if (!b->split_ok) { nnsp_set_error("this model has no scan-split formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
+        int first, n_inf;
+        inference_frames(b->slides, T, &first, &n_inf);
+        NNLaunch l{};
+        l.tables = b->tables; l.st = b->st; l.logmel = b->logmel; l.s0 = s0; l.ns = ns; l.T = T; l.results = results;
+        if (taps) l.taps = *taps;
+        l.thresh_prob = b->thresh_prob; l.th_count = b->th_count;
+        if ((rc = launch_nn_split(b->mm, l, first, n_inf, b->sp_planes[0], b->sp_planes[1], b->sp_dec, b->device, st))) return rc;
+    } else if (path == 2) {
         if (!b->mma_ok) { nnsp_set_error("this model has no IMMA formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
         NNLaunch l{};
         l.tables = b->tables; l.st = b->st; l.logmel = b->logmel; l.s0 = s0; l.ns = ns; l.T = T; l.results = results;
@@ -590,7 +631,7 @@ int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device, 
     if ((rc = get_device_tables(device, &b->tables))) return fail(rc);
     if ((rc = upload_model(m, &b->dm))) return fail(rc);
     rc = upload_model_mma(m, &b->mm);
-    if (rc == NNSP_B200_OK) b->mma_ok = true;
+    if (rc == NNSP_B200_OK) { b->mma_ok = true; b->split_ok = split_supported(b->mm) != 0; }
     else if (rc != NNSP_B200_ERR_UNSUPPORTED) return fail(rc);
     b->lay = nn_layout(b->dm.h);
     if (b->lay.total > 227 * 1024) { nnsp_set_error("model needs %zu bytes of shared memory (> 227 KB)", b->lay.total); return fail(NNSP_B200_ERR_UNSUPPORTED); }
@@ -624,6 +665,7 @@ int nnsp_b200_batch_reset(nnsp_b200_batch *b)
     reset_kernel<<<b->S, 128, 0, b->stream>>>(b->dm.d, b->st, b->S, NNSP_B200_FRAME);
     NNSP_LAUNCH_CHECK();
     NNSP_CUDA(cudaStreamSynchronize(b->stream));
+    b->slides = 1;                                                      /* nn_speech.c:62 */
     return NNSP_B200_OK;
 }
 
@@ -645,7 +687,10 @@ int nnsp_b200_batch_exec(nnsp_b200_batch *b, const int16_t *pcm_dev, long long s
     if (rc) return rc;
     NNSP_CUDA(cudaSetDevice(b->device));
     if ((rc = batch_ensure_logmel(b, n_frames))) return rc;
-    return batch_launch(b, pcm_dev, stream_stride, n_frames, 0, b->S, results_dev, taps, b->stream, true);
+    if ((rc = batch_ensure_split(b, (n_frames + 1) / 2))) return rc;
+    rc = batch_launch(b, pcm_dev, stream_stride, n_frames, 0, b->S, results_dev, taps, b->stream, true);
+    if (rc == NNSP_B200_OK) b->slides = (b->slides + n_frames) % 2;
+    return rc;
 }
 
 int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long stream_stride, int n_frames,
@@ -657,6 +702,7 @@ int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
     NNSP_CUDA(cudaSetDevice(b->device));
     const int T = n_frames;
     if ((rc = batch_ensure_logmel(b, T))) return rc;
+    if ((rc = batch_ensure_split(b, (T + 1) / 2))) return rc;
     if (T > b->d_pcm_frames) {
         NNSP_CUDA(cudaDeviceSynchronize());
         if (b->d_pcm) cudaFree(b->d_pcm);
@@ -671,7 +717,9 @@ int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
     const long long dstride = (long long)T * NNSP_B200_FRAME;
     int nsl = b->S >= 4096 ? 8 : (b->S >= 256 ? 4 : 1);
     for (int k = 0; k < nsl; k++) {
-        const int s0 = (int)((long long)b->S * k / nsl), s1 = (int)((long long)b->S * (k + 1) / nsl);
+        /* slice boundaries on 16-stream tiles (the tensor-core paths work on tiles) */
+        const int s0 = (int)(((long long)b->S * k / nsl) & ~15LL);
+        const int s1 = (k == nsl - 1) ? b->S : (int)(((long long)b->S * (k + 1) / nsl) & ~15LL);
         if (s1 <= s0) continue;
         cudaStream_t st = b->xs[k % 3];
         if (stream_stride == dstride) {
@@ -689,6 +737,7 @@ int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
                                       (size_t)(s1 - s0) * T * sizeof(nnsp_b200_result), cudaMemcpyDeviceToHost, st));
     }
     for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    b->slides = (b->slides + T) % 2;
     return NNSP_B200_OK;
 }
 
@@ -727,8 +776,9 @@ void *nnsp_b200_batch_stream(nnsp_b200_batch *b) { return b ? (void *)b->stream 
 
 int nnsp_b200_batch_set_nn_path(nnsp_b200_batch *b, int path)
 {
-    if (!b || path < 0 || path > 2) return NNSP_B200_ERR_ARG;
+    if (!b || path < 0 || path > 3) return NNSP_B200_ERR_ARG;
     if (path == 2 && !b->mma_ok) { nnsp_set_error("this model has no IMMA formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
+    if (path == 3 && !b->split_ok) { nnsp_set_error("this model has no scan-split formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
     b->nn_path = path;
     return NNSP_B200_OK;
 }
@@ -742,6 +792,7 @@ void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
     free_model_mma(&b->mm);
     cudaFree(b->st.ctx); cudaFree(b->st.h); cudaFree(b->st.c); cudaFree(b->st.scal); cudaFree(b->st.hist);
     cudaFree(b->logmel); cudaFree(b->d_pcm); cudaFree(b->d_res);
+    cudaFree(b->sp_planes[0]); cudaFree(b->sp_planes[1]); cudaFree(b->sp_dec);
     if (b->stream) cudaStreamDestroy(b->stream);
     for (auto s : b->xs) if (s) cudaStreamDestroy(s);
     for (auto e : b->ev) if (e) cudaEventDestroy(e);

@@ -77,4 +77,12 @@ struct NNLaunch {
 };
 int launch_nn_mma(const MmaDeviceModel &mm, const NNLaunch &a, int device, cudaStream_t st);
 
+/* scan-split network path, nnsp_split.cu: fc runs for all (stream, inference) rows at once, the LSTM as a scan.
+ * first / n_inf: first inference frame (0 or 1) and number of inferences of this call (stride 2). planes0/1:
+ * two buffers of split_plane_bytes(); dec: [S rounded up to 16][n_inf] int32. l.s0 must be a multiple of 16. */
+int split_supported(const MmaDeviceModel &mm);
+size_t split_plane_bytes(const MmaDeviceModel &mm, int n_streams, int n_inf);
+int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, int first, int n_inf, uint8_t *planes0,
+                    uint8_t *planes1, int32_t *dec, int device, cudaStream_t st);
+
 }  // namespace nnsp

@@ -1,0 +1,730 @@
+/* nnsp_split.cu -- "scan-split" network path: NeuralNetClass_exe reorganised around its only recurrence.
+ *
+ * Reference semantics (unchanged, bit for bit): NeuralNetClass_exe (neural_nets.c:44-168) runs the layer
+ * list once per inference; fc_8x16 (affine.c:409-490), lstm_8x16 (lstm.c:15-214) -> rc_Krows_8x16
+ * (affine.c:348-407), activations (activation.c:6-86), then s2i_post_proc / binary_post_proc
+ * (nn_speech.c:146-227) and the stride-2 gate of NNSPClass_exec (nn_speech.c:84,125).
+ *
+ * Observation: within one exec call of T frames only the LSTM's recurrent half and the post-processing
+ * counters depend on the previous inference. Everything else is a function of data that is known for all
+ * T frames up front, so it is computed for every (stream, inference) row at once:
+ *
+ *   seg_kernel<feat>   layers before the LSTM (layer 0: 240 -> H0) for all rows. The A operand of row
+ *                      (s, t) is the 6x40 context window = 240 consecutive bytes of the stream's
+ *                      standardised feature rows, so 16 consecutive inferences share one 36-row plane.
+ *   scan_kernel        the LSTM, one CTA per 16-stream tile, one warp per 8-unit group, sequential over the
+ *                      inferences: input planes arrive by TMA bulk copies through a 4-deep mbarrier ring,
+ *                      Wx.x of step k+1 is issued before the barrier of step k, cell state and biases live
+ *                      in registers, h goes back to HBM by one TMA bulk store per step.
+ *   seg_kernel<planes> layers after the LSTM for all rows, logits -> per-row decision record
+ *                      (argmax triple or the softmax-threshold flag of binary_post_proc).
+ *   post_kernel        the NNSPClass counters / trigger / outputs over the decision records, per stream.
+ *   ctx_kernel         normFeatContext for the next call (feature_module.c:54-73).
+ *
+ * The contraction itself is the exact hi/lo byte-plane IMMA of nnsp_mma.cuh (16 streams x 8 units x 32 k per
+ * mma.sync.m16n8k32, s8/u8 x s8, int32). Activation planes between kernels: [tile][inference][hi|lo][16][pa]
+ * bytes, so one tile-step is a contiguous, 16-byte aligned block (bulk-copyable, conflict-free as A operand).
+ * Only models whose every layer has the exact 32-bit finish (MmaLayer.fast) take this path. */
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nnsp_host.h"
+#include "nnsp_mma.cuh"
+#include "nnsp_tma.cuh"
+
+namespace nnsp {
+
+constexpr int SEG_WARPS = 4;
+constexpr int SEG_THREADS = SEG_WARPS * 32;
+constexpr int SEG_KC = 16;                          /* inferences per CTA work item                      */
+constexpr int SEG_FROWS = 2 * SEG_KC + 4;           /* feature rows covering 16 windows of 6, stride 2   */
+constexpr int SEG_PC = SEG_FROWS * 40 + 16;         /* plane pitch: 364 words = 12 mod 32, conflict-free */
+constexpr int SCAN_NST = 4;                         /* depth of the input ring of the scan               */
+
+static_assert((SEG_PC % 16) == 0 && ((SEG_PC / 4) % 8) == 4, "feature plane pitch");
+
+/* ---- packed tanh LUT: one 32-bit word = (value, slope) of a segment (activation.c:5) ------------------- */
+__device__ __forceinline__ int32_t tanh_q15p(int32_t x, const uint32_t *__restrict__ lut32)
+{
+    const bool neg = x < 0;
+    const int32_t xi = neg ? (int32_t)(0u - (uint32_t)x) : x;
+    const bool big = (uint32_t)xi >= (5u << 15);            /* also x == INT32_MIN (see nnsp_device.cuh) */
+    int32_t kx = (xi - 512) >> 10;
+    kx = (big || kx < 0) ? 0 : kx;
+    const int32_t dx = xi - 512 - (kx << 10);
+    const uint32_t w = lut32[kx];
+    int32_t v = (int32_t)(int16_t)(w & 0xffffu) + ((dx * ((int32_t)w >> 16)) >> 15);
+    v = v > 0 ? v : 0;
+    v = big ? 0x7fff : v;
+    return neg ? -v : v;
+}
+__device__ __forceinline__ int32_t sigmoid_q15p(int32_t x, const uint32_t *__restrict__ lut32)
+{
+    return (tanh_q15p(x >> 1, lut32) >> 1) + 16384;
+}
+__device__ __forceinline__ int32_t activate16p(int act, int32_t pre, const uint32_t *lut32)
+{
+    switch (act) {
+    case ACT_TANH: return tanh_q15p(pre, lut32);
+    case ACT_SIGMOID: return sigmoid_q15p(pre, lut32);
+    default: return relu6_q12(pre);
+    }
+}
+__device__ __forceinline__ void fill_lut32(uint32_t *lut32, const DevTables *__restrict__ tb, int tid, int nthr)
+{
+    for (int i = tid; i < 192; i += nthr)
+        lut32[i] = (uint32_t)(uint16_t)tb->tanh_lut[2 * i] | ((uint32_t)(uint16_t)tb->tanh_lut[2 * i + 1] << 16);
+}
+
+/* ---- decision records: the part of the post-processing that does not depend on earlier frames ---------- */
+/* binary_post_proc, nn_speech.c:191-227 up to the comparison; 1 when this frame counts towards the streak */
+__device__ __forceinline__ int binary_flag(int32_t l0, int32_t l1, int16_t thresh_prob)
+{
+    const int32_t mx = l0 > l1 ? l0 : l1;
+    int32_t est[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int32_t val = (int32_t)((uint32_t)(i ? l1 : l0) - (uint32_t)mx);
+        const int64_t ref = ((int64_t)val * 0xB8AA) >> 15;
+        est[i] = pwr2_q15(sat32_dev(ref));
+    }
+    const int32_t den = (int32_t)((uint32_t)est[0] + (uint32_t)est[1]);
+    const int32_t thresh = 32768 - (int32_t)thresh_prob;
+    const int32_t tmp = (int32_t)(((int64_t)thresh * (int64_t)den) >> 15);
+    return est[0] <= tmp ? 1 : 0;
+}
+__device__ __forceinline__ void apply_binary(int16_t *sc, int flag, int16_t th_count)
+{
+    const int16_t cnt = flag ? (int16_t)(sc[SC_CNT0] + 1) : (int16_t)0;
+    sc[SC_CNT0] = cnt;
+    sc[SC_TRIGGER] = (cnt >= th_count) ? 1 : 0;
+}
+/* s2i_post_proc, nn_speech.c:146-189, on (argmax intent, argmax slot0, argmax slot1) */
+__device__ __forceinline__ void apply_s2i(int16_t *sc, int dec, int16_t th_count)
+{
+    const int ai = dec & 0xff;
+    sc[SC_TRIGGER] = 0;
+    sc[SC_OUT0] = sc[SC_OUT0 + 1] = sc[SC_OUT0 + 2] = 0;
+    const int last = sc[SC_ARGMAX_LAST];
+    if (last == 0 || last == ai) {
+        if (ai != 0) {
+            const int16_t cnt = (int16_t)(sc[SC_CNT0 + ai] + 1);
+            sc[SC_CNT0 + ai] = cnt;
+            if (cnt > th_count) {
+                sc[SC_TRIGGER] = 1;
+                sc[SC_OUT0] = (int16_t)ai;
+                sc[SC_OUT0 + 1] = (int16_t)((dec >> 8) & 0xff);
+                sc[SC_OUT0 + 2] = (int16_t)((dec >> 16) & 0xff);
+            }
+        }
+    } else {
+        for (int i = 0; i < 7; i++) sc[SC_CNT0 + i] = 0;
+    }
+    sc[SC_ARGMAX_LAST] = (int16_t)ai;
+}
+
+/* ======================================================================================================== */
+/* seg_kernel: a run of fc layers [l0, l1) for every (16-stream tile, inference) row block                   */
+/* ======================================================================================================== */
+struct SegArgs {
+    const MmaModel *model;
+    const uint2 *frag;
+    const int32_t *bias32;
+    const DevTables *tables;
+    int l0, l1;
+    int s0, ns, T, first, n_inf;
+    const int32_t *logmel;          /* [S][T][40]                      (FROM_FEAT) */
+    const int16_t *ctx;             /* [S][240] context before the call (FROM_FEAT) */
+    const uint8_t *in_planes;       /* [tile][n_inf][2][16][pa]         (!FROM_FEAT) */
+    uint8_t *out_planes;            /* same layout, when l1 < numlayers */
+    int32_t *dec;                   /* [S][n_inf], when l1 == numlayers */
+    int16_t *tap_act;               /* [S][T][act_stride] or null */
+    int32_t *tap_logits;            /* [S][T][n_out] or null */
+    int ao0;                        /* offset of layer l0's output inside an act row */
+    int16_t thresh_prob;
+};
+
+template <int NC>
+__device__ __forceinline__ void fc_tiles(const MmaLayer &L, const uint2 *__restrict__ wf, const uint8_t *in_hi,
+                                         const uint8_t *in_lo, int pitch, int g, int q, int (&ch)[4][4], int (&cl)[4][4])
+{
+    for (int ks = 0; ks < L.kt; ks++) {
+        uint32_t fh[4], fl[4];
+        load_a(in_hi, pitch, 32 * ks, g, q, fh);
+        load_a(in_lo, pitch, 32 * ks, g, q, fl);
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const uint2 b = __ldg(wf + (j * L.kt + ks) * 32);
+            imma_s8s8(ch[j], fh, b);
+            imma_u8s8(cl[j], fl, b);
+        }
+    }
+}
+
+template <bool FROM_FEAT>
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_kernel(SegArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    MmaModel &M = *reinterpret_cast<MmaModel *>(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    {
+        const int *src = reinterpret_cast<const int *>(a.model);
+        int *dst = reinterpret_cast<int *>(&M);
+        for (int i = tid; i < (int)(sizeof(MmaModel) / 4); i += SEG_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    size_t off = (sizeof(MmaModel) + 15) & ~(size_t)15;
+    int32_t *bias32 = reinterpret_cast<int32_t *>(smem + off); off += (size_t)M.bias_count * 4;
+    uint32_t *lut32 = reinterpret_cast<uint32_t *>(smem + off); off += 192 * 4;
+    uint8_t *fplanes = smem + off; if (FROM_FEAT) off += 2 * 16 * SEG_PC;
+    const int XB = 32 * M.pa;                                    /* bytes of one tile-step: [hi|lo][16][pa] */
+    uint8_t *wb = smem + off + (size_t)warp * 2 * XB;
+    {   /* ping-pong planes start zeroed: padded units / k columns must hold defined bytes */
+        uint32_t *z = reinterpret_cast<uint32_t *>(smem + off);
+        for (int i = tid; i < SEG_WARPS * 2 * XB / 4; i += SEG_THREADS) z[i] = 0;
+    }
+    off += (size_t)SEG_WARPS * 2 * XB;
+    int32_t *wlog = reinterpret_cast<int32_t *>(smem + off) + warp * 16 * M.no;
+    for (int i = tid; i < M.bias_count; i += SEG_THREADS) bias32[i] = a.bias32[i];
+    fill_lut32(lut32, a.tables, tid, SEG_THREADS);
+
+    const int tile = blockIdx.y, k0 = blockIdx.x * SEG_KC;
+    const int sb = a.s0 + 16 * tile;
+    const int nvalid = min(16, a.s0 + a.ns - sb);
+    const size_t tile_abs = (size_t)(a.s0 >> 4) + tile;
+    const int T = a.T;
+
+    if (FROM_FEAT) {
+        /* standardised feature rows (feature_module.c:67-73) of frames f_first .. f_first+35 as byte planes;
+         * frames before the call come from the carried context rows 1..5 (feature_module.c:54-57) */
+        const int f_first = a.first + 2 * k0 - 5;
+        for (int e = tid; e < 16 * SEG_FROWS * 10; e += SEG_THREADS) {
+            const int r = e / (SEG_FROWS * 10), rem = e - r * (SEG_FROWS * 10), j = rem / 10, i4 = (rem - j * 10) * 4;
+            const int f = f_first + j;
+            int v[4] = { 0, 0, 0, 0 };
+            if (r < nvalid) {
+                const long long s = sb + r;
+                if (f < 0) {
+                    const uint2 c = *reinterpret_cast<const uint2 *>(a.ctx + s * 240 + (6 + f) * 40 + i4);
+                    v[0] = (int16_t)(c.x & 0xffff); v[1] = (int32_t)c.x >> 16;
+                    v[2] = (int16_t)(c.y & 0xffff); v[3] = (int32_t)c.y >> 16;
+                } else if (f < T) {
+                    const int4 lm = __ldg(reinterpret_cast<const int4 *>(a.logmel + (s * T + f) * NNSP_B200_NMEL + i4));
+                    v[0] = standardise(lm.x, M.mean[i4], M.stdR[i4], M.feat_rshift);
+                    v[1] = standardise(lm.y, M.mean[i4 + 1], M.stdR[i4 + 1], M.feat_rshift);
+                    v[2] = standardise(lm.z, M.mean[i4 + 2], M.stdR[i4 + 2], M.feat_rshift);
+                    v[3] = standardise(lm.w, M.mean[i4 + 3], M.stdR[i4 + 3], M.feat_rshift);
+                }
+            }
+            const uint32_t hi = ((uint32_t)(v[0] >> 8) & 0xff) | (((uint32_t)(v[1] >> 8) & 0xff) << 8) |
+                                (((uint32_t)(v[2] >> 8) & 0xff) << 16) | (((uint32_t)(v[3] >> 8) & 0xff) << 24);
+            const uint32_t lo = ((uint32_t)v[0] & 0xff) | (((uint32_t)v[1] & 0xff) << 8) |
+                                (((uint32_t)v[2] & 0xff) << 16) | (((uint32_t)v[3] & 0xff) << 24);
+            *reinterpret_cast<uint32_t *>(fplanes + r * SEG_PC + j * 40 + i4) = hi;
+            *reinterpret_cast<uint32_t *>(fplanes + (16 + r) * SEG_PC + j * 40 + i4) = lo;
+        }
+        for (int e = tid; e < 32 * 4; e += SEG_THREADS)              /* k-step over-read of the last window */
+            *reinterpret_cast<uint32_t *>(fplanes + (e >> 2) * SEG_PC + SEG_FROWS * 40 + (e & 3) * 4) = 0;
+    }
+    __syncthreads();
+
+    for (int i = warp; i < SEG_KC; i += SEG_WARPS) {
+        const int k = k0 + i;
+        if (k >= a.n_inf) break;
+        const int t = a.first + 2 * k;                               /* frame of this inference */
+        const uint8_t *in_hi, *in_lo;
+        int in_pitch;
+        if (FROM_FEAT) {
+            in_hi = fplanes + 80 * i; in_lo = in_hi + 16 * SEG_PC; in_pitch = SEG_PC;
+        } else {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.in_planes + (tile_abs * a.n_inf + k) * (size_t)XB);
+            uint4 *dst = reinterpret_cast<uint4 *>(wb + XB);
+            for (int x = lane; x < XB / 16; x += 32) dst[x] = __ldg(src + x);
+            __syncwarp();
+            in_hi = wb + XB; in_lo = in_hi + 16 * M.pa; in_pitch = M.pa;
+        }
+        int pp = 0, ao = a.ao0;
+        for (int li = a.l0; li < a.l1; li++) {
+            const MmaLayer &L = M.layer[li];
+            const bool last = (li == M.numlayers - 1);
+            const int32_t *B = bias32 + L.bias_off;
+            const int rs = -L.sh_out;
+            uint8_t *oh = wb + pp * XB, *ol = oh + 16 * M.pa;
+            for (int n0 = 0; n0 < L.nt; n0 += 4) {
+                const int nc = min(4, L.nt - n0);
+                int ch[4][4] = {}, cl[4][4] = {};
+                const uint2 *wf = a.frag + L.w_off + (long long)n0 * L.kt * 32 + lane;
+                switch (nc) {
+                case 4: fc_tiles<4>(L, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
+                case 3: fc_tiles<3>(L, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
+                case 2: fc_tiles<2>(L, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
+                default: fc_tiles<1>(L, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (j < nc) {
+                        const int nb = (n0 + j) * 8 + 2 * q;
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++) {
+                            const int row = g + 8 * rr;
+                            int y[2];
+#pragma unroll
+                            for (int cc = 0; cc < 2; cc++) {
+                                const int e = 2 * rr + cc, n = nb + cc;
+                                int o = 0;
+                                if (n < L.rows) {
+                                    /* exact 32-bit finish (MmaLayer.fast): affine.c:190-249 without reachable clamps */
+                                    const int32_t pre = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e] + (uint32_t)B[n]) >> rs;
+                                    if (L.act == ACT_LINEAR) { wlog[row * M.no + n] = pre; }          /* activation.c:19-29 */
+                                    else {
+                                        o = activate16p(L.act, pre, lut32);
+                                        if (last) wlog[row * M.no + n] = o;                              /* neural_nets.c:160-166 */
+                                        else if (a.tap_act && row < nvalid)
+                                            a.tap_act[((long long)(sb + row) * T + t) * M.act_stride + ao + n] = (int16_t)o;
+                                    }
+                                }
+                                y[cc] = o;
+                            }
+                            store_pair(oh, ol, row * M.pa + nb, y[0], y[1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            in_hi = oh; in_lo = ol; in_pitch = M.pa;
+            pp ^= 1;
+            if (!last) ao += L.rows;
+        }
+        if (a.l1 < M.numlayers) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(wb + (pp ^ 1) * XB);
+            uint4 *dst = reinterpret_cast<uint4 *>(a.out_planes + (tile_abs * a.n_inf + k) * (size_t)XB);
+            for (int x = lane; x < XB / 16; x += 32) dst[x] = src[x];
+        } else {
+            if (lane < nvalid) {
+                const int32_t *lg = wlog + lane * M.no;
+                int d;
+                if (M.nn_id == NNSP_B200_ID_S2I)
+                    d = argmax_last_wins(lg, 7) | (argmax_last_wins(lg + 7, 17) << 8) | (argmax_last_wins(lg + 24, 17) << 16);
+                else
+                    d = binary_flag(lg[0], lg[1], a.thresh_prob);
+                a.dec[(size_t)(sb + lane) * a.n_inf + k] = d;
+            }
+            if (a.tap_logits)
+                for (int x = lane; x < 16 * M.n_out; x += 32) {
+                    const int row = x / M.n_out, n = x - row * M.n_out;
+                    if (row < nvalid) a.tap_logits[((long long)(sb + row) * T + t) * M.n_out + n] = wlog[row * M.no + n];
+                }
+        }
+        __syncwarp();
+    }
+}
+
+/* ======================================================================================================== */
+/* scan_kernel: one LSTM layer over the inferences of a 16-stream tile                                       */
+/* ======================================================================================================== */
+struct ScanArgs {
+    const uint2 *frag;              /* fragment image; the layer's Wx tiles at w_off, Wh tiles right behind */
+    const int32_t *bias32;
+    const DevTables *tables;
+    int H, kt, ktr, nt, rs, w_off, bias_off, pa;
+    int ho, hs, ao, act_stride, tap_out;   /* state offset / stride, act-row offset, 1: layer output is tapped */
+    int s0, ns, T, first, n_inf;
+    const uint8_t *xin;             /* [tile][n_inf][2][16][pa] */
+    uint8_t *hout;                  /* same layout */
+    int16_t *h;                     /* [S][hs] */
+    int32_t *c;
+    int16_t *tap_act, *tap_h;
+    int32_t *tap_c;
+};
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(512, 1)
+scan_kernel(ScanArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);             /* [0..NST) input ring, [NST] weights */
+    const int WB = 4 * a.nt * (a.kt + a.ktr) * 256, XB = 32 * a.pa;
+    const uint2 *wsm = reinterpret_cast<const uint2 *>(smem + 64);
+    uint32_t *lut32 = reinterpret_cast<uint32_t *>(smem + 64 + WB);
+    uint8_t *xs = smem + 64 + WB + 768;
+    uint8_t *hb = xs + SCAN_NST * XB;
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int tile = blockIdx.x, sb = a.s0 + 16 * tile;
+    const int nvalid = min(16, a.s0 + a.ns - sb);
+    const size_t tile_abs = (size_t)(a.s0 >> 4) + tile;
+    const uint8_t *xg = a.xin + tile_abs * a.n_inf * (size_t)XB;
+    uint8_t *hg = a.hout + tile_abs * a.n_inf * (size_t)XB;
+    const int H = a.H, pa = a.pa, HS = a.hs, T = a.T, n_inf = a.n_inf;
+
+    if (tid == 0) {
+        for (int i = 0; i <= SCAN_NST; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 3 * XB / 4; i += nthr) reinterpret_cast<uint32_t *>(hb)[i] = 0;
+    fill_lut32(lut32, a.tables, tid, nthr);
+    __syncthreads();
+    uint8_t *h2 = hb + 2 * XB;                                       /* h before the first inference */
+    for (int idx = tid; idx < 16 * H; idx += nthr) {
+        const int r = idx / H, u = idx - r * H;
+        const int v = (r < nvalid) ? (int)a.h[(long long)(sb + r) * HS + a.ho + u] : 0;
+        h2[r * pa + u] = (uint8_t)(v >> 8);
+        h2[(16 + r) * pa + u] = (uint8_t)v;
+    }
+    if (tid == 0) {
+        const unsigned char *wsrc = reinterpret_cast<const unsigned char *>(a.frag + a.w_off);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bars + SCAN_NST)), "r"((uint32_t)WB) : "memory");
+        for (int o = 0; o < WB; o += 32768) {
+            const uint32_t n = (uint32_t)min(32768, WB - o);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem + 64 + o)), "l"(wsrc + o), "r"(n), "r"(smem_u32(bars + SCAN_NST)) : "memory");
+        }
+        for (int m = 0; m < SCAN_NST && m < n_inf; m++) bulk_load(xs + m * XB, xg + (size_t)m * XB, XB, bars + m);
+    }
+    /* the lane's cells: rows g, g+8 x units u0, u0+1 of group `warp`; their biases and cell state stay in registers */
+    const int u0 = 8 * warp + 2 * q;
+    int32_t bz[4][2], cst[2][2];
+#pragma unroll
+    for (int gt = 0; gt < 4; gt++)
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) bz[gt][cc] = (u0 + cc < H) ? a.bias32[a.bias_off + gt * H + u0 + cc] : 0;
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int row = g + 8 * rr, u = u0 + cc;
+            cst[rr][cc] = (row < nvalid && u < H) ? a.c[(long long)(sb + row) * HS + a.ho + u] : 0;
+        }
+    __syncthreads();
+    mbar_wait(bars + SCAN_NST, 0);
+
+    const uint2 *wx = wsm + (size_t)warp * 4 * a.kt * 32 + lane;
+    const uint2 *wh = wsm + (size_t)a.nt * 4 * a.kt * 32 + (size_t)warp * 4 * a.ktr * 32 + lane;
+    int ach[4][4], acl[4][4];
+    auto zero_acc = [&]() {
+#pragma unroll
+        for (int gt = 0; gt < 4; gt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) { ach[gt][e] = 0; acl[gt][e] = 0; }
+    };
+    auto half = [&](const uint8_t *plane, const uint2 *w, int nk) {          /* acc += W . plane (rc_Krows_8x16) */
+        for (int ks = 0; ks < nk; ks++) {
+            uint32_t fh[4], fl[4];
+            load_a(plane, pa, 32 * ks, g, q, fh);
+            load_a(plane + 16 * pa, pa, 32 * ks, g, q, fl);
+#pragma unroll
+            for (int gt = 0; gt < 4; gt++) {
+                const uint2 b = w[(gt * nk + ks) * 32];
+                imma_s8s8(ach[gt], fh, b);
+                imma_u8s8(acl[gt], fl, b);
+            }
+        }
+    };
+    auto tap_state = [&](const uint8_t *hp, int t) {                         /* debug taps only */
+        if (a.tap_h)
+            for (int idx = tid; idx < nvalid * H; idx += nthr) {
+                const int r = idx / H, u = idx - r * H;
+                a.tap_h[((long long)(sb + r) * T + t) * HS + a.ho + u] = (int16_t)(((int)(int8_t)hp[r * pa + u] << 8) | hp[(16 + r) * pa + u]);
+            }
+        if (a.tap_c) {
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+                    const int row = g + 8 * rr, u = u0 + cc;
+                    if (row < nvalid && u < H) a.tap_c[((long long)(sb + row) * T + t) * HS + a.ho + u] = cst[rr][cc];
+                }
+        }
+    };
+
+    mbar_wait(bars + 0, 0);
+    zero_acc();
+    half(xs, wx, a.kt);                                               /* Wx . x of inference 0 */
+    __syncthreads();
+    if (tid == 0 && SCAN_NST < n_inf) bulk_load(xs, xg + (size_t)SCAN_NST * XB, XB, bars + 0);
+    if (a.first == 1) tap_state(h2, 0);                               /* frame 0 ran no inference */
+
+    for (int k = 0; k < n_inf; k++) {
+        const uint8_t *hp = hb + ((k + 2) % 3) * XB;                  /* h of the previous inference */
+        uint8_t *hn = hb + (k % 3) * XB;
+        const int t = a.first + 2 * k;
+        half(hp, wh, a.ktr);                                          /* + Wh . h_old (lstm.c:54-104 all read the old h) */
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int row = g + 8 * rr;
+            int y[2];
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const int e = 2 * rr + cc, u = u0 + cc;
+                int o = 0;
+                if (u < H) {
+                    int32_t pre[4];
+#pragma unroll
+                    for (int gt = 0; gt < 4; gt++)
+                        pre[gt] = (int32_t)(((uint32_t)ach[gt][e] << 8) + (uint32_t)acl[gt][e] + (uint32_t)bz[gt][cc]) >> a.rs;
+                    const int32_t gi = sigmoid_q15p(pre[0], lut32), gj = tanh_q15p(pre[1], lut32);
+                    const int32_t gf = sigmoid_q15p(pre[2], lut32), go = sigmoid_q15p(pre[3], lut32);
+                    const int64_t tt = ((int64_t)gi * (int64_t)gj + (int64_t)gf * (int64_t)cst[rr][cc]) >> 15;   /* lstm.c:108-109 */
+                    const int32_t cn = sat32_dev(tt);
+                    cst[rr][cc] = cn;
+                    o = (tanh_q15p(cn, lut32) * go) >> 15;                                                      /* lstm.c:111-115 */
+                    o = o > 32767 ? 32767 : (o < -32768 ? -32768 : o);
+                    if (a.tap_out && a.tap_act && row < nvalid)
+                        a.tap_act[((long long)(sb + row) * T + t) * a.act_stride + a.ao + u] = (int16_t)o;
+                }
+                y[cc] = o;
+            }
+            store_pair(hn, hn + 16 * pa, row * pa + u0, y[0], y[1]);
+        }
+        if (k + 1 < n_inf) {                                          /* Wx . x of the next inference, off the recurrence */
+            mbar_wait(bars + ((k + 1) % SCAN_NST), (uint32_t)(((k + 1) / SCAN_NST) & 1));
+            zero_acc();
+            half(xs + ((k + 1) % SCAN_NST) * XB, wx, a.kt);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  /* h planes -> visible to the bulk store */
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   /* buffer of step k-2 is free again */
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(hg + (size_t)k * XB), "r"(smem_u32(hn)), "r"((uint32_t)XB) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            const int m = k + 1 + SCAN_NST;
+            if (m < n_inf) bulk_load(xs + ((k + 1) % SCAN_NST) * XB, xg + (size_t)m * XB, XB, bars + ((k + 1) % SCAN_NST));
+        }
+        if (a.tap_h || a.tap_c) {
+            tap_state(hn, t);
+            if (t + 1 < T) tap_state(hn, t + 1);
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    /* state for the next call */
+    const uint8_t *hf = hb + ((n_inf + 2) % 3) * XB;
+    for (int idx = tid; idx < nvalid * H; idx += nthr) {
+        const int r = idx / H, u = idx - r * H;
+        a.h[(long long)(sb + r) * HS + a.ho + u] = (int16_t)(((int)(int8_t)hf[r * pa + u] << 8) | hf[(16 + r) * pa + u]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int row = g + 8 * rr, u = u0 + cc;
+            if (row < nvalid && u < H) a.c[(long long)(sb + row) * HS + a.ho + u] = cst[rr][cc];
+        }
+}
+
+/* ======================================================================================================== */
+/* post_kernel / ctx_kernel / feat_tap_kernel                                                                */
+/* ======================================================================================================== */
+struct PostArgs {
+    int nn_id, s0, ns, T, first, n_inf;
+    const int32_t *dec;
+    int16_t *scal;
+    nnsp_b200_result *results;
+    int16_t *tap_post;
+    int16_t th_count;
+};
+
+__global__ void __launch_bounds__(128) post_kernel(PostArgs a)
+{
+    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= a.ns) return;
+    const long long s = a.s0 + si;
+    int16_t sc[SC_N];
+    {
+        const uint4 *p = reinterpret_cast<const uint4 *>(a.scal + s * SC_N);
+        *reinterpret_cast<uint4 *>(&sc[0]) = p[0];
+        *reinterpret_cast<uint4 *>(&sc[8]) = p[1];
+    }
+    const int32_t *d = a.dec + s * a.n_inf;
+    int k = 0;
+    for (int t = 0; t < a.T; t++) {
+        const bool ran = (t >= a.first) && (((t - a.first) & 1) == 0);                   /* nn_speech.c:84 */
+        if (ran) {
+            const int dv = d[k++];
+            if (a.nn_id == NNSP_B200_ID_S2I) apply_s2i(sc, dv, a.th_count);               /* nn_speech.c:97-119 */
+            else apply_binary(sc, dv, a.th_count);
+        }
+        sc[SC_SLIDES] = (int16_t)((sc[SC_SLIDES] + 1) % 2);                               /* nn_speech.c:125 */
+        if (a.results) {
+            nnsp_b200_result r;
+            r.trigger = sc[SC_TRIGGER];
+            r.outputs[0] = sc[SC_OUT0]; r.outputs[1] = sc[SC_OUT0 + 1]; r.outputs[2] = sc[SC_OUT0 + 2];
+            a.results[s * a.T + t] = r;
+        }
+        if (a.tap_post) {
+            int16_t *o = a.tap_post + (s * a.T + t) * SC_N;
+            for (int i = 0; i < SC_N; i++) o[i] = sc[i];
+            o[SC_RAN] = ran ? 1 : 0;
+            o[SC_STAGE] = (int16_t)a.nn_id;
+        }
+    }
+    {
+        uint4 *p = reinterpret_cast<uint4 *>(a.scal + s * SC_N);
+        p[0] = *reinterpret_cast<uint4 *>(&sc[0]);
+        p[1] = *reinterpret_cast<uint4 *>(&sc[8]);
+    }
+}
+
+/* normFeatContext after the call: the newest 6 rows of (old rows ++ this call's standardised rows) */
+__global__ void __launch_bounds__(256) ctx_kernel(const MmaModel *__restrict__ M, const int32_t *__restrict__ logmel,
+                                                  int16_t *ctx, int s0, int T)
+{
+    const long long s = s0 + blockIdx.x;
+    const int i = threadIdx.x;
+    int16_t v = 0;
+    if (i < 240) {
+        const int j = i / 40, fi = i - j * 40, f = T - 6 + j;
+        v = (f >= 0) ? standardise(logmel[(s * T + f) * NNSP_B200_NMEL + fi], M->mean[fi], M->stdR[fi], M->feat_rshift)
+                     : ctx[s * 240 + (j + T) * 40 + fi];
+    }
+    __syncthreads();
+    if (i < 240) ctx[s * 240 + i] = v;
+}
+
+__global__ void feat_tap_kernel(const MmaModel *__restrict__ M, const int32_t *__restrict__ logmel, int16_t *feat,
+                                int32_t *logmel_out, long long base, long long n)
+{
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int fi = (int)((base + e) % NNSP_B200_NMEL);
+        const int32_t lm = logmel[base + e];
+        if (feat) feat[base + e] = standardise(lm, M->mean[fi], M->stdR[fi], M->feat_rshift);
+        if (logmel_out) logmel_out[base + e] = lm;
+    }
+}
+
+/* ======================================================================================================== */
+/* host                                                                                                      */
+/* ======================================================================================================== */
+static size_t seg_smem(const MmaModel *D, bool from_feat)
+{
+    size_t b = (sizeof(MmaModel) + 15) & ~(size_t)15;
+    b += (size_t)D->bias_count * 4 + 192 * 4;
+    if (from_feat) b += 2 * 16 * SEG_PC;
+    b += (size_t)SEG_WARPS * 2 * 32 * D->pa;
+    b += (size_t)SEG_WARPS * 16 * D->no * 4;
+    return b;
+}
+static size_t scan_smem(const MmaModel *D, const MmaLayer &L)
+{
+    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + 768 + (size_t)(SCAN_NST + 3) * 32 * D->pa;
+}
+
+int split_supported(const MmaDeviceModel &mm)
+{
+    const MmaModel *D = mm.h;
+    if (!D || D->numlayers < 1) return 0;
+    if (D->layer[0].type != LAYER_FC || D->layer[D->numlayers - 1].type != LAYER_FC) return 0;
+    if (D->nn_id == NNSP_B200_ID_S2I ? D->n_out < 41 : D->n_out < 2) return 0;
+    for (int i = 0; i < D->numlayers; i++) {
+        const MmaLayer &L = D->layer[i];
+        if (!L.fast) return 0;
+        if (L.type == LAYER_LSTM && (L.nt > 16 || scan_smem(D, L) > 227 * 1024)) return 0;
+        if (L.type == LAYER_LSTM && L.wh_off != L.w_off + 4 * L.nt * L.kt * 32) return 0;
+    }
+    if (seg_smem(D, true) > 227 * 1024) return 0;
+    return 1;
+}
+
+size_t split_plane_bytes(const MmaDeviceModel &mm, int n_streams, int n_inf)
+{
+    return (size_t)((n_streams + 15) / 16) * (size_t)n_inf * 32 * mm.h->pa;
+}
+
+int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, int first, int n_inf, uint8_t *planes0,
+                    uint8_t *planes1, int32_t *dec, int device, cudaStream_t st)
+{
+    const MmaModel *D = mm.h;
+    static bool attr_done[64] = { false };
+    if (!attr_done[device]) {
+        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done[device] = true;
+    }
+    if (l.ns <= 0 || l.T <= 0) return NNSP_B200_OK;
+    if ((l.s0 & 15) != 0) { nnsp_set_error("stream slices of the split path must start at a multiple of 16"); return NNSP_B200_ERR_ARG; }
+    const int T = l.T, ntiles = (l.ns + 15) / 16, nchunks = (n_inf + SEG_KC - 1) / SEG_KC;
+    const nnsp_b200_taps &tp = l.taps;
+    const long long fbase = (long long)l.s0 * T * NNSP_B200_NMEL, fcount = (long long)l.ns * T * NNSP_B200_NMEL;
+    if (tp.feat || tp.logmel) {
+        feat_tap_kernel<<<(unsigned)((fcount + 255) / 256 > 4096 ? 4096 : (fcount + 255) / 256), 256, 0, st>>>(mm.d, l.logmel, tp.feat, tp.logmel, fbase, fcount);
+        NNSP_LAUNCH_CHECK();
+    }
+    if (tp.act) NNSP_CUDA(cudaMemsetAsync(tp.act + (long long)l.s0 * T * D->act_stride, 0, (size_t)l.ns * T * D->act_stride * 2, st));
+    if (tp.logits) NNSP_CUDA(cudaMemsetAsync(tp.logits + (long long)l.s0 * T * D->n_out, 0, (size_t)l.ns * T * D->n_out * 4, st));
+
+    if (n_inf > 0) {
+        uint8_t *cur_in = nullptr, *bufs[2] = { planes0, planes1 };
+        int which = 0, li = 0, ao = 0, ho = 0;
+        bool from_feat = true;
+        while (li < D->numlayers) {
+            int l1 = li;
+            while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
+            if (l1 > li) {                                           /* a run of fc layers */
+                SegArgs a{};
+                a.model = mm.d; a.frag = (const uint2 *)mm.frag; a.bias32 = mm.bias32; a.tables = l.tables;
+                a.l0 = li; a.l1 = l1; a.s0 = l.s0; a.ns = l.ns; a.T = T; a.first = first; a.n_inf = n_inf;
+                a.logmel = l.logmel; a.ctx = l.st.ctx; a.in_planes = cur_in;
+                a.out_planes = (l1 < D->numlayers) ? bufs[which] : nullptr;
+                a.dec = dec; a.tap_act = tp.act; a.tap_logits = tp.logits; a.ao0 = ao; a.thresh_prob = l.thresh_prob;
+                const dim3 grid((unsigned)nchunks, (unsigned)ntiles);
+                if (from_feat) seg_kernel<true><<<grid, SEG_THREADS, seg_smem(D, true), st>>>(a);
+                else seg_kernel<false><<<grid, SEG_THREADS, seg_smem(D, false), st>>>(a);
+                NNSP_LAUNCH_CHECK();
+                for (int i = li; i < l1; i++) if (i < D->numlayers - 1) ao += D->layer[i].rows;
+                if (l1 < D->numlayers) { cur_in = bufs[which]; which ^= 1; }
+                from_feat = false;
+                li = l1;
+            }
+            if (li < D->numlayers) {                                 /* an lstm layer */
+                const MmaLayer &L = D->layer[li];
+                ScanArgs a{};
+                a.frag = (const uint2 *)mm.frag; a.bias32 = mm.bias32; a.tables = l.tables;
+                a.H = L.rows; a.kt = L.kt; a.ktr = L.ktr; a.nt = L.nt; a.rs = -L.sh_out; a.w_off = L.w_off; a.bias_off = L.bias_off; a.pa = D->pa;
+                a.ho = ho; a.hs = D->h_stride; a.ao = ao; a.act_stride = D->act_stride; a.tap_out = (li < D->numlayers - 1);
+                a.s0 = l.s0; a.ns = l.ns; a.T = T; a.first = first; a.n_inf = n_inf;
+                a.xin = cur_in; a.hout = bufs[which]; a.h = l.st.h; a.c = l.st.c;
+                a.tap_act = tp.act; a.tap_h = tp.hstate; a.tap_c = tp.cstate;
+                scan_kernel<<<ntiles, 32 * L.nt, scan_smem(D, L), st>>>(a);
+                NNSP_LAUNCH_CHECK();
+                cur_in = bufs[which]; which ^= 1;
+                ao += L.rows; ho += L.rows;
+                li++;
+            }
+        }
+    } else if ((tp.hstate || tp.cstate) && D->h_stride > 0) {
+        /* a call without any inference (one frame, slides == 0): the state taps repeat the stored state */
+        for (int si = 0; si < l.ns; si++) {
+            const long long s = l.s0 + si;
+            if (tp.hstate) NNSP_CUDA(cudaMemcpyAsync(tp.hstate + s * T * D->h_stride, l.st.h + s * D->h_stride, (size_t)D->h_stride * 2, cudaMemcpyDeviceToDevice, st));
+            if (tp.cstate) NNSP_CUDA(cudaMemcpyAsync(tp.cstate + s * T * D->h_stride, l.st.c + s * D->h_stride, (size_t)D->h_stride * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    {
+        PostArgs p{};
+        p.nn_id = D->nn_id; p.s0 = l.s0; p.ns = l.ns; p.T = T; p.first = first; p.n_inf = n_inf;
+        p.dec = dec; p.scal = l.st.scal; p.results = l.results; p.tap_post = tp.post; p.th_count = l.th_count;
+        post_kernel<<<(l.ns + 127) / 128, 128, 0, st>>>(p);
+        NNSP_LAUNCH_CHECK();
+    }
+    ctx_kernel<<<l.ns, 256, 0, st>>>(mm.d, l.logmel, l.st.ctx, l.s0, T);
+    NNSP_LAUNCH_CHECK();
+    return NNSP_B200_OK;
+}
+
+}  // namespace nnsp

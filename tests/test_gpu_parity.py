@@ -39,10 +39,10 @@ def test_feature_stages_bit_exact(nb, oracle):
             assert (out[k][i] == ref[k]).all(), "stage %s differs for window %d" % (k, i)
 
 
-@pytest.mark.parametrize("path", ["imma", "dp2a"])
+@pytest.mark.parametrize("path", ["split", "imma", "dp2a"])
 @pytest.mark.parametrize("nn_id,acc32", [(1, False), (2, True), (0, False), (0, True), (1, True), (2, False)])
 def test_batch_matches_oracle_every_tap(nb, oracle, nn_id, acc32, path):
-    """Both network kernels: tensor-core IMMA (16 streams per warp) and dp2a (warp per stream)."""
+    """All network paths: scan-split (default), tensor-core IMMA in the time loop, dp2a warp per stream."""
     S, T = 53, 64                      # 53: a partial 16-stream tile at the end
     pcm = nb.synth_pcm(S, T)
     m = _model(nb, nn_id, acc32)
@@ -135,3 +135,24 @@ def test_thresholds_are_honoured(nb, oracle):
             r, _ = oracle.nnsp_run(m_or, pcm[s], thresh_prob=th[0], th_count=th[1], taps=False)
             assert (r == res[s]).all()
         b.close()
+
+
+def test_network_paths_share_one_state(nb, oracle):
+    """Switching the network path between calls must not disturb a stream: context, LSTM state, counters and
+    the stride-2 phase are one canonical state whichever kernels advance it (odd chunk lengths flip the phase)."""
+    S, T = 37, 45
+    pcm = nb.synth_pcm(S, T, first_stream=5)
+    m = _model(nb, 0, False)
+    b = nb.NNSPBatch(m, S)
+    parts, t = [], 0
+    for n, path in ((7, "split"), (5, "imma"), (1, "split"), (9, "dp2a"), (23, "split")):
+        b.set_nn_path(path)
+        parts.append(b.exec(pcm[:, t * 160:(t + n) * 160]))
+        t += n
+    assert t == T
+    got = np.concatenate(parts, axis=1)
+    m_or = oracle.model(0, False)
+    for s in range(S):
+        r, _ = oracle.nnsp_run(m_or, pcm[s], taps=False)
+        assert (r == got[s]).all(), "stream %d" % s
+    b.close()

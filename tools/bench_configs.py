@@ -31,7 +31,7 @@ def time_handle(h, exec_fn, T, S, steps=8, warm=3):
 
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    paths = ["imma", "dp2a"]
+    paths = ["split", "imma"]
     for a in sys.argv[1:]:
         if a.startswith("--paths"):
             paths = a.split("=")[1].split(",")
