@@ -198,16 +198,19 @@ constexpr int FEAT_THREADS = FEAT_WARPS * 32;
 struct FeatSmem {
     FeatSmemTables tb;
     FrameScratch fs[FEAT_WARPS * 2];
+    int32_t norm[84];              /* mean[40], stdR[40], rshift: only when the kernel standardises */
 };
 
 __global__ void __launch_bounds__(FEAT_THREADS, FEAT_CTAS_PER_SM)
 feat_kernel(const DevTables *__restrict__ tables, const int16_t *__restrict__ pcm, long long stride,
             const int16_t *__restrict__ hist, int hist_frames, int s0, int ns, int T,
-            int32_t *__restrict__ logmel)
+            int32_t *__restrict__ logmel, const int32_t *__restrict__ norm, int16_t *__restrict__ feat16)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FeatSmem &sm = *reinterpret_cast<FeatSmem *>(smem_raw);
     load_feat_tables(&sm.tb, tables, threadIdx.x, FEAT_THREADS);
+    if (norm && threadIdx.x < 81) sm.norm[threadIdx.x] = norm[threadIdx.x];
+    const int32_t *snorm = norm ? sm.norm : nullptr;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, L = lane & 15;
     FrameScratch &fs = sm.fs[warp * 2 + half];
@@ -226,7 +229,8 @@ feat_kernel(const DevTables *__restrict__ tables, const int16_t *__restrict__ pc
             const int16_t *q = (g < 0) ? (hs + g) : (ps + g);
             return __ldg(reinterpret_cast<const unsigned int *>(q));
         };
-        frame_logmel<false>(sm.tb, fs, L, load_pair, logmel + ((long long)s * T + t) * NNSP_B200_NMEL, valid, FeatDump{});
+        const long long row = ((long long)s * T + t) * NNSP_B200_NMEL;
+        frame_logmel<false>(sm.tb, fs, L, load_pair, logmel + row, valid, FeatDump{}, snorm, feat16 + row);
     }
 }
 
@@ -243,7 +247,7 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
     const long long cap = (long long)sm_count(device) * FEAT_CTAS_PER_SM;   /* persistent grid: every CTA resident */
     if (blocks > cap) blocks = cap;
     feat_kernel<<<(unsigned)blocks, FEAT_THREADS, sizeof(FeatSmem), st>>>(tb, a.pcm, a.stride, a.hist, a.hist_frames,
-                                                                            a.s0, a.ns, a.T, a.logmel);
+                                                                            a.s0, a.ns, a.T, a.logmel, a.norm, a.feat16);
     NNSP_LAUNCH_CHECK();
     return NNSP_B200_OK;
 }
@@ -516,6 +520,8 @@ struct nnsp_b200_batch {
     uint8_t *sp_planes[2] = { nullptr, nullptr };  /* scan-split activation planes [tile][inference][hi|lo][16][pa] */
     int32_t *sp_dec = nullptr;              /* decision records [S][inference] */
     long long sp_cap_inf = 0;
+    int16_t *feat16 = nullptr; long long feat16_frames = 0;       /* scan-split: standardised rows [S][T][40] */
+    int32_t *norm_dev = nullptr;            /* mean[40], stdR[40], rshift for feat_kernel's standardising mode */
     StreamState st{};
     int16_t thresh_prob = 0, th_count = 0;
     int32_t *logmel = nullptr; long long logmel_frames = 0;       /* capacity in frames per stream */
@@ -527,8 +533,17 @@ struct nnsp_b200_batch {
     bool ev_valid = false;
 };
 
+static int batch_nn_path(const nnsp_b200_batch *b);
+
 static int batch_ensure_logmel(nnsp_b200_batch *b, int T)
 {
+    if (batch_nn_path(b) == 3) {                       /* the scan-split path consumes standardised int16 rows */
+        if (T <= b->feat16_frames) return NNSP_B200_OK;
+        if (b->feat16) { NNSP_CUDA(cudaStreamSynchronize(b->stream)); for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s)); cudaFree(b->feat16); b->feat16 = nullptr; }
+        NNSP_CUDA(cudaMalloc(&b->feat16, (size_t)b->S * T * NNSP_B200_NMEL * sizeof(int16_t)));
+        b->feat16_frames = T;
+        return NNSP_B200_OK;
+    }
     if (T <= b->logmel_frames) return NNSP_B200_OK;
     if (b->logmel) { NNSP_CUDA(cudaStreamSynchronize(b->stream)); for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s)); cudaFree(b->logmel); b->logmel = nullptr; }
     NNSP_CUDA(cudaMalloc(&b->logmel, (size_t)b->S * T * NNSP_B200_NMEL * sizeof(int32_t)));
@@ -567,12 +582,17 @@ static int batch_ensure_split(nnsp_b200_batch *b, int n_inf)
 static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride, int T, int s0, int ns,
                         nnsp_b200_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed)
 {
+    const int path = batch_nn_path(b);
     FeatLaunch fl{ pcm, stride, b->st.hist, 2, s0, ns, T, b->logmel };
+    if (path == 3) { fl.logmel = nullptr; fl.norm = b->norm_dev; fl.feat16 = b->feat16; }
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[0], st));
     int rc = launch_feature(b->tables, fl, b->device, st);
     if (rc) return rc;
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[1], st));
-    const int path = batch_nn_path(b);
+    if (path == 3 && taps && taps->logmel) {            /* debug tap: a second, log-mel pass straight into the tap */
+        FeatLaunch ft{ pcm, stride, b->st.hist, 2, s0, ns, T, taps->logmel };
+        if ((rc = launch_feature(b->tables, ft, b->device, st))) return rc;
+    }
     if (path == 3) {
         if (!b->split_ok) { nnsp_set_error("this model has no scan-split formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
         int first, n_inf;
@@ -581,7 +601,7 @@ static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride
         l.tables = b->tables; l.st = b->st; l.logmel = b->logmel; l.s0 = s0; l.ns = ns; l.T = T; l.results = results;
         if (taps) l.taps = *taps;
         l.thresh_prob = b->thresh_prob; l.th_count = b->th_count;
-        if ((rc = launch_nn_split(b->mm, l, first, n_inf, b->sp_planes[0], b->sp_planes[1], b->sp_dec, b->device, st))) return rc;
+        if ((rc = launch_nn_split(b->mm, l, b->feat16, first, n_inf, b->sp_planes[0], b->sp_planes[1], b->sp_dec, b->device, st))) return rc;
     } else if (path == 2) {
         if (!b->mma_ok) { nnsp_set_error("this model has no IMMA formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
         NNLaunch l{};
@@ -651,6 +671,14 @@ int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device, 
     TRY(cudaMalloc(&b->st.c, S * HS * sizeof(int32_t)));
     TRY(cudaMalloc(&b->st.scal, S * SC_N * sizeof(int16_t)));
     TRY(cudaMalloc(&b->st.hist, S * 2 * NNSP_B200_FRAME * sizeof(int16_t)));
+    {
+        int32_t norm[84] = { 0 };
+        memcpy(norm, b->dm.h.mean, 160);
+        memcpy(norm + 40, b->dm.h.stdR, 160);
+        norm[80] = b->dm.h.feat_rshift;
+        TRY(cudaMalloc(&b->norm_dev, sizeof norm));
+        TRY(cudaMemcpy(b->norm_dev, norm, sizeof norm, cudaMemcpyHostToDevice));
+    }
 #undef TRY
     if ((rc = nnsp_b200_batch_reset(b))) return fail(rc);
     *out = b;
@@ -793,6 +821,7 @@ void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
     cudaFree(b->st.ctx); cudaFree(b->st.h); cudaFree(b->st.c); cudaFree(b->st.scal); cudaFree(b->st.hist);
     cudaFree(b->logmel); cudaFree(b->d_pcm); cudaFree(b->d_res);
     cudaFree(b->sp_planes[0]); cudaFree(b->sp_planes[1]); cudaFree(b->sp_dec);
+    cudaFree(b->feat16); cudaFree(b->norm_dev);
     if (b->stream) cudaStreamDestroy(b->stream);
     for (auto s : b->xs) if (s) cudaStreamDestroy(s);
     for (auto e : b->ev) if (e) cudaEventDestroy(e);

@@ -84,10 +84,13 @@ __device__ __forceinline__ int xpad(int p) { return p + (p >> 4); }
 /* One frame by the 16 lanes of a half-warp (L = lane & 15). `load_pair(p)` returns PCM samples
  * 2p and 2p+1 of the 480-sample analysis window packed in one word (p = 0..239).
  * Every lane of the WARP must call this together (full-warp __syncwarp inside). */
+/* norm (optional, shared memory): mean[40], stdR[40], rshift of a model. When given, the standardised row
+ * (feature_module.c:67-73) is written to out_feat as int16 instead of the log-mel row to out_logmel. */
 template <bool DUMP, typename LoadPair>
 __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScratch &fs, int L,
                                              LoadPair load_pair, int32_t *__restrict__ out_logmel,
-                                             bool store, FeatDump dump)
+                                             bool store, FeatDump dump, const int32_t *norm = nullptr,
+                                             int16_t *__restrict__ out_feat = nullptr)
 {
     int32_t xr[16], xi[16];
     /* window, Q15 x Q15 >> 15 (spectrogram_module.c:62-66); zero padding 480..511 (:68-71) */
@@ -191,7 +194,11 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
             for (int j = s; j <= e; j++) mac += (int64_t)(*tap++) * (int64_t)fs.ps[j];
             const int32_t mel = sat32_dev(mac >> 15);
             if (DUMP && dump.mel && store) dump.mel[b] = mel;
-            if (store) out_logmel[b] = log10_q15(mel, tb.log_lut);
+            if (store) {
+                const int32_t lm = log10_q15(mel, tb.log_lut);
+                if (norm) out_feat[b] = standardise(lm, norm[b], norm[40 + b], norm[80]);
+                else out_logmel[b] = lm;
+            }
         }
     }
     __syncwarp();

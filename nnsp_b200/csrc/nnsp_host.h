@@ -51,6 +51,8 @@ struct FeatLaunch {
     const int16_t *hist; int hist_frames;    /* [S][hist_frames*160], newest frames last */
     int s0, ns, T;
     int32_t *logmel;                          /* [S][T][40] */
+    const int32_t *norm = nullptr;            /* device: mean[40], stdR[40], rshift -> write feat16 instead of logmel */
+    int16_t *feat16 = nullptr;                /* [S][T][40] standardised rows (feature_module.c:67-73) */
 };
 int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStream_t st);
 /* hist <- newest hist_frames frames of (hist ++ src[0..T)); frames are words_per_frame 32-bit words */
@@ -78,11 +80,11 @@ struct NNLaunch {
 int launch_nn_mma(const MmaDeviceModel &mm, const NNLaunch &a, int device, cudaStream_t st);
 
 /* scan-split network path, nnsp_split.cu: fc runs for all (stream, inference) rows at once, the LSTM as a scan.
- * first / n_inf: first inference frame (0 or 1) and number of inferences of this call (stride 2). planes0/1:
+ * feat16: [S][T][40] standardised rows written by feat_kernel. first / n_inf: first inference frame (0 or 1) and number of inferences of this call (stride 2). planes0/1:
  * two buffers of split_plane_bytes(); dec: [S rounded up to 16][n_inf] int32. l.s0 must be a multiple of 16. */
 int split_supported(const MmaDeviceModel &mm);
 size_t split_plane_bytes(const MmaDeviceModel &mm, int n_streams, int n_inf);
-int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, int first, int n_inf, uint8_t *planes0,
-                    uint8_t *planes1, int32_t *dec, int device, cudaStream_t st);
+int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *feat16, int first, int n_inf,
+                    uint8_t *planes0, uint8_t *planes1, int32_t *dec, int device, cudaStream_t st);
 
 }  // namespace nnsp

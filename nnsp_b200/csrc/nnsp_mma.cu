@@ -269,7 +269,7 @@ int upload_model_mma(const nnsp_b200_model *m, MmaDeviceModel *out)
     D->hc = (D->h_stride + 7) & ~7; if (D->hc == 0) D->hc = 8;
     D->no = (D->n_out + 7) & ~7;
     D->frag_count = (int)((foff + 1) & ~1LL);
-    D->bias_count = (boff + 3) & ~3;
+    D->bias_count = (boff + 8 + 3) & ~3;                   /* 8 of slack: padded units read past their layer's rows */
     D->warp_bytes = (2 * 16 * MMA_PC + 8 * 16 * D->pa + 16 * D->hc * 4 + 16 * D->no * 4 + 16 * SC_N * 2 + 15) & ~15;
     uint2 *hf = (uint2 *)calloc((size_t)D->frag_count + 2, sizeof(uint2));
     int32_t *hb = (int32_t *)calloc((size_t)D->bias_count + 4, sizeof(int32_t));

@@ -20,6 +20,8 @@
  *                      (argmax triple or the softmax-threshold flag of binary_post_proc).
  *   post_kernel        the NNSPClass counters / trigger / outputs over the decision records, per stream.
  *   ctx_kernel         normFeatContext for the next call (feature_module.c:54-73).
+ * feat_kernel runs in its standardising mode for this path: it writes the int16 feature row of every frame
+ * (feature_module.c:67-73) instead of the int32 log-mel row.
  *
  * The contraction itself is the exact hi/lo byte-plane IMMA of nnsp_mma.cuh (16 streams x 8 units x 32 k per
  * mma.sync.m16n8k32, s8/u8 x s8, int32). Activation planes between kernels: [tile][inference][hi|lo][16][pa]
@@ -35,46 +37,40 @@
 
 namespace nnsp {
 
-constexpr int SEG_WARPS = 4;
+constexpr int SEG_WARPS = 8;
 constexpr int SEG_THREADS = SEG_WARPS * 32;
-constexpr int SEG_KC = 16;                          /* inferences per CTA work item                      */
+constexpr int SEG_KC = 16;                          /* inferences per work item                          */
 constexpr int SEG_FROWS = 2 * SEG_KC + 4;           /* feature rows covering 16 windows of 6, stride 2   */
 constexpr int SEG_PC = SEG_FROWS * 40 + 16;         /* plane pitch: 364 words = 12 mod 32, conflict-free */
 constexpr int SCAN_NST = 4;                         /* depth of the input ring of the scan               */
+constexpr int LUT2_N = 160;                         /* reachable segments of coeffs_tanh (activation.c:5) */
 
 static_assert((SEG_PC % 16) == 0 && ((SEG_PC / 4) % 8) == 4, "feature plane pitch");
 
-/* ---- packed tanh LUT: one 32-bit word = (value, slope) of a segment (activation.c:5) ------------------- */
-__device__ __forceinline__ int32_t tanh_q15p(int32_t x, const uint32_t *__restrict__ lut32)
+/* ---- tanh LUT as (value, slope) pairs: one 64-bit shared load per evaluation, no unpacking --------------- */
+/* tanh_fix, activation.c:31-69; x == INT32_MIN as in nnsp_device.cuh (-0x7fff). Branch-free so that the
+ * evaluations of one epilogue interleave. */
+__device__ __forceinline__ int32_t tanh_q15v(int32_t x, const int2 *__restrict__ lut2)
 {
-    const bool neg = x < 0;
-    const int32_t xi = neg ? (int32_t)(0u - (uint32_t)x) : x;
-    const bool big = (uint32_t)xi >= (5u << 15);            /* also x == INT32_MIN (see nnsp_device.cuh) */
-    int32_t kx = (xi - 512) >> 10;
-    kx = (big || kx < 0) ? 0 : kx;
-    const int32_t dx = xi - 512 - (kx << 10);
-    const uint32_t w = lut32[kx];
-    int32_t v = (int32_t)(int16_t)(w & 0xffffu) + ((dx * ((int32_t)w >> 16)) >> 15);
+    const uint32_t xi = (x < 0) ? (0u - (uint32_t)x) : (uint32_t)x;
+    const int32_t t = (int32_t)(xi - 512u);
+    int32_t k = t >> 10;
+    k = k < 0 ? 0 : k;
+    k = k > LUT2_N - 1 ? LUT2_N - 1 : k;
+    const int32_t dx = t - (k << 10);
+    const int2 e = lut2[k];
+    int32_t v = e.x + ((int32_t)((uint32_t)dx * (uint32_t)e.y) >> 15);
     v = v > 0 ? v : 0;
-    v = big ? 0x7fff : v;
-    return neg ? -v : v;
+    v = (xi >= (5u << 15)) ? 0x7fff : v;
+    return x < 0 ? -v : v;
 }
-__device__ __forceinline__ int32_t sigmoid_q15p(int32_t x, const uint32_t *__restrict__ lut32)
+__device__ __forceinline__ int32_t sigmoid_q15v(int32_t x, const int2 *__restrict__ lut2)     /* activation.c:72-86 */
 {
-    return (tanh_q15p(x >> 1, lut32) >> 1) + 16384;
+    return (tanh_q15v(x >> 1, lut2) >> 1) + 16384;
 }
-__device__ __forceinline__ int32_t activate16p(int act, int32_t pre, const uint32_t *lut32)
+__device__ __forceinline__ void fill_lut2(int2 *lut2, const DevTables *__restrict__ tb, int tid, int nthr)
 {
-    switch (act) {
-    case ACT_TANH: return tanh_q15p(pre, lut32);
-    case ACT_SIGMOID: return sigmoid_q15p(pre, lut32);
-    default: return relu6_q12(pre);
-    }
-}
-__device__ __forceinline__ void fill_lut32(uint32_t *lut32, const DevTables *__restrict__ tb, int tid, int nthr)
-{
-    for (int i = tid; i < 192; i += nthr)
-        lut32[i] = (uint32_t)(uint16_t)tb->tanh_lut[2 * i] | ((uint32_t)(uint16_t)tb->tanh_lut[2 * i + 1] << 16);
+    for (int i = tid; i < LUT2_N; i += nthr) lut2[i] = make_int2((int)tb->tanh_lut[2 * i], (int)tb->tanh_lut[2 * i + 1]);
 }
 
 /* ---- decision records: the part of the post-processing that does not depend on earlier frames ---------- */
@@ -129,14 +125,16 @@ __device__ __forceinline__ void apply_s2i(int16_t *sc, int dec, int16_t th_count
 /* ======================================================================================================== */
 struct SegArgs {
     const MmaModel *model;
-    const uint2 *frag;
+    const uint2 *frag;              /* fragment image of the whole model */
     const int32_t *bias32;
     const DevTables *tables;
     int l0, l1;
-    int s0, ns, T, first, n_inf;
-    const int32_t *logmel;          /* [S][T][40]                      (FROM_FEAT) */
-    const int16_t *ctx;             /* [S][240] context before the call (FROM_FEAT) */
-    const uint8_t *in_planes;       /* [tile][n_inf][2][16][pa]         (!FROM_FEAT) */
+    int w_base, w_bytes;            /* fragments of layers [l0, l1): uint2 offset in the image, byte count */
+    int off_bias, off_lut, off_w, off_fp, off_wb, off_log, nbuf;   /* shared-memory layout (seg_layout) */
+    int s0, ns, T, first, n_inf, nchunks, nitems;
+    const int16_t *feat16;          /* [S][T][40] standardised rows of this call (FROM_FEAT) */
+    const int16_t *ctx;             /* [S][240] context before the call          (FROM_FEAT) */
+    const uint8_t *in_planes;       /* [tile][n_inf][2][16][pa]                  (!FROM_FEAT) */
     uint8_t *out_planes;            /* same layout, when l1 < numlayers */
     int32_t *dec;                   /* [S][n_inf], when l1 == numlayers */
     int16_t *tap_act;               /* [S][T][act_stride] or null */
@@ -146,16 +144,16 @@ struct SegArgs {
 };
 
 template <int NC>
-__device__ __forceinline__ void fc_tiles(const MmaLayer &L, const uint2 *__restrict__ wf, const uint8_t *in_hi,
-                                         const uint8_t *in_lo, int pitch, int g, int q, int (&ch)[4][4], int (&cl)[4][4])
+__device__ __forceinline__ void fc_tiles(int kt, const uint2 *wf, const uint8_t *in_hi, const uint8_t *in_lo,
+                                         int pitch, int g, int q, int (&ch)[4][4], int (&cl)[4][4])
 {
-    for (int ks = 0; ks < L.kt; ks++) {
+    for (int ks = 0; ks < kt; ks++) {
         uint32_t fh[4], fl[4];
         load_a(in_hi, pitch, 32 * ks, g, q, fh);
         load_a(in_lo, pitch, 32 * ks, g, q, fl);
 #pragma unroll
         for (int j = 0; j < NC; j++) {
-            const uint2 b = __ldg(wf + (j * L.kt + ks) * 32);
+            const uint2 b = wf[(j * kt + ks) * 32];
             imma_s8s8(ch[j], fh, b);
             imma_u8s8(cl[j], fl, b);
         }
@@ -163,161 +161,204 @@ __device__ __forceinline__ void fc_tiles(const MmaLayer &L, const uint2 *__restr
 }
 
 template <bool FROM_FEAT>
-__global__ void __launch_bounds__(SEG_THREADS)
+__global__ void __launch_bounds__(SEG_THREADS, 2)
 seg_kernel(SegArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    MmaModel &M = *reinterpret_cast<MmaModel *>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    MmaModel &M = *reinterpret_cast<MmaModel *>(smem + 16);
+    int32_t *bias32 = reinterpret_cast<int32_t *>(smem + a.off_bias);
+    int2 *lut2 = reinterpret_cast<int2 *>(smem + a.off_lut);
+    const uint2 *wsm = reinterpret_cast<const uint2 *>(smem + a.off_w);
+    uint8_t *fplanes = smem + a.off_fp;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+
+    /* once per (persistent) CTA: descriptor, biases, LUT by plain loads; the segment's weight fragments by TMA */
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     {
         const int *src = reinterpret_cast<const int *>(a.model);
         int *dst = reinterpret_cast<int *>(&M);
         for (int i = tid; i < (int)(sizeof(MmaModel) / 4); i += SEG_THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    size_t off = (sizeof(MmaModel) + 15) & ~(size_t)15;
-    int32_t *bias32 = reinterpret_cast<int32_t *>(smem + off); off += (size_t)M.bias_count * 4;
-    uint32_t *lut32 = reinterpret_cast<uint32_t *>(smem + off); off += 192 * 4;
-    uint8_t *fplanes = smem + off; if (FROM_FEAT) off += 2 * 16 * SEG_PC;
-    const int XB = 32 * M.pa;                                    /* bytes of one tile-step: [hi|lo][16][pa] */
-    uint8_t *wb = smem + off + (size_t)warp * 2 * XB;
-    {   /* ping-pong planes start zeroed: padded units / k columns must hold defined bytes */
-        uint32_t *z = reinterpret_cast<uint32_t *>(smem + off);
-        for (int i = tid; i < SEG_WARPS * 2 * XB / 4; i += SEG_THREADS) z[i] = 0;
+    if (tid == 0) {
+        const unsigned char *wsrc = reinterpret_cast<const unsigned char *>(a.frag + a.w_base);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"((uint32_t)a.w_bytes) : "memory");
+        for (int o = 0; o < a.w_bytes; o += 32768) {
+            const uint32_t n = (uint32_t)min(32768, a.w_bytes - o);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem + a.off_w + o)), "l"(wsrc + o), "r"(n), "r"(smem_u32(bar)) : "memory");
+        }
     }
-    off += (size_t)SEG_WARPS * 2 * XB;
-    int32_t *wlog = reinterpret_cast<int32_t *>(smem + off) + warp * 16 * M.no;
+    const int XB = 32 * M.pa;                                    /* bytes of one tile-step: [hi|lo][16][pa] */
+    uint8_t *wb = smem + a.off_wb + (size_t)warp * a.nbuf * XB;
+    int32_t *wlog = reinterpret_cast<int32_t *>(smem + a.off_log) + warp * 16 * M.no;
+    {   /* activation planes start zeroed: padded k columns must hold defined bytes (they meet zero weights) */
+        uint32_t *z = reinterpret_cast<uint32_t *>(smem + a.off_wb);
+        for (int i = tid; i < SEG_WARPS * a.nbuf * XB / 4; i += SEG_THREADS) z[i] = 0;
+    }
     for (int i = tid; i < M.bias_count; i += SEG_THREADS) bias32[i] = a.bias32[i];
-    fill_lut32(lut32, a.tables, tid, SEG_THREADS);
-
-    const int tile = blockIdx.y, k0 = blockIdx.x * SEG_KC;
-    const int sb = a.s0 + 16 * tile;
-    const int nvalid = min(16, a.s0 + a.ns - sb);
-    const size_t tile_abs = (size_t)(a.s0 >> 4) + tile;
+    fill_lut2(lut2, a.tables, tid, SEG_THREADS);
+    if (FROM_FEAT)
+        for (int e = tid; e < 32 * 4; e += SEG_THREADS)              /* k-step over-read behind the last window */
+            *reinterpret_cast<uint32_t *>(fplanes + (e >> 2) * SEG_PC + SEG_FROWS * 40 + (e & 3) * 4) = 0;
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+    }
     const int T = a.T;
 
-    if (FROM_FEAT) {
-        /* standardised feature rows (feature_module.c:67-73) of frames f_first .. f_first+35 as byte planes;
-         * frames before the call come from the carried context rows 1..5 (feature_module.c:54-57) */
-        const int f_first = a.first + 2 * k0 - 5;
-        for (int e = tid; e < 16 * SEG_FROWS * 10; e += SEG_THREADS) {
-            const int r = e / (SEG_FROWS * 10), rem = e - r * (SEG_FROWS * 10), j = rem / 10, i4 = (rem - j * 10) * 4;
-            const int f = f_first + j;
-            int v[4] = { 0, 0, 0, 0 };
-            if (r < nvalid) {
-                const long long s = sb + r;
-                if (f < 0) {
-                    const uint2 c = *reinterpret_cast<const uint2 *>(a.ctx + s * 240 + (6 + f) * 40 + i4);
-                    v[0] = (int16_t)(c.x & 0xffff); v[1] = (int32_t)c.x >> 16;
-                    v[2] = (int16_t)(c.y & 0xffff); v[3] = (int32_t)c.y >> 16;
-                } else if (f < T) {
-                    const int4 lm = __ldg(reinterpret_cast<const int4 *>(a.logmel + (s * T + f) * NNSP_B200_NMEL + i4));
-                    v[0] = standardise(lm.x, M.mean[i4], M.stdR[i4], M.feat_rshift);
-                    v[1] = standardise(lm.y, M.mean[i4 + 1], M.stdR[i4 + 1], M.feat_rshift);
-                    v[2] = standardise(lm.z, M.mean[i4 + 2], M.stdR[i4 + 2], M.feat_rshift);
-                    v[3] = standardise(lm.w, M.mean[i4 + 3], M.stdR[i4 + 3], M.feat_rshift);
-                }
-            }
-            const uint32_t hi = ((uint32_t)(v[0] >> 8) & 0xff) | (((uint32_t)(v[1] >> 8) & 0xff) << 8) |
-                                (((uint32_t)(v[2] >> 8) & 0xff) << 16) | (((uint32_t)(v[3] >> 8) & 0xff) << 24);
-            const uint32_t lo = ((uint32_t)v[0] & 0xff) | (((uint32_t)v[1] & 0xff) << 8) |
-                                (((uint32_t)v[2] & 0xff) << 16) | (((uint32_t)v[3] & 0xff) << 24);
-            *reinterpret_cast<uint32_t *>(fplanes + r * SEG_PC + j * 40 + i4) = hi;
-            *reinterpret_cast<uint32_t *>(fplanes + (16 + r) * SEG_PC + j * 40 + i4) = lo;
-        }
-        for (int e = tid; e < 32 * 4; e += SEG_THREADS)              /* k-step over-read of the last window */
-            *reinterpret_cast<uint32_t *>(fplanes + (e >> 2) * SEG_PC + SEG_FROWS * 40 + (e & 3) * 4) = 0;
-    }
-    __syncthreads();
-
-    for (int i = warp; i < SEG_KC; i += SEG_WARPS) {
-        const int k = k0 + i;
-        if (k >= a.n_inf) break;
-        const int t = a.first + 2 * k;                               /* frame of this inference */
-        const uint8_t *in_hi, *in_lo;
-        int in_pitch;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int chunk = item % a.nchunks, tile = item / a.nchunks;
+        const int k0 = chunk * SEG_KC;
+        const int sb = a.s0 + 16 * tile;
+        const int nvalid = min(16, a.s0 + a.ns - sb);
+        const size_t tile_abs = (size_t)(a.s0 >> 4) + tile;
+        __syncthreads();                                             /* planes of the previous item are free */
         if (FROM_FEAT) {
-            in_hi = fplanes + 80 * i; in_lo = in_hi + 16 * SEG_PC; in_pitch = SEG_PC;
-        } else {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.in_planes + (tile_abs * a.n_inf + k) * (size_t)XB);
-            uint4 *dst = reinterpret_cast<uint4 *>(wb + XB);
-            for (int x = lane; x < XB / 16; x += 32) dst[x] = __ldg(src + x);
-            __syncwarp();
-            in_hi = wb + XB; in_lo = in_hi + 16 * M.pa; in_pitch = M.pa;
-        }
-        int pp = 0, ao = a.ao0;
-        for (int li = a.l0; li < a.l1; li++) {
-            const MmaLayer &L = M.layer[li];
-            const bool last = (li == M.numlayers - 1);
-            const int32_t *B = bias32 + L.bias_off;
-            const int rs = -L.sh_out;
-            uint8_t *oh = wb + pp * XB, *ol = oh + 16 * M.pa;
-            for (int n0 = 0; n0 < L.nt; n0 += 4) {
-                const int nc = min(4, L.nt - n0);
-                int ch[4][4] = {}, cl[4][4] = {};
-                const uint2 *wf = a.frag + L.w_off + (long long)n0 * L.kt * 32 + lane;
-                switch (nc) {
-                case 4: fc_tiles<4>(L, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
-                case 3: fc_tiles<3>(L, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
-                case 2: fc_tiles<2>(L, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
-                default: fc_tiles<1>(L, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
-                }
+            /* standardised rows of frames f_first .. f_first+35 as byte planes; frames before the call are the
+             * carried context rows 1..5 (feature_module.c:54-57); loads of a batch are issued before its stores */
+            const int f_first = a.first + 2 * k0 - 5;
+            constexpr int NQ = 16 * SEG_FROWS * 5;                   /* 16-byte pieces: 8 features each */
+            for (int e0 = 0; e0 < NQ; e0 += 4 * SEG_THREADS) {
+                uint4 v[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (j < nc) {
-                        const int nb = (n0 + j) * 8 + 2 * q;
-#pragma unroll
-                        for (int rr = 0; rr < 2; rr++) {
-                            const int row = g + 8 * rr;
-                            int y[2];
-#pragma unroll
-                            for (int cc = 0; cc < 2; cc++) {
-                                const int e = 2 * rr + cc, n = nb + cc;
-                                int o = 0;
-                                if (n < L.rows) {
-                                    /* exact 32-bit finish (MmaLayer.fast): affine.c:190-249 without reachable clamps */
-                                    const int32_t pre = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e] + (uint32_t)B[n]) >> rs;
-                                    if (L.act == ACT_LINEAR) { wlog[row * M.no + n] = pre; }          /* activation.c:19-29 */
-                                    else {
-                                        o = activate16p(L.act, pre, lut32);
-                                        if (last) wlog[row * M.no + n] = o;                              /* neural_nets.c:160-166 */
-                                        else if (a.tap_act && row < nvalid)
-                                            a.tap_act[((long long)(sb + row) * T + t) * M.act_stride + ao + n] = (int16_t)o;
-                                    }
-                                }
-                                y[cc] = o;
-                            }
-                            store_pair(oh, ol, row * M.pa + nb, y[0], y[1]);
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * SEG_THREADS + tid;
+                    v[u] = make_uint4(0, 0, 0, 0);
+                    if (e < NQ) {
+                        const int r = e / (SEG_FROWS * 5), rem = e - r * (SEG_FROWS * 5), j = rem / 5, x = rem - j * 5;
+                        const int f = f_first + j;
+                        if (r < nvalid) {
+                            const long long s = sb + r;
+                            if (f < 0) v[u] = *reinterpret_cast<const uint4 *>(a.ctx + s * 240 + (6 + f) * 40 + x * 8);
+                            else if (f < T) v[u] = __ldg(reinterpret_cast<const uint4 *>(a.feat16 + (s * T + f) * NNSP_B200_NMEL + x * 8));
                         }
                     }
                 }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * SEG_THREADS + tid;
+                    if (e < NQ) {
+                        const int r = e / (SEG_FROWS * 5), rem = e - r * (SEG_FROWS * 5), j = rem / 5, x = rem - j * 5;
+                        uint2 hi, lo;
+                        lo.x = __byte_perm(v[u].x, v[u].y, 0x6420); hi.x = __byte_perm(v[u].x, v[u].y, 0x7531);
+                        lo.y = __byte_perm(v[u].z, v[u].w, 0x6420); hi.y = __byte_perm(v[u].z, v[u].w, 0x7531);
+                        *reinterpret_cast<uint2 *>(fplanes + r * SEG_PC + j * 40 + x * 8) = hi;
+                        *reinterpret_cast<uint2 *>(fplanes + (16 + r) * SEG_PC + j * 40 + x * 8) = lo;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        for (int i = warp; i < SEG_KC; i += SEG_WARPS) {
+            const int k = k0 + i;
+            if (k >= a.n_inf) break;
+            const int t = a.first + 2 * k;                               /* frame of this inference */
+            const uint8_t *in_hi, *in_lo;
+            int in_pitch;
+            if (FROM_FEAT) {
+                in_hi = fplanes + 80 * i; in_lo = in_hi + 16 * SEG_PC; in_pitch = SEG_PC;
+            } else {
+                const uint4 *src = reinterpret_cast<const uint4 *>(a.in_planes + (tile_abs * a.n_inf + k) * (size_t)XB);
+                uint4 *dst = reinterpret_cast<uint4 *>(wb + XB);
+                for (int x = lane; x < XB / 16; x += 32) dst[x] = __ldg(src + x);
+                __syncwarp();
+                in_hi = wb + XB; in_lo = in_hi + 16 * M.pa; in_pitch = M.pa;
+            }
+            int pp = 0, ao = a.ao0;
+            for (int li = a.l0; li < a.l1; li++) {
+                const MmaLayer &L = M.layer[li];
+                const bool last = (li == M.numlayers - 1);
+                const int32_t *B = bias32 + L.bias_off;
+                const int rs = -L.sh_out, act = L.act, kt = L.kt;
+                uint8_t *oh = wb + pp * XB, *ol = oh + 16 * M.pa;
+                for (int n0 = 0; n0 < L.nt; n0 += 4) {
+                    const int nc = min(4, L.nt - n0);
+                    int ch[4][4] = {}, cl[4][4] = {};
+                    const uint2 *wf = wsm + (L.w_off - a.w_base) + n0 * kt * 32 + lane;
+                    switch (nc) {
+                    case 4: fc_tiles<4>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
+                    case 3: fc_tiles<3>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
+                    case 2: fc_tiles<2>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
+                    default: fc_tiles<1>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (j < nc) {
+                            /* the lane's 2 rows x 2 units of this tile, branch-free so the four evaluations interleave.
+                             * exact 32-bit finish (MmaLayer.fast): affine.c:190-249 without reachable clamps; units past
+                             * L.rows are computed too (zero weights), they only ever meet zero weights downstream */
+                            const int nb = (n0 + j) * 8 + 2 * q;
+                            const int32_t b0 = B[nb], b1 = B[nb + 1];
+                            int32_t pre[4], o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                                pre[e] = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e] + (uint32_t)((e & 1) ? b1 : b0)) >> rs;
+                            if (act == ACT_LINEAR) {                                            /* activation.c:19-29 */
+#pragma unroll
+                                for (int e = 0; e < 4; e++) { o[e] = 0; wlog[(g + 8 * (e >> 1)) * M.no + nb + (e & 1)] = pre[e]; }
+                            } else {
+                                if (act == ACT_TANH) {
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) o[e] = tanh_q15v(pre[e], lut2);
+                                } else if (act == ACT_SIGMOID) {
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) o[e] = sigmoid_q15v(pre[e], lut2);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) o[e] = relu6_q12(pre[e]);
+                                }
+                                if (last) {                                                     /* neural_nets.c:160-166 */
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) wlog[(g + 8 * (e >> 1)) * M.no + nb + (e & 1)] = o[e];
+                                } else if (a.tap_act) {
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) {
+                                        const int row = g + 8 * (e >> 1), n = nb + (e & 1);
+                                        if (row < nvalid && n < L.rows)
+                                            a.tap_act[((long long)(sb + row) * T + t) * M.act_stride + ao + n] = (int16_t)o[e];
+                                    }
+                                }
+                            }
+                            store_pair(oh, ol, g * M.pa + nb, o[0], o[1]);
+                            store_pair(oh, ol, (g + 8) * M.pa + nb, o[2], o[3]);
+                        }
+                    }
+                }
+                __syncwarp();
+                in_hi = oh; in_lo = ol; in_pitch = M.pa;
+                pp ^= 1;
+                if (!last) ao += L.rows;
+            }
+            if (a.l1 < M.numlayers) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(wb + (pp ^ 1) * XB);
+                uint4 *dst = reinterpret_cast<uint4 *>(a.out_planes + (tile_abs * a.n_inf + k) * (size_t)XB);
+                for (int x = lane; x < XB / 16; x += 32) dst[x] = src[x];
+            } else {
+                if (lane < nvalid) {
+                    const int32_t *lg = wlog + lane * M.no;
+                    int d;
+                    if (M.nn_id == NNSP_B200_ID_S2I)
+                        d = argmax_last_wins(lg, 7) | (argmax_last_wins(lg + 7, 17) << 8) | (argmax_last_wins(lg + 24, 17) << 16);
+                    else
+                        d = binary_flag(lg[0], lg[1], a.thresh_prob);
+                    a.dec[(size_t)(sb + lane) * a.n_inf + k] = d;
+                }
+                if (a.tap_logits)
+                    for (int x = lane; x < 16 * M.n_out; x += 32) {
+                        const int row = x / M.n_out, n = x - row * M.n_out;
+                        if (row < nvalid) a.tap_logits[((long long)(sb + row) * T + t) * M.n_out + n] = wlog[row * M.no + n];
+                    }
             }
             __syncwarp();
-            in_hi = oh; in_lo = ol; in_pitch = M.pa;
-            pp ^= 1;
-            if (!last) ao += L.rows;
         }
-        if (a.l1 < M.numlayers) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(wb + (pp ^ 1) * XB);
-            uint4 *dst = reinterpret_cast<uint4 *>(a.out_planes + (tile_abs * a.n_inf + k) * (size_t)XB);
-            for (int x = lane; x < XB / 16; x += 32) dst[x] = src[x];
-        } else {
-            if (lane < nvalid) {
-                const int32_t *lg = wlog + lane * M.no;
-                int d;
-                if (M.nn_id == NNSP_B200_ID_S2I)
-                    d = argmax_last_wins(lg, 7) | (argmax_last_wins(lg + 7, 17) << 8) | (argmax_last_wins(lg + 24, 17) << 16);
-                else
-                    d = binary_flag(lg[0], lg[1], a.thresh_prob);
-                a.dec[(size_t)(sb + lane) * a.n_inf + k] = d;
-            }
-            if (a.tap_logits)
-                for (int x = lane; x < 16 * M.n_out; x += 32) {
-                    const int row = x / M.n_out, n = x - row * M.n_out;
-                    if (row < nvalid) a.tap_logits[((long long)(sb + row) * T + t) * M.n_out + n] = wlog[row * M.no + n];
-                }
-        }
-        __syncwarp();
     }
 }
 
@@ -354,15 +395,17 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(512, 1)
+/* NW = warps per CTA (>= unit groups of the layer), MINB = CTAs per SM the register budget is sized for */
+template <int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
 scan_kernel(ScanArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);             /* [0..NST) input ring, [NST] weights */
     const int WB = 4 * a.nt * (a.kt + a.ktr) * 256, XB = 32 * a.pa;
     const uint2 *wsm = reinterpret_cast<const uint2 *>(smem + 64);
-    uint32_t *lut32 = reinterpret_cast<uint32_t *>(smem + 64 + WB);
-    uint8_t *xs = smem + 64 + WB + 768;
+    int2 *lut2 = reinterpret_cast<int2 *>(smem + 64 + WB);
+    uint8_t *xs = smem + 64 + WB + LUT2_N * 8;
     uint8_t *hb = xs + SCAN_NST * XB;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int tile = blockIdx.x, sb = a.s0 + 16 * tile;
@@ -370,14 +413,14 @@ scan_kernel(ScanArgs a)
     const size_t tile_abs = (size_t)(a.s0 >> 4) + tile;
     const uint8_t *xg = a.xin + tile_abs * a.n_inf * (size_t)XB;
     uint8_t *hg = a.hout + tile_abs * a.n_inf * (size_t)XB;
-    const int H = a.H, pa = a.pa, HS = a.hs, T = a.T, n_inf = a.n_inf;
+    const int H = a.H, pa = a.pa, HS = a.hs, T = a.T, n_inf = a.n_inf, rs = a.rs;
 
     if (tid == 0) {
         for (int i = 0; i <= SCAN_NST; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 3 * XB / 4; i += nthr) reinterpret_cast<uint32_t *>(hb)[i] = 0;
-    fill_lut32(lut32, a.tables, tid, nthr);
+    fill_lut2(lut2, a.tables, tid, nthr);
     __syncthreads();
     uint8_t *h2 = hb + 2 * XB;                                       /* h before the first inference */
     for (int idx = tid; idx < 16 * H; idx += nthr) {
@@ -396,23 +439,23 @@ scan_kernel(ScanArgs a)
         }
         for (int m = 0; m < SCAN_NST && m < n_inf; m++) bulk_load(xs + m * XB, xg + (size_t)m * XB, XB, bars + m);
     }
-    /* the lane's cells: rows g, g+8 x units u0, u0+1 of group `warp`; their biases and cell state stay in registers */
+    /* the lane's cells: rows g, g+8 x units u0, u0+1 of group `warp`; their biases and cell state stay in registers.
+     * Units past H (last group) have zero weights and biases: they are computed like the rest and never stored. */
     const int u0 = 8 * warp + 2 * q;
-    int32_t bz[4][2], cst[2][2];
+    int32_t bz[4][2], cst[4];
 #pragma unroll
     for (int gt = 0; gt < 4; gt++)
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) bz[gt][cc] = (u0 + cc < H) ? a.bias32[a.bias_off + gt * H + u0 + cc] : 0;
 #pragma unroll
-    for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int row = g + 8 * rr, u = u0 + cc;
-            cst[rr][cc] = (row < nvalid && u < H) ? a.c[(long long)(sb + row) * HS + a.ho + u] : 0;
-        }
+    for (int e = 0; e < 4; e++) {
+        const int row = g + 8 * (e >> 1), u = u0 + (e & 1);
+        cst[e] = (row < nvalid && u < H) ? a.c[(long long)(sb + row) * HS + a.ho + u] : 0;
+    }
     __syncthreads();
     mbar_wait(bars + SCAN_NST, 0);
 
+    const bool active = warp < a.nt;                                  /* spare warps only help with copies and barriers */
     const uint2 *wx = wsm + (size_t)warp * 4 * a.kt * 32 + lane;
     const uint2 *wh = wsm + (size_t)a.nt * 4 * a.kt * 32 + (size_t)warp * 4 * a.ktr * 32 + lane;
     int ach[4][4], acl[4][4];
@@ -441,20 +484,18 @@ scan_kernel(ScanArgs a)
                 const int r = idx / H, u = idx - r * H;
                 a.tap_h[((long long)(sb + r) * T + t) * HS + a.ho + u] = (int16_t)(((int)(int8_t)hp[r * pa + u] << 8) | hp[(16 + r) * pa + u]);
             }
-        if (a.tap_c) {
+        if (a.tap_c && active) {
 #pragma unroll
-            for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-                for (int cc = 0; cc < 2; cc++) {
-                    const int row = g + 8 * rr, u = u0 + cc;
-                    if (row < nvalid && u < H) a.tap_c[((long long)(sb + row) * T + t) * HS + a.ho + u] = cst[rr][cc];
-                }
+            for (int e = 0; e < 4; e++) {
+                const int row = g + 8 * (e >> 1), u = u0 + (e & 1);
+                if (row < nvalid && u < H) a.tap_c[((long long)(sb + row) * T + t) * HS + a.ho + u] = cst[e];
+            }
         }
     };
 
     mbar_wait(bars + 0, 0);
     zero_acc();
-    half(xs, wx, a.kt);                                               /* Wx . x of inference 0 */
+    if (active) half(xs, wx, a.kt);                                   /* Wx . x of inference 0 */
     __syncthreads();
     if (tid == 0 && SCAN_NST < n_inf) bulk_load(xs, xg + (size_t)SCAN_NST * XB, XB, bars + 0);
     if (a.first == 1) tap_state(h2, 0);                               /* frame 0 ran no inference */
@@ -463,38 +504,40 @@ scan_kernel(ScanArgs a)
         const uint8_t *hp = hb + ((k + 2) % 3) * XB;                  /* h of the previous inference */
         uint8_t *hn = hb + (k % 3) * XB;
         const int t = a.first + 2 * k;
-        half(hp, wh, a.ktr);                                          /* + Wh . h_old (lstm.c:54-104 all read the old h) */
+        if (active) {
+            half(hp, wh, a.ktr);                                      /* + Wh . h_old (lstm.c:54-104 all read the old h) */
+            int32_t gate[4][4];
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            const int row = g + 8 * rr;
-            int y[2];
+            for (int gt = 0; gt < 4; gt++)
 #pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int e = 2 * rr + cc, u = u0 + cc;
-                int o = 0;
-                if (u < H) {
-                    int32_t pre[4];
-#pragma unroll
-                    for (int gt = 0; gt < 4; gt++)
-                        pre[gt] = (int32_t)(((uint32_t)ach[gt][e] << 8) + (uint32_t)acl[gt][e] + (uint32_t)bz[gt][cc]) >> a.rs;
-                    const int32_t gi = sigmoid_q15p(pre[0], lut32), gj = tanh_q15p(pre[1], lut32);
-                    const int32_t gf = sigmoid_q15p(pre[2], lut32), go = sigmoid_q15p(pre[3], lut32);
-                    const int64_t tt = ((int64_t)gi * (int64_t)gj + (int64_t)gf * (int64_t)cst[rr][cc]) >> 15;   /* lstm.c:108-109 */
-                    const int32_t cn = sat32_dev(tt);
-                    cst[rr][cc] = cn;
-                    o = (tanh_q15p(cn, lut32) * go) >> 15;                                                      /* lstm.c:111-115 */
-                    o = o > 32767 ? 32767 : (o < -32768 ? -32768 : o);
-                    if (a.tap_out && a.tap_act && row < nvalid)
-                        a.tap_act[((long long)(sb + row) * T + t) * a.act_stride + a.ao + u] = (int16_t)o;
+                for (int e = 0; e < 4; e++) {
+                    const int32_t pre = (int32_t)(((uint32_t)ach[gt][e] << 8) + (uint32_t)acl[gt][e] + (uint32_t)bz[gt][e & 1]) >> rs;
+                    gate[gt][e] = (gt == 1) ? tanh_q15v(pre, lut2) : sigmoid_q15v(pre, lut2);      /* lstm.c:65,78,91,104 */
                 }
-                y[cc] = o;
+            int32_t y[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int64_t tt = ((int64_t)gate[0][e] * (int64_t)gate[1][e] + (int64_t)gate[2][e] * (int64_t)cst[e]) >> 15;   /* lstm.c:108-109 */
+                const int32_t cn = sat32_dev(tt);
+                cst[e] = cn;
+                int32_t o = (tanh_q15v(cn, lut2) * gate[3][e]) >> 15;                               /* lstm.c:111-115 */
+                o = o > 32767 ? 32767 : (o < -32768 ? -32768 : o);
+                y[e] = o;
             }
-            store_pair(hn, hn + 16 * pa, row * pa + u0, y[0], y[1]);
-        }
-        if (k + 1 < n_inf) {                                          /* Wx . x of the next inference, off the recurrence */
-            mbar_wait(bars + ((k + 1) % SCAN_NST), (uint32_t)(((k + 1) / SCAN_NST) & 1));
-            zero_acc();
-            half(xs + ((k + 1) % SCAN_NST) * XB, wx, a.kt);
+            store_pair(hn, hn + 16 * pa, g * pa + u0, y[0], y[1]);
+            store_pair(hn, hn + 16 * pa, (g + 8) * pa + u0, y[2], y[3]);
+            if (a.tap_out && a.tap_act) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int row = g + 8 * (e >> 1), u = u0 + (e & 1);
+                    if (row < nvalid && u < H) a.tap_act[((long long)(sb + row) * T + t) * a.act_stride + a.ao + u] = (int16_t)y[e];
+                }
+            }
+            if (k + 1 < n_inf) {                                      /* Wx . x of the next inference, off the recurrence */
+                mbar_wait(bars + ((k + 1) % SCAN_NST), (uint32_t)(((k + 1) / SCAN_NST) & 1));
+                zero_acc();
+                half(xs + ((k + 1) % SCAN_NST) * XB, wx, a.kt);
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  /* h planes -> visible to the bulk store */
         if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   /* buffer of step k-2 is free again */
@@ -518,18 +561,21 @@ scan_kernel(ScanArgs a)
         const int r = idx / H, u = idx - r * H;
         a.h[(long long)(sb + r) * HS + a.ho + u] = (int16_t)(((int)(int8_t)hf[r * pa + u] << 8) | hf[(16 + r) * pa + u]);
     }
+    if (active) {
 #pragma unroll
-    for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int row = g + 8 * rr, u = u0 + cc;
-            if (row < nvalid && u < H) a.c[(long long)(sb + row) * HS + a.ho + u] = cst[rr][cc];
+        for (int e = 0; e < 4; e++) {
+            const int row = g + 8 * (e >> 1), u = u0 + (e & 1);
+            if (row < nvalid && u < H) a.c[(long long)(sb + row) * HS + a.ho + u] = cst[e];
         }
+    }
 }
 
 /* ======================================================================================================== */
 /* post_kernel / ctx_kernel / feat_tap_kernel                                                                */
 /* ======================================================================================================== */
+constexpr int POST_THREADS = 64;                    /* streams per CTA */
+constexpr int POST_KCH = 64;                        /* decision records staged per round */
+
 struct PostArgs {
     int nn_id, s0, ns, T, first, n_inf;
     const int32_t *dec;
@@ -539,89 +585,116 @@ struct PostArgs {
     int16_t th_count;
 };
 
-__global__ void __launch_bounds__(128) post_kernel(PostArgs a)
+/* the NNSPClass state machine of every stream over the call's frames (nn_speech.c:84-125); one thread per stream,
+ * decision records staged through shared memory so that the loop has no dependent global load */
+__global__ void __launch_bounds__(POST_THREADS) post_kernel(PostArgs a)
 {
-    const int si = blockIdx.x * blockDim.x + threadIdx.x;
-    if (si >= a.ns) return;
-    const long long s = a.s0 + si;
+    __shared__ int32_t dsm[POST_THREADS][POST_KCH + 1];
+    const int si0 = blockIdx.x * POST_THREADS, si = si0 + threadIdx.x;
+    const bool valid = si < a.ns;
+    const long long s = a.s0 + (valid ? si : 0);
     int16_t sc[SC_N];
     {
         const uint4 *p = reinterpret_cast<const uint4 *>(a.scal + s * SC_N);
         *reinterpret_cast<uint4 *>(&sc[0]) = p[0];
         *reinterpret_cast<uint4 *>(&sc[8]) = p[1];
     }
-    const int32_t *d = a.dec + s * a.n_inf;
-    int k = 0;
-    for (int t = 0; t < a.T; t++) {
-        const bool ran = (t >= a.first) && (((t - a.first) & 1) == 0);                   /* nn_speech.c:84 */
-        if (ran) {
-            const int dv = d[k++];
-            if (a.nn_id == NNSP_B200_ID_S2I) apply_s2i(sc, dv, a.th_count);               /* nn_speech.c:97-119 */
-            else apply_binary(sc, dv, a.th_count);
+    const int nstr = min(POST_THREADS, a.ns - si0);
+    int t = 0, k = 0;
+    for (int kc = 0; kc <= a.n_inf; kc += POST_KCH) {                 /* (one pass even when n_inf == 0) */
+        const int nk = min(POST_KCH, a.n_inf - kc);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nstr * nk; e += POST_THREADS) {
+            const int r = e / nk, kk = e - r * nk;
+            dsm[r][kk] = a.dec[(size_t)(a.s0 + si0 + r) * a.n_inf + kc + kk];
         }
-        sc[SC_SLIDES] = (int16_t)((sc[SC_SLIDES] + 1) % 2);                               /* nn_speech.c:125 */
-        if (a.results) {
-            nnsp_b200_result r;
-            r.trigger = sc[SC_TRIGGER];
-            r.outputs[0] = sc[SC_OUT0]; r.outputs[1] = sc[SC_OUT0 + 1]; r.outputs[2] = sc[SC_OUT0 + 2];
-            a.results[s * a.T + t] = r;
+        __syncthreads();
+        /* frames up to (and excluding) the first inference of the next round */
+        const int t_end = (kc + POST_KCH < a.n_inf) ? a.first + 2 * (kc + POST_KCH) : a.T;
+        if (valid) {
+            for (; t < t_end; t++) {
+                const bool ran = (t >= a.first) && (((t - a.first) & 1) == 0);               /* nn_speech.c:84 */
+                if (ran) {
+                    const int dv = dsm[threadIdx.x][k - kc];
+                    k++;
+                    if (a.nn_id == NNSP_B200_ID_S2I) apply_s2i(sc, dv, a.th_count);           /* nn_speech.c:97-119 */
+                    else apply_binary(sc, dv, a.th_count);
+                }
+                sc[SC_SLIDES] = (int16_t)((sc[SC_SLIDES] + 1) % 2);                           /* nn_speech.c:125 */
+                if (a.results) {
+                    nnsp_b200_result r;
+                    r.trigger = sc[SC_TRIGGER];
+                    r.outputs[0] = sc[SC_OUT0]; r.outputs[1] = sc[SC_OUT0 + 1]; r.outputs[2] = sc[SC_OUT0 + 2];
+                    a.results[s * a.T + t] = r;
+                }
+                if (a.tap_post) {
+                    int16_t *o = a.tap_post + (s * a.T + t) * SC_N;
+                    for (int i = 0; i < SC_N; i++) o[i] = sc[i];
+                    o[SC_RAN] = ran ? 1 : 0;
+                    o[SC_STAGE] = (int16_t)a.nn_id;
+                }
+            }
         }
-        if (a.tap_post) {
-            int16_t *o = a.tap_post + (s * a.T + t) * SC_N;
-            for (int i = 0; i < SC_N; i++) o[i] = sc[i];
-            o[SC_RAN] = ran ? 1 : 0;
-            o[SC_STAGE] = (int16_t)a.nn_id;
-        }
+        if (nk <= 0) break;
     }
-    {
+    if (valid) {
         uint4 *p = reinterpret_cast<uint4 *>(a.scal + s * SC_N);
         p[0] = *reinterpret_cast<uint4 *>(&sc[0]);
         p[1] = *reinterpret_cast<uint4 *>(&sc[8]);
     }
 }
 
-/* normFeatContext after the call: the newest 6 rows of (old rows ++ this call's standardised rows) */
-__global__ void __launch_bounds__(256) ctx_kernel(const MmaModel *__restrict__ M, const int32_t *__restrict__ logmel,
-                                                  int16_t *ctx, int s0, int T)
+/* normFeatContext after the call: the newest 6 rows of (old rows ++ this call's standardised rows); a warp per stream */
+__global__ void __launch_bounds__(256) ctx_kernel(const int16_t *__restrict__ feat16, int16_t *ctx, int s0, int ns, int T)
 {
-    const long long s = s0 + blockIdx.x;
-    const int i = threadIdx.x;
-    int16_t v = 0;
-    if (i < 240) {
-        const int j = i / 40, fi = i - j * 40, f = T - 6 + j;
-        v = (f >= 0) ? standardise(logmel[(s * T + f) * NNSP_B200_NMEL + fi], M->mean[fi], M->stdR[fi], M->feat_rshift)
-                     : ctx[s * 240 + (j + T) * 40 + fi];
+    const int si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (si >= ns) return;
+    const long long s = s0 + si;
+    uint4 *c4 = reinterpret_cast<uint4 *>(ctx + s * 240);                /* 30 pieces of 8 features */
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (lane < 30) {
+        const int j = lane / 5, x = lane - j * 5, f = T - 6 + j;         /* new row j <- frame f of this call, or old row j + T */
+        v = (f >= 0) ? __ldg(reinterpret_cast<const uint4 *>(feat16 + (s * T + f) * NNSP_B200_NMEL) + x) : c4[(j + T) * 5 + x];
     }
-    __syncthreads();
-    if (i < 240) ctx[s * 240 + i] = v;
+    __syncwarp();
+    if (lane < 30) c4[lane] = v;
 }
 
-__global__ void feat_tap_kernel(const MmaModel *__restrict__ M, const int32_t *__restrict__ logmel, int16_t *feat,
-                                int32_t *logmel_out, long long base, long long n)
+/* debug taps of the front end: standardised row and (from a second, log-mel pass of feat_kernel) the log-mel row */
+__global__ void feat_tap_kernel(const int16_t *__restrict__ feat16, int16_t *feat, long long base, long long n)
 {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const int fi = (int)((base + e) % NNSP_B200_NMEL);
-        const int32_t lm = logmel[base + e];
-        if (feat) feat[base + e] = standardise(lm, M->mean[fi], M->stdR[fi], M->feat_rshift);
-        if (logmel_out) logmel_out[base + e] = lm;
-    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        feat[base + e] = feat16[base + e];
 }
 
 /* ======================================================================================================== */
 /* host                                                                                                      */
 /* ======================================================================================================== */
-static size_t seg_smem(const MmaModel *D, bool from_feat)
+struct SegLayout { int off_bias, off_lut, off_w, off_fp, off_wb, off_log, nbuf, w_base, w_bytes; size_t total; };
+
+static SegLayout seg_layout(const MmaModel *D, int l0, int l1, bool from_feat)
 {
-    size_t b = (sizeof(MmaModel) + 15) & ~(size_t)15;
-    b += (size_t)D->bias_count * 4 + 192 * 4;
-    if (from_feat) b += 2 * 16 * SEG_PC;
-    b += (size_t)SEG_WARPS * 2 * 32 * D->pa;
-    b += (size_t)SEG_WARPS * 16 * D->no * 4;
-    return b;
+    SegLayout s{};
+    auto a16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t off = a16(16 + sizeof(MmaModel));
+    s.off_bias = (int)off; off = a16(off + (size_t)D->bias_count * 4);
+    s.off_lut = (int)off; off += LUT2_N * 8;
+    s.w_base = D->layer[l0].w_off;
+    long long cnt = 0;
+    for (int i = l0; i < l1; i++) cnt += (long long)D->layer[i].nt * D->layer[i].kt * 32;
+    s.w_bytes = (int)(cnt * 8);
+    off = (off + 127) & ~(size_t)127;
+    s.off_w = (int)off; off += (size_t)s.w_bytes;
+    s.off_fp = (int)off; if (from_feat) off += 2 * 16 * SEG_PC;
+    s.nbuf = (from_feat && l1 - l0 == 1) ? 1 : 2;
+    s.off_wb = (int)off; off += (size_t)SEG_WARPS * s.nbuf * 32 * D->pa;
+    s.off_log = (int)off; if (l1 == D->numlayers) off += (size_t)SEG_WARPS * 16 * D->no * 4;
+    s.total = off;
+    return s;
 }
 static size_t scan_smem(const MmaModel *D, const MmaLayer &L)
 {
-    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + 768 + (size_t)(SCAN_NST + 3) * 32 * D->pa;
+    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + LUT2_N * 8 + (size_t)(SCAN_NST + 3) * 32 * D->pa;
 }
 
 int split_supported(const MmaDeviceModel &mm)
@@ -633,10 +706,16 @@ int split_supported(const MmaDeviceModel &mm)
     for (int i = 0; i < D->numlayers; i++) {
         const MmaLayer &L = D->layer[i];
         if (!L.fast) return 0;
+        if (L.type == LAYER_FC && L.act == ACT_LINEAR && i != D->numlayers - 1) return 0;
         if (L.type == LAYER_LSTM && (L.nt > 16 || scan_smem(D, L) > 227 * 1024)) return 0;
         if (L.type == LAYER_LSTM && L.wh_off != L.w_off + 4 * L.nt * L.kt * 32) return 0;
     }
-    if (seg_smem(D, true) > 227 * 1024) return 0;
+    for (int l0 = 0; l0 < D->numlayers;) {                           /* every fc run must fit shared memory */
+        int l1 = l0;
+        while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
+        if (l1 > l0 && seg_layout(D, l0, l1, l0 == 0).total > 227 * 1024) return 0;
+        l0 = (l1 > l0) ? l1 : l0 + 1;
+    }
     return 1;
 }
 
@@ -645,24 +724,38 @@ size_t split_plane_bytes(const MmaDeviceModel &mm, int n_streams, int n_inf)
     return (size_t)((n_streams + 15) / 16) * (size_t)n_inf * 32 * mm.h->pa;
 }
 
-int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, int first, int n_inf, uint8_t *planes0,
-                    uint8_t *planes1, int32_t *dec, int device, cudaStream_t st)
+template <int NW, int MINB>
+static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, cudaStream_t st)
+{
+    static bool attr_done[64] = { false };
+    if (!attr_done[device]) {
+        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done[device] = true;
+    }
+    scan_kernel<NW, MINB><<<ntiles, 32 * NW, smem, st>>>(a);
+    NNSP_LAUNCH_CHECK();
+    return NNSP_B200_OK;
+}
+
+int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *feat16, int first, int n_inf,
+                    uint8_t *planes0, uint8_t *planes1, int32_t *dec, int device, cudaStream_t st)
 {
     const MmaModel *D = mm.h;
     static bool attr_done[64] = { false };
     if (!attr_done[device]) {
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done[device] = true;
     }
     if (l.ns <= 0 || l.T <= 0) return NNSP_B200_OK;
     if ((l.s0 & 15) != 0) { nnsp_set_error("stream slices of the split path must start at a multiple of 16"); return NNSP_B200_ERR_ARG; }
     const int T = l.T, ntiles = (l.ns + 15) / 16, nchunks = (n_inf + SEG_KC - 1) / SEG_KC;
     const nnsp_b200_taps &tp = l.taps;
-    const long long fbase = (long long)l.s0 * T * NNSP_B200_NMEL, fcount = (long long)l.ns * T * NNSP_B200_NMEL;
-    if (tp.feat || tp.logmel) {
-        feat_tap_kernel<<<(unsigned)((fcount + 255) / 256 > 4096 ? 4096 : (fcount + 255) / 256), 256, 0, st>>>(mm.d, l.logmel, tp.feat, tp.logmel, fbase, fcount);
+    int rc;
+    if (tp.feat) {
+        const long long fbase = (long long)l.s0 * T * NNSP_B200_NMEL, fcount = (long long)l.ns * T * NNSP_B200_NMEL;
+        const long long nb = (fcount + 255) / 256;
+        feat_tap_kernel<<<(unsigned)(nb > 4096 ? 4096 : nb), 256, 0, st>>>(feat16, tp.feat, fbase, fcount);
         NNSP_LAUNCH_CHECK();
     }
     if (tp.act) NNSP_CUDA(cudaMemsetAsync(tp.act + (long long)l.s0 * T * D->act_stride, 0, (size_t)l.ns * T * D->act_stride * 2, st));
@@ -676,15 +769,22 @@ int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, int first, int 
             int l1 = li;
             while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
             if (l1 > li) {                                           /* a run of fc layers */
+                const SegLayout lay = seg_layout(D, li, l1, from_feat);
                 SegArgs a{};
                 a.model = mm.d; a.frag = (const uint2 *)mm.frag; a.bias32 = mm.bias32; a.tables = l.tables;
-                a.l0 = li; a.l1 = l1; a.s0 = l.s0; a.ns = l.ns; a.T = T; a.first = first; a.n_inf = n_inf;
-                a.logmel = l.logmel; a.ctx = l.st.ctx; a.in_planes = cur_in;
+                a.l0 = li; a.l1 = l1; a.w_base = lay.w_base; a.w_bytes = lay.w_bytes;
+                a.off_bias = lay.off_bias; a.off_lut = lay.off_lut; a.off_w = lay.off_w; a.off_fp = lay.off_fp;
+                a.off_wb = lay.off_wb; a.off_log = lay.off_log; a.nbuf = lay.nbuf;
+                a.s0 = l.s0; a.ns = l.ns; a.T = T; a.first = first; a.n_inf = n_inf; a.nchunks = nchunks; a.nitems = nchunks * ntiles;
+                a.feat16 = feat16; a.ctx = l.st.ctx; a.in_planes = cur_in;
                 a.out_planes = (l1 < D->numlayers) ? bufs[which] : nullptr;
                 a.dec = dec; a.tap_act = tp.act; a.tap_logits = tp.logits; a.ao0 = ao; a.thresh_prob = l.thresh_prob;
-                const dim3 grid((unsigned)nchunks, (unsigned)ntiles);
-                if (from_feat) seg_kernel<true><<<grid, SEG_THREADS, seg_smem(D, true), st>>>(a);
-                else seg_kernel<false><<<grid, SEG_THREADS, seg_smem(D, false), st>>>(a);
+                int per_sm = (int)((227 * 1024) / (lay.total + 1024));
+                per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);     /* __launch_bounds__(256, 2) */
+                int grid = sm_count(device) * per_sm;
+                if (grid > a.nitems) grid = a.nitems;
+                if (from_feat) seg_kernel<true><<<grid, SEG_THREADS, lay.total, st>>>(a);
+                else seg_kernel<false><<<grid, SEG_THREADS, lay.total, st>>>(a);
                 NNSP_LAUNCH_CHECK();
                 for (int i = li; i < l1; i++) if (i < D->numlayers - 1) ao += D->layer[i].rows;
                 if (l1 < D->numlayers) { cur_in = bufs[which]; which ^= 1; }
@@ -700,8 +800,11 @@ int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, int first, int 
                 a.s0 = l.s0; a.ns = l.ns; a.T = T; a.first = first; a.n_inf = n_inf;
                 a.xin = cur_in; a.hout = bufs[which]; a.h = l.st.h; a.c = l.st.c;
                 a.tap_act = tp.act; a.tap_h = tp.hstate; a.tap_c = tp.cstate;
-                scan_kernel<<<ntiles, 32 * L.nt, scan_smem(D, L), st>>>(a);
-                NNSP_LAUNCH_CHECK();
+                const size_t smem = scan_smem(D, L);
+                if (L.nt <= 4) rc = launch_scan<4, 4>(a, ntiles, smem, device, st);
+                else if (L.nt <= 9) rc = launch_scan<9, 2>(a, ntiles, smem, device, st);
+                else rc = launch_scan<16, 1>(a, ntiles, smem, device, st);
+                if (rc) return rc;
                 cur_in = bufs[which]; which ^= 1;
                 ao += L.rows; ho += L.rows;
                 li++;
@@ -719,10 +822,10 @@ int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, int first, int 
         PostArgs p{};
         p.nn_id = D->nn_id; p.s0 = l.s0; p.ns = l.ns; p.T = T; p.first = first; p.n_inf = n_inf;
         p.dec = dec; p.scal = l.st.scal; p.results = l.results; p.tap_post = tp.post; p.th_count = l.th_count;
-        post_kernel<<<(l.ns + 127) / 128, 128, 0, st>>>(p);
+        post_kernel<<<(l.ns + POST_THREADS - 1) / POST_THREADS, POST_THREADS, 0, st>>>(p);
         NNSP_LAUNCH_CHECK();
     }
-    ctx_kernel<<<l.ns, 256, 0, st>>>(mm.d, l.logmel, l.st.ctx, l.s0, T);
+    ctx_kernel<<<(l.ns * 32 + 255) / 256, 256, 0, st>>>(feat16, l.st.ctx, l.s0, l.ns, T);
     NNSP_LAUNCH_CHECK();
     return NNSP_B200_OK;
 }
