@@ -90,34 +90,41 @@ __device__ __forceinline__ int binary_flag(int32_t l0, int32_t l1, int16_t thres
     const int32_t tmp = (int32_t)(((int64_t)thresh * (int64_t)den) >> 15);
     return est[0] <= tmp ? 1 : 0;
 }
-__device__ __forceinline__ void apply_binary(int16_t *sc, int flag, int16_t th_count)
+/* NNSPClass scalars of one stream in registers (no dynamically indexed array: the counters are updated by
+ * compare-and-add over the seven categories) */
+struct PostRegs {
+    int trig, out0, out1, out2, last, slides;
+    int cnt[8];
+};
+__device__ __forceinline__ void apply_binary(PostRegs &r, int flag, int th_count)
 {
-    const int16_t cnt = flag ? (int16_t)(sc[SC_CNT0] + 1) : (int16_t)0;
-    sc[SC_CNT0] = cnt;
-    sc[SC_TRIGGER] = (cnt >= th_count) ? 1 : 0;
+    const int cnt = flag ? (int)(int16_t)(r.cnt[0] + 1) : 0;
+    r.cnt[0] = cnt;
+    r.trig = (cnt >= th_count) ? 1 : 0;
 }
 /* s2i_post_proc, nn_speech.c:146-189, on (argmax intent, argmax slot0, argmax slot1) */
-__device__ __forceinline__ void apply_s2i(int16_t *sc, int dec, int16_t th_count)
+__device__ __forceinline__ void apply_s2i(PostRegs &r, int dec, int th_count)
 {
     const int ai = dec & 0xff;
-    sc[SC_TRIGGER] = 0;
-    sc[SC_OUT0] = sc[SC_OUT0 + 1] = sc[SC_OUT0 + 2] = 0;
-    const int last = sc[SC_ARGMAX_LAST];
-    if (last == 0 || last == ai) {
-        if (ai != 0) {
-            const int16_t cnt = (int16_t)(sc[SC_CNT0 + ai] + 1);
-            sc[SC_CNT0 + ai] = cnt;
-            if (cnt > th_count) {
-                sc[SC_TRIGGER] = 1;
-                sc[SC_OUT0] = (int16_t)ai;
-                sc[SC_OUT0 + 1] = (int16_t)((dec >> 8) & 0xff);
-                sc[SC_OUT0 + 2] = (int16_t)((dec >> 16) & 0xff);
-            }
+    r.trig = 0; r.out0 = 0; r.out1 = 0; r.out2 = 0;
+    if (r.last == 0 || r.last == ai) {
+        int hit = 0;
+#pragma unroll
+        for (int i = 1; i < 7; i++) {
+            const int c = (int)(int16_t)(r.cnt[i] + 1);
+            if (ai == i) { r.cnt[i] = c; hit = c > th_count; }
+        }
+        if (hit) {
+            r.trig = 1;
+            r.out0 = ai;
+            r.out1 = (dec >> 8) & 0xff;
+            r.out2 = (dec >> 16) & 0xff;
         }
     } else {
-        for (int i = 0; i < 7; i++) sc[SC_CNT0 + i] = 0;
+#pragma unroll
+        for (int i = 0; i < 7; i++) r.cnt[i] = 0;
     }
-    sc[SC_ARGMAX_LAST] = (int16_t)ai;
+    r.last = ai;
 }
 
 /* ======================================================================================================== */
@@ -593,51 +600,63 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostArgs a)
     const int si0 = blockIdx.x * POST_THREADS, si = si0 + threadIdx.x;
     const bool valid = si < a.ns;
     const long long s = a.s0 + (valid ? si : 0);
-    int16_t sc[SC_N];
+    PostRegs r;
     {
+        int16_t sc[SC_N];
         const uint4 *p = reinterpret_cast<const uint4 *>(a.scal + s * SC_N);
         *reinterpret_cast<uint4 *>(&sc[0]) = p[0];
         *reinterpret_cast<uint4 *>(&sc[8]) = p[1];
+        r.trig = sc[SC_TRIGGER]; r.out0 = sc[SC_OUT0]; r.out1 = sc[SC_OUT0 + 1]; r.out2 = sc[SC_OUT0 + 2];
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.cnt[i] = sc[SC_CNT0 + i];
+        r.last = sc[SC_ARGMAX_LAST]; r.slides = sc[SC_SLIDES];
     }
+    const int th = a.th_count;
     const int nstr = min(POST_THREADS, a.ns - si0);
-    int t = 0, k = 0;
-    for (int kc = 0; kc <= a.n_inf; kc += POST_KCH) {                 /* (one pass even when n_inf == 0) */
+    auto emit = [&](int t, bool ran) {                                /* frame t is over: result record (+ tap) */
+        r.slides ^= 1;                                                /* nn_speech.c:125 */
+        if (a.results) {
+            uint2 w;
+            w.x = (uint32_t)(uint16_t)r.trig | ((uint32_t)(uint16_t)r.out0 << 16);
+            w.y = (uint32_t)(uint16_t)r.out1 | ((uint32_t)(uint16_t)r.out2 << 16);
+            *reinterpret_cast<uint2 *>(a.results + s * a.T + t) = w;
+        }
+        if (a.tap_post) {
+            int16_t *o = a.tap_post + (s * a.T + t) * SC_N;
+            o[SC_TRIGGER] = (int16_t)r.trig; o[SC_OUT0] = (int16_t)r.out0; o[SC_OUT0 + 1] = (int16_t)r.out1; o[SC_OUT0 + 2] = (int16_t)r.out2;
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[SC_CNT0 + i] = (int16_t)r.cnt[i];
+            o[SC_ARGMAX_LAST] = (int16_t)r.last; o[SC_SLIDES] = (int16_t)r.slides;
+            o[SC_RAN] = ran ? 1 : 0; o[SC_STAGE] = (int16_t)a.nn_id;
+        }
+    };
+    if (valid && a.first == 1) emit(0, false);                        /* frame 0 ran no inference (nn_speech.c:84) */
+    for (int kc = 0; kc < a.n_inf; kc += POST_KCH) {
         const int nk = min(POST_KCH, a.n_inf - kc);
         __syncthreads();
         for (int e = threadIdx.x; e < nstr * nk; e += POST_THREADS) {
-            const int r = e / nk, kk = e - r * nk;
-            dsm[r][kk] = a.dec[(size_t)(a.s0 + si0 + r) * a.n_inf + kc + kk];
+            const int rr = e / nk, kk = e - rr * nk;
+            dsm[rr][kk] = a.dec[(size_t)(a.s0 + si0 + rr) * a.n_inf + kc + kk];
         }
         __syncthreads();
-        /* frames up to (and excluding) the first inference of the next round */
-        const int t_end = (kc + POST_KCH < a.n_inf) ? a.first + 2 * (kc + POST_KCH) : a.T;
         if (valid) {
-            for (; t < t_end; t++) {
-                const bool ran = (t >= a.first) && (((t - a.first) & 1) == 0);               /* nn_speech.c:84 */
-                if (ran) {
-                    const int dv = dsm[threadIdx.x][k - kc];
-                    k++;
-                    if (a.nn_id == NNSP_B200_ID_S2I) apply_s2i(sc, dv, a.th_count);           /* nn_speech.c:97-119 */
-                    else apply_binary(sc, dv, a.th_count);
-                }
-                sc[SC_SLIDES] = (int16_t)((sc[SC_SLIDES] + 1) % 2);                           /* nn_speech.c:125 */
-                if (a.results) {
-                    nnsp_b200_result r;
-                    r.trigger = sc[SC_TRIGGER];
-                    r.outputs[0] = sc[SC_OUT0]; r.outputs[1] = sc[SC_OUT0 + 1]; r.outputs[2] = sc[SC_OUT0 + 2];
-                    a.results[s * a.T + t] = r;
-                }
-                if (a.tap_post) {
-                    int16_t *o = a.tap_post + (s * a.T + t) * SC_N;
-                    for (int i = 0; i < SC_N; i++) o[i] = sc[i];
-                    o[SC_RAN] = ran ? 1 : 0;
-                    o[SC_STAGE] = (int16_t)a.nn_id;
-                }
+            for (int kk = 0; kk < nk; kk++) {
+                const int t = a.first + 2 * (kc + kk);
+                const int dv = dsm[threadIdx.x][kk];
+                if (a.nn_id == NNSP_B200_ID_S2I) apply_s2i(r, dv, th);                        /* nn_speech.c:97-119 */
+                else apply_binary(r, dv, th);
+                emit(t, true);
+                if (t + 1 < a.T) emit(t + 1, false);
             }
         }
-        if (nk <= 0) break;
     }
     if (valid) {
+        int16_t sc[SC_N];
+        sc[SC_TRIGGER] = (int16_t)r.trig; sc[SC_OUT0] = (int16_t)r.out0; sc[SC_OUT0 + 1] = (int16_t)r.out1; sc[SC_OUT0 + 2] = (int16_t)r.out2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) sc[SC_CNT0 + i] = (int16_t)r.cnt[i];
+        sc[SC_ARGMAX_LAST] = (int16_t)r.last; sc[SC_SLIDES] = (int16_t)r.slides;
+        sc[SC_RAN] = 0; sc[SC_STAGE] = 0;
         uint4 *p = reinterpret_cast<uint4 *>(a.scal + s * SC_N);
         p[0] = *reinterpret_cast<uint4 *>(&sc[0]);
         p[1] = *reinterpret_cast<uint4 *>(&sc[8]);
