@@ -151,7 +151,7 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
                  * window = [0, (age ? frame tf-1 : 0), frame tf]; both half-warps compute the same frame */
                 const int base = (tf - 2) * NNSP_B200_FRAME;
                 const int first_live = (2 - age) * NNSP_B200_FRAME;
-                auto load_pair = [&](int p) -> uint32_t {
+                auto load_pair = [&](int, int p) -> uint32_t {
                     if (2 * p < first_live) return 0u;
                     const int g = base + 2 * p;
                     const int16_t *q = (g < 0) ? (hs + g) : (ps + g);

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(32) legacy_kernel(LegacyIO *io, const DevTable
     __syncwarp();
     if (mode & LG_FEATURE) {
         const int16_t *w = io->win;
-        auto load_pair = [&](int p) -> uint32_t { return *reinterpret_cast<const unsigned int *>(w + 2 * p); };
+        auto load_pair = [&](int, int p) -> uint32_t { return *reinterpret_cast<const unsigned int *>(w + 2 * p); };
         frame_logmel<false>(sm.ft, sm.fs, lane & 15, load_pair, io->logmel, lane < 16, FeatDump{});
         __syncwarp();
         __threadfence_block();

@@ -56,8 +56,7 @@ int sm_count(int device) { return g_sm_count[device] ? g_sm_count[device] : 148;
 static void fill_dev_tables(const nnsp_tables *t, DevTables *d)
 {
     memset(d, 0, sizeof *d);
-    for (int p = 0; p < 240; p++)
-        d->win2[p] = (uint32_t)(uint16_t)t->stft_win[2 * p] | ((uint32_t)(uint16_t)t->stft_win[2 * p + 1] << 16);
+    for (int p = 0; p < 240; p++) d->win2[p] = make_int2((int)t->stft_win[2 * p], (int)t->stft_win[2 * p + 1]);
     auto unpack = [](int32_t w) { return make_int2((int)(int16_t)(w & 0xffff), (int)(w >> 16)); };   /* COMPLEX16: lo = re, hi = im */
     for (int a = 0; a < 4; a++)
         for (int n = 0; n < 3; n++)
@@ -68,10 +67,21 @@ static void fill_dev_tables(const nnsp_tables *t, DevTables *d)
         for (int n = 0; n < 3; n++) d->tw2[m][n] = unpack(t->fft_tw[64 * m + 1 + n]);
     for (int k = 0; k < 256; k++) d->rtw[k] = unpack(t->rfft_tw[k]);
     d->rtw[256] = make_int2(0, 0);
-    memcpy(d->mel_taps, t->mel_taps, sizeof t->mel_taps);
-    memcpy(d->mel_start, t->mel_start, sizeof d->mel_start);
-    memcpy(d->mel_end, t->mel_end, sizeof d->mel_end);
-    memcpy(d->mel_off, t->mel_off, sizeof d->mel_off);
+    {   /* regroup the filterbank: per band, aligned groups of 4 bins with zero taps outside [start, end] */
+        int g = 0;
+        for (int b = 0; b < 40; b++) {
+            const int s0 = t->mel_start[b], e0 = t->mel_end[b], bin0 = s0 & ~3, ng = ((e0 | 3) - bin0 + 1) / 4;
+            d->mel_meta[b] = (uint32_t)g | ((uint32_t)ng << 8) | ((uint32_t)bin0 << 16);
+            for (int i = 0; i < ng; i++, g++) {
+                int w[4];
+                for (int k = 0; k < 4; k++) {
+                    const int bin = bin0 + 4 * i + k;
+                    w[k] = (bin >= s0 && bin <= e0) ? (int)t->mel_taps[t->mel_off[b] + bin - s0] : 0;
+                }
+                if (g < MEL_GROUPS) d->mel_tap4[g] = make_int4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
     memcpy(d->log_lut, t->log_lut, sizeof d->log_lut);
     memcpy(d->tanh_lut, t->tanh_lut, sizeof d->tanh_lut);
 }
@@ -221,14 +231,13 @@ feat_kernel(const DevTables *__restrict__ tables, const int16_t *__restrict__ pc
         const bool valid = f < F;
         const long long fc = valid ? f : 0;
         const int s = s0 + (int)(fc / T), t = (int)(fc % T);
-        const int16_t *ps = pcm + (long long)s * stride;
-        const int16_t *hs = hist + (long long)s * hist_len + hist_len;     /* hs[g], g < 0: samples before this call */
-        const int base = (t - 2) * NNSP_B200_FRAME;                        /* first sample of the 480-sample window */
-        auto load_pair = [&](int p) -> uint32_t {
-            const int g = base + 2 * p;
-            const int16_t *q = (g < 0) ? (hs + g) : (ps + g);
-            return __ldg(reinterpret_cast<const unsigned int *>(q));
-        };
+        /* the 480-sample window starts two frames back: word L + 16a of it comes from this call's PCM or, for
+         * the first two frames, from the carried history (both 4-byte aligned; immediates after unrolling) */
+        const int base = (t - 2) * NNSP_B200_FRAME;                        /* first sample of the window */
+        const unsigned int *pw = reinterpret_cast<const unsigned int *>(pcm + (long long)s * stride + base) + L;
+        const unsigned int *hw = reinterpret_cast<const unsigned int *>(hist + (long long)s * hist_len + hist_len + base) + L;
+        const int pth = (2 - t) * (NNSP_B200_FRAME / 2);                   /* pairs below pth precede the call */
+        auto load_pair = [&](int a, int p) -> uint32_t { return (p < pth) ? __ldg(hw + 16 * a) : __ldg(pw + 16 * a); };
         const long long row = ((long long)s * T + t) * NNSP_B200_NMEL;
         frame_logmel<false>(sm.tb, fs, L, load_pair, logmel + row, valid, FeatDump{}, snorm, feat16 + row);
     }
@@ -490,7 +499,7 @@ feat_stages_kernel(const DevTables *__restrict__ tables, const int16_t *__restri
         const bool valid = f < n;
         const int fc = valid ? f : 0;
         const int16_t *w = windows + (long long)fc * 480;
-        auto load_pair = [&](int p) -> uint32_t { return *reinterpret_cast<const unsigned int *>(w + 2 * p); };
+        auto load_pair = [&](int a, int p) -> uint32_t { return *reinterpret_cast<const unsigned int *>(w + 2 * p); };
         FeatDump d;
         d.fft_in = fft_in ? fft_in + (long long)fc * 512 : nullptr;
         d.spec = spec ? spec + (long long)fc * 514 : nullptr;

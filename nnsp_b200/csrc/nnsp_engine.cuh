@@ -6,8 +6,14 @@
 namespace nnsp {
 
 /* ---- constant tables as the kernels see them (global memory, copied to SMEM per CTA) ---- */
+constexpr int MEL_GROUPS = 144;    /* 4-bin groups of the 40 mel bands, each band padded to aligned groups */
+
 struct DevTables {
-    uint32_t win2[240];        /* stft window, two Q15 coefficients per word (sample 2p, 2p+1)   */
+    /* mel filterbank (melSpec_coeff.c:5) regrouped for 128-bit loads: band b owns groups g0 .. g0+ng-1, group i
+     * holds the taps of bins bin0+4i .. bin0+4i+3 (bin0 = first bin rounded down to 4; taps outside the band are 0);
+     * mel_meta[b] = g0 | ng << 8 | bin0 << 16 */
+    int4     mel_tap4[MEL_GROUPS];
+    int2     win2[240];        /* stft window, sign-extended Q15 coefficients of samples 2p, 2p+1 */
     /* radix-4 twiddles, sign-extended (re, im), laid out in the order the half-warp reads them:
      *   tw0[a][n][L] = tw^(n+1 column) of butterfly k = L + 16a (stage 0), tw1[n][L] of k = 4L (stage 1),
      *   tw2[m][n] of k = 16m (stage 2, same for every lane); column order tw^2, tw^1, tw^3 (fft.c:182) */
@@ -15,8 +21,7 @@ struct DevTables {
     int2     tw1[3][16];
     int2     tw2[4][3];
     int2     rtw[257];         /* real-FFT split twiddles exp(-2 pi j k / 512), k = 0..256 (k = 256 unused) */
-    int16_t  mel_taps[456];    /* 454 taps (+2 pad)                                              */
-    int16_t  mel_start[40], mel_end[40], mel_off[40];
+    uint32_t mel_meta[40];
     int16_t  log_lut[256];
     int16_t  tanh_lut[384];
 };

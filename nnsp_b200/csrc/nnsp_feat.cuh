@@ -19,20 +19,20 @@
 
 namespace nnsp {
 
-struct FeatSmemTables {
-    uint32_t win2[240];
+struct FeatSmemTables {            /* = the leading members of DevTables, same order */
+    int4     mel_tap4[MEL_GROUPS];
+    int2     win2[240];
     int2     tw0[4][3][16];
     int2     tw1[3][16];
     int2     tw2[4][3];
     int2     rtw[257];
-    int16_t  mel_taps[456];
-    int16_t  mel_start[40], mel_end[40], mel_off[40];
+    uint32_t mel_meta[40];
     int16_t  log_lut[256];
 };
 
-struct FrameScratch {              /* per half-warp */
+struct alignas(16) FrameScratch {  /* per half-warp */
     int2    x[272];                /* 256 complex points, one pad slot per 16 */
-    int32_t ps[260];               /* power spectrum, bins 0..256             */
+    int32_t ps[260];               /* power spectrum, bins 0..256 (16-byte aligned: read in groups of 4 bins) */
 };
 
 struct FeatDump {                  /* optional stage taps (global memory), all may be null */
@@ -81,8 +81,9 @@ __device__ __forceinline__ void bfly4(int32_t &ar, int32_t &ai, int32_t &cr, int
 
 __device__ __forceinline__ int xpad(int p) { return p + (p >> 4); }
 
-/* One frame by the 16 lanes of a half-warp (L = lane & 15). `load_pair(p)` returns PCM samples
- * 2p and 2p+1 of the 480-sample analysis window packed in one word (p = 0..239).
+/* One frame by the 16 lanes of a half-warp (L = lane & 15). `load_pair(a, p)` returns PCM samples
+ * 2p and 2p+1 of the 480-sample analysis window packed in one word (p = L + 16a = 0..239; `a` is a
+ * compile-time constant after unrolling, so callers can address with immediates).
  * Every lane of the WARP must call this together (full-warp __syncwarp inside). */
 /* norm (optional, shared memory): mean[40], stdR[40], rshift of a model. When given, the standardised row
  * (feature_module.c:67-73) is written to out_feat as int16 instead of the log-mel row to out_logmel. */
@@ -97,9 +98,10 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
 #pragma unroll
     for (int a = 0; a < 15; a++) {
         const int p = L + 16 * a;
-        const uint32_t s = load_pair(p), w = tb.win2[p];
-        xr[a] = ((int32_t)(int16_t)(w & 0xffff) * (int32_t)(int16_t)(s & 0xffff)) >> 15;
-        xi[a] = ((int32_t)(int16_t)(w >> 16) * (int32_t)(int16_t)(s >> 16)) >> 15;
+        const uint32_t s = load_pair(a, p);
+        const int2 w = tb.win2[p];
+        xr[a] = (w.x * (int32_t)(int16_t)(s & 0xffff)) >> 15;
+        xi[a] = (w.y * ((int32_t)s >> 16)) >> 15;
     }
     xr[15] = 0; xi[15] = 0;
     if (DUMP && dump.fft_in && store) {
@@ -183,16 +185,24 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
     __syncwarp();
     if (DUMP && dump.pspec && store)
         for (int i = L; i < 257; i += 16) dump.pspec[i] = fs.ps[i];
-    /* mel filterbank (melSpecProc.c:6-27) + log10 (fixlog10.c:53-61) */
+    /* mel filterbank (melSpecProc.c:6-27) + log10 (fixlog10.c:53-61). Bands are handed out widest first
+     * (b = 39 - L - 16r) so that the lanes of a round have similar trip counts; taps and bins come in groups of 4
+     * (one 128-bit load each), two independent 64-bit accumulators. The int64 sum is exact in any order. */
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const int b = L + 16 * r;
-        if (b < 40) {
-            const int s = tb.mel_start[b], e = tb.mel_end[b];
-            const int16_t *tap = &tb.mel_taps[tb.mel_off[b]];
-            int64_t mac = 0;
-            for (int j = s; j <= e; j++) mac += (int64_t)(*tap++) * (int64_t)fs.ps[j];
-            const int32_t mel = sat32_dev(mac >> 15);
+        const int b = 39 - L - 16 * r;
+        if (b >= 0) {
+            const uint32_t meta = tb.mel_meta[b];
+            const int ng = (meta >> 8) & 0xff;
+            const int4 *tap = &tb.mel_tap4[meta & 0xff];
+            const int4 *bin = reinterpret_cast<const int4 *>(&fs.ps[meta >> 16]);
+            int64_t m0 = 0, m1 = 0;
+            for (int i = 0; i < ng; i++) {
+                const int4 w = tap[i], v = bin[i];
+                m0 += (int64_t)w.x * (int64_t)v.x; m1 += (int64_t)w.y * (int64_t)v.y;
+                m0 += (int64_t)w.z * (int64_t)v.z; m1 += (int64_t)w.w * (int64_t)v.w;
+            }
+            const int32_t mel = sat32_dev((m0 + m1) >> 15);
             if (DUMP && dump.mel && store) dump.mel[b] = mel;
             if (store) {
                 const int32_t lm = log10_q15(mel, tb.log_lut);
