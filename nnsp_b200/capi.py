@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnnsp_b200.so")
+LIB_PATH = os.environ.get("NNSP_B200_LIB") or os.path.join(HERE, "libnnsp_b200.so")   # env override: kernel-variant experiments only
 
 RESULT_DT = np.dtype([("trigger", "<i2"), ("outputs", "<i2", (3,))])
 CASCADE_RESULT_DT = np.dtype([("stage_id", "i1"), ("pos_after", "i1"), ("detected", "<i2"),

@@ -53,8 +53,9 @@ int select_device(int device)
 }
 int sm_count(int device) { return g_sm_count[device] ? g_sm_count[device] : 148; }
 
-static void fill_dev_tables(const nnsp_tables *t, DevTables *d)
+static bool fill_dev_tables(const nnsp_tables *t, DevTables *d)
 {
+    bool ok = true;
     memset(d, 0, sizeof *d);
     for (int p = 0; p < 240; p++) d->win2[p] = make_int2((int)t->stft_win[2 * p], (int)t->stft_win[2 * p + 1]);
     auto unpack = [](int32_t w) { return make_int2((int)(int16_t)(w & 0xffff), (int)(w >> 16)); };   /* COMPLEX16: lo = re, hi = im */
@@ -72,6 +73,7 @@ static void fill_dev_tables(const nnsp_tables *t, DevTables *d)
         for (int b = 0; b < 40; b++) {
             const int s0 = t->mel_start[b], e0 = t->mel_end[b], bin0 = s0 & ~3, ng = ((e0 | 3) - bin0 + 1) / 4;
             d->mel_meta[b] = (uint32_t)g | ((uint32_t)ng << 8) | ((uint32_t)bin0 << 16);
+            if (ng > (b >= 24 ? MEL_MAXG0 : (b >= 8 ? MEL_MAXG1 : MEL_MAXG2)) || g + ng > MEL_GROUPS) ok = false;
             for (int i = 0; i < ng; i++, g++) {
                 int w[4];
                 for (int k = 0; k < 4; k++) {
@@ -84,6 +86,7 @@ static void fill_dev_tables(const nnsp_tables *t, DevTables *d)
     }
     memcpy(d->log_lut, t->log_lut, sizeof d->log_lut);
     memcpy(d->tanh_lut, t->tanh_lut, sizeof d->tanh_lut);
+    return ok;
 }
 
 int get_device_tables(int device, const DevTables **out)
@@ -93,7 +96,7 @@ int get_device_tables(int device, const DevTables **out)
         const nnsp_tables *t = nnsp_tables_get();
         if (!t) { nnsp_set_error("constant-table self check failed (fingerprint mismatch)"); return NNSP_B200_ERR_ARG; }
         DevTables h;
-        fill_dev_tables(t, &h);
+        if (!fill_dev_tables(t, &h)) { nnsp_set_error("mel filterbank does not fit the kernel's group bounds"); return NNSP_B200_ERR_ARG; }
         DevTables *d = nullptr;
         NNSP_CUDA(cudaMalloc(&d, sizeof h));
         NNSP_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
@@ -519,7 +522,7 @@ using namespace nnsp;
 struct nnsp_b200_batch {
     int device = 0, S = 0;
     cudaStream_t stream = nullptr;          /* device-buffer API */
-    cudaStream_t xs[3] = { nullptr, nullptr, nullptr };   /* host-buffer API pipeline */
+    cudaStream_t xs[4] = { nullptr, nullptr, nullptr, nullptr };   /* host-buffer API pipeline */
     const DevTables *tables = nullptr;
     DeviceModel dm;
     MmaDeviceModel mm;
@@ -750,15 +753,18 @@ int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
         b->d_pcm_frames = T; b->d_res_frames = T;
     }
     NNSP_CUDA(cudaStreamSynchronize(b->stream));
-    /* slices of streams pipelined over three CUDA streams: H2D(k+1) overlaps kernels(k) overlaps D2H(k-1) */
+    /* slices of streams pipelined over four CUDA streams: H2D(k+1) overlaps kernels(k) overlaps D2H(k-1). The call
+     * is bound by the host link (320 B of PCM per stream-frame), so slices are small enough that the work left
+     * after the last H2D -- one slice of kernels and its D2H -- is short, and large enough to fill the GPU */
     const long long dstride = (long long)T * NNSP_B200_FRAME;
-    int nsl = b->S >= 4096 ? 8 : (b->S >= 256 ? 4 : 1);
+    int nsl = b->S / 256;
+    nsl = nsl < 1 ? 1 : (nsl > 16 ? 16 : nsl);
     for (int k = 0; k < nsl; k++) {
         /* slice boundaries on 16-stream tiles (the tensor-core paths work on tiles) */
         const int s0 = (int)(((long long)b->S * k / nsl) & ~15LL);
         const int s1 = (k == nsl - 1) ? b->S : (int)(((long long)b->S * (k + 1) / nsl) & ~15LL);
         if (s1 <= s0) continue;
-        cudaStream_t st = b->xs[k % 3];
+        cudaStream_t st = b->xs[k % 4];
         if (stream_stride == dstride) {
             NNSP_CUDA(cudaMemcpyAsync(b->d_pcm + (size_t)s0 * dstride, pcm + (size_t)s0 * stream_stride,
                                       (size_t)(s1 - s0) * dstride * sizeof(int16_t), cudaMemcpyHostToDevice, st));

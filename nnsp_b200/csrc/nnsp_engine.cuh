@@ -6,7 +6,9 @@
 namespace nnsp {
 
 /* ---- constant tables as the kernels see them (global memory, copied to SMEM per CTA) ---- */
-constexpr int MEL_GROUPS = 144;    /* 4-bin groups of the 40 mel bands, each band padded to aligned groups */
+constexpr int MEL_GROUPS = 144;
+/* most groups of any band in mel round r (bands 39-16r .. 24-16r, widest first): bands 24..39, 8..23, 0..7 */
+constexpr int MEL_MAXG0 = 8, MEL_MAXG1 = 4, MEL_MAXG2 = 2;    /* 4-bin groups of the 40 mel bands, each band padded to aligned groups */
 
 struct DevTables {
     /* mel filterbank (melSpec_coeff.c:5) regrouped for 128-bit loads: band b owns groups g0 .. g0+ng-1, group i

@@ -31,8 +31,8 @@ struct FeatSmemTables {            /* = the leading members of DevTables, same o
 };
 
 struct alignas(16) FrameScratch {  /* per half-warp */
-    int2    x[272];                /* 256 complex points, one pad slot per 16 */
-    int32_t ps[260];               /* power spectrum, bins 0..256 (16-byte aligned: read in groups of 4 bins) */
+    int2    x[272];                /* 256 complex points, one pad slot per 16; later the power spectrum
+                                      (int32 bins 0..256 over the first 1040 bytes, read in groups of 4 bins) */
 };
 
 struct FeatDump {                  /* optional stage taps (global memory), all may be null */
@@ -146,45 +146,55 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
         fs.x[m] = make_int2(xr[b], xi[b]);
     }
     __syncwarp();
-    /* real-FFT split (fft.c:66-124) and power spectrum (spectrogram_module.c:33-45) */
+    /* real-FFT split (fft.c:66-124) and power spectrum (spectrogram_module.c:33-45): each lane turns the pairs
+     * (Z[i], Z[256-i]), i = L + 16j, into bins i and 256-i. Lane 0's pair (0, 0) would give bins 0 and 256, which no
+     * mel band reads (melSpec_coeff.c: bins 1..255), so it takes the self-mirrored centre bin 128 in that turn
+     * instead. The power spectrum is kept in registers until every lane has read its Z pairs, then it overwrites
+     * the front of the same scratch (ps[] aliases x[]). */
+    int32_t pa[8], pb[8];
+    int32_t p0 = 0, p256 = 0;
 #pragma unroll
-    for (int j = 0; j < 9; j++) {
-        const int i = L + 16 * j;
-        if (j < 8 || L == 0) {
-            const int2 zi = fs.x[i], zr = fs.x[(256 - i) & 255];
-            const int2 w = tb.rtw[i & 255];
-            const int32_t wr = w.x, wi = w.y;
-            const int32_t er = (zi.x + zr.x) >> 1, ei = (zi.y - zr.y) >> 1;
-            const int32_t orr = (zi.y + zr.y) >> 1, oi = (zr.x - zi.x) >> 1;
-            if (i == 128 && j == 8) {
-                /* lane 0's extra turn: Nyquist bin X[256] = Xe[0] - Xo[0] (fft.c:123-124) */
-                const int2 z0 = fs.x[0];
-                const int32_t re = z0.x - z0.y, im = 0;
-                if (DUMP && dump.spec && store) { dump.spec[512] = re; dump.spec[513] = im; }
-                fs.ps[256] = (int32_t)(((int64_t)re * re + (int64_t)im * im) >> 15);
-                /* and the centre bin 128, whose mirror is itself */
-                const int32_t cr = er + msub_q15(orr, wr, oi, wi), ci = ei + madd_q15(orr, wi, oi, wr);
-                if (DUMP && dump.spec && store) { dump.spec[256] = cr; dump.spec[257] = ci; }
-                fs.ps[128] = (int32_t)(((int64_t)cr * cr + (int64_t)ci * ci) >> 15);
-            } else {
-                const int32_t xr0 = er + msub_q15(orr, wr, oi, wi), xi0 = ei + madd_q15(orr, wi, oi, wr);
-                if (DUMP && dump.spec && store) { dump.spec[2 * i] = xr0; dump.spec[2 * i + 1] = xi0; }
-                fs.ps[i] = (int32_t)(((int64_t)xr0 * xr0 + (int64_t)xi0 * xi0) >> 15);
-                if (i != 0) {
-                    /* mirrored bin 256 - i from the same pair, roles of Z[i] and Z[256-i] swapped */
-                    const int2 v = tb.rtw[256 - i];
-                    const int32_t vr = v.x, vi = v.y;
-                    const int32_t fi = (zr.y - zi.y) >> 1, pi = (zi.x - zr.x) >> 1;
-                    const int32_t xr1 = er + msub_q15(orr, vr, pi, vi), xi1 = fi + madd_q15(orr, vi, pi, vr);
-                    if (DUMP && dump.spec && store) { dump.spec[2 * (256 - i)] = xr1; dump.spec[2 * (256 - i) + 1] = xi1; }
-                    fs.ps[256 - i] = (int32_t)(((int64_t)xr1 * xr1 + (int64_t)xi1 * xi1) >> 15);
-                }
-            }
+    for (int j = 0; j < 8; j++) {
+        const bool centre = (j == 0 && L == 0);
+        const int i = centre ? 128 : L + 16 * j;
+        const int2 zi = fs.x[i], zr = fs.x[256 - i];
+        const int2 w = tb.rtw[i], v = tb.rtw[256 - i];
+        const int32_t er = (zi.x + zr.x) >> 1, ei = (zi.y - zr.y) >> 1;
+        const int32_t orr = (zi.y + zr.y) >> 1, oi = (zr.x - zi.x) >> 1;
+        const int32_t xr0 = er + msub_q15(orr, w.x, oi, w.y), xi0 = ei + madd_q15(orr, w.y, oi, w.x);
+        pa[j] = (int32_t)(((int64_t)xr0 * xr0 + (int64_t)xi0 * xi0) >> 15);
+        /* mirrored bin 256 - i from the same pair, roles of Z[i] and Z[256-i] swapped */
+        const int32_t fi = (zr.y - zi.y) >> 1, pi = (zi.x - zr.x) >> 1;
+        const int32_t xr1 = er + msub_q15(orr, v.x, pi, v.y), xi1 = fi + madd_q15(orr, v.y, pi, v.x);
+        pb[j] = (int32_t)(((int64_t)xr1 * xr1 + (int64_t)xi1 * xi1) >> 15);
+        if (DUMP && dump.spec && store) {
+            dump.spec[2 * i] = xr0; dump.spec[2 * i + 1] = xi0;
+            if (!centre) { dump.spec[2 * (256 - i)] = xr1; dump.spec[2 * (256 - i) + 1] = xi1; }
         }
     }
+    if (DUMP && L == 0) {
+        /* taps only: bin 0 from the pair (Z[0], Z[0]) and the Nyquist bin X[256] = Xe[0] - Xo[0] (fft.c:123-124) */
+        const int2 z0 = fs.x[0], w = tb.rtw[0];
+        const int32_t er = z0.x, orr = z0.y;
+        const int32_t xr0 = er + msub_q15(orr, w.x, 0, w.y), xi0 = madd_q15(orr, w.y, 0, w.x);
+        const int32_t re = z0.x - z0.y;
+        p0 = (int32_t)(((int64_t)xr0 * xr0 + (int64_t)xi0 * xi0) >> 15);
+        p256 = (int32_t)(((int64_t)re * re) >> 15);
+        if (dump.spec && store) { dump.spec[0] = xr0; dump.spec[1] = xi0; dump.spec[512] = re; dump.spec[513] = 0; }
+    }
+    __syncwarp();
+    int32_t *ps = reinterpret_cast<int32_t *>(fs.x);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const bool centre = (j == 0 && L == 0);
+        const int i = centre ? 128 : L + 16 * j;
+        ps[i] = pa[j];
+        if (!centre) ps[256 - i] = pb[j];
+    }
+    if (DUMP && L == 0) { ps[0] = p0; ps[256] = p256; }
     __syncwarp();
     if (DUMP && dump.pspec && store)
-        for (int i = L; i < 257; i += 16) dump.pspec[i] = fs.ps[i];
+        for (int i = L; i < 257; i += 16) dump.pspec[i] = ps[i];
     /* mel filterbank (melSpecProc.c:6-27) + log10 (fixlog10.c:53-61). Bands are handed out widest first
      * (b = 39 - L - 16r) so that the lanes of a round have similar trip counts; taps and bins come in groups of 4
      * (one 128-bit load each), two independent 64-bit accumulators. The int64 sum is exact in any order. */
@@ -195,12 +205,17 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
             const uint32_t meta = tb.mel_meta[b];
             const int ng = (meta >> 8) & 0xff;
             const int4 *tap = &tb.mel_tap4[meta & 0xff];
-            const int4 *bin = reinterpret_cast<const int4 *>(&fs.ps[meta >> 16]);
+            const int4 *bin = reinterpret_cast<const int4 *>(&ps[meta >> 16]);
             int64_t m0 = 0, m1 = 0;
-            for (int i = 0; i < ng; i++) {
-                const int4 w = tap[i], v = bin[i];
-                m0 += (int64_t)w.x * (int64_t)v.x; m1 += (int64_t)w.y * (int64_t)v.y;
-                m0 += (int64_t)w.z * (int64_t)v.z; m1 += (int64_t)w.w * (int64_t)v.w;
+            /* trip counts are bounded per round (MEL_MAXG, checked when the tables are built): fully unrolled and
+             * predicated, so the loads of a round are issued together */
+#pragma unroll
+            for (int i = 0; i < (r == 0 ? MEL_MAXG0 : (r == 1 ? MEL_MAXG1 : MEL_MAXG2)); i++) {
+                if (i < ng) {
+                    const int4 w = tap[i], v = bin[i];
+                    m0 += (int64_t)w.x * (int64_t)v.x; m1 += (int64_t)w.y * (int64_t)v.y;
+                    m0 += (int64_t)w.z * (int64_t)v.z; m1 += (int64_t)w.w * (int64_t)v.w;
+                }
             }
             const int32_t mel = sat32_dev((m0 + m1) >> 15);
             if (DUMP && dump.mel && store) dump.mel[b] = mel;

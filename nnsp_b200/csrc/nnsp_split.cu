@@ -219,6 +219,7 @@ seg_kernel(SegArgs a)
                          : "=r"(done) : "r"(smem_u32(bar)) : "memory");
     }
     const int T = a.T;
+    __syncthreads();
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int chunk = item % a.nchunks, tile = item / a.nchunks;
@@ -226,8 +227,8 @@ seg_kernel(SegArgs a)
         const int sb = a.s0 + 16 * tile;
         const int nvalid = min(16, a.s0 + a.ns - sb);
         const size_t tile_abs = (size_t)(a.s0 >> 4) + tile;
-        __syncthreads();                                             /* planes of the previous item are free */
         if (FROM_FEAT) {
+            __syncthreads();                                         /* planes of the previous item are free */
             /* standardised rows of frames f_first .. f_first+35 as byte planes; frames before the call are the
              * carried context rows 1..5 (feature_module.c:54-57); loads of a batch are issued before its stores */
             const int f_first = a.first + 2 * k0 - 5;
@@ -408,7 +409,8 @@ __global__ void __launch_bounds__(32 * NW, MINB)
 scan_kernel(ScanArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);             /* [0..NST) input ring, [NST] weights */
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);             /* [0..NST) input ring, [NST] weights, [NST+1] h */
+    uint64_t *hbar = bars + SCAN_NST + 1;
     const int WB = 4 * a.nt * (a.kt + a.ktr) * 256, XB = 32 * a.pa;
     const uint2 *wsm = reinterpret_cast<const uint2 *>(smem + 64);
     int2 *lut2 = reinterpret_cast<int2 *>(smem + 64 + WB);
@@ -424,6 +426,7 @@ scan_kernel(ScanArgs a)
 
     if (tid == 0) {
         for (int i = 0; i <= SCAN_NST; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(hbar)), "r"(a.nt));   /* one arrival per active warp */
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 3 * XB / 4; i += nthr) reinterpret_cast<uint32_t *>(hb)[i] = 0;
@@ -466,11 +469,11 @@ scan_kernel(ScanArgs a)
     const uint2 *wx = wsm + (size_t)warp * 4 * a.kt * 32 + lane;
     const uint2 *wh = wsm + (size_t)a.nt * 4 * a.kt * 32 + (size_t)warp * 4 * a.ktr * 32 + lane;
     int ach[4][4], acl[4][4];
-    auto zero_acc = [&]() {
+    auto init_acc = [&]() {                                           /* the bias rides in the low-plane accumulator */
 #pragma unroll
         for (int gt = 0; gt < 4; gt++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) { ach[gt][e] = 0; acl[gt][e] = 0; }
+            for (int e = 0; e < 4; e++) { ach[gt][e] = 0; acl[gt][e] = bz[gt][e & 1]; }
     };
     auto half = [&](const uint8_t *plane, const uint2 *w, int nk) {          /* acc += W . plane (rc_Krows_8x16) */
         for (int ks = 0; ks < nk; ks++) {
@@ -501,12 +504,13 @@ scan_kernel(ScanArgs a)
     };
 
     mbar_wait(bars + 0, 0);
-    zero_acc();
+    init_acc();
     if (active) half(xs, wx, a.kt);                                   /* Wx . x of inference 0 */
-    __syncthreads();
-    if (tid == 0 && SCAN_NST < n_inf) bulk_load(xs, xg + (size_t)SCAN_NST * XB, XB, bars + 0);
     if (a.first == 1) tap_state(h2, 0);                               /* frame 0 ran no inference */
 
+    /* per inference: recurrent half + cell on the accumulators that already hold Wx.x + b; the warp then ARRIVES
+     * on the h barrier, issues Wx.x of the next inference (independent of the recurrence), and only then WAITS
+     * for the other warps' h slices: the barrier latency hides behind tensor work */
     for (int k = 0; k < n_inf; k++) {
         const uint8_t *hp = hb + ((k + 2) % 3) * XB;                  /* h of the previous inference */
         uint8_t *hn = hb + (k % 3) * XB;
@@ -518,7 +522,7 @@ scan_kernel(ScanArgs a)
             for (int gt = 0; gt < 4; gt++)
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const int32_t pre = (int32_t)(((uint32_t)ach[gt][e] << 8) + (uint32_t)acl[gt][e] + (uint32_t)bz[gt][e & 1]) >> rs;
+                    const int32_t pre = (int32_t)(((uint32_t)ach[gt][e] << 8) + (uint32_t)acl[gt][e]) >> rs;
                     gate[gt][e] = (gt == 1) ? tanh_q15v(pre, lut2) : sigmoid_q15v(pre, lut2);      /* lstm.c:65,78,91,104 */
                 }
             int32_t y[4];
@@ -540,21 +544,24 @@ scan_kernel(ScanArgs a)
                     if (row < nvalid && u < H) a.tap_act[((long long)(sb + row) * T + t) * a.act_stride + a.ao + u] = (int16_t)y[e];
                 }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  /* h slice -> visible to the bulk store */
+            __syncwarp();
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   /* buffer of step k-2 is free again */
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(hbar)) : "memory");
             if (k + 1 < n_inf) {                                      /* Wx . x of the next inference, off the recurrence */
                 mbar_wait(bars + ((k + 1) % SCAN_NST), (uint32_t)(((k + 1) / SCAN_NST) & 1));
-                zero_acc();
+                init_acc();
                 half(xs + ((k + 1) % SCAN_NST) * XB, wx, a.kt);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  /* h planes -> visible to the bulk store */
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   /* buffer of step k-2 is free again */
-        __syncthreads();
+        mbar_wait(hbar, (uint32_t)(k & 1));                           /* every slice of h(k) is in hn */
         if (tid == 0) {
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                          ::"l"(hg + (size_t)k * XB), "r"(smem_u32(hn)), "r"((uint32_t)XB) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            const int m = k + 1 + SCAN_NST;
-            if (m < n_inf) bulk_load(xs + ((k + 1) % SCAN_NST) * XB, xg + (size_t)m * XB, XB, bars + ((k + 1) % SCAN_NST));
+            /* x(k) was consumed before anyone arrived for step k - 1 .. k: its slot takes x(k + NST) */
+            const int m = k + SCAN_NST;
+            if (m < n_inf) bulk_load(xs + (k % SCAN_NST) * XB, xg + (size_t)m * XB, XB, bars + (k % SCAN_NST));
         }
         if (a.tap_h || a.tap_c) {
             tap_state(hn, t);
@@ -713,7 +720,7 @@ static SegLayout seg_layout(const MmaModel *D, int l0, int l1, bool from_feat)
 }
 static size_t scan_smem(const MmaModel *D, const MmaLayer &L)
 {
-    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + LUT2_N * 8 + (size_t)(SCAN_NST + 3) * 32 * D->pa;
+    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + LUT2_N * 8 + (size_t)(SCAN_NST + 3) * 32 * D->pa;   /* 64: 6 mbarriers */
 }
 
 int split_supported(const MmaDeviceModel &mm)
