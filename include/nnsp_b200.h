@@ -11,6 +11,7 @@
  * What each entry point replaces in the reference (AmbiqAI/nnsp, file:line):
  *   nnsp_b200_model_from_net ........ reading a linked model table, e.g. evb/src/def_nn1_vad.c:8-110
  *                                     (mean/stdR arrays + the `NeuralNetClass net_*` literal)
+ *   nnsp_b200_model_from_table_text . compiling + linking a generated table file, python/c_code_table_converter.py:143-347
  *   nnsp_b200_batch_create .......... NNSPClass_init            ns-nnsp/src/nn_speech.c:23-55
  *                                     (+ FeatureClass_construct  ns-nnsp/src/feature_module.c:12-24)
  *   nnsp_b200_batch_reset ........... NNSPClass_reset           ns-nnsp/src/nn_speech.c:57-72
@@ -68,6 +69,13 @@ typedef struct nnsp_b200_model nnsp_b200_model;
  * Accumulator width per layer is taken from layer_func[] (== &fc_8x16_acc32b etc.). */
 int nnsp_b200_model_from_net(const void *neural_net_class, const int32_t *feature_mean,
                              const int32_t *feature_stdR, int nn_id, nnsp_b200_model **out);
+/* The reference's on-disk model format: the generated C source `evb/src/def_nn{id}_{name}.c`
+ * (python/c_code_table_converter.py:143-347; weight layout python/nnsp_pack/c_weight_man.py:5-124), parsed as
+ * text -- no C compiler involved. nn_id < 0: inferred from the table name (s2i / vad / kws*). acc32: 1 selects
+ * the `#ifdef DEF_ACC32BIT_OPT` branch (wrapping 32-bit accumulators), 0 the 64-bit one, -1 = 0.
+ * model_to_table_text writes the same text back (call with buf = NULL to get the size). */
+int nnsp_b200_model_from_table_text(const char *text, size_t nbytes, int nn_id, int acc32, nnsp_b200_model **out);
+int nnsp_b200_model_to_table_text(const nnsp_b200_model *m, const char *nn_name, char *buf, size_t cap, size_t *nbytes);
 /* Same model from / to the flat little-endian container described in DESIGN.md ("NNSPM1"). */
 int nnsp_b200_model_from_blob(const void *blob, size_t nbytes, nnsp_b200_model **out);
 int nnsp_b200_model_to_blob(const nnsp_b200_model *m, void *buf, size_t cap, size_t *nbytes);

@@ -44,6 +44,25 @@ class Model:
         return m
 
     @classmethod
+    def from_table_text(cls, text, nn_id=-1, acc32=False):
+        """A model from the reference's generated table source (evb/src/def_nn{id}_{name}.c), parsed as text."""
+        if isinstance(text, (str, os.PathLike)) and os.path.exists(text):
+            with open(text, "rb") as f:
+                text = f.read()
+        if isinstance(text, str):
+            text = text.encode()
+        h = C.c_void_p()
+        check(lib().nnsp_b200_model_from_table_text(text, len(text), nn_id, int(bool(acc32)), C.byref(h)), "model_from_table_text")
+        return cls(h)
+
+    def to_table_text(self, nn_name):
+        n = C.c_size_t()
+        check(lib().nnsp_b200_model_to_table_text(self.h, nn_name.encode(), None, 0, C.byref(n)), "model_to_table_text")
+        buf = C.create_string_buffer(n.value + 1)
+        check(lib().nnsp_b200_model_to_table_text(self.h, nn_name.encode(), buf, n.value, C.byref(n)), "model_to_table_text")
+        return buf.raw[: n.value]
+
+    @classmethod
     def from_net(cls, net_ptr, mean_ptr, stdr_ptr, nn_id):
         h = C.c_void_p()
         check(lib().nnsp_b200_model_from_net(net_ptr, mean_ptr, stdr_ptr, nn_id, C.byref(h)), "model_from_net")

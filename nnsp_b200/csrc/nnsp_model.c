@@ -127,6 +127,19 @@ void nnsp_model_layer_from_table(nnsp_layer *L, const int8_t *kernel, const int8
     }
 }
 
+/* the inverse: table-layout arrays of layer L from its canonical arrays */
+void nnsp_model_layer_to_table(const nnsp_layer *L, int8_t *kernel, int8_t *kernel_rec, int16_t *bias)
+{
+    if (L->type == NNSP_LAYER_LSTM) {
+        lstm_xfer(kernel, L->w, L->rows, L->cols, 1);
+        lstm_xfer(kernel_rec, L->wrec, L->rows, L->rows, 1);
+        lstm_bias_xfer(bias, L->bias, L->rows, 1);
+    } else {
+        matrix_xfer(kernel, L->w, L->rows, L->cols, 1);
+        memcpy(bias, L->bias, (size_t)L->rows * sizeof(int16_t));
+    }
+}
+
 int nnsp_model_validate(const struct nnsp_b200_model *m)
 {
     if (m->numlayers < 1 || m->numlayers > NNSP_B200_MAX_LAYERS) {
