@@ -20,6 +20,7 @@
  *   nnsp_b200_cascade_create ........ nnCntrlClass_init         evb/src/nnCntrlClass.c:56-128
  *   nnsp_b200_cascade_reset ......... nnCntrlClass_reset        evb/src/nnCntrlClass.c:130-150
  *   nnsp_b200_cascade_exec[_host] ... nnCntrlClass_exec         evb/src/nnCntrlClass.c:152-272
+ *   nnsp_b200_ingest_audadc ......... audio_frame_callback      evb/src/main_nnsp.cc:58-65 (mask + glitch fix)
  *   nnsp_b200_feature_stages ........ stftModule_analyze/spec2pspec/melSpecProc/log10_vec
  *                                     ns-nnsp/src/spectrogram_module.c:33-77, melSpecProc.c:6-27,
  *                                     fixlog10.c:53-61 (debug tap of every intermediate)
@@ -191,6 +192,15 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c);
  * Any output pointer may be NULL. */
 int nnsp_b200_feature_stages(int device, const int16_t *windows, int n, int32_t *fft_in,
                              int32_t *spec, int32_t *pspec, int32_t *mel, int32_t *logmel);
+
+/* ------------------------------------------------------------------------------------ */
+/* Ingest: the application's PCM conditioning in front of the path                      */
+/* ------------------------------------------------------------------------------------ */
+/* evb/src/main_nnsp.cc:58-65 (audio_frame_callback): raw AUDADC words -> int16 PCM, `raw & 0x0000FFF0`, and
+ * sample 3 of each 160-sample frame := (sample 2 + sample 4) >> 1. raw_dev: n_frames*160 uint32 (device),
+ * pcm_dev: n_frames*160 int16 (device), both 16-byte aligned; frames are consecutive in both, so any
+ * [stream][frame] arrangement works. Asynchronous on `stream` (a handle's stream or NULL). */
+int nnsp_b200_ingest_audadc(int device, const uint32_t *raw_dev, int16_t *pcm_dev, long long n_frames, void *stream);
 
 /* Constant tables the engine generates at load time (host copies; see nnsp_tables.c).
  * name: "stft_win" int16[480], "fft_tw" int32[256], "rfft_tw" int32[256], "bitrev" int16[256],

@@ -322,6 +322,18 @@ def feature_stages(windows, device=0):
     return out
 
 
+def ingest_audadc(raw, device=0):
+    """raw: uint32 [..., n*160] AUDADC words -> conditioned int16 PCM of the same shape (main_nnsp.cc:58-65), on the GPU."""
+    raw = np.ascontiguousarray(raw, np.uint32)
+    assert raw.size % FRAME == 0
+    d_raw = DeviceArray.from_host(raw, device)
+    d_pcm = DeviceArray(raw.shape, np.int16, device, zero=False)
+    check(lib().nnsp_b200_ingest_audadc(device, d_raw.ptr, d_pcm.ptr, raw.size // FRAME, None), "ingest_audadc")
+    out = d_pcm.to_host()
+    d_raw.free(); d_pcm.free()
+    return out
+
+
 def table(name):
     p, eb = C.c_void_p(), C.c_int()
     n = lib().nnsp_b200_table(name.encode(), C.byref(p), C.byref(eb))

@@ -447,6 +447,25 @@ __global__ void reset_kernel(const DevModel *__restrict__ M, StreamState st, int
     for (int i = threadIdx.x; i < hist_words; i += blockDim.x) h[i] = 0;                  /* spectrogram_module.c:25-31 */
 }
 
+/* The application's PCM conditioning in front of the path (evb/src/main_nnsp.cc:58-65): the AUDADC delivers one
+ * 32-bit word per sample, the 12-bit sample sits in bits 4..15 (`& 0x0000FFF0`, kept as int16), and sample 3 of
+ * every 160-sample frame is replaced by the mean of its neighbours (sample-glitch workaround, :61-64).
+ * One thread converts 8 samples (two 128-bit loads, one 128-bit store); frames are 20 such groups, so the
+ * glitch fix (samples 2, 3, 4) is local to the thread that owns group 0 of a frame. HBM-bound: 6 B per sample. */
+__global__ void __launch_bounds__(256) ingest_audadc_kernel(const uint4 *__restrict__ raw, uint4 *__restrict__ pcm, long long n_groups)
+{
+    for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_groups; gidx += (long long)gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(raw + 2 * gidx), b = __ldg(raw + 2 * gidx + 1);
+        uint32_t s0 = a.x & 0xfff0u, s1 = a.y & 0xfff0u, s2 = a.z & 0xfff0u, s3 = a.w & 0xfff0u;
+        const uint32_t s4 = b.x & 0xfff0u, s5 = b.y & 0xfff0u, s6 = b.z & 0xfff0u, s7 = b.w & 0xfff0u;
+        if (gidx % (NNSP_B200_FRAME / 8) == 0)
+            s3 = (uint32_t)(((int32_t)(int16_t)s2 + (int32_t)(int16_t)s4) >> 1) & 0xffffu;
+        uint4 o;
+        o.x = s0 | (s1 << 16); o.y = s2 | (s3 << 16); o.z = s4 | (s5 << 16); o.w = s6 | (s7 << 16);
+        pcm[gidx] = o;
+    }
+}
+
 /* integer-pipe peaks: 8 independent register chains per thread, 16 operations per chain-iteration
  *   mode 0: IMAD (32-bit multiply-add)          mode 1: IMAD + independent ALU ops (add / shift / xor), 1:1
  *   mode 2: IMAD.WIDE (32x32 -> 64 accumulate)  mode 3: IDP.2A (two int16 x int8 MACs per instruction) */
@@ -873,6 +892,24 @@ int nnsp_b200_feature_stages(int device, const int16_t *windows, int n, int32_t 
     if (logmel) NNSP_CUDA(cudaMemcpy(logmel, d_lm, (size_t)n * 40 * 4, cudaMemcpyDeviceToHost));
     cudaFree(dw);
     cudaFree(dbuf);
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_ingest_audadc(int device, const uint32_t *raw_dev, int16_t *pcm_dev, long long n_frames, void *stream)
+{
+    if (!raw_dev || !pcm_dev || n_frames < 0 || ((uintptr_t)raw_dev & 15) || ((uintptr_t)pcm_dev & 15)) {
+        nnsp_set_error("ingest: null or not 16-byte aligned buffers");
+        return NNSP_B200_ERR_ARG;
+    }
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (n_frames == 0) return NNSP_B200_OK;
+    const long long groups = n_frames * (NNSP_B200_FRAME / 8);
+    long long blocks = (groups + 255) / 256;
+    const long long cap = (long long)sm_count(device) * 8;
+    if (blocks > cap) blocks = cap;
+    ingest_audadc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4 *)raw_dev, (uint4 *)pcm_dev, groups);
+    NNSP_LAUNCH_CHECK();
     return NNSP_B200_OK;
 }
 

@@ -717,3 +717,16 @@ double nnsp_oracle_cascade_batch_run(const nnsp_b200_model *const models[3], con
     j.n_frames = n_frames; j.cres = results;
     return run_jobs(&j, n_streams, n_threads, job_cascade);
 }
+
+/* ---- ingest (evb/src/main_nnsp.cc:58-65, audio_frame_callback) --------------------------------------- */
+void nnsp_oracle_ingest_audadc(const uint32_t *raw, int16_t *pcm, long long n_frames)
+{
+    for (long long f = 0; f < n_frames; f++) {
+        const uint32_t *r = raw + f * 160;
+        int16_t *o = pcm + f * 160;
+        for (int i = 0; i < 160; i++) {
+            o[i] = (int16_t)(r[i] & 0x0000FFF0);                 /* :59 */
+            if (i == 4) o[3] = (int16_t)((o[2] + o[4]) >> 1);       /* :61-64 */
+        }
+    }
+}

@@ -41,6 +41,9 @@ int nnsp_oracle_nnsp_run(const nnsp_b200_model *m, nnsp_oracle_stream *s, int do
 int nnsp_oracle_net_eval(const nnsp_b200_model *m, const int16_t *input, int16_t *h_inout,
                          int32_t *c_inout, int16_t *act, int32_t *logits);
 
+/* evb/src/main_nnsp.cc:58-65: raw AUDADC words -> conditioned int16 PCM, frame by frame */
+void nnsp_oracle_ingest_audadc(const uint32_t *raw, int16_t *pcm, long long n_frames);
+
 void nnsp_oracle_default_params(nnsp_b200_cascade_params *p);
 nnsp_oracle_cascade *nnsp_oracle_cascade_new(void);
 void nnsp_oracle_cascade_free(nnsp_oracle_cascade *c);

@@ -81,6 +81,7 @@ class Oracle:
         L.nnsp_oracle_cascade_batch_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                                     C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
         L.nnsp_oracle_default_params.argtypes = [C.c_void_p]
+        L.nnsp_oracle_ingest_audadc.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
         self._models = {}
 
     # -- models ---------------------------------------------------------------------------
@@ -117,6 +118,12 @@ class Oracle:
                    pspec=np.zeros(257, np.int32), mel=np.zeros(40, np.int32), logmel=np.zeros(40, np.int32))
         self.lib.nnsp_oracle_feature_stages(_p(win480), _p(out["fft_in"]), _p(out["spec"]),
                                             _p(out["pspec"]), _p(out["mel"]), _p(out["logmel"]))
+        return out
+
+    def ingest_audadc(self, raw):
+        raw = np.ascontiguousarray(raw, np.uint32)
+        out = np.zeros(raw.shape, np.int16)
+        self.lib.nnsp_oracle_ingest_audadc(_p(raw), _p(out), raw.size // 160)
         return out
 
     # -- one stream ---------------------------------------------------------------------------

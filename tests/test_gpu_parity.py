@@ -156,3 +156,18 @@ def test_network_paths_share_one_state(nb, oracle):
         r, _ = oracle.nnsp_run(m_or, pcm[s], taps=False)
         assert (r == got[s]).all(), "stream %d" % s
     b.close()
+
+
+def test_ingest_conditioning_matches_the_application(nb, oracle):
+    """evb/src/main_nnsp.cc:58-65: `raw & 0xFFF0` as int16 and the sample-3 glitch interpolation of every frame."""
+    rng = np.random.default_rng(7)
+    raw = rng.integers(0, 2**32, (37, 9 * 160), dtype=np.uint64).astype(np.uint32)
+    raw[0, :160] = 0xFFFFFFFF
+    raw[1, 2] = 0x00007FF0; raw[1, 4] = 0x00007FF0          # (32752 + 32752) >> 1 needs more than 16 bits
+    raw[2, 2] = 0x00008000; raw[2, 4] = 0x00008000          # two negative neighbours
+    got = nb.ingest_audadc(raw)
+    want = oracle.ingest_audadc(raw)
+    assert (got == want).all()
+    ref = (raw & 0xFFF0).astype(np.uint16).view(np.int16).reshape(37, 9, 160).copy()
+    ref[:, :, 3] = (ref[:, :, 2].astype(np.int32) + ref[:, :, 4]) >> 1
+    assert (want.reshape(37, 9, 160) == ref).all()
