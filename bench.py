@@ -37,6 +37,18 @@ ALGO_INTOPS_PER_FRAME_FEATURE = 17700            # SURVEY.md section 8(d), featu
 AUDIO_S_PER_FRAME = FRAME / 16000.0
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on the bench workload, from the
+    committed ncu --set full capture (profiles/traffic.json); None when no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)[kernel]
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -280,15 +292,18 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "feat_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": measured_traffic("feat_kernel"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STREAM_FRAME * frames_per_launch,
                          "launch_ms": feat_ms,
-                         "note": "the path is integer-issue bound, not HBM bound (SURVEY.md 8d); see int_alu"},
+                         "note": "achieved = SURVEY.md 8(d) whole-path algorithmic bytes (2608 B per stream-frame, VAD) / feat_kernel "
+                                 "launch time; the kernel itself moves 154.8 MB per launch (traffic, = its own 320 B PCM in + 80 B feature "
+                                 "row out per frame, no re-reads). The path is integer-issue bound, not HBM bound: see int_alu"},
             "int_alu": {"kernel": "feat_kernel", "achieved_gops": int_ach, "peak_gops_imad": imad,
                         "peak_gops_mixed": mixed, "peak_gops_imad_wide": ipk["imad_wide"], "peak_gops_idp2a": ipk["idp2a"], "frac_of_mixed_peak": int_ach / mixed if mixed else None,
                         "algorithmic_int_ops_per_frame": ALGO_INTOPS_PER_FRAME_FEATURE,
                         "peak_source": "self-measured nnsp_b200_int_peak (register-resident IMAD / IMAD+ALU chains)"},
-            "kernel_ms": {"feat_kernel": feat_ms, "nn_kernel": nn_ms},
+            "kernel_ms": {"feat_kernel": feat_ms, "network_kernels": nn_ms,
+                          "network_path": "scan-split: seg_kernel<feat> + scan_kernel + seg_kernel<planes> + post_kernel + ctx_kernel"},
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
