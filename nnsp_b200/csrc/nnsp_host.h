@@ -82,6 +82,26 @@ int launch_nn_mma(const MmaDeviceModel &mm, const NNLaunch &a, int device, cudaS
 /* scan-split network path, nnsp_split.cu: fc runs for all (stream, inference) rows at once, the LSTM as a scan.
  * feat16: [S][T][40] standardised rows written by feat_kernel. first / n_inf: first inference frame (0 or 1) and number of inferences of this call (stride 2). planes0/1:
  * two buffers of split_plane_bytes(); dec: [S rounded up to 16][n_inf] int32. l.s0 must be a multiple of 16. */
+/* one model over one selection of streams (the building block of launch_nn_split and of the cascade) */
+struct SplitGroup {
+    const DevTables *tables = nullptr;
+    const int *list = nullptr, *count = nullptr, *tile_off = nullptr;   /* device-side selection, or ... */
+    int s0 = 0, ns = 0;                                                 /* ... the range s0 .. s0+ns-1   */
+    int tile0 = 0;                   /* first plane tile of the range / of the caller's plane region     */
+    int max_streams = 0;             /* upper bound of the selection's size (sizes the grids)             */
+    long long tile_bytes = 0;        /* plane bytes reserved per tile (0: n_inf * 32 * pa)               */
+    int T = 0, first = 0, n_inf = 0;
+    int mode = 1;                    /* 1: feat16 rows, 2: log-mel rows + look-back                       */
+    const int16_t *feat16 = nullptr;
+    const int32_t *logmel = nullptr, *lmhist = nullptr; int dmax = 0, dback = 0;
+    const int16_t *ctx = nullptr;    /* [S][240] */
+    int16_t *h = nullptr; int32_t *c = nullptr; int h_stride = 0;       /* LSTM state arrays [S][h_stride] */
+    uint8_t *planes0 = nullptr, *planes1 = nullptr;
+    int32_t *dec = nullptr; int dec_stride = 0;
+    int16_t thresh_prob = 0;
+    nnsp_b200_taps taps{};
+};
+int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int device, cudaStream_t st);
 int split_supported(const MmaDeviceModel &mm);
 size_t split_plane_bytes(const MmaDeviceModel &mm, int n_streams, int n_inf);
 int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *feat16, int first, int n_inf,

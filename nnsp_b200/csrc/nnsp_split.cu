@@ -43,6 +43,7 @@ constexpr int SEG_KC = 16;                          /* inferences per work item 
 constexpr int SEG_FROWS = 2 * SEG_KC + 4;           /* feature rows covering 16 windows of 6, stride 2   */
 constexpr int SEG_PC = SEG_FROWS * 40 + 16;         /* plane pitch: 364 words = 12 mod 32, conflict-free */
 constexpr int SCAN_NST = 4;                         /* depth of the input ring of the scan               */
+constexpr int SPLIT_MAX_DYN_SMEM = 227 * 1024 - 256;   /* the kernels also hold 64 B of static shared memory */
 constexpr int LUT2_N = 160;                         /* reachable segments of coeffs_tanh (activation.c:5) */
 
 static_assert((SEG_PC % 16) == 0 && ((SEG_PC / 4) % 8) == 4, "feature plane pitch");
@@ -130,6 +131,20 @@ __device__ __forceinline__ void apply_s2i(PostRegs &r, int dec, int th_count)
 /* ======================================================================================================== */
 /* seg_kernel: a run of fc layers [l0, l1) for every (16-stream tile, inference) row block                   */
 /* ======================================================================================================== */
+/* Which streams a launch works on: a contiguous range (batched NNSPClass: s0 .. s0+ns-1) or a device-side list
+ * (cascade: the streams whose live instance runs this model with this inference phase; list, its length and its
+ * first plane tile are produced on the device by the classify kernels, so no host round trip sizes the launch). */
+struct StreamSel {
+    const int *list;
+    const int *count;
+    const int *tile_off;
+    int s0, ns;
+    int tile0;                      /* plane tile of s0 (range) / first tile of the slice's plane region (list) */
+};
+__device__ __forceinline__ int sel_count(const StreamSel &q) { return q.list ? *q.count : q.ns; }
+__device__ __forceinline__ size_t sel_tile_base(const StreamSel &q) { return (size_t)q.tile0 + (q.list ? (size_t)*q.tile_off : 0); }
+__device__ __forceinline__ int sel_sid(const StreamSel &q, int tile, int row) { return q.list ? q.list[16 * tile + row] : q.s0 + 16 * tile + row; }
+
 struct SegArgs {
     const MmaModel *model;
     const uint2 *frag;              /* fragment image of the whole model */
@@ -138,12 +153,18 @@ struct SegArgs {
     int l0, l1;
     int w_base, w_bytes;            /* fragments of layers [l0, l1): uint2 offset in the image, byte count */
     int off_bias, off_lut, off_w, off_fp, off_wb, off_log, nbuf;   /* shared-memory layout (seg_layout) */
-    int s0, ns, T, first, n_inf, nchunks, nitems;
-    const int16_t *feat16;          /* [S][T][40] standardised rows of this call (FROM_FEAT) */
-    const int16_t *ctx;             /* [S][240] context before the call          (FROM_FEAT) */
-    const uint8_t *in_planes;       /* [tile][n_inf][2][16][pa]                  (!FROM_FEAT) */
+    StreamSel sel;
+    int T, first, n_inf, nchunks;
+    long long tile_bytes;           /* bytes of one tile's plane region (>= n_inf * 32 * pa) */
+    int dec_stride;                 /* decision records per stream */
+    const int16_t *feat16;          /* [S][T][40] standardised rows of this call (MODE 1) */
+    const int32_t *logmel;          /* [S][T][40] log-mel rows of this call      (MODE 2) */
+    const int32_t *lmhist;          /* [S][dmax][40] log-mel rows before the call (MODE 2) */
+    int dmax, dback;                /* rows in lmhist; look-back of this model: frame t reads row t - dback (MODE 2) */
+    const int16_t *ctx;             /* [S][240] context before the call          (MODE 1, 2) */
+    const uint8_t *in_planes;       /* [tile][n_inf][2][16][pa]                  (MODE 0) */
     uint8_t *out_planes;            /* same layout, when l1 < numlayers */
-    int32_t *dec;                   /* [S][n_inf], when l1 == numlayers */
+    int32_t *dec;                   /* [S][dec_stride], when l1 == numlayers */
     int16_t *tap_act;               /* [S][T][act_stride] or null */
     int32_t *tap_logits;            /* [S][T][n_out] or null */
     int ao0;                        /* offset of layer l0's output inside an act row */
@@ -167,10 +188,14 @@ __device__ __forceinline__ void fc_tiles(int kt, const uint2 *wf, const uint8_t 
     }
 }
 
-template <bool FROM_FEAT>
+/* MODE 0: input = activation planes; 1: input = feat16 rows (batched NNSPClass); 2: input = log-mel rows with
+ * look-back, standardised while staging (cascade) */
+template <int MODE>
 __global__ void __launch_bounds__(SEG_THREADS, 2)
 seg_kernel(SegArgs a)
 {
+    constexpr bool FROM_FEAT = MODE != 0;
+    __shared__ int sids[16];
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     MmaModel &M = *reinterpret_cast<MmaModel *>(smem + 16);
@@ -219,46 +244,102 @@ seg_kernel(SegArgs a)
                          : "=r"(done) : "r"(smem_u32(bar)) : "memory");
     }
     const int T = a.T;
+    const int nsel = sel_count(a.sel);
+    const int nitems = ((nsel + 15) >> 4) * a.nchunks;
+    const size_t tile_base = sel_tile_base(a.sel);
     __syncthreads();
 
-    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int chunk = item % a.nchunks, tile = item / a.nchunks;
         const int k0 = chunk * SEG_KC;
-        const int sb = a.s0 + 16 * tile;
-        const int nvalid = min(16, a.s0 + a.ns - sb);
-        const size_t tile_abs = (size_t)(a.s0 >> 4) + tile;
+        const int nvalid = min(16, nsel - 16 * tile);
+        const size_t tile_abs = tile_base + tile;
         if (FROM_FEAT) {
             __syncthreads();                                         /* planes of the previous item are free */
+            if (tid < 16) sids[tid] = (tid < nvalid) ? sel_sid(a.sel, tile, tid) : 0;
+            __syncthreads();
             /* standardised rows of frames f_first .. f_first+35 as byte planes; frames before the call are the
              * carried context rows 1..5 (feature_module.c:54-57); loads of a batch are issued before its stores */
             const int f_first = a.first + 2 * k0 - 5;
-            constexpr int NQ = 16 * SEG_FROWS * 5;                   /* 16-byte pieces: 8 features each */
-            for (int e0 = 0; e0 < NQ; e0 += 4 * SEG_THREADS) {
-                uint4 v[4];
+            if (MODE == 1) {
+                constexpr int NQ = 16 * SEG_FROWS * 5;               /* 16-byte pieces: 8 features each */
+                for (int e0 = 0; e0 < NQ; e0 += 4 * SEG_THREADS) {
+                    uint4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int e = e0 + u * SEG_THREADS + tid;
-                    v[u] = make_uint4(0, 0, 0, 0);
-                    if (e < NQ) {
-                        const int r = e / (SEG_FROWS * 5), rem = e - r * (SEG_FROWS * 5), j = rem / 5, x = rem - j * 5;
-                        const int f = f_first + j;
-                        if (r < nvalid) {
-                            const long long s = sb + r;
-                            if (f < 0) v[u] = *reinterpret_cast<const uint4 *>(a.ctx + s * 240 + (6 + f) * 40 + x * 8);
-                            else if (f < T) v[u] = __ldg(reinterpret_cast<const uint4 *>(a.feat16 + (s * T + f) * NNSP_B200_NMEL + x * 8));
+                    for (int u = 0; u < 4; u++) {
+                        const int e = e0 + u * SEG_THREADS + tid;
+                        v[u] = make_uint4(0, 0, 0, 0);
+                        if (e < NQ) {
+                            const int r = e / (SEG_FROWS * 5), rem = e - r * (SEG_FROWS * 5), j = rem / 5, x = rem - j * 5;
+                            const int f = f_first + j;
+                            if (r < nvalid) {
+                                const long long s = sids[r];
+                                if (f < 0) v[u] = *reinterpret_cast<const uint4 *>(a.ctx + s * 240 + (6 + f) * 40 + x * 8);
+                                else if (f < T) v[u] = __ldg(reinterpret_cast<const uint4 *>(a.feat16 + (s * T + f) * NNSP_B200_NMEL + x * 8));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = e0 + u * SEG_THREADS + tid;
+                        if (e < NQ) {
+                            const int r = e / (SEG_FROWS * 5), rem = e - r * (SEG_FROWS * 5), j = rem / 5, x = rem - j * 5;
+                            uint2 hi, lo;
+                            lo.x = __byte_perm(v[u].x, v[u].y, 0x6420); hi.x = __byte_perm(v[u].x, v[u].y, 0x7531);
+                            lo.y = __byte_perm(v[u].z, v[u].w, 0x6420); hi.y = __byte_perm(v[u].z, v[u].w, 0x7531);
+                            *reinterpret_cast<uint2 *>(fplanes + r * SEG_PC + j * 40 + x * 8) = hi;
+                            *reinterpret_cast<uint2 *>(fplanes + (16 + r) * SEG_PC + j * 40 + x * 8) = lo;
                         }
                     }
                 }
+            } else {
+                /* cascade: frame f of the instance is raw frame f - dback (PcmBufClass_getData look-back,
+                 * PcmBufClass.c:38-85): its log-mel row comes from this call or from the carried history and is
+                 * standardised with this model's statistics (feature_module.c:67-73) */
+                constexpr int NQ = 16 * SEG_FROWS * 10;              /* pieces of 4 features */
+                for (int e0 = 0; e0 < NQ; e0 += 4 * SEG_THREADS) {
+                    int4 v[4];
+                    int from_ctx[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int e = e0 + u * SEG_THREADS + tid;
-                    if (e < NQ) {
-                        const int r = e / (SEG_FROWS * 5), rem = e - r * (SEG_FROWS * 5), j = rem / 5, x = rem - j * 5;
-                        uint2 hi, lo;
-                        lo.x = __byte_perm(v[u].x, v[u].y, 0x6420); hi.x = __byte_perm(v[u].x, v[u].y, 0x7531);
-                        lo.y = __byte_perm(v[u].z, v[u].w, 0x6420); hi.y = __byte_perm(v[u].z, v[u].w, 0x7531);
-                        *reinterpret_cast<uint2 *>(fplanes + r * SEG_PC + j * 40 + x * 8) = hi;
-                        *reinterpret_cast<uint2 *>(fplanes + (16 + r) * SEG_PC + j * 40 + x * 8) = lo;
+                    for (int u = 0; u < 4; u++) {
+                        const int e = e0 + u * SEG_THREADS + tid;
+                        v[u] = make_int4(0, 0, 0, 0);
+                        from_ctx[u] = 1;
+                        if (e < NQ) {
+                            const int r = e / (SEG_FROWS * 10), rem = e - r * (SEG_FROWS * 10), j = rem / 10, x = rem - j * 10;
+                            const int f = f_first + j;
+                            if (r < nvalid) {
+                                const long long s = sids[r];
+                                if (f < 0) {
+                                    const uint2 c = *reinterpret_cast<const uint2 *>(a.ctx + s * 240 + (6 + f) * 40 + x * 4);
+                                    v[u] = make_int4((int16_t)(c.x & 0xffff), (int32_t)c.x >> 16, (int16_t)(c.y & 0xffff), (int32_t)c.y >> 16);
+                                } else if (f < T) {
+                                    const int fr = f - a.dback;
+                                    const int32_t *row = (fr >= 0) ? a.logmel + (s * T + fr) * NNSP_B200_NMEL
+                                                                   : a.lmhist + (s * a.dmax + a.dmax + fr) * NNSP_B200_NMEL;
+                                    v[u] = __ldg(reinterpret_cast<const int4 *>(row + x * 4));
+                                    from_ctx[u] = 0;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = e0 + u * SEG_THREADS + tid;
+                        if (e < NQ) {
+                            const int r = e / (SEG_FROWS * 10), rem = e - r * (SEG_FROWS * 10), j = rem / 10, x = rem - j * 10;
+                            int w[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+                            if (!from_ctx[u]) {
+#pragma unroll
+                                for (int c = 0; c < 4; c++) w[c] = standardise(w[c], M.mean[4 * x + c], M.stdR[4 * x + c], M.feat_rshift);
+                            }
+                            const uint32_t hi = ((uint32_t)(w[0] >> 8) & 0xff) | (((uint32_t)(w[1] >> 8) & 0xff) << 8) |
+                                                (((uint32_t)(w[2] >> 8) & 0xff) << 16) | (((uint32_t)(w[3] >> 8) & 0xff) << 24);
+                            const uint32_t lo = ((uint32_t)w[0] & 0xff) | (((uint32_t)w[1] & 0xff) << 8) |
+                                                (((uint32_t)w[2] & 0xff) << 16) | (((uint32_t)w[3] & 0xff) << 24);
+                            *reinterpret_cast<uint32_t *>(fplanes + r * SEG_PC + j * 40 + x * 4) = hi;
+                            *reinterpret_cast<uint32_t *>(fplanes + (16 + r) * SEG_PC + j * 40 + x * 4) = lo;
+                        }
                     }
                 }
             }
@@ -274,7 +355,7 @@ seg_kernel(SegArgs a)
             if (FROM_FEAT) {
                 in_hi = fplanes + 80 * i; in_lo = in_hi + 16 * SEG_PC; in_pitch = SEG_PC;
             } else {
-                const uint4 *src = reinterpret_cast<const uint4 *>(a.in_planes + (tile_abs * a.n_inf + k) * (size_t)XB);
+                const uint4 *src = reinterpret_cast<const uint4 *>(a.in_planes + tile_abs * (size_t)a.tile_bytes + (size_t)k * XB);
                 uint4 *dst = reinterpret_cast<uint4 *>(wb + XB);
                 for (int x = lane; x < XB / 16; x += 32) dst[x] = __ldg(src + x);
                 __syncwarp();
@@ -331,7 +412,7 @@ seg_kernel(SegArgs a)
                                     for (int e = 0; e < 4; e++) {
                                         const int row = g + 8 * (e >> 1), n = nb + (e & 1);
                                         if (row < nvalid && n < L.rows)
-                                            a.tap_act[((long long)(sb + row) * T + t) * M.act_stride + ao + n] = (int16_t)o[e];
+                                            a.tap_act[((long long)sel_sid(a.sel, tile, row) * T + t) * M.act_stride + ao + n] = (int16_t)o[e];
                                     }
                                 }
                             }
@@ -347,7 +428,7 @@ seg_kernel(SegArgs a)
             }
             if (a.l1 < M.numlayers) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(wb + (pp ^ 1) * XB);
-                uint4 *dst = reinterpret_cast<uint4 *>(a.out_planes + (tile_abs * a.n_inf + k) * (size_t)XB);
+                uint4 *dst = reinterpret_cast<uint4 *>(a.out_planes + tile_abs * (size_t)a.tile_bytes + (size_t)k * XB);
                 for (int x = lane; x < XB / 16; x += 32) dst[x] = src[x];
             } else {
                 if (lane < nvalid) {
@@ -357,12 +438,12 @@ seg_kernel(SegArgs a)
                         d = argmax_last_wins(lg, 7) | (argmax_last_wins(lg + 7, 17) << 8) | (argmax_last_wins(lg + 24, 17) << 16);
                     else
                         d = binary_flag(lg[0], lg[1], a.thresh_prob);
-                    a.dec[(size_t)(sb + lane) * a.n_inf + k] = d;
+                    a.dec[(size_t)sel_sid(a.sel, tile, lane) * a.dec_stride + k] = d;
                 }
                 if (a.tap_logits)
                     for (int x = lane; x < 16 * M.n_out; x += 32) {
                         const int row = x / M.n_out, n = x - row * M.n_out;
-                        if (row < nvalid) a.tap_logits[((long long)(sb + row) * T + t) * M.n_out + n] = wlog[row * M.no + n];
+                        if (row < nvalid) a.tap_logits[((long long)sel_sid(a.sel, tile, row) * T + t) * M.n_out + n] = wlog[row * M.no + n];
                     }
             }
             __syncwarp();
@@ -379,7 +460,9 @@ struct ScanArgs {
     const DevTables *tables;
     int H, kt, ktr, nt, rs, w_off, bias_off, pa;
     int ho, hs, ao, act_stride, tap_out;   /* state offset / stride, act-row offset, 1: layer output is tapped */
-    int s0, ns, T, first, n_inf;
+    StreamSel sel;
+    int T, first, n_inf;
+    long long tile_bytes;           /* bytes of one tile's plane region */
     const uint8_t *xin;             /* [tile][n_inf][2][16][pa] */
     uint8_t *hout;                  /* same layout */
     int16_t *h;                     /* [S][hs] */
@@ -417,11 +500,15 @@ scan_kernel(ScanArgs a)
     uint8_t *xs = smem + 64 + WB + LUT2_N * 8;
     uint8_t *hb = xs + SCAN_NST * XB;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-    const int tile = blockIdx.x, sb = a.s0 + 16 * tile;
-    const int nvalid = min(16, a.s0 + a.ns - sb);
-    const size_t tile_abs = (size_t)(a.s0 >> 4) + tile;
-    const uint8_t *xg = a.xin + tile_abs * a.n_inf * (size_t)XB;
-    uint8_t *hg = a.hout + tile_abs * a.n_inf * (size_t)XB;
+    __shared__ int sids[16];
+    const int tile = blockIdx.x;
+    const int nsel = sel_count(a.sel);
+    if (16 * tile >= nsel) return;                                   /* (list launches are sized for the worst case) */
+    const int nvalid = min(16, nsel - 16 * tile);
+    const size_t tile_abs = sel_tile_base(a.sel) + tile;
+    const uint8_t *xg = a.xin + tile_abs * (size_t)a.tile_bytes;
+    uint8_t *hg = a.hout + tile_abs * (size_t)a.tile_bytes;
+    if (threadIdx.x < 16) sids[threadIdx.x] = ((int)threadIdx.x < nvalid) ? sel_sid(a.sel, tile, threadIdx.x) : 0;
     const int H = a.H, pa = a.pa, HS = a.hs, T = a.T, n_inf = a.n_inf, rs = a.rs;
 
     if (tid == 0) {
@@ -435,7 +522,7 @@ scan_kernel(ScanArgs a)
     uint8_t *h2 = hb + 2 * XB;                                       /* h before the first inference */
     for (int idx = tid; idx < 16 * H; idx += nthr) {
         const int r = idx / H, u = idx - r * H;
-        const int v = (r < nvalid) ? (int)a.h[(long long)(sb + r) * HS + a.ho + u] : 0;
+        const int v = (r < nvalid) ? (int)a.h[(long long)sids[r] * HS + a.ho + u] : 0;
         h2[r * pa + u] = (uint8_t)(v >> 8);
         h2[(16 + r) * pa + u] = (uint8_t)v;
     }
@@ -460,7 +547,7 @@ scan_kernel(ScanArgs a)
 #pragma unroll
     for (int e = 0; e < 4; e++) {
         const int row = g + 8 * (e >> 1), u = u0 + (e & 1);
-        cst[e] = (row < nvalid && u < H) ? a.c[(long long)(sb + row) * HS + a.ho + u] : 0;
+        cst[e] = (row < nvalid && u < H) ? a.c[(long long)sids[row] * HS + a.ho + u] : 0;
     }
     __syncthreads();
     mbar_wait(bars + SCAN_NST, 0);
@@ -492,13 +579,13 @@ scan_kernel(ScanArgs a)
         if (a.tap_h)
             for (int idx = tid; idx < nvalid * H; idx += nthr) {
                 const int r = idx / H, u = idx - r * H;
-                a.tap_h[((long long)(sb + r) * T + t) * HS + a.ho + u] = (int16_t)(((int)(int8_t)hp[r * pa + u] << 8) | hp[(16 + r) * pa + u]);
+                a.tap_h[((long long)sids[r] * T + t) * HS + a.ho + u] = (int16_t)(((int)(int8_t)hp[r * pa + u] << 8) | hp[(16 + r) * pa + u]);
             }
         if (a.tap_c && active) {
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int row = g + 8 * (e >> 1), u = u0 + (e & 1);
-                if (row < nvalid && u < H) a.tap_c[((long long)(sb + row) * T + t) * HS + a.ho + u] = cst[e];
+                if (row < nvalid && u < H) a.tap_c[((long long)sids[row] * T + t) * HS + a.ho + u] = cst[e];
             }
         }
     };
@@ -541,7 +628,7 @@ scan_kernel(ScanArgs a)
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int row = g + 8 * (e >> 1), u = u0 + (e & 1);
-                    if (row < nvalid && u < H) a.tap_act[((long long)(sb + row) * T + t) * a.act_stride + a.ao + u] = (int16_t)y[e];
+                    if (row < nvalid && u < H) a.tap_act[((long long)sids[row] * T + t) * a.act_stride + a.ao + u] = (int16_t)y[e];
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  /* h slice -> visible to the bulk store */
@@ -573,13 +660,13 @@ scan_kernel(ScanArgs a)
     const uint8_t *hf = hb + ((n_inf + 2) % 3) * XB;
     for (int idx = tid; idx < nvalid * H; idx += nthr) {
         const int r = idx / H, u = idx - r * H;
-        a.h[(long long)(sb + r) * HS + a.ho + u] = (int16_t)(((int)(int8_t)hf[r * pa + u] << 8) | hf[(16 + r) * pa + u]);
+        a.h[(long long)sids[r] * HS + a.ho + u] = (int16_t)(((int)(int8_t)hf[r * pa + u] << 8) | hf[(16 + r) * pa + u]);
     }
     if (active) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int row = g + 8 * (e >> 1), u = u0 + (e & 1);
-            if (row < nvalid && u < H) a.c[(long long)(sb + row) * HS + a.ho + u] = cst[e];
+            if (row < nvalid && u < H) a.c[(long long)sids[row] * HS + a.ho + u] = cst[e];
         }
     }
 }
@@ -733,13 +820,13 @@ int split_supported(const MmaDeviceModel &mm)
         const MmaLayer &L = D->layer[i];
         if (!L.fast) return 0;
         if (L.type == LAYER_FC && L.act == ACT_LINEAR && i != D->numlayers - 1) return 0;
-        if (L.type == LAYER_LSTM && (L.nt > 16 || scan_smem(D, L) > 227 * 1024)) return 0;
+        if (L.type == LAYER_LSTM && (L.nt > 16 || scan_smem(D, L) > (size_t)SPLIT_MAX_DYN_SMEM)) return 0;
         if (L.type == LAYER_LSTM && L.wh_off != L.w_off + 4 * L.nt * L.kt * 32) return 0;
     }
     for (int l0 = 0; l0 < D->numlayers;) {                           /* every fc run must fit shared memory */
         int l1 = l0;
         while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
-        if (l1 > l0 && seg_layout(D, l0, l1, l0 == 0).total > 227 * 1024) return 0;
+        if (l1 > l0 && seg_layout(D, l0, l1, l0 == 0).total > (size_t)SPLIT_MAX_DYN_SMEM) return 0;
         l0 = (l1 > l0) ? l1 : l0 + 1;
     }
     return 1;
@@ -755,7 +842,7 @@ static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, c
 {
     static bool attr_done[64] = { false };
     if (!attr_done[device]) {
-        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
         attr_done[device] = true;
     }
     scan_kernel<NW, MINB><<<ntiles, 32 * NW, smem, st>>>(a);
@@ -763,19 +850,85 @@ static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, c
     return NNSP_B200_OK;
 }
 
-int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *feat16, int first, int n_inf,
-                    uint8_t *planes0, uint8_t *planes1, int32_t *dec, int device, cudaStream_t st)
+/* the fc runs and lstm scans of one model over one stream selection (launch_nn_split: a range of a batch;
+ * cascade: a device-side list). mode: 1 = feat16 input, 2 = log-mel input with look-back. Returns through *dec. */
+int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int device, cudaStream_t st)
 {
     const MmaModel *D = mm.h;
     static bool attr_done[64] = { false };
     if (!attr_done[device]) {
-        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
+        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
+        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
         attr_done[device] = true;
     }
+    if (q.n_inf <= 0 || q.max_streams <= 0) return NNSP_B200_OK;
+    StreamSel sel{};
+    sel.list = q.list; sel.count = q.count; sel.tile_off = q.tile_off; sel.s0 = q.s0; sel.ns = q.ns; sel.tile0 = q.tile0;
+    const int ntiles = (q.max_streams + 15) / 16, nchunks = (q.n_inf + SEG_KC - 1) / SEG_KC;
+    const long long tile_bytes = q.tile_bytes ? q.tile_bytes : (long long)q.n_inf * 32 * D->pa;
+    const nnsp_b200_taps &tp = q.taps;
+    uint8_t *cur_in = nullptr, *bufs[2] = { q.planes0, q.planes1 };
+    int which = 0, li = 0, ao = 0, ho = 0, rc;
+    bool from_feat = true;
+    while (li < D->numlayers) {
+        int l1 = li;
+        while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
+        if (l1 > li) {                                           /* a run of fc layers */
+            const SegLayout lay = seg_layout(D, li, l1, from_feat);
+            SegArgs a{};
+            a.model = mm.d; a.frag = (const uint2 *)mm.frag; a.bias32 = mm.bias32; a.tables = q.tables;
+            a.l0 = li; a.l1 = l1; a.w_base = lay.w_base; a.w_bytes = lay.w_bytes;
+            a.off_bias = lay.off_bias; a.off_lut = lay.off_lut; a.off_w = lay.off_w; a.off_fp = lay.off_fp;
+            a.off_wb = lay.off_wb; a.off_log = lay.off_log; a.nbuf = lay.nbuf;
+            a.sel = sel; a.T = q.T; a.first = q.first; a.n_inf = q.n_inf; a.nchunks = nchunks;
+            a.tile_bytes = tile_bytes; a.dec_stride = q.dec_stride;
+            a.feat16 = q.feat16; a.logmel = q.logmel; a.lmhist = q.lmhist; a.dmax = q.dmax; a.dback = q.dback;
+            a.ctx = q.ctx; a.in_planes = cur_in;
+            a.out_planes = (l1 < D->numlayers) ? bufs[which] : nullptr;
+            a.dec = q.dec; a.tap_act = tp.act; a.tap_logits = tp.logits; a.ao0 = ao; a.thresh_prob = q.thresh_prob;
+            int per_sm = (int)((227 * 1024) / (lay.total + 1024));
+            per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);     /* __launch_bounds__(256, 2) */
+            int grid = sm_count(device) * per_sm;
+            if (grid > nchunks * ntiles) grid = nchunks * ntiles;
+            if (!from_feat) seg_kernel<0><<<grid, SEG_THREADS, lay.total, st>>>(a);
+            else if (q.mode == 2) seg_kernel<2><<<grid, SEG_THREADS, lay.total, st>>>(a);
+            else seg_kernel<1><<<grid, SEG_THREADS, lay.total, st>>>(a);
+            NNSP_LAUNCH_CHECK();
+            for (int i = li; i < l1; i++) if (i < D->numlayers - 1) ao += D->layer[i].rows;
+            if (l1 < D->numlayers) { cur_in = bufs[which]; which ^= 1; }
+            from_feat = false;
+            li = l1;
+        }
+        if (li < D->numlayers) {                                 /* an lstm layer */
+            const MmaLayer &L = D->layer[li];
+            ScanArgs a{};
+            a.frag = (const uint2 *)mm.frag; a.bias32 = mm.bias32; a.tables = q.tables;
+            a.H = L.rows; a.kt = L.kt; a.ktr = L.ktr; a.nt = L.nt; a.rs = -L.sh_out; a.w_off = L.w_off; a.bias_off = L.bias_off; a.pa = D->pa;
+            a.ho = ho; a.hs = q.h_stride; a.ao = ao; a.act_stride = D->act_stride; a.tap_out = (li < D->numlayers - 1);
+            a.sel = sel; a.T = q.T; a.first = q.first; a.n_inf = q.n_inf; a.tile_bytes = tile_bytes;
+            a.xin = cur_in; a.hout = bufs[which]; a.h = q.h; a.c = q.c;
+            a.tap_act = tp.act; a.tap_h = tp.hstate; a.tap_c = tp.cstate;
+            const size_t smem = scan_smem(D, L);
+            if (L.nt <= 4) rc = launch_scan<4, 4>(a, ntiles, smem, device, st);
+            else if (L.nt <= 9) rc = launch_scan<9, 2>(a, ntiles, smem, device, st);
+            else rc = launch_scan<16, 1>(a, ntiles, smem, device, st);
+            if (rc) return rc;
+            cur_in = bufs[which]; which ^= 1;
+            ao += L.rows; ho += L.rows;
+            li++;
+        }
+    }
+    return NNSP_B200_OK;
+}
+
+int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *feat16, int first, int n_inf,
+                    uint8_t *planes0, uint8_t *planes1, int32_t *dec, int device, cudaStream_t st)
+{
+    const MmaModel *D = mm.h;
     if (l.ns <= 0 || l.T <= 0) return NNSP_B200_OK;
     if ((l.s0 & 15) != 0) { nnsp_set_error("stream slices of the split path must start at a multiple of 16"); return NNSP_B200_ERR_ARG; }
-    const int T = l.T, ntiles = (l.ns + 15) / 16, nchunks = (n_inf + SEG_KC - 1) / SEG_KC;
+    const int T = l.T;
     const nnsp_b200_taps &tp = l.taps;
     int rc;
     if (tp.feat) {
@@ -788,54 +941,12 @@ int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *
     if (tp.logits) NNSP_CUDA(cudaMemsetAsync(tp.logits + (long long)l.s0 * T * D->n_out, 0, (size_t)l.ns * T * D->n_out * 4, st));
 
     if (n_inf > 0) {
-        uint8_t *cur_in = nullptr, *bufs[2] = { planes0, planes1 };
-        int which = 0, li = 0, ao = 0, ho = 0;
-        bool from_feat = true;
-        while (li < D->numlayers) {
-            int l1 = li;
-            while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
-            if (l1 > li) {                                           /* a run of fc layers */
-                const SegLayout lay = seg_layout(D, li, l1, from_feat);
-                SegArgs a{};
-                a.model = mm.d; a.frag = (const uint2 *)mm.frag; a.bias32 = mm.bias32; a.tables = l.tables;
-                a.l0 = li; a.l1 = l1; a.w_base = lay.w_base; a.w_bytes = lay.w_bytes;
-                a.off_bias = lay.off_bias; a.off_lut = lay.off_lut; a.off_w = lay.off_w; a.off_fp = lay.off_fp;
-                a.off_wb = lay.off_wb; a.off_log = lay.off_log; a.nbuf = lay.nbuf;
-                a.s0 = l.s0; a.ns = l.ns; a.T = T; a.first = first; a.n_inf = n_inf; a.nchunks = nchunks; a.nitems = nchunks * ntiles;
-                a.feat16 = feat16; a.ctx = l.st.ctx; a.in_planes = cur_in;
-                a.out_planes = (l1 < D->numlayers) ? bufs[which] : nullptr;
-                a.dec = dec; a.tap_act = tp.act; a.tap_logits = tp.logits; a.ao0 = ao; a.thresh_prob = l.thresh_prob;
-                int per_sm = (int)((227 * 1024) / (lay.total + 1024));
-                per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);     /* __launch_bounds__(256, 2) */
-                int grid = sm_count(device) * per_sm;
-                if (grid > a.nitems) grid = a.nitems;
-                if (from_feat) seg_kernel<true><<<grid, SEG_THREADS, lay.total, st>>>(a);
-                else seg_kernel<false><<<grid, SEG_THREADS, lay.total, st>>>(a);
-                NNSP_LAUNCH_CHECK();
-                for (int i = li; i < l1; i++) if (i < D->numlayers - 1) ao += D->layer[i].rows;
-                if (l1 < D->numlayers) { cur_in = bufs[which]; which ^= 1; }
-                from_feat = false;
-                li = l1;
-            }
-            if (li < D->numlayers) {                                 /* an lstm layer */
-                const MmaLayer &L = D->layer[li];
-                ScanArgs a{};
-                a.frag = (const uint2 *)mm.frag; a.bias32 = mm.bias32; a.tables = l.tables;
-                a.H = L.rows; a.kt = L.kt; a.ktr = L.ktr; a.nt = L.nt; a.rs = -L.sh_out; a.w_off = L.w_off; a.bias_off = L.bias_off; a.pa = D->pa;
-                a.ho = ho; a.hs = D->h_stride; a.ao = ao; a.act_stride = D->act_stride; a.tap_out = (li < D->numlayers - 1);
-                a.s0 = l.s0; a.ns = l.ns; a.T = T; a.first = first; a.n_inf = n_inf;
-                a.xin = cur_in; a.hout = bufs[which]; a.h = l.st.h; a.c = l.st.c;
-                a.tap_act = tp.act; a.tap_h = tp.hstate; a.tap_c = tp.cstate;
-                const size_t smem = scan_smem(D, L);
-                if (L.nt <= 4) rc = launch_scan<4, 4>(a, ntiles, smem, device, st);
-                else if (L.nt <= 9) rc = launch_scan<9, 2>(a, ntiles, smem, device, st);
-                else rc = launch_scan<16, 1>(a, ntiles, smem, device, st);
-                if (rc) return rc;
-                cur_in = bufs[which]; which ^= 1;
-                ao += L.rows; ho += L.rows;
-                li++;
-            }
-        }
+        SplitGroup q{};
+        q.tables = l.tables; q.s0 = l.s0; q.ns = l.ns; q.tile0 = l.s0 >> 4; q.max_streams = l.ns;
+        q.T = T; q.first = first; q.n_inf = n_inf; q.mode = 1; q.feat16 = feat16; q.ctx = l.st.ctx;
+        q.h = l.st.h; q.c = l.st.c; q.h_stride = D->h_stride; q.planes0 = planes0; q.planes1 = planes1;
+        q.dec = dec; q.dec_stride = n_inf; q.thresh_prob = l.thresh_prob; q.taps = tp;
+        if ((rc = launch_split_layers(mm, q, device, st))) return rc;
     } else if ((tp.hstate || tp.cstate) && D->h_stride > 0) {
         /* a call without any inference (one frame, slides == 0): the state taps repeat the stored state */
         for (int si = 0; si < l.ns; si++) {
