@@ -178,6 +178,10 @@ int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
 int nnsp_b200_cascade_sync(nnsp_b200_cascade *c);
 int nnsp_b200_cascade_last_kernel_ms(nnsp_b200_cascade *c, float ms[3]);
 void *nnsp_b200_cascade_stream(nnsp_b200_cascade *c);
+/* 0 = automatic, 1 = sequential warp-per-stream kernel only, 2 = stage-sorted pass (the scan-split network kernels
+ * over the streams of each (model, phase) group) + replay of the frames after a stage change. Bit-exact either way;
+ * calls that request debug taps always take 1. */
+int nnsp_b200_cascade_set_path(nnsp_b200_cascade *c, int path);
 void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c);
 
 /* ------------------------------------------------------------------------------------ */

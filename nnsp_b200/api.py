@@ -249,6 +249,11 @@ class Cascade:
         self.h = C.c_void_p()
         check(L.nnsp_b200_cascade_create(arr, seq_a, len(seq), C.byref(p), self.S, device, C.byref(self.h)), "cascade_create")
 
+    PATH = {"auto": 0, "sequential": 1, "sorted": 2}
+
+    def set_path(self, path):
+        check(lib().nnsp_b200_cascade_set_path(self.h, self.PATH[path]), "cascade_set_path")
+
     def params_array(self):
         return np.array([getattr(self.params, n) for n, _ in capi.CascadeParams._fields_], np.int16)
 

@@ -40,7 +40,7 @@ nnsp_b200_model_info nnsp_b200_model_free nnsp_b200_batch_create nnsp_b200_batch
 nnsp_b200_batch_exec_host nnsp_b200_batch_sync nnsp_b200_batch_last_kernel_ms nnsp_b200_batch_dims
 nnsp_b200_batch_stream nnsp_b200_batch_set_nn_path nnsp_b200_batch_destroy nnsp_b200_cascade_default_params nnsp_b200_cascade_create
 nnsp_b200_cascade_reset nnsp_b200_cascade_exec nnsp_b200_cascade_exec_host nnsp_b200_cascade_sync
-nnsp_b200_cascade_last_kernel_ms nnsp_b200_cascade_stream nnsp_b200_cascade_destroy nnsp_b200_feature_stages
+nnsp_b200_cascade_last_kernel_ms nnsp_b200_cascade_stream nnsp_b200_cascade_set_path nnsp_b200_cascade_destroy nnsp_b200_feature_stages
 nnsp_b200_table nnsp_b200_ingest_audadc nnsp_b200_device_count nnsp_b200_dev_alloc nnsp_b200_dev_free nnsp_b200_host_alloc_pinned
 nnsp_b200_host_free_pinned nnsp_b200_memcpy_h2d nnsp_b200_memcpy_d2h nnsp_b200_memset nnsp_b200_event_create
 nnsp_b200_event_record nnsp_b200_event_elapsed_ms nnsp_b200_event_destroy nnsp_b200_int_peak""".split()
@@ -93,6 +93,7 @@ def lib():
         L.nnsp_b200_cascade_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
         L.nnsp_b200_cascade_stream.argtypes = [vp]
         L.nnsp_b200_cascade_stream.restype = vp
+        L.nnsp_b200_cascade_set_path.argtypes = [vp, ci]
         L.nnsp_b200_cascade_destroy.argtypes = [vp]
         L.nnsp_b200_cascade_destroy.restype = None
     L.nnsp_b200_feature_stages.argtypes = [ci, vp, ci, vp, vp, vp, vp, vp]

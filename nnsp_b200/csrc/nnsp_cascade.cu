@@ -21,6 +21,7 @@
 
 #include "nnsp_feat.cuh"
 #include "nnsp_host.h"
+#include "nnsp_mma.cuh"
 #include "nnsp_net.cuh"
 #include "nnsp_tma.cuh"
 
@@ -51,6 +52,7 @@ struct CascadeArgs {
     nnsp_b200_cascade_result *results;
     nnsp_b200_taps taps;
     CascadeDev cd;
+    const int *t0;                    /* per stream: first frame this kernel still has to process (null: 0) */
 };
 
 struct CascadeSmem {
@@ -122,6 +124,8 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
 
     for (int si = blockIdx.x * CS_WARPS + warp; si < a.ns; si += gridDim.x * CS_WARPS) {
         const int s = a.s0 + si;
+        const int t_begin = a.t0 ? a.t0[s] : 0;                       /* frames before it were done by the stage-sorted pass */
+        if (t_begin >= a.T) continue;
         for (int i = lane; i < 240; i += 32) ws->ctx[i] = a.st.ctx[(long long)s * 240 + i];
         for (int i = lane; i < HS; i += 32) { ws->h[i] = a.st.h[(long long)s * HS + i]; ws->c[i] = a.st.c[(long long)s * HS + i]; }
         if (lane < SC_N) ws->scal[lane] = a.st.scal[(long long)s * SC_N + lane];
@@ -134,7 +138,7 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
         const int32_t *lm_now = a.logmel + (long long)s * T * NNSP_B200_NMEL;
         const int32_t *lm_old = a.st.lmhist + ((long long)s * cd.dmax + cd.dmax) * NNSP_B200_NMEL;   /* lm_old[r*40], r < 0 */
 
-        for (int t = 0; t < T; t++) {
+        for (int t = t_begin; t < T; t++) {
             const long long ft = (long long)s * T + t;
             const int id = cd.seq[pos];
             const DevModel &M = sm.model[id];
@@ -260,6 +264,198 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
     }
 }
 
+
+/* ======================================================================================================== */
+/* stage-sorted pass: the scan-split network kernels (nnsp_split.cu) over the streams of each (stage, phase)   */
+/* ======================================================================================================== */
+/* Within a call most streams stay in the stage they are in. Streams are therefore sorted by (live model, phase of
+ * the stride-2 gate) on the device, each group runs through the batched scan-split kernels as if nothing changed,
+ * and cascade_post_kernel then walks every stream's frames through the controller (nnCntrlClass.c:172-269). At
+ * the first frame where the controller leaves the instance, that instance is reset -- which is all the reference
+ * keeps of it (plus context row 5) -- the speculative rest is dropped, and the stream's remaining frames are
+ * replayed by cascade_kernel from t0[s]. Streams whose instance is younger than two frames (its STFT buffer
+ * still holds zeros) take the sequential kernel for the whole call. */
+constexpr int CG_GROUPS = 6;                        /* group = id * 2 + first inference frame (0 or 1) */
+constexpr int CPOST_THREADS = 64, CPOST_KCH = 64;
+
+__global__ void cascade_classify_kernel(StreamState st, CascadeDev cd, int s0, int ns, int S, int *list, int *count, int *t0)
+{
+    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= ns) return;
+    const long long s = s0 + si;
+    const int pos = st.casc[s * CS_N + CS_POS], age = st.casc[s * CS_N + CS_AGE];
+    if (age < 2) { t0[s] = 0; return; }
+    const int id = cd.seq[pos];
+    const int first = (st.scal[s * SC_N + SC_SLIDES] == 1) ? 0 : 1;
+    const int g = id * 2 + first;
+    const int idx = atomicAdd(&count[g], 1);
+    list[(long long)g * S + s0 + idx] = (int)s;
+    t0[s] = -1;
+}
+__global__ void cascade_offsets_kernel(const int *count, int *tile_off)
+{
+    int o = 0;
+    for (int g = 0; g < CG_GROUPS; g++) { tile_off[g] = o; o += (count[g] + 15) >> 4; }
+}
+
+struct CascadePostArgs {
+    const MmaModel *model[3];        /* statistics and silence rows of each model */
+    StreamState st;
+    int16_t *stale;
+    const int32_t *logmel;
+    const int32_t *dec;
+    int dec_stride;
+    int *t0;
+    int s0, ns, T;
+    nnsp_b200_cascade_result *results;
+    CascadeDev cd;
+};
+
+__device__ __forceinline__ const int32_t *cascade_lm_row(const CascadePostArgs &a, long long s, int fr)
+{
+    return (fr >= 0) ? a.logmel + (s * a.T + fr) * NNSP_B200_NMEL
+                     : a.st.lmhist + (s * a.cd.dmax + a.cd.dmax + fr) * NNSP_B200_NMEL;
+}
+
+__global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePostArgs a)
+{
+    __shared__ int32_t dsm[CPOST_THREADS][CPOST_KCH + 1];
+    const CascadeDev &cd = a.cd;
+    const int si0 = blockIdx.x * CPOST_THREADS, si = si0 + threadIdx.x;
+    const long long s = a.s0 + (si < a.ns ? si : 0);
+    bool live = si < a.ns && a.t0[s] < 0;                             /* took part in the stage-sorted pass */
+    const int T = a.T;
+    int pos = a.st.casc[s * CS_N + CS_POS];
+    int cnt_kws = a.st.casc[s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[s * CS_N + CS_CNT_S2I];
+    const int id = cd.seq[pos];
+    const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
+    const int th_cnt = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_cnts_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_cnts_kws : cd.P.thresh_cnts_s2i);
+    int16_t sc[SC_N];
+    {
+        const uint4 *p = reinterpret_cast<const uint4 *>(a.st.scal + s * SC_N);
+        *reinterpret_cast<uint4 *>(&sc[0]) = p[0];
+        *reinterpret_cast<uint4 *>(&sc[8]) = p[1];
+    }
+    const int first = (sc[SC_SLIDES] == 1) ? 0 : 1;
+    const int n_inf = (T > first) ? (T - first + 1) / 2 : 0;
+    const int n_inf_max = (T + 1) / 2;
+    const int nstr = min(CPOST_THREADS, a.ns - si0);
+    int t = 0, t_exit = -1, next_pos_exit = 0;
+
+    for (int kc = 0; kc == 0 || kc < n_inf_max; kc += CPOST_KCH) {
+        const int nk = min(CPOST_KCH, n_inf_max - kc);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nstr * nk; e += CPOST_THREADS) {
+            const int rr = e / nk, kk = e - rr * nk;
+            dsm[rr][kk] = a.dec[(size_t)(a.s0 + si0 + rr) * a.dec_stride + kc + kk];
+        }
+        __syncthreads();
+        /* frames whose inference index lies in this round */
+        const int t_end = (kc + CPOST_KCH < n_inf) ? first + 2 * (kc + CPOST_KCH) : T;
+        if (live) {
+            for (; t < t_end; t++) {
+                const bool ran = (t >= first) && (((t - first) & 1) == 0);                 /* nn_speech.c:84 */
+                if (ran) {
+                    const int dv = dsm[threadIdx.x][((t - first) >> 1) - kc];
+                    if (id == NNSP_B200_ID_S2I) {                                           /* s2i_post_proc, nn_speech.c:146-189 */
+                        const int ai = dv & 0xff;
+                        sc[SC_TRIGGER] = 0; sc[SC_OUT0] = sc[SC_OUT0 + 1] = sc[SC_OUT0 + 2] = 0;
+                        const int last = sc[SC_ARGMAX_LAST];
+                        if (last == 0 || last == ai) {
+                            if (ai != 0) {
+                                const int16_t cnt = (int16_t)(sc[SC_CNT0 + ai] + 1);
+                                sc[SC_CNT0 + ai] = cnt;
+                                if (cnt > th_cnt) { sc[SC_TRIGGER] = 1; sc[SC_OUT0] = (int16_t)ai; sc[SC_OUT0 + 1] = (int16_t)((dv >> 8) & 0xff); sc[SC_OUT0 + 2] = (int16_t)((dv >> 16) & 0xff); }
+                            }
+                        } else {
+                            for (int i = 0; i < 7; i++) sc[SC_CNT0 + i] = 0;
+                        }
+                        sc[SC_ARGMAX_LAST] = (int16_t)ai;
+                    } else {                                                                /* binary_post_proc, nn_speech.c:219-226 */
+                        const int16_t cnt = dv ? (int16_t)(sc[SC_CNT0] + 1) : (int16_t)0;
+                        sc[SC_CNT0] = cnt;
+                        sc[SC_TRIGGER] = (cnt >= th_cnt) ? 1 : 0;
+                    }
+                }
+                sc[SC_SLIDES] = (int16_t)((sc[SC_SLIDES] + 1) % 2);
+                /* controller, nnCntrlClass.c:172-269 (same code as cascade_kernel) */
+                const int detected = sc[SC_TRIGGER];
+                int next_pos = pos, do_reset = 0, cnt_out = 0;
+                if (id == NNSP_B200_ID_S2I) {
+                    cnt_s2i = (cnt_s2i + 1) % cd.P.thresh_timeout_s2i;
+                    if (detected || cnt_s2i == cd.P.thresh_timeout_s2i - 1) {
+                        next_pos = (pos + 1) % cd.len_seq;
+                        if (detected || cd.seq[next_pos] != id) { cnt_s2i = 0; do_reset = 1; }
+                    }
+                    cnt_out = cnt_s2i;
+                } else if (id == NNSP_B200_ID_KWS) {
+                    cnt_kws = (cnt_kws + 1) % cd.P.thresh_timeout_kws;
+                    if (detected || cnt_kws == cd.P.thresh_timeout_kws - 1) {
+                        if (detected) next_pos = (pos + 1) % cd.len_seq;
+                        else { next_pos = (pos - 1) % cd.len_seq; if (next_pos < 0) next_pos += cd.len_seq; }
+                        if (detected || cd.seq[next_pos] != id) { cnt_kws = 0; do_reset = 1; }
+                    }
+                    cnt_out = cnt_kws;
+                } else if (detected) {
+                    next_pos = (pos + 1) % cd.len_seq;
+                    do_reset = 1;
+                }
+                if (a.results) {
+                    nnsp_b200_cascade_result r;
+                    r.stage_id = (int8_t)id; r.pos_after = (int8_t)next_pos; r.detected = (int16_t)detected;
+                    r.outputs[0] = sc[SC_OUT0]; r.outputs[1] = sc[SC_OUT0 + 1]; r.outputs[2] = sc[SC_OUT0 + 2];
+                    r.cnt_timeout = (uint16_t)cnt_out;
+                    a.results[s * T + t] = r;
+                }
+                if (do_reset) { t_exit = t; next_pos_exit = next_pos; live = false; break; }
+            }
+        }
+        if (nk <= 0) break;
+    }
+    if (si >= a.ns || a.t0[s] >= 0) return;                           /* sequential-only stream */
+    const MmaModel &M = *a.model[id];
+    int16_t *ctx = a.st.ctx + s * 240;
+    if (t_exit >= 0) {
+        /* NNSPClass_reset of the instance the controller leaves (nn_speech.c:57-72): its newest context row stays
+         * behind as that instance's stale row 5 (feature_module.c:39-42) ... */
+        const int32_t *row = cascade_lm_row(a, s, t_exit - d);
+        int16_t *stale = a.stale + (s * 3 + id) * 40;
+        for (int i = 0; i < 40; i++) stale[i] = standardise(row[i], M.mean[i], M.stdR[i], M.feat_rshift);
+        /* ... and the instance entered starts from ITS reset state plus ITS stale row */
+        const int nid = cd.seq[next_pos_exit];
+        const MmaModel &N = *a.model[nid];
+        const int16_t *st2 = a.stale + (s * 3 + nid) * 40;
+        for (int i = 0; i < 200; i++) ctx[i] = N.silence[i % 40];
+        for (int i = 0; i < 40; i++) ctx[200 + i] = st2[i];
+        for (int i = 0; i < NNSP_B200_MAX_WIDTH; i++) { a.st.h[s * NNSP_B200_MAX_WIDTH + i] = 0; a.st.c[s * NNSP_B200_MAX_WIDTH + i] = 0; }
+        for (int i = 0; i < SC_N; i++) sc[i] = (i == SC_SLIDES) ? 1 : 0;
+        a.st.casc[s * CS_N + CS_POS] = (uint16_t)next_pos_exit;
+        a.st.casc[s * CS_N + CS_AGE] = 0;
+        a.t0[s] = t_exit + 1;
+    } else {
+        /* the instance lived through the call: its context is the newest six standardised rows */
+        int16_t nc[240];
+        for (int j = 0; j < 6; j++) {
+            const int f = T - 6 + j;
+            if (f >= 0) {
+                const int32_t *row = cascade_lm_row(a, s, f - d);
+                for (int i = 0; i < 40; i++) nc[j * 40 + i] = standardise(row[i], M.mean[i], M.stdR[i], M.feat_rshift);
+            } else {
+                for (int i = 0; i < 40; i++) nc[j * 40 + i] = ctx[(j + T) * 40 + i];
+            }
+        }
+        for (int i = 0; i < 240; i++) ctx[i] = nc[i];
+        a.t0[s] = T;
+    }
+    a.st.casc[s * CS_N + CS_CNT_KWS] = (uint16_t)cnt_kws;
+    a.st.casc[s * CS_N + CS_CNT_S2I] = (uint16_t)cnt_s2i;
+    {
+        uint4 *p = reinterpret_cast<uint4 *>(a.st.scal + s * SC_N);
+        p[0] = *reinterpret_cast<uint4 *>(&sc[0]);
+        p[1] = *reinterpret_cast<uint4 *>(&sc[8]);
+    }
+}
+
 struct ResetModels { const DevModel *m[3]; int seq[CS_MAXSEQ]; };
 
 /* nnCntrlClass_reset (nnCntrlClass.c:130-150): every instance reset, ring cleared, timeout counters
@@ -308,7 +504,40 @@ struct nnsp_b200_cascade {
     size_t smem_total = 0; int off_w = 0, off_b = 0;
     cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
     bool ev_valid = false;
+    /* stage-sorted pass (scan-split kernels per (model, phase) group + replay) */
+    MmaDeviceModel mm[3];
+    bool split_ok = false;
+    int path = 0;                              /* 0 auto, 1 sequential kernel only, 2 stage-sorted pass + replay */
+    int pa_max = 0;
+    int *grp_list = nullptr, *grp_count = nullptr, *grp_tile_off = nullptr, *t0 = nullptr;
+    uint8_t *planes[2] = { nullptr, nullptr };
+    int32_t *dec = nullptr;
+    long long split_cap_T = 0;
 };
+
+constexpr int CS_MAX_SLICES = 8;
+
+static bool cascade_use_split(const nnsp_b200_cascade *c, const nnsp_b200_taps *taps)
+{
+    if (c->path == 1 || !c->split_ok) return false;
+    if (taps && (taps->logmel || taps->feat || taps->act || taps->logits || taps->hstate || taps->cstate || taps->post))
+        return false;                          /* the debug taps are produced by the sequential kernel */
+    return true;
+}
+
+static int cascade_ensure_split(nnsp_b200_cascade *c, int T)
+{
+    if (!c->split_ok || c->path == 1 || T <= c->split_cap_T) return NNSP_B200_OK;
+    NNSP_CUDA(cudaDeviceSynchronize());
+    for (auto &p : c->planes) { if (p) cudaFree(p); p = nullptr; }
+    if (c->dec) { cudaFree(c->dec); c->dec = nullptr; }
+    c->split_cap_T = 0;
+    const size_t n_inf_max = (size_t)(T + 1) / 2, tiles = (size_t)c->S / 16 + (size_t)(CG_GROUPS + 1) * CS_MAX_SLICES + 2;
+    for (auto &p : c->planes) NNSP_CUDA(cudaMalloc(&p, tiles * n_inf_max * 32 * c->pa_max));
+    NNSP_CUDA(cudaMalloc(&c->dec, ((size_t)c->S + 16) * n_inf_max * sizeof(int32_t)));
+    c->split_cap_T = T;
+    return NNSP_B200_OK;
+}
 
 static int cascade_ensure_logmel(nnsp_b200_cascade *c, int T)
 {
@@ -322,7 +551,8 @@ static int cascade_ensure_logmel(nnsp_b200_cascade *c, int T)
 }
 
 static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long stride, int T, int s0, int ns,
-                          nnsp_b200_cascade_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed)
+                          nnsp_b200_cascade_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed,
+                          int slice = 0)
 {
     const int hist_frames = c->cd.dmax + 2;
     FeatLaunch fl{ pcm, stride, c->st.hist, hist_frames, s0, ns, T, c->logmel };
@@ -335,6 +565,44 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
     a.tables = c->tables; a.st = c->st; a.stale = c->stale; a.pcm = pcm; a.stride = stride; a.logmel = c->logmel;
     a.s0 = s0; a.ns = ns; a.T = T; a.results = results; a.cd = c->cd;
     if (taps) a.taps = *taps;
+    if (cascade_use_split(c, taps)) {
+        /* stage-sorted pass: sort the slice's streams by (live model, inference phase) on the device ... */
+        int *count = c->grp_count + slice * 8, *toff = c->grp_tile_off + slice * 8;
+        NNSP_CUDA(cudaMemsetAsync(count, 0, 8 * sizeof(int), st));
+        cascade_classify_kernel<<<(ns + 255) / 256, 256, 0, st>>>(c->st, c->cd, s0, ns, c->S, c->grp_list, count, c->t0);
+        NNSP_LAUNCH_CHECK();
+        cascade_offsets_kernel<<<1, 1, 0, st>>>(count, toff);
+        NNSP_LAUNCH_CHECK();
+        /* ... run every group through the scan-split kernels ... */
+        const int n_inf_max = (T + 1) / 2;
+        for (int k = 0; k < c->cd.len_seq; k++) {
+            const int id = c->cd.seq[k];
+            for (int first = 0; first < 2; first++) {
+                const int g = id * 2 + first;
+                SplitGroup q{};
+                q.tables = c->tables;
+                q.list = c->grp_list + (size_t)g * c->S + s0; q.count = count + g; q.tile_off = toff + g;
+                q.tile0 = (s0 >> 4) + (CG_GROUPS + 1) * slice; q.max_streams = ns;
+                q.tile_bytes = (long long)n_inf_max * 32 * c->pa_max;
+                q.T = T; q.first = first; q.n_inf = (T > first) ? (T - first + 1) / 2 : 0;
+                q.mode = 2; q.logmel = c->logmel; q.lmhist = c->st.lmhist; q.dmax = c->cd.dmax;
+                q.dback = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? c->cd.P.frs_vbufBk_kws : c->cd.P.frs_vbufBk_s2i);
+                q.ctx = c->st.ctx; q.h = c->st.h; q.c = c->st.c; q.h_stride = NNSP_B200_MAX_WIDTH;
+                q.planes0 = c->planes[0]; q.planes1 = c->planes[1];
+                q.dec = c->dec; q.dec_stride = n_inf_max;
+                q.thresh_prob = (id == NNSP_B200_ID_VAD) ? c->cd.P.thresh_prob_vad : (id == NNSP_B200_ID_KWS ? c->cd.P.thresh_prob_kws : c->cd.P.thresh_prob_s2i);
+                if ((rc = launch_split_layers(c->mm[id], q, c->device, st))) return rc;
+            }
+        }
+        /* ... walk the controller over the decisions, cut at the first stage change ... */
+        CascadePostArgs p{};
+        for (int i = 0; i < 3; i++) p.model[i] = c->mm[i].d;
+        p.st = c->st; p.stale = c->stale; p.logmel = c->logmel; p.dec = c->dec; p.dec_stride = n_inf_max; p.t0 = c->t0;
+        p.s0 = s0; p.ns = ns; p.T = T; p.results = results; p.cd = c->cd;
+        cascade_post_kernel<<<(ns + CPOST_THREADS - 1) / CPOST_THREADS, CPOST_THREADS, 0, st>>>(p);
+        NNSP_LAUNCH_CHECK();
+        a.t0 = c->t0;                          /* ... and replay what is left with the sequential kernel */
+    }
     int blocks = (ns + CS_WARPS - 1) / CS_WARPS;
     const int cap = sm_count(c->device);
     if (blocks > cap) blocks = cap;
@@ -399,6 +667,15 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
         c->cd.woff_words[id] = (int)(wtot / 4); c->cd.wbytes[id] = c->dm[id].h.weight_words * 4; wtot += (size_t)c->cd.wbytes[id];
         c->cd.boff[id] = (int)btot; btot += (size_t)c->dm[id].h.bias_count;
     }
+    c->split_ok = true;
+    for (int id = 0; id < 3; id++) {
+        if (!seen[id]) continue;
+        rc = upload_model_mma(models[id], &c->mm[id]);
+        if (rc == NNSP_B200_ERR_UNSUPPORTED) { c->split_ok = false; continue; }
+        if (rc) return fail(rc);
+        if (!split_supported(c->mm[id])) c->split_ok = false;
+        if (c->mm[id].h && c->mm[id].h->pa > c->pa_max) c->pa_max = c->mm[id].h->pa;
+    }
     c->off_w = (int)((16 + sizeof(CascadeSmem) + 127) & ~(size_t)127);
     c->off_b = (int)(c->off_w + wtot);
     c->smem_total = (size_t)c->off_b + btot * 2 + 16;
@@ -418,6 +695,10 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaMalloc(&c->st.hist, S * hist_frames * NNSP_B200_FRAME * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.lmhist, S * lm_rows * NNSP_B200_NMEL * sizeof(int32_t)));
     TRY(cudaMalloc(&c->stale, S * 120 * sizeof(int16_t)));
+    TRY(cudaMalloc(&c->grp_list, (size_t)CG_GROUPS * S * sizeof(int)));
+    TRY(cudaMalloc(&c->grp_count, CS_MAX_SLICES * 8 * sizeof(int)));
+    TRY(cudaMalloc(&c->grp_tile_off, CS_MAX_SLICES * 8 * sizeof(int)));
+    TRY(cudaMalloc(&c->t0, S * sizeof(int)));
 #undef TRY
     ResetModels rm{};
     for (int i = 0; i < 3; i++) rm.m[i] = c->dm[i].d;
@@ -464,6 +745,7 @@ int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long lo
     if (rc) return rc;
     NNSP_CUDA(cudaSetDevice(c->device));
     if ((rc = cascade_ensure_logmel(c, n_frames))) return rc;
+    if ((rc = cascade_ensure_split(c, n_frames))) return rc;
     return cascade_launch(c, pcm_dev, stream_stride, n_frames, 0, c->S, results_dev, taps, c->stream, true);
 }
 
@@ -476,6 +758,7 @@ int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
     NNSP_CUDA(cudaSetDevice(c->device));
     const int T = n_frames;
     if ((rc = cascade_ensure_logmel(c, T))) return rc;
+    if ((rc = cascade_ensure_split(c, T))) return rc;
     if (T > c->d_pcm_frames) {
         NNSP_CUDA(cudaDeviceSynchronize());
         if (c->d_pcm) cudaFree(c->d_pcm);
@@ -489,13 +772,14 @@ int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
     const long long dstride = (long long)T * NNSP_B200_FRAME;
     const int nsl = c->S >= 4096 ? 8 : (c->S >= 256 ? 4 : 1);
     for (int k = 0; k < nsl; k++) {
-        const int s0 = (int)((long long)c->S * k / nsl), s1 = (int)((long long)c->S * (k + 1) / nsl);
+        const int s0 = (int)(((long long)c->S * k / nsl) & ~15LL);
+        const int s1 = (k == nsl - 1) ? c->S : (int)(((long long)c->S * (k + 1) / nsl) & ~15LL);
         if (s1 <= s0) continue;
         cudaStream_t st = c->xs[k % 3];
         NNSP_CUDA(cudaMemcpy2DAsync(c->d_pcm + (size_t)s0 * dstride, dstride * sizeof(int16_t),
                                     pcm + (size_t)s0 * stream_stride, stream_stride * sizeof(int16_t),
                                     dstride * sizeof(int16_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
-        rc = cascade_launch(c, c->d_pcm, dstride, T, s0, s1 - s0, results ? c->d_res : nullptr, nullptr, st, false);
+        rc = cascade_launch(c, c->d_pcm, dstride, T, s0, s1 - s0, results ? c->d_res : nullptr, nullptr, st, false, k);
         if (rc) return rc;
         if (results)
             NNSP_CUDA(cudaMemcpyAsync(results + (size_t)s0 * T, c->d_res + (size_t)s0 * T,
@@ -528,6 +812,14 @@ int nnsp_b200_cascade_last_kernel_ms(nnsp_b200_cascade *c, float ms[3])
 
 void *nnsp_b200_cascade_stream(nnsp_b200_cascade *c) { return c ? (void *)c->stream : nullptr; }
 
+int nnsp_b200_cascade_set_path(nnsp_b200_cascade *c, int path)
+{
+    if (!c || path < 0 || path > 2) return NNSP_B200_ERR_ARG;
+    if (path == 2 && !c->split_ok) { nnsp_set_error("a model of this cascade has no scan-split formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
+    c->path = path;
+    return NNSP_B200_OK;
+}
+
 void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
 {
     if (!c) return;
@@ -537,6 +829,9 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     cudaFree(c->st.ctx); cudaFree(c->st.h); cudaFree(c->st.c); cudaFree(c->st.scal); cudaFree(c->st.casc);
     cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale);
     cudaFree(c->logmel); cudaFree(c->d_pcm); cudaFree(c->d_res);
+    for (int i = 0; i < 3; i++) free_model_mma(&c->mm[i]);
+    cudaFree(c->grp_list); cudaFree(c->grp_count); cudaFree(c->grp_tile_off); cudaFree(c->t0);
+    cudaFree(c->planes[0]); cudaFree(c->planes[1]); cudaFree(c->dec);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto s : c->xs) if (s) cudaStreamDestroy(s);
     for (auto e : c->ev) if (e) cudaEventDestroy(e);

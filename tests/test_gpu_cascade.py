@@ -113,3 +113,56 @@ def test_cascade_exec_host(nb):
     for f in dev.dtype.names:
         assert (dev[f] == host[f]).all(), f
     c.close()
+
+
+@pytest.mark.parametrize("seq,params,chunks", [
+    ((1, 2, 0), None, (100, 100, 37, 1, 2, 160, 300, 100, 100, 100, 100, 100, 100, 100, 100, 100, 100)),
+    ((1, 2, 0), dict(frs_vbufBk_kws=99, frs_vbufBk_s2i=1, thresh_timeout_kws=45, thresh_timeout_s2i=30, thresh_prob_kws=100, thresh_cnts_kws=2),
+     (64, 3, 100, 1, 1, 31, 100, 100, 200)),
+    ((1, 0), dict(frs_vbufBk_s2i=5, thresh_timeout_s2i=60, thresh_cnts_vad=2), (100, 100, 100, 50, 7, 143, 100)),
+    ((0,), dict(frs_vbufBk_s2i=0, thresh_timeout_s2i=37, thresh_cnts_s2i=1), (100, 99, 101, 100)),
+])
+def test_cascade_stage_sorted_pass(nb, oracle, seq, params, chunks):
+    """The stage-sorted pass (scan-split kernels per (model, phase) group, controller walk, replay after a stage
+    change) against the oracle on every frame, any chunking; the last chunk runs on the sequential kernel with
+    all taps, so the state the sorted pass leaves behind (context, LSTM, counters, stale rows) is checked too."""
+    S = 75                                             # 4 full tiles + a partial one, spread over the groups
+    T = sum(chunks)
+    pcm = nb.synth_pcm(S, T, first_stream=17)
+    c = nb.Cascade(_models(nb), S, seq=seq, params=params)
+    c.set_path("sorted")
+    parts, t = [], 0
+    for n in chunks[:-1]:
+        parts.append(c.exec(pcm[:, t * 160:(t + n) * 160]))
+        t += n
+    c.set_path("sequential")
+    last, taps = c.exec(pcm[:, t * 160:], taps=True)
+    res = np.concatenate(parts + [last], axis=1)
+    om = _oracle_models(oracle)
+    par = c.params_array()
+    transitions = 0
+    for s in range(S):
+        r, tp, valid = oracle.cascade_run(om, pcm[s], seq=seq, params=par)
+        _check(res, None, s, r, None, None)
+        for g, o in (("feat", "feat"), ("hstate", "h"), ("cstate", "c"), ("post", "post")):
+            assert (taps[g][s] == getattr(tp, o)[t:]).all(), "state after the sorted pass: tap %s stream %d" % (g, s)
+        transitions += int((np.diff(r["pos_after"][:t].astype(int)) != 0).sum())
+    if len(seq) > 1:
+        assert transitions > 5                         # stage changes happened inside sorted-pass chunks
+    c.close()
+
+
+def test_cascade_sorted_exec_host_equals_sequential(nb):
+    S, T = 530, 120
+    pcm = nb.synth_pcm(S, 2 * T, first_stream=9)
+    models = _models(nb)
+    out = {}
+    for path in ("sequential", "sorted"):
+        c = nb.Cascade(models, S)
+        c.set_path(path)
+        a = c.exec_host(pcm[:, :T * 160].copy())
+        b = c.exec_host(pcm[:, T * 160:].copy())
+        out[path] = np.concatenate([a, b], axis=1)
+        c.close()
+    for f in out["sorted"].dtype.names:
+        assert (out["sorted"][f] == out["sequential"][f]).all(), f

@@ -48,12 +48,16 @@ def main():
         d = [nb.DeviceArray.from_host(pcm), nb.DeviceArray.from_host(np.roll(pcm, 7, axis=0))]
         if name == "cascade":
             models = [nb.Model.from_blob(os.path.join(nb.MODEL_DIR, FILES[k]), acc32=acc32) for k in ("s2i", "vad", "kws")]
-            h = nb.Cascade(models, S)
-            res = nb.DeviceArray((S, T), nb.CASCADE_RESULT_DT)
-            ms, km = time_handle(h, lambda i: h.exec_device(d[i & 1], T * 160, T, res), T, S)
-            print(json.dumps({"config": spec, "kernel": "cascade", "ms_per_step": ms, "audio_s_per_s": S * T * 0.01 / (ms * 1e-3),
-                              "feat_ms": km[0], "nn_ms": km[1]}), flush=True)
-            h.close()
+            for cp in ("sorted", "sequential"):
+                h = nb.Cascade(models, S)
+                h.set_path(cp)
+                res = nb.DeviceArray((S, T), nb.CASCADE_RESULT_DT)
+                ms, km = time_handle(h, lambda i: h.exec_device(d[i & 1], T * 160, T, res), T, S, steps=20, warm=10)
+                stage = np.bincount(res.to_host()["stage_id"].ravel().astype(np.int64), minlength=3)
+                print(json.dumps({"config": spec, "kernel": "cascade-" + cp, "ms_per_step": ms, "audio_s_per_s": S * T * 0.01 / (ms * 1e-3),
+                                  "feat_ms": km[0], "nn_ms": km[1], "stage_frames_last_step": stage.tolist()}), flush=True)
+                h.close()
+                res.free()
         else:
             m = nb.Model.from_blob(os.path.join(nb.MODEL_DIR, FILES[name]), acc32=acc32)
             for p in paths:
