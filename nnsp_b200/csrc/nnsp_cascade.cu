@@ -53,6 +53,8 @@ struct CascadeArgs {
     nnsp_b200_taps taps;
     CascadeDev cd;
     const int *t0;                    /* per stream: first frame this kernel still has to process (null: 0) */
+    const int *replay_list;           /* with t0: the streams that still have frames left, handed out dynamically ... */
+    int *replay_ctl;                  /* ... [0] = how many, [1] = cursor                                         */
 };
 
 struct CascadeSmem {
@@ -122,8 +124,19 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
     const int T = a.T, HS = NNSP_B200_MAX_WIDTH;
     const int hist_frames = cd.dmax + 2, hist_len = hist_frames * NNSP_B200_FRAME;
 
-    for (int si = blockIdx.x * CS_WARPS + warp; si < a.ns; si += gridDim.x * CS_WARPS) {
-        const int s = a.s0 + si;
+    for (int it = 0;; it++) {
+        int s;
+        if (a.replay_list) {                                          /* replay after the stage-sorted pass: dynamic hand-out */
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(a.replay_ctl + 1, 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx >= a.replay_ctl[0]) break;
+            s = a.replay_list[idx];
+        } else {
+            const int si = blockIdx.x * CS_WARPS + warp + it * gridDim.x * CS_WARPS;
+            if (si >= a.ns) break;
+            s = a.s0 + si;
+        }
         const int t_begin = a.t0 ? a.t0[s] : 0;                       /* frames before it were done by the stage-sorted pass */
         if (t_begin >= a.T) continue;
         for (int i = lane; i < 240; i += 32) ws->ctx[i] = a.st.ctx[(long long)s * 240 + i];
@@ -278,13 +291,14 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
 constexpr int CG_GROUPS = 6;                        /* group = id * 2 + first inference frame (0 or 1) */
 constexpr int CPOST_THREADS = 64, CPOST_KCH = 64;
 
-__global__ void cascade_classify_kernel(StreamState st, CascadeDev cd, int s0, int ns, int S, int *list, int *count, int *t0)
+__global__ void cascade_classify_kernel(StreamState st, CascadeDev cd, int s0, int ns, int S, int *list, int *count, int *t0,
+                                        int *replay_list)
 {
     const int si = blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= ns) return;
     const long long s = s0 + si;
     const int pos = st.casc[s * CS_N + CS_POS], age = st.casc[s * CS_N + CS_AGE];
-    if (age < 2) { t0[s] = 0; return; }
+    if (age < 2) { t0[s] = 0; replay_list[s0 + atomicAdd(&count[8], 1)] = (int)s; return; }
     const int id = cd.seq[pos];
     const int first = (st.scal[s * SC_N + SC_SLIDES] == 1) ? 0 : 1;
     const int g = id * 2 + first;
@@ -292,8 +306,9 @@ __global__ void cascade_classify_kernel(StreamState st, CascadeDev cd, int s0, i
     list[(long long)g * S + s0 + idx] = (int)s;
     t0[s] = -1;
 }
-__global__ void cascade_offsets_kernel(const int *count, int *tile_off)
+__global__ void cascade_offsets_kernel(int *count, int *tile_off)
 {
+    count[9] = 0;                                                     /* replay cursor */
     int o = 0;
     for (int g = 0; g < CG_GROUPS; g++) { tile_off[g] = o; o += (count[g] + 15) >> 4; }
 }
@@ -306,6 +321,7 @@ struct CascadePostArgs {
     const int32_t *dec;
     int dec_stride;
     int *t0;
+    int *replay_list, *replay_count;
     int s0, ns, T;
     nnsp_b200_cascade_result *results;
     CascadeDev cd;
@@ -330,13 +346,19 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
     const int id = cd.seq[pos];
     const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
     const int th_cnt = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_cnts_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_cnts_kws : cd.P.thresh_cnts_s2i);
-    int16_t sc[SC_N];
+    /* NNSPClass scalars in registers (counters updated by compare-and-add, no dynamically indexed array) */
+    int trig, out0, out1, out2, last, slides, cnt[8];
     {
+        int16_t sc[SC_N];
         const uint4 *p = reinterpret_cast<const uint4 *>(a.st.scal + s * SC_N);
         *reinterpret_cast<uint4 *>(&sc[0]) = p[0];
         *reinterpret_cast<uint4 *>(&sc[8]) = p[1];
+        trig = sc[SC_TRIGGER]; out0 = sc[SC_OUT0]; out1 = sc[SC_OUT0 + 1]; out2 = sc[SC_OUT0 + 2];
+#pragma unroll
+        for (int i = 0; i < 8; i++) cnt[i] = sc[SC_CNT0 + i];
+        last = sc[SC_ARGMAX_LAST]; slides = sc[SC_SLIDES];
     }
-    const int first = (sc[SC_SLIDES] == 1) ? 0 : 1;
+    const int first = (slides == 1) ? 0 : 1;
     const int n_inf = (T > first) ? (T - first + 1) / 2 : 0;
     const int n_inf_max = (T + 1) / 2;
     const int nstr = min(CPOST_THREADS, a.ns - si0);
@@ -359,27 +381,29 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
                     const int dv = dsm[threadIdx.x][((t - first) >> 1) - kc];
                     if (id == NNSP_B200_ID_S2I) {                                           /* s2i_post_proc, nn_speech.c:146-189 */
                         const int ai = dv & 0xff;
-                        sc[SC_TRIGGER] = 0; sc[SC_OUT0] = sc[SC_OUT0 + 1] = sc[SC_OUT0 + 2] = 0;
-                        const int last = sc[SC_ARGMAX_LAST];
+                        trig = 0; out0 = 0; out1 = 0; out2 = 0;
                         if (last == 0 || last == ai) {
-                            if (ai != 0) {
-                                const int16_t cnt = (int16_t)(sc[SC_CNT0 + ai] + 1);
-                                sc[SC_CNT0 + ai] = cnt;
-                                if (cnt > th_cnt) { sc[SC_TRIGGER] = 1; sc[SC_OUT0] = (int16_t)ai; sc[SC_OUT0 + 1] = (int16_t)((dv >> 8) & 0xff); sc[SC_OUT0 + 2] = (int16_t)((dv >> 16) & 0xff); }
+                            int hit = 0;
+#pragma unroll
+                            for (int i = 1; i < 7; i++) {
+                                const int c1 = (int)(int16_t)(cnt[i] + 1);
+                                if (ai == i) { cnt[i] = c1; hit = c1 > th_cnt; }
                             }
+                            if (hit) { trig = 1; out0 = ai; out1 = (dv >> 8) & 0xff; out2 = (dv >> 16) & 0xff; }
                         } else {
-                            for (int i = 0; i < 7; i++) sc[SC_CNT0 + i] = 0;
+#pragma unroll
+                            for (int i = 0; i < 7; i++) cnt[i] = 0;
                         }
-                        sc[SC_ARGMAX_LAST] = (int16_t)ai;
+                        last = ai;
                     } else {                                                                /* binary_post_proc, nn_speech.c:219-226 */
-                        const int16_t cnt = dv ? (int16_t)(sc[SC_CNT0] + 1) : (int16_t)0;
-                        sc[SC_CNT0] = cnt;
-                        sc[SC_TRIGGER] = (cnt >= th_cnt) ? 1 : 0;
+                        const int c0 = dv ? (int)(int16_t)(cnt[0] + 1) : 0;
+                        cnt[0] = c0;
+                        trig = (c0 >= th_cnt) ? 1 : 0;
                     }
                 }
-                sc[SC_SLIDES] = (int16_t)((sc[SC_SLIDES] + 1) % 2);
+                slides ^= 1;
                 /* controller, nnCntrlClass.c:172-269 (same code as cascade_kernel) */
-                const int detected = sc[SC_TRIGGER];
+                const int detected = trig;
                 int next_pos = pos, do_reset = 0, cnt_out = 0;
                 if (id == NNSP_B200_ID_S2I) {
                     cnt_s2i = (cnt_s2i + 1) % cd.P.thresh_timeout_s2i;
@@ -403,7 +427,7 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
                 if (a.results) {
                     nnsp_b200_cascade_result r;
                     r.stage_id = (int8_t)id; r.pos_after = (int8_t)next_pos; r.detected = (int16_t)detected;
-                    r.outputs[0] = sc[SC_OUT0]; r.outputs[1] = sc[SC_OUT0 + 1]; r.outputs[2] = sc[SC_OUT0 + 2];
+                    r.outputs[0] = (int16_t)out0; r.outputs[1] = (int16_t)out1; r.outputs[2] = (int16_t)out2;
                     r.cnt_timeout = (uint16_t)cnt_out;
                     a.results[s * T + t] = r;
                 }
@@ -428,10 +452,13 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
         for (int i = 0; i < 200; i++) ctx[i] = N.silence[i % 40];
         for (int i = 0; i < 40; i++) ctx[200 + i] = st2[i];
         for (int i = 0; i < NNSP_B200_MAX_WIDTH; i++) { a.st.h[s * NNSP_B200_MAX_WIDTH + i] = 0; a.st.c[s * NNSP_B200_MAX_WIDTH + i] = 0; }
-        for (int i = 0; i < SC_N; i++) sc[i] = (i == SC_SLIDES) ? 1 : 0;
+        trig = out0 = out1 = out2 = last = 0; slides = 1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) cnt[i] = 0;
         a.st.casc[s * CS_N + CS_POS] = (uint16_t)next_pos_exit;
         a.st.casc[s * CS_N + CS_AGE] = 0;
         a.t0[s] = t_exit + 1;
+        if (t_exit + 1 < T) a.replay_list[a.s0 + atomicAdd(a.replay_count, 1)] = (int)s;
     } else {
         /* the instance lived through the call: its context is the newest six standardised rows */
         int16_t nc[240];
@@ -450,6 +477,11 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
     a.st.casc[s * CS_N + CS_CNT_KWS] = (uint16_t)cnt_kws;
     a.st.casc[s * CS_N + CS_CNT_S2I] = (uint16_t)cnt_s2i;
     {
+        int16_t sc[SC_N];
+        sc[SC_TRIGGER] = (int16_t)trig; sc[SC_OUT0] = (int16_t)out0; sc[SC_OUT0 + 1] = (int16_t)out1; sc[SC_OUT0 + 2] = (int16_t)out2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) sc[SC_CNT0 + i] = (int16_t)cnt[i];
+        sc[SC_ARGMAX_LAST] = (int16_t)last; sc[SC_SLIDES] = (int16_t)slides; sc[SC_RAN] = 0; sc[SC_STAGE] = 0;
         uint4 *p = reinterpret_cast<uint4 *>(a.st.scal + s * SC_N);
         p[0] = *reinterpret_cast<uint4 *>(&sc[0]);
         p[1] = *reinterpret_cast<uint4 *>(&sc[8]);
@@ -509,7 +541,7 @@ struct nnsp_b200_cascade {
     bool split_ok = false;
     int path = 0;                              /* 0 auto, 1 sequential kernel only, 2 stage-sorted pass + replay */
     int pa_max = 0;
-    int *grp_list = nullptr, *grp_count = nullptr, *grp_tile_off = nullptr, *t0 = nullptr;
+    int *grp_list = nullptr, *grp_count = nullptr, *grp_tile_off = nullptr, *t0 = nullptr, *replay_list = nullptr;
     uint8_t *planes[2] = { nullptr, nullptr };
     int32_t *dec = nullptr;
     long long split_cap_T = 0;
@@ -567,9 +599,9 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
     if (taps) a.taps = *taps;
     if (cascade_use_split(c, taps)) {
         /* stage-sorted pass: sort the slice's streams by (live model, inference phase) on the device ... */
-        int *count = c->grp_count + slice * 8, *toff = c->grp_tile_off + slice * 8;
-        NNSP_CUDA(cudaMemsetAsync(count, 0, 8 * sizeof(int), st));
-        cascade_classify_kernel<<<(ns + 255) / 256, 256, 0, st>>>(c->st, c->cd, s0, ns, c->S, c->grp_list, count, c->t0);
+        int *count = c->grp_count + slice * 16, *toff = c->grp_tile_off + slice * 8;   /* count[8], [9]: replay length, cursor */
+        NNSP_CUDA(cudaMemsetAsync(count, 0, 16 * sizeof(int), st));
+        cascade_classify_kernel<<<(ns + 255) / 256, 256, 0, st>>>(c->st, c->cd, s0, ns, c->S, c->grp_list, count, c->t0, c->replay_list);
         NNSP_LAUNCH_CHECK();
         cascade_offsets_kernel<<<1, 1, 0, st>>>(count, toff);
         NNSP_LAUNCH_CHECK();
@@ -599,9 +631,11 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
         for (int i = 0; i < 3; i++) p.model[i] = c->mm[i].d;
         p.st = c->st; p.stale = c->stale; p.logmel = c->logmel; p.dec = c->dec; p.dec_stride = n_inf_max; p.t0 = c->t0;
         p.s0 = s0; p.ns = ns; p.T = T; p.results = results; p.cd = c->cd;
+        p.replay_list = c->replay_list; p.replay_count = count + 8;
         cascade_post_kernel<<<(ns + CPOST_THREADS - 1) / CPOST_THREADS, CPOST_THREADS, 0, st>>>(p);
         NNSP_LAUNCH_CHECK();
         a.t0 = c->t0;                          /* ... and replay what is left with the sequential kernel */
+        a.replay_list = c->replay_list + s0; a.replay_ctl = count + 8;
     }
     int blocks = (ns + CS_WARPS - 1) / CS_WARPS;
     const int cap = sm_count(c->device);
@@ -696,7 +730,8 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaMalloc(&c->st.lmhist, S * lm_rows * NNSP_B200_NMEL * sizeof(int32_t)));
     TRY(cudaMalloc(&c->stale, S * 120 * sizeof(int16_t)));
     TRY(cudaMalloc(&c->grp_list, (size_t)CG_GROUPS * S * sizeof(int)));
-    TRY(cudaMalloc(&c->grp_count, CS_MAX_SLICES * 8 * sizeof(int)));
+    TRY(cudaMalloc(&c->grp_count, CS_MAX_SLICES * 16 * sizeof(int)));
+    TRY(cudaMalloc(&c->replay_list, S * sizeof(int)));
     TRY(cudaMalloc(&c->grp_tile_off, CS_MAX_SLICES * 8 * sizeof(int)));
     TRY(cudaMalloc(&c->t0, S * sizeof(int)));
 #undef TRY
@@ -830,7 +865,7 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale);
     cudaFree(c->logmel); cudaFree(c->d_pcm); cudaFree(c->d_res);
     for (int i = 0; i < 3; i++) free_model_mma(&c->mm[i]);
-    cudaFree(c->grp_list); cudaFree(c->grp_count); cudaFree(c->grp_tile_off); cudaFree(c->t0);
+    cudaFree(c->replay_list); cudaFree(c->grp_list); cudaFree(c->grp_count); cudaFree(c->grp_tile_off); cudaFree(c->t0);
     cudaFree(c->planes[0]); cudaFree(c->planes[1]); cudaFree(c->dec);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto s : c->xs) if (s) cudaStreamDestroy(s);
