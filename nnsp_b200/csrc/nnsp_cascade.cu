@@ -545,6 +545,8 @@ struct nnsp_b200_cascade {
     uint8_t *planes[2] = { nullptr, nullptr };
     int32_t *dec = nullptr;
     long long split_cap_T = 0;
+    cudaStream_t gs[CG_GROUPS] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* one per (model, phase) group */
+    cudaEvent_t ev_fork = nullptr, ev_join[CG_GROUPS] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 
 constexpr int CS_MAX_SLICES = 8;
@@ -605,8 +607,10 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
         NNSP_LAUNCH_CHECK();
         cascade_offsets_kernel<<<1, 1, 0, st>>>(count, toff);
         NNSP_LAUNCH_CHECK();
-        /* ... run every group through the scan-split kernels ... */
+        /* ... run every group through the scan-split kernels, the groups side by side on their own CUDA streams
+         * (their chains are independent and the scans are latency-bound) ... */
         const int n_inf_max = (T + 1) / 2;
+        NNSP_CUDA(cudaEventRecord(c->ev_fork, st));
         for (int k = 0; k < c->cd.len_seq; k++) {
             const int id = c->cd.seq[k];
             for (int first = 0; first < 2; first++) {
@@ -623,7 +627,11 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
                 q.planes0 = c->planes[0]; q.planes1 = c->planes[1];
                 q.dec = c->dec; q.dec_stride = n_inf_max;
                 q.thresh_prob = (id == NNSP_B200_ID_VAD) ? c->cd.P.thresh_prob_vad : (id == NNSP_B200_ID_KWS ? c->cd.P.thresh_prob_kws : c->cd.P.thresh_prob_s2i);
-                if ((rc = launch_split_layers(c->mm[id], q, c->device, st))) return rc;
+                if (q.n_inf <= 0) continue;
+                NNSP_CUDA(cudaStreamWaitEvent(c->gs[g], c->ev_fork, 0));
+                if ((rc = launch_split_layers(c->mm[id], q, c->device, c->gs[g]))) return rc;
+                NNSP_CUDA(cudaEventRecord(c->ev_join[g], c->gs[g]));
+                NNSP_CUDA(cudaStreamWaitEvent(st, c->ev_join[g], 0));
             }
         }
         /* ... walk the controller over the decisions, cut at the first stage change ... */
@@ -721,6 +729,9 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &e : c->ev) TRY(cudaEventCreate(&e));
+    for (auto &g : c->gs) TRY(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (auto &e : c->ev_join) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRY(cudaMalloc(&c->st.ctx, S * 240 * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.h, S * HS * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.c, S * HS * sizeof(int32_t)));
@@ -870,6 +881,9 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto s : c->xs) if (s) cudaStreamDestroy(s);
     for (auto e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto g : c->gs) if (g) cudaStreamDestroy(g);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (auto e : c->ev_join) if (e) cudaEventDestroy(e);
     delete c;
 }
 
