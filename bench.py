@@ -234,9 +234,12 @@ def main():
     sampler.start()
     n0 = nb.kernel_launches()
     feat_ms = nn_ms = 0.0
+    # calls are asynchronous and pipelined inside the engine (front end of step i+1 on one CUDA stream while the network
+    # kernels of step i finish on another): the closing event is recorded once every stream of the handle has drained
     ev0.record(batch.stream)
     for i in range(args.steps):
         step(i)
+    batch.sync()
     ev1.record(batch.stream)
     batch.sync()
     ms_total = ev0.elapsed_ms_to(ev1)

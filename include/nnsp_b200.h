@@ -121,7 +121,10 @@ int nnsp_b200_batch_reset(nnsp_b200_batch *b);
 /* Advance every stream by n_frames hops.
  *   pcm      device pointer; sample i of frame t of stream s at pcm[s*stream_stride + t*160 + i]
  *   results  device pointer [n_streams][n_frames] (may be NULL)
- * Asynchronous on the handle's stream; call nnsp_b200_batch_sync to wait.               */
+ * Asynchronous: the call returns once the work is queued. On the default network path consecutive calls are
+ * pipelined over two CUDA streams (front end of call N+1 while the network kernels of call N finish), so results
+ * and state are complete only after nnsp_b200_batch_sync; the PCM buffer of a call may be reused once the next
+ * call has been issued or after a sync.                                                   */
 int nnsp_b200_batch_exec(nnsp_b200_batch *b, const int16_t *pcm_dev, long long stream_stride,
                          int n_frames, nnsp_b200_result *results_dev,
                          const nnsp_b200_taps *taps);
@@ -140,7 +143,8 @@ int nnsp_b200_batch_dims(const nnsp_b200_batch *b, int *n_streams, int *act_stri
  * for all frames of the call at once, only the LSTM recurrence sequential; nnsp_split.cu). 2 and 3 return an
  * error when the model does not fit them. All three are bit-exact. */
 int nnsp_b200_batch_set_nn_path(nnsp_b200_batch *b, int path);
-/* CUDA stream the handle launches on (cudaStream_t as void*), for callers that time it. */
+/* CUDA stream the front end is launched on (cudaStream_t as void*), for callers that time it; the network
+ * kernels of the default path run on a second, internal stream -- bracket timed regions with nnsp_b200_batch_sync. */
 void *nnsp_b200_batch_stream(nnsp_b200_batch *b);
 void nnsp_b200_batch_destroy(nnsp_b200_batch *b);
 

@@ -207,6 +207,9 @@ constexpr int FEAT_THREADS = FEAT_WARPS * 32;
 #ifndef FEAT_CTAS_PER_SM
 #define FEAT_CTAS_PER_SM 3
 #endif
+#ifndef FEAT_ITERS
+#define FEAT_ITERS 8
+#endif
 
 struct FeatSmem {
     FeatSmemTables tb;
@@ -256,8 +259,12 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
     const long long F = (long long)a.ns * a.T;
     if (F <= 0) return NNSP_B200_OK;
     long long blocks = (F + FEAT_WARPS * 2 - 1) / (FEAT_WARPS * 2);
-    const long long cap = (long long)sm_count(device) * FEAT_CTAS_PER_SM;   /* persistent grid: every CTA resident */
-    if (blocks > cap) blocks = cap;
+    /* at least one resident wave; beyond that a CTA takes FEAT_ITERS rounds of 16 frames and retires, so that the
+     * (higher-priority, latency-bound) network kernels of the previous call find room on every SM while this
+     * kernel streams through (the table prologue is ~2 % of such a CTA) */
+    const long long cap = (long long)sm_count(device) * FEAT_CTAS_PER_SM;
+    const long long chunked = (blocks + FEAT_ITERS - 1) / FEAT_ITERS;
+    if (blocks > cap) blocks = chunked > cap ? chunked : cap;
     feat_kernel<<<(unsigned)blocks, FEAT_THREADS, sizeof(FeatSmem), st>>>(tb, a.pcm, a.stride, a.hist, a.hist_frames,
                                                                             a.s0, a.ns, a.T, a.logmel, a.norm, a.feat16);
     NNSP_LAUNCH_CHECK();
@@ -551,7 +558,13 @@ struct nnsp_b200_batch {
     uint8_t *sp_planes[2] = { nullptr, nullptr };  /* scan-split activation planes [tile][inference][hi|lo][16][pa] */
     int32_t *sp_dec = nullptr;              /* decision records [S][inference] */
     long long sp_cap_inf = 0;
-    int16_t *feat16 = nullptr; long long feat16_frames = 0;       /* scan-split: standardised rows [S][T][40] */
+    int16_t *feat16[2] = { nullptr, nullptr }; long long feat16_frames = 0;   /* scan-split: standardised rows [S][T][40], double buffered */
+    /* device-buffer calls on the scan-split path are pipelined over two CUDA streams: the front end of call N+1
+     * (throughput-bound, `stream`) overlaps the latency-bound network kernels of call N (`nn_stream`) */
+    cudaStream_t nn_stream = nullptr;
+    cudaEvent_t ev_feat[2] = { nullptr, nullptr }, ev_nn[2] = { nullptr, nullptr }, ev_nn0 = nullptr;
+    bool nn_pending[2] = { false, false }, last_piped = false;
+    unsigned pipe = 0;
     int32_t *norm_dev = nullptr;            /* mean[40], stdR[40], rshift for feat_kernel's standardising mode */
     StreamState st{};
     int16_t thresh_prob = 0, th_count = 0;
@@ -570,8 +583,10 @@ static int batch_ensure_logmel(nnsp_b200_batch *b, int T)
 {
     if (batch_nn_path(b) == 3) {                       /* the scan-split path consumes standardised int16 rows */
         if (T <= b->feat16_frames) return NNSP_B200_OK;
-        if (b->feat16) { NNSP_CUDA(cudaStreamSynchronize(b->stream)); for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s)); cudaFree(b->feat16); b->feat16 = nullptr; }
-        NNSP_CUDA(cudaMalloc(&b->feat16, (size_t)b->S * T * NNSP_B200_NMEL * sizeof(int16_t)));
+        NNSP_CUDA(cudaStreamSynchronize(b->stream)); NNSP_CUDA(cudaStreamSynchronize(b->nn_stream));
+        for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+        for (auto &f : b->feat16) { if (f) cudaFree(f); f = nullptr; }
+        for (auto &f : b->feat16) NNSP_CUDA(cudaMalloc(&f, (size_t)b->S * T * NNSP_B200_NMEL * sizeof(int16_t)));
         b->feat16_frames = T;
         return NNSP_B200_OK;
     }
@@ -599,6 +614,7 @@ static int batch_ensure_split(nnsp_b200_batch *b, int n_inf)
 {
     if (batch_nn_path(b) != 3 || n_inf <= b->sp_cap_inf) return NNSP_B200_OK;
     NNSP_CUDA(cudaStreamSynchronize(b->stream));
+    NNSP_CUDA(cudaStreamSynchronize(b->nn_stream));
     for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
     for (auto &p : b->sp_planes) { if (p) cudaFree(p); p = nullptr; }
     if (b->sp_dec) { cudaFree(b->sp_dec); b->sp_dec = nullptr; }
@@ -610,16 +626,29 @@ static int batch_ensure_split(nnsp_b200_batch *b, int n_inf)
     return NNSP_B200_OK;
 }
 
+/* st: stream of the front end (and of everything else unless st_nn is given); st_nn + ev_feat: the network kernels go
+ * to st_nn once ev_feat (recorded on st behind the front end and the history roll) has fired */
 static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride, int T, int s0, int ns,
-                        nnsp_b200_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed)
+                        nnsp_b200_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed,
+                        int fbuf = 0, cudaStream_t st_nn = nullptr, cudaEvent_t ev_feat = nullptr)
 {
     const int path = batch_nn_path(b);
+    int16_t *feat16 = b->feat16[fbuf];
     FeatLaunch fl{ pcm, stride, b->st.hist, 2, s0, ns, T, b->logmel };
-    if (path == 3) { fl.logmel = nullptr; fl.norm = b->norm_dev; fl.feat16 = b->feat16; }
+    if (path == 3) { fl.logmel = nullptr; fl.norm = b->norm_dev; fl.feat16 = feat16; }
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[0], st));
     int rc = launch_feature(b->tables, fl, b->device, st);
     if (rc) return rc;
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[1], st));
+    const bool piped = st_nn != nullptr;
+    if (piped) {
+        /* the history roll only needs the PCM and must precede the next call's front end: it stays on st */
+        if ((rc = launch_hist_update(pcm, stride / 2, b->st.hist, 2, NNSP_B200_FRAME / 2, s0, ns, T, st))) return rc;
+        NNSP_CUDA(cudaEventRecord(ev_feat, st));
+        NNSP_CUDA(cudaStreamWaitEvent(st_nn, ev_feat, 0));
+        st = st_nn;
+        if (timed) NNSP_CUDA(cudaEventRecord(b->ev_nn0, st));
+    }
     if (path == 3 && taps && taps->logmel) {            /* debug tap: a second, log-mel pass straight into the tap */
         FeatLaunch ft{ pcm, stride, b->st.hist, 2, s0, ns, T, taps->logmel };
         if ((rc = launch_feature(b->tables, ft, b->device, st))) return rc;
@@ -632,7 +661,7 @@ static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride
         l.tables = b->tables; l.st = b->st; l.logmel = b->logmel; l.s0 = s0; l.ns = ns; l.T = T; l.results = results;
         if (taps) l.taps = *taps;
         l.thresh_prob = b->thresh_prob; l.th_count = b->th_count;
-        if ((rc = launch_nn_split(b->mm, l, b->feat16, first, n_inf, b->sp_planes[0], b->sp_planes[1], b->sp_dec, b->device, st))) return rc;
+        if ((rc = launch_nn_split(b->mm, l, feat16, first, n_inf, b->sp_planes[0], b->sp_planes[1], b->sp_dec, b->device, st))) return rc;
     } else if (path == 2) {
         if (!b->mma_ok) { nnsp_set_error("this model has no IMMA formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
         NNLaunch l{};
@@ -653,9 +682,17 @@ static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride
         NNSP_LAUNCH_CHECK();
     }
     if (timed) NNSP_CUDA(cudaEventRecord(b->ev[2], st));
-    rc = launch_hist_update(pcm, stride / 2, b->st.hist, 2, NNSP_B200_FRAME / 2, s0, ns, T, st);
-    if (timed) b->ev_valid = true;
+    if (!piped) rc = launch_hist_update(pcm, stride / 2, b->st.hist, 2, NNSP_B200_FRAME / 2, s0, ns, T, st);
+    if (timed) { b->ev_valid = true; b->last_piped = piped; }
     return rc;
+}
+
+/* everything the network stream still has in flight must be over before `st` touches the stream state */
+static int batch_join_nn(nnsp_b200_batch *b, cudaStream_t st)
+{
+    for (int i = 0; i < 2; i++)
+        if (b->nn_pending[i]) { NNSP_CUDA(cudaStreamWaitEvent(st, b->ev_nn[i], 0)); b->nn_pending[i] = false; }
+    return NNSP_B200_OK;
 }
 
 extern "C" {
@@ -695,7 +732,15 @@ int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device, 
     TRY(cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lay.total > 48 * 1024 ? 227 * 1024 : 48 * 1024));
     TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     for (auto &s : b->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;                                /* the network stream outranks the front-end stream */
+        TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        TRY(cudaStreamCreateWithPriority(&b->nn_stream, cudaStreamNonBlocking, hi));
+    }
     for (auto &e : b->ev) TRY(cudaEventCreate(&e));
+    TRY(cudaEventCreate(&b->ev_nn0));
+    for (auto &e : b->ev_feat) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : b->ev_nn) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRY(cudaMalloc(&b->st.ctx, S * 240 * sizeof(int16_t)));
     TRY(cudaMemset(b->st.ctx, 0, S * 240 * sizeof(int16_t)));
     TRY(cudaMalloc(&b->st.h, S * HS * sizeof(int16_t)));
@@ -721,6 +766,8 @@ int nnsp_b200_batch_reset(nnsp_b200_batch *b)
     if (!b) return NNSP_B200_ERR_ARG;
     NNSP_CUDA(cudaSetDevice(b->device));
     for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    if (b->nn_stream) NNSP_CUDA(cudaStreamSynchronize(b->nn_stream));
+    b->nn_pending[0] = b->nn_pending[1] = false;
     reset_kernel<<<b->S, 128, 0, b->stream>>>(b->dm.d, b->st, b->S, NNSP_B200_FRAME);
     NNSP_LAUNCH_CHECK();
     NNSP_CUDA(cudaStreamSynchronize(b->stream));
@@ -747,7 +794,17 @@ int nnsp_b200_batch_exec(nnsp_b200_batch *b, const int16_t *pcm_dev, long long s
     NNSP_CUDA(cudaSetDevice(b->device));
     if ((rc = batch_ensure_logmel(b, n_frames))) return rc;
     if ((rc = batch_ensure_split(b, (n_frames + 1) / 2))) return rc;
-    rc = batch_launch(b, pcm_dev, stream_stride, n_frames, 0, b->S, results_dev, taps, b->stream, true);
+    if (batch_nn_path(b) == 3 && !taps) {
+        /* pipelined: front end of this call on `stream` while the network kernels of the previous call still run on
+         * `nn_stream`; the feature buffer alternates, a buffer is rewritten only after its network pass (two calls ago) */
+        const int i = (int)(b->pipe++ & 1u);
+        if (b->nn_pending[i]) NNSP_CUDA(cudaStreamWaitEvent(b->stream, b->ev_nn[i], 0));
+        rc = batch_launch(b, pcm_dev, stream_stride, n_frames, 0, b->S, results_dev, nullptr, b->stream, true, i, b->nn_stream, b->ev_feat[i]);
+        if (rc == NNSP_B200_OK) { NNSP_CUDA(cudaEventRecord(b->ev_nn[i], b->nn_stream)); b->nn_pending[i] = true; }
+    } else {
+        if ((rc = batch_join_nn(b, b->stream))) return rc;
+        rc = batch_launch(b, pcm_dev, stream_stride, n_frames, 0, b->S, results_dev, taps, b->stream, true);
+    }
     if (rc == NNSP_B200_OK) b->slides = (b->slides + n_frames) % 2;
     return rc;
 }
@@ -772,6 +829,8 @@ int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
         b->d_pcm_frames = T; b->d_res_frames = T;
     }
     NNSP_CUDA(cudaStreamSynchronize(b->stream));
+    NNSP_CUDA(cudaStreamSynchronize(b->nn_stream));
+    b->nn_pending[0] = b->nn_pending[1] = false;
     /* slices of streams pipelined over four CUDA streams: H2D(k+1) overlaps kernels(k) overlaps D2H(k-1). The call
      * is bound by the host link (320 B of PCM per stream-frame), so slices are small enough that the work left
      * after the last H2D -- one slice of kernels and its D2H -- is short, and large enough to fill the GPU */
@@ -808,6 +867,7 @@ int nnsp_b200_batch_sync(nnsp_b200_batch *b)
     if (!b) return NNSP_B200_ERR_ARG;
     NNSP_CUDA(cudaSetDevice(b->device));
     NNSP_CUDA(cudaStreamSynchronize(b->stream));
+    NNSP_CUDA(cudaStreamSynchronize(b->nn_stream));
     for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
     return NNSP_B200_OK;
 }
@@ -820,7 +880,7 @@ int nnsp_b200_batch_last_kernel_ms(nnsp_b200_batch *b, float ms[3])
     NNSP_CUDA(cudaSetDevice(b->device));
     NNSP_CUDA(cudaEventSynchronize(b->ev[2]));
     NNSP_CUDA(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[1]));
-    NNSP_CUDA(cudaEventElapsedTime(&ms[1], b->ev[1], b->ev[2]));
+    NNSP_CUDA(cudaEventElapsedTime(&ms[1], b->last_piped ? b->ev_nn0 : b->ev[1], b->ev[2]));
     return NNSP_B200_OK;
 }
 
@@ -855,7 +915,11 @@ void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
     cudaFree(b->st.ctx); cudaFree(b->st.h); cudaFree(b->st.c); cudaFree(b->st.scal); cudaFree(b->st.hist);
     cudaFree(b->logmel); cudaFree(b->d_pcm); cudaFree(b->d_res);
     cudaFree(b->sp_planes[0]); cudaFree(b->sp_planes[1]); cudaFree(b->sp_dec);
-    cudaFree(b->feat16); cudaFree(b->norm_dev);
+    cudaFree(b->feat16[0]); cudaFree(b->feat16[1]); cudaFree(b->norm_dev);
+    if (b->nn_stream) cudaStreamDestroy(b->nn_stream);
+    if (b->ev_nn0) cudaEventDestroy(b->ev_nn0);
+    for (auto e : b->ev_feat) if (e) cudaEventDestroy(e);
+    for (auto e : b->ev_nn) if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
     for (auto s : b->xs) if (s) cudaStreamDestroy(s);
     for (auto e : b->ev) if (e) cudaEventDestroy(e);

@@ -21,6 +21,7 @@ def time_handle(h, exec_fn, T, S, steps=8, warm=3):
     ev0.record(h.stream)
     for i in range(steps):
         exec_fn(i)
+    h.sync()                       # every stream of the handle (calls are pipelined over two)
     ev1.record(h.stream)
     h.sync()
     ms = ev0.elapsed_ms_to(ev1) / steps
