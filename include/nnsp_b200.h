@@ -174,6 +174,9 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
                              const nnsp_b200_cascade_params *params, int n_streams, int device,
                              nnsp_b200_cascade **out);
 int nnsp_b200_cascade_reset(nnsp_b200_cascade *c);
+/* Asynchronous and pipelined like nnsp_b200_batch_exec: results, state and the PCM buffer of a call are settled
+ * after nnsp_b200_cascade_sync (the replay of stage changes reads the call's PCM while the next call's front end
+ * already runs). */
 int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long long stream_stride,
                            int n_frames, nnsp_b200_cascade_result *results_dev,
                            const nnsp_b200_taps *taps);

@@ -546,6 +546,14 @@ struct nnsp_b200_cascade {
     int32_t *dec = nullptr;
     long long split_cap_T = 0;
     cudaStream_t gs[CG_GROUPS] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* one per (model, phase) group */
+    /* device-buffer calls are pipelined like the batched path: front end + PCM history roll of call N+1 on `stream`,
+     * controller / network work of call N on `nn_stream`; log-mel rows and PCM history are double buffered */
+    cudaStream_t nn_stream = nullptr;
+    cudaEvent_t ev_feat[2] = { nullptr, nullptr }, ev_nn[2] = { nullptr, nullptr }, ev_nn0 = nullptr;
+    bool nn_pending[2] = { false, false }, last_piped = false;
+    unsigned pipe = 0;
+    int32_t *logmel2 = nullptr;                /* second log-mel buffer */
+    int16_t *hist2 = nullptr;                  /* second PCM history buffer */
     cudaEvent_t ev_fork = nullptr, ev_join[CG_GROUPS] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 
@@ -578,25 +586,41 @@ static int cascade_ensure_logmel(nnsp_b200_cascade *c, int T)
     if (T <= c->logmel_frames) return NNSP_B200_OK;
     NNSP_CUDA(cudaDeviceSynchronize());
     if (c->logmel) cudaFree(c->logmel);
-    c->logmel = nullptr;
+    if (c->logmel2) cudaFree(c->logmel2);
+    c->logmel = nullptr; c->logmel2 = nullptr;
     NNSP_CUDA(cudaMalloc(&c->logmel, (size_t)c->S * T * NNSP_B200_NMEL * sizeof(int32_t)));
+    NNSP_CUDA(cudaMalloc(&c->logmel2, (size_t)c->S * T * NNSP_B200_NMEL * sizeof(int32_t)));
     c->logmel_frames = T;
     return NNSP_B200_OK;
 }
 
+/* st_nn (with ev_feat): pipelined call -- everything behind the front end goes to st_nn, the PCM history is rolled out
+ * of place on st right behind the front end (c->st.hist is swapped by the caller afterwards) */
 static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long stride, int T, int s0, int ns,
                           nnsp_b200_cascade_result *results, const nnsp_b200_taps *taps, cudaStream_t st, bool timed,
-                          int slice = 0)
+                          int slice = 0, int32_t *logmel = nullptr, cudaStream_t st_nn = nullptr, cudaEvent_t ev_feat = nullptr,
+                          cudaEvent_t ev_prev_nn = nullptr)
 {
     const int hist_frames = c->cd.dmax + 2;
-    FeatLaunch fl{ pcm, stride, c->st.hist, hist_frames, s0, ns, T, c->logmel };
+    if (!logmel) logmel = c->logmel;
+    const bool piped = st_nn != nullptr;
+    FeatLaunch fl{ pcm, stride, c->st.hist, hist_frames, s0, ns, T, logmel };
     if (timed) NNSP_CUDA(cudaEventRecord(c->ev[0], st));
     int rc = launch_feature(c->tables, fl, c->device, st);
     if (rc) return rc;
     if (timed) NNSP_CUDA(cudaEventRecord(c->ev[1], st));
+    if (piped) {
+        NNSP_CUDA(cudaEventRecord(ev_feat, st));
+        NNSP_CUDA(cudaStreamWaitEvent(st_nn, ev_feat, 0));
+        /* the spare history buffer is the one the previous call's replay may still read: roll into it only then */
+        if (ev_prev_nn) NNSP_CUDA(cudaStreamWaitEvent(st, ev_prev_nn, 0));
+        if ((rc = launch_hist_roll(pcm, stride / 2, c->st.hist, c->hist2, hist_frames, NNSP_B200_FRAME / 2, s0, ns, T, st))) return rc;
+        st = st_nn;
+        if (timed) NNSP_CUDA(cudaEventRecord(c->ev_nn0, st));
+    }
     CascadeArgs a{};
     for (int i = 0; i < 3; i++) { a.model[i] = c->dm[i].d; a.wimg[i] = c->dm[i].wimg; a.bimg[i] = c->dm[i].bimg; }
-    a.tables = c->tables; a.st = c->st; a.stale = c->stale; a.pcm = pcm; a.stride = stride; a.logmel = c->logmel;
+    a.tables = c->tables; a.st = c->st; a.stale = c->stale; a.pcm = pcm; a.stride = stride; a.logmel = logmel;
     a.s0 = s0; a.ns = ns; a.T = T; a.results = results; a.cd = c->cd;
     if (taps) a.taps = *taps;
     if (cascade_use_split(c, taps)) {
@@ -621,7 +645,7 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
                 q.tile0 = (s0 >> 4) + (CG_GROUPS + 1) * slice; q.max_streams = ns;
                 q.tile_bytes = (long long)n_inf_max * 32 * c->pa_max;
                 q.T = T; q.first = first; q.n_inf = (T > first) ? (T - first + 1) / 2 : 0;
-                q.mode = 2; q.logmel = c->logmel; q.lmhist = c->st.lmhist; q.dmax = c->cd.dmax;
+                q.mode = 2; q.logmel = logmel; q.lmhist = c->st.lmhist; q.dmax = c->cd.dmax;
                 q.dback = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? c->cd.P.frs_vbufBk_kws : c->cd.P.frs_vbufBk_s2i);
                 q.ctx = c->st.ctx; q.h = c->st.h; q.c = c->st.c; q.h_stride = NNSP_B200_MAX_WIDTH;
                 q.planes0 = c->planes[0]; q.planes1 = c->planes[1];
@@ -637,7 +661,7 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
         /* ... walk the controller over the decisions, cut at the first stage change ... */
         CascadePostArgs p{};
         for (int i = 0; i < 3; i++) p.model[i] = c->mm[i].d;
-        p.st = c->st; p.stale = c->stale; p.logmel = c->logmel; p.dec = c->dec; p.dec_stride = n_inf_max; p.t0 = c->t0;
+        p.st = c->st; p.stale = c->stale; p.logmel = logmel; p.dec = c->dec; p.dec_stride = n_inf_max; p.t0 = c->t0;
         p.s0 = s0; p.ns = ns; p.T = T; p.results = results; p.cd = c->cd;
         p.replay_list = c->replay_list; p.replay_count = count + 8;
         cascade_post_kernel<<<(ns + CPOST_THREADS - 1) / CPOST_THREADS, CPOST_THREADS, 0, st>>>(p);
@@ -650,11 +674,18 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
     if (blocks > cap) blocks = cap;
     cascade_kernel<<<blocks, CS_THREADS, c->smem_total, st>>>(a, c->off_w, c->off_b);
     NNSP_LAUNCH_CHECK();
-    if (timed) { NNSP_CUDA(cudaEventRecord(c->ev[2], st)); c->ev_valid = true; }
-    if ((rc = launch_hist_update(pcm, stride / 2, c->st.hist, hist_frames, NNSP_B200_FRAME / 2, s0, ns, T, st))) return rc;
+    if (timed) { NNSP_CUDA(cudaEventRecord(c->ev[2], st)); c->ev_valid = true; c->last_piped = piped; }
+    if (!piped && (rc = launch_hist_update(pcm, stride / 2, c->st.hist, hist_frames, NNSP_B200_FRAME / 2, s0, ns, T, st))) return rc;
     if (c->cd.dmax > 0)
-        rc = launch_hist_update(c->logmel, (long long)T * NNSP_B200_NMEL, c->st.lmhist, c->cd.dmax, NNSP_B200_NMEL, s0, ns, T, st);
+        rc = launch_hist_update(logmel, (long long)T * NNSP_B200_NMEL, c->st.lmhist, c->cd.dmax, NNSP_B200_NMEL, s0, ns, T, st);
     return rc;
+}
+
+static int cascade_join_nn(nnsp_b200_cascade *c, cudaStream_t st)
+{
+    for (int i = 0; i < 2; i++)
+        if (c->nn_pending[i]) { NNSP_CUDA(cudaStreamWaitEvent(st, c->ev_nn[i], 0)); c->nn_pending[i] = false; }
+    return NNSP_B200_OK;
 }
 
 extern "C" {
@@ -730,6 +761,14 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &e : c->ev) TRY(cudaEventCreate(&e));
     for (auto &g : c->gs) TRY(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        TRY(cudaStreamCreateWithPriority(&c->nn_stream, cudaStreamNonBlocking, hi));
+    }
+    TRY(cudaEventCreate(&c->ev_nn0));
+    for (auto &e : c->ev_feat) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : c->ev_nn) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (auto &e : c->ev_join) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRY(cudaMalloc(&c->st.ctx, S * 240 * sizeof(int16_t)));
@@ -738,6 +777,7 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaMalloc(&c->st.scal, S * SC_N * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.casc, S * CS_N * sizeof(uint16_t)));
     TRY(cudaMalloc(&c->st.hist, S * hist_frames * NNSP_B200_FRAME * sizeof(int16_t)));
+    TRY(cudaMalloc(&c->hist2, S * hist_frames * NNSP_B200_FRAME * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.lmhist, S * lm_rows * NNSP_B200_NMEL * sizeof(int32_t)));
     TRY(cudaMalloc(&c->stale, S * 120 * sizeof(int16_t)));
     TRY(cudaMalloc(&c->grp_list, (size_t)CG_GROUPS * S * sizeof(int)));
@@ -762,6 +802,7 @@ int nnsp_b200_cascade_reset(nnsp_b200_cascade *c)
     if (!c) return NNSP_B200_ERR_ARG;
     NNSP_CUDA(cudaSetDevice(c->device));
     NNSP_CUDA(cudaDeviceSynchronize());
+    c->nn_pending[0] = c->nn_pending[1] = false;
     const int hist_frames = c->cd.dmax + 2, lm_rows = c->cd.dmax > 0 ? c->cd.dmax : 1;
     ResetModels rm{};
     for (int i = 0; i < 3; i++) rm.m[i] = c->dm[i].d;
@@ -792,6 +833,18 @@ int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long lo
     NNSP_CUDA(cudaSetDevice(c->device));
     if ((rc = cascade_ensure_logmel(c, n_frames))) return rc;
     if ((rc = cascade_ensure_split(c, n_frames))) return rc;
+    if (cascade_use_split(c, taps)) {
+        const int i = (int)(c->pipe++ & 1u);
+        if (c->nn_pending[i]) NNSP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_nn[i], 0));   /* log-mel buffer i / PCM history in use two calls ago */
+        rc = cascade_launch(c, pcm_dev, stream_stride, n_frames, 0, c->S, results_dev, nullptr, c->stream, true, 0,
+                            i ? c->logmel2 : c->logmel, c->nn_stream, c->ev_feat[i], c->nn_pending[i ^ 1] ? c->ev_nn[i ^ 1] : nullptr);
+        if (rc) return rc;
+        NNSP_CUDA(cudaEventRecord(c->ev_nn[i], c->nn_stream));
+        c->nn_pending[i] = true;
+        int16_t *t = c->st.hist; c->st.hist = c->hist2; c->hist2 = t;      /* the rolled history is the live one from here on */
+        return NNSP_B200_OK;
+    }
+    if ((rc = cascade_join_nn(c, c->stream))) return rc;
     return cascade_launch(c, pcm_dev, stream_stride, n_frames, 0, c->S, results_dev, taps, c->stream, true);
 }
 
@@ -815,6 +868,8 @@ int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
         c->d_pcm_frames = T;
     }
     NNSP_CUDA(cudaStreamSynchronize(c->stream));
+    NNSP_CUDA(cudaStreamSynchronize(c->nn_stream));
+    c->nn_pending[0] = c->nn_pending[1] = false;
     const long long dstride = (long long)T * NNSP_B200_FRAME;
     const int nsl = c->S >= 4096 ? 8 : (c->S >= 256 ? 4 : 1);
     for (int k = 0; k < nsl; k++) {
@@ -840,6 +895,7 @@ int nnsp_b200_cascade_sync(nnsp_b200_cascade *c)
     if (!c) return NNSP_B200_ERR_ARG;
     NNSP_CUDA(cudaSetDevice(c->device));
     NNSP_CUDA(cudaStreamSynchronize(c->stream));
+    NNSP_CUDA(cudaStreamSynchronize(c->nn_stream));
     for (auto s : c->xs) NNSP_CUDA(cudaStreamSynchronize(s));
     return NNSP_B200_OK;
 }
@@ -852,7 +908,7 @@ int nnsp_b200_cascade_last_kernel_ms(nnsp_b200_cascade *c, float ms[3])
     NNSP_CUDA(cudaSetDevice(c->device));
     NNSP_CUDA(cudaEventSynchronize(c->ev[2]));
     NNSP_CUDA(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
-    NNSP_CUDA(cudaEventElapsedTime(&ms[1], c->ev[1], c->ev[2]));
+    NNSP_CUDA(cudaEventElapsedTime(&ms[1], c->last_piped ? c->ev_nn0 : c->ev[1], c->ev[2]));
     return NNSP_B200_OK;
 }
 
@@ -874,7 +930,11 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     for (int i = 0; i < 3; i++) if (c->have[i]) free_model(&c->dm[i]);
     cudaFree(c->st.ctx); cudaFree(c->st.h); cudaFree(c->st.c); cudaFree(c->st.scal); cudaFree(c->st.casc);
     cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale);
-    cudaFree(c->logmel); cudaFree(c->d_pcm); cudaFree(c->d_res);
+    cudaFree(c->logmel); cudaFree(c->logmel2); cudaFree(c->hist2); cudaFree(c->d_pcm); cudaFree(c->d_res);
+    if (c->nn_stream) cudaStreamDestroy(c->nn_stream);
+    if (c->ev_nn0) cudaEventDestroy(c->ev_nn0);
+    for (auto e : c->ev_feat) if (e) cudaEventDestroy(e);
+    for (auto e : c->ev_nn) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) free_model_mma(&c->mm[i]);
     cudaFree(c->replay_list); cudaFree(c->grp_list); cudaFree(c->grp_count); cudaFree(c->grp_tile_off); cudaFree(c->t0);
     cudaFree(c->planes[0]); cudaFree(c->planes[1]); cudaFree(c->dec);

@@ -301,6 +301,31 @@ __global__ void hist_kernel(const unsigned int *__restrict__ src, long long stri
     }
 }
 
+/* out of place: hist_out <- newest hist_frames frames of (hist_in ++ src[0..T)) */
+__global__ void hist_roll_kernel(const unsigned int *__restrict__ src, long long stride_words, const unsigned int *__restrict__ hist_in,
+                                 unsigned int *__restrict__ hist_out, int hist_frames, int wpf, int s0, int ns, int T)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= ns) return;
+    const long long s = s0 + warp;
+    const int words = hist_frames * wpf, keep = (hist_frames - T) * wpf;       /* words of the old history that survive */
+    const unsigned int *hi = hist_in + s * words, *p = src + s * stride_words;
+    unsigned int *ho = hist_out + s * words;
+    for (int i = lane; i < words; i += 32)
+        ho[i] = (i < keep) ? hi[i + T * wpf] : p[(long long)(T - hist_frames) * wpf + i];
+}
+
+int launch_hist_roll(const void *src, long long stride_words, const void *hist_in, void *hist_out, int hist_frames,
+                     int words_per_frame, int s0, int ns, int T, cudaStream_t st)
+{
+    if (ns <= 0 || T <= 0 || hist_frames <= 0) return NNSP_B200_OK;
+    const int threads = 256, blocks = (ns * 32 + threads - 1) / threads;
+    hist_roll_kernel<<<blocks, threads, 0, st>>>((const unsigned int *)src, stride_words, (const unsigned int *)hist_in,
+                                                 (unsigned int *)hist_out, hist_frames, words_per_frame, s0, ns, T);
+    NNSP_LAUNCH_CHECK();
+    return NNSP_B200_OK;
+}
+
 int launch_hist_update(const void *src, long long stride_words, void *hist, int hist_frames, int words_per_frame,
                        int s0, int ns, int T, cudaStream_t st)
 {

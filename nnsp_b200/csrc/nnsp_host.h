@@ -58,6 +58,10 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
 /* hist <- newest hist_frames frames of (hist ++ src[0..T)); frames are words_per_frame 32-bit words */
 int launch_hist_update(const void *src, long long stride_words, void *hist, int hist_frames, int words_per_frame,
                        int s0, int ns, int T, cudaStream_t st);
+/* the same, out of place (hist_in and hist_out distinct): lets the next call's front end start while kernels of this
+ * call still read the old history */
+int launch_hist_roll(const void *src, long long stride_words, const void *hist_in, void *hist_out, int hist_frames,
+                     int words_per_frame, int s0, int ns, int T, cudaStream_t st);
 
 
 /* tensor-core (IMMA) network path, nnsp_mma.cu */

@@ -166,3 +166,32 @@ def test_cascade_sorted_exec_host_equals_sequential(nb):
         c.close()
     for f in out["sorted"].dtype.names:
         assert (out["sorted"][f] == out["sequential"][f]).all(), f
+
+
+def test_cascade_back_to_back_calls_are_pipelined_correctly(nb, oracle):
+    """Cascade calls issued without a sync in between (front end of call N+1 overlaps the controller / network work of
+    call N; log-mel rows and the PCM history are double buffered, the replay reads the previous call's PCM)."""
+    S = 60
+    lens = [50, 50, 3, 47, 100, 50, 1, 49, 50, 100]
+    T = sum(lens)
+    pcm = nb.synth_pcm(S, T, first_stream=33)
+    params = dict(frs_vbufBk_kws=99, frs_vbufBk_s2i=1, thresh_timeout_kws=45, thresh_timeout_s2i=30, thresh_prob_kws=100, thresh_cnts_kws=2)
+    c = nb.Cascade(_models(nb), S, params=params)
+    c.set_path("sorted")
+    d_pcm, d_res, t = [], [], 0
+    for n in lens:
+        d_pcm.append(nb.DeviceArray.from_host(pcm[:, t * 160:(t + n) * 160]))
+        d_res.append(nb.DeviceArray((S, n), nb.CASCADE_RESULT_DT))
+        t += n
+    for k, n in enumerate(lens):
+        c.exec_device(d_pcm[k], n * 160, n, d_res[k])
+    c.sync()
+    res = np.concatenate([r.to_host() for r in d_res], axis=1)
+    om = _oracle_models(oracle)
+    par = c.params_array()
+    for s in range(S):
+        r, tp, valid = oracle.cascade_run(om, pcm[s], params=par)
+        _check(res, None, s, r, None, None)
+    for x in d_pcm + d_res:
+        x.free()
+    c.close()

@@ -171,3 +171,30 @@ def test_ingest_conditioning_matches_the_application(nb, oracle):
     ref = (raw & 0xFFF0).astype(np.uint16).view(np.int16).reshape(37, 9, 160).copy()
     ref[:, :, 3] = (ref[:, :, 2].astype(np.int32) + ref[:, :, 4]) >> 1
     assert (want.reshape(37, 9, 160) == ref).all()
+
+
+def test_back_to_back_calls_are_pipelined_correctly(nb, oracle):
+    """Device-buffer calls issued without a sync in between: the engine runs the front end of call N+1 while the network
+    kernels of call N are still in flight (double-buffered features). Results of every call must still be exact."""
+    S, n_calls = 100, 9
+    lens = [10, 1, 7, 10, 3, 10, 2, 10, 11]
+    T = sum(lens)
+    pcm = nb.synth_pcm(S, T, first_stream=21)
+    m = _model(nb, 0, False)
+    b = nb.NNSPBatch(m, S)
+    d_pcm, d_res, t = [], [], 0
+    for n in lens:
+        d_pcm.append(nb.DeviceArray.from_host(pcm[:, t * 160:(t + n) * 160]))
+        d_res.append(nb.DeviceArray((S, n), nb.RESULT_DT))
+        t += n
+    for k, n in enumerate(lens):                       # no sync between the calls
+        b.exec_device(d_pcm[k], n * 160, n, d_res[k])
+    b.sync()
+    got = np.concatenate([r.to_host() for r in d_res], axis=1)
+    m_or = oracle.model(0, False)
+    for s in range(S):
+        r, _ = oracle.nnsp_run(m_or, pcm[s], taps=False)
+        assert (r == got[s]).all(), "stream %d" % s
+    for x in d_pcm + d_res:
+        x.free()
+    b.close()
