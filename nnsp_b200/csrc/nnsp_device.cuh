@@ -27,6 +27,35 @@ __device__ __forceinline__ int32_t madd_q15(int32_t ar, int32_t wi, int32_t ai, 
 {
     return (int32_t)(((int64_t)ar * (int64_t)wi + (int64_t)ai * (int64_t)wr) >> 15);
 }
+/* Three-input adds. The FMA-heavy pipe (IMAD at 2, IMAD.WIDE at 4 cycles per warp) is the busiest one in the front
+ * end (ncu: sm__pipe_fmaheavy_cycles_active 71 %, ALU 51 %). A private-temporary add pair is fused by ptxas into ONE
+ * IADD3 on the ALU pipe: fewer instructions, on the pipe that has room. (Forcing the remaining two-input adds onto the
+ * ALU pipe with a run-time-zero third operand was measured and is slower: 0.508 vs 0.482 ms.) */
+__device__ __forceinline__ int32_t add3(int32_t a, int32_t b, int32_t c)        /* a + b + c */
+{
+    int32_t r;
+    asm("{\n\t.reg .s32 t;\n\tadd.s32 t, %1, %2;\n\tadd.s32 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int32_t add2sub(int32_t a, int32_t b, int32_t c)     /* a + b - c */
+{
+    int32_t r;
+    asm("{\n\t.reg .s32 t;\n\tadd.s32 t, %1, %2;\n\tsub.s32 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int32_t sub2add(int32_t a, int32_t b, int32_t c)     /* a - b + c */
+{
+    int32_t r;
+    asm("{\n\t.reg .s32 t;\n\tsub.s32 t, %1, %2;\n\tadd.s32 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int32_t sub3(int32_t a, int32_t b, int32_t c)        /* a - b - c */
+{
+    int32_t r;
+    asm("{\n\t.reg .s32 t;\n\tsub.s32 t, %1, %2;\n\tsub.s32 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 /* a * 0x7fff >> 15 == a + floor(-a / 2^15): the reference's Q15 "1.0" (twiddle_fft_dif.c:9) */
 __device__ __forceinline__ int32_t mul_one_q15(int32_t a) { return a + ((-a) >> 15); }
 

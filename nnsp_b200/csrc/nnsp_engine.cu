@@ -202,7 +202,10 @@ void free_model(DeviceModel *dm)
 /* ======================================================================================== */
 /* feature kernel                                                                             */
 /* ======================================================================================== */
-constexpr int FEAT_WARPS = 8;                 /* 16 frames in flight per CTA */
+#ifndef FEAT_WARPS_PER_CTA
+#define FEAT_WARPS_PER_CTA 8
+#endif
+constexpr int FEAT_WARPS = FEAT_WARPS_PER_CTA;   /* two frames in flight per warp */
 constexpr int FEAT_THREADS = FEAT_WARPS * 32;
 #ifndef FEAT_CTAS_PER_SM
 #define FEAT_CTAS_PER_SM 3

@@ -59,12 +59,12 @@ __device__ __forceinline__ void bfly4(int32_t &ar, int32_t &ai, int32_t &cr, int
                                       int32_t &br, int32_t &bi, int32_t &dr, int32_t &di,
                                       int2 w1, int2 w2, int2 w3)
 {
-    const int32_t s0r = ar + br, s0i = ai + bi, d0r = ar - br, d0i = ai - bi;
+    /* 12 three-input adds instead of 16 two-input ones (wrapping int32 adds: any association gives the same bits) */
     const int32_t s1r = cr + dr, s1i = ci + di, d1r = cr - dr, d1i = ci - di;
-    const int32_t o0r = s0r + s1r, o0i = s0i + s1i;
-    const int32_t o1r = s0r - s1r, o1i = s0i - s1i;
-    const int32_t o2r = d0r + d1i, o2i = d0i - d1r;
-    const int32_t o3r = d0r - d1i, o3i = d0i + d1r;
+    const int32_t o0r = add3(ar, br, s1r), o0i = add3(ai, bi, s1i);
+    const int32_t o1r = add2sub(ar, br, s1r), o1i = add2sub(ai, bi, s1i);
+    const int32_t o2r = sub2add(ar, br, d1i), o2i = sub3(ai, bi, d1r);
+    const int32_t o3r = sub3(ar, br, d1i), o3i = sub2add(ai, bi, d1r);
     ar = mul_one_q15(o0r);
     ai = mul_one_q15(o0i);
     if (ALLONE) {

@@ -191,7 +191,10 @@ __device__ __forceinline__ void fc_tiles(int kt, const uint2 *wf, const uint8_t 
 /* MODE 0: input = activation planes; 1: input = feat16 rows (batched NNSPClass); 2: input = log-mel rows with
  * look-back, standardised while staging (cascade) */
 template <int MODE>
-__global__ void __launch_bounds__(SEG_THREADS, 2)
+#ifndef SEG_MINB
+#define SEG_MINB 2
+#endif
+__global__ void __launch_bounds__(SEG_THREADS, SEG_MINB)
 seg_kernel(SegArgs a)
 {
     constexpr bool FROM_FEAT = MODE != 0;
