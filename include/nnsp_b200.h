@@ -143,6 +143,8 @@ int nnsp_b200_batch_dims(const nnsp_b200_batch *b, int *n_streams, int *act_stri
  * for all frames of the call at once, only the LSTM recurrence sequential; nnsp_split.cu). 2 and 3 return an
  * error when the model does not fit them. All three are bit-exact. */
 int nnsp_b200_batch_set_nn_path(nnsp_b200_batch *b, int path);
+/* the path the next call will take (1, 2 or 3): what `automatic` resolved to for this model */
+int nnsp_b200_batch_get_nn_path(const nnsp_b200_batch *b);
 /* CUDA stream the front end is launched on (cudaStream_t as void*), for callers that time it; the network
  * kernels of the default path run on a second, internal stream -- bracket timed regions with nnsp_b200_batch_sync. */
 void *nnsp_b200_batch_stream(nnsp_b200_batch *b);

@@ -166,6 +166,11 @@ class NNSPBatch:
         check(lib().nnsp_b200_batch_dims(self.h, None, C.byref(a), C.byref(hs), C.byref(no)), "batch_dims")
         self.act_stride, self.h_stride, self.n_out = a.value, hs.value, no.value
 
+    @property
+    def nn_path(self):
+        """'dp2a' / 'imma' / 'split': the network path the next call takes."""
+        return {v: k for k, v in self.NN_PATH.items()}[lib().nnsp_b200_batch_get_nn_path(self.h)]
+
     def set_nn_path(self, nn_path):
         check(lib().nnsp_b200_batch_set_nn_path(self.h, self.NN_PATH[nn_path]), "batch_set_nn_path")
 

@@ -38,7 +38,7 @@ SYMBOLS = """nnsp_b200_version nnsp_b200_strerror nnsp_b200_last_error nnsp_b200
 nnsp_b200_model_from_net nnsp_b200_model_from_table_text nnsp_b200_model_to_table_text nnsp_b200_model_from_blob nnsp_b200_model_to_blob nnsp_b200_model_set_acc32
 nnsp_b200_model_info nnsp_b200_model_free nnsp_b200_batch_create nnsp_b200_batch_reset nnsp_b200_batch_exec
 nnsp_b200_batch_exec_host nnsp_b200_batch_sync nnsp_b200_batch_last_kernel_ms nnsp_b200_batch_dims
-nnsp_b200_batch_stream nnsp_b200_batch_set_nn_path nnsp_b200_batch_destroy nnsp_b200_cascade_default_params nnsp_b200_cascade_create
+nnsp_b200_batch_stream nnsp_b200_batch_set_nn_path nnsp_b200_batch_get_nn_path nnsp_b200_batch_destroy nnsp_b200_cascade_default_params nnsp_b200_cascade_create
 nnsp_b200_cascade_reset nnsp_b200_cascade_exec nnsp_b200_cascade_exec_host nnsp_b200_cascade_sync
 nnsp_b200_cascade_last_kernel_ms nnsp_b200_cascade_stream nnsp_b200_cascade_set_path nnsp_b200_cascade_destroy nnsp_b200_feature_stages
 nnsp_b200_table nnsp_b200_ingest_audadc nnsp_b200_device_count nnsp_b200_dev_alloc nnsp_b200_dev_free nnsp_b200_host_alloc_pinned
@@ -80,6 +80,7 @@ def lib():
     L.nnsp_b200_batch_stream.argtypes = [vp]
     L.nnsp_b200_batch_stream.restype = vp
     L.nnsp_b200_batch_set_nn_path.argtypes = [vp, ci]
+    L.nnsp_b200_batch_get_nn_path.argtypes = [vp]
     L.nnsp_b200_batch_destroy.argtypes = [vp]
     L.nnsp_b200_batch_destroy.restype = None
     if hasattr(L, "nnsp_b200_cascade_create"):

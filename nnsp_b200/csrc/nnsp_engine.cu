@@ -933,6 +933,8 @@ int nnsp_b200_batch_set_nn_path(nnsp_b200_batch *b, int path)
     return NNSP_B200_OK;
 }
 
+int nnsp_b200_batch_get_nn_path(const nnsp_b200_batch *b) { return b ? batch_nn_path(b) : NNSP_B200_ERR_ARG; }
+
 void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
 {
     if (!b) return;

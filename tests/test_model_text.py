@@ -10,37 +10,11 @@ import tempfile
 import numpy as np
 import pytest
 
-from common import ROOT, have_reference_tree
+from common import ROOT, have_reference_tree, make_blob
 
 REF_SRC = "/root/reference/evb/src"
 FILES = {"s2i": ("def_nn0_s2i.c", 0, "s2i.nnspm"), "vad": ("def_nn1_vad.c", 1, "vad.nnspm"),
          "kws_galaxy": ("def_nn2_kws_galaxy.c", 2, "kws_galaxy.nnspm")}
-
-
-def make_blob(nn_id, sizes, types, acts, qk, qi, qb, seed=0):
-    """NNSPM1 container with random table-layout weights: any byte string is a valid table."""
-    rng = np.random.default_rng(seed)
-    nl = len(types)
-    hdr = b"NNSPM1\0\0" + struct.pack("<ii", nn_id, nl)
-    sl = list(sizes) + [0] * (11 - len(sizes))
-    hdr += struct.pack("<11h", *sl) + b"\0\0"
-    hdr += rng.integers(-200000, 200000, 40, dtype=np.int32).tobytes() + rng.integers(1, 40000, 40, dtype=np.int32).tobytes()
-    recs, body = b"", b""
-    for i in range(10):
-        if i < nl:
-            rows, cols = sizes[i + 1], sizes[i]
-            nr = 4 * rows if types[i] == 1 else rows
-            kb, rb, bc = nr * cols, (nr * rows if types[i] == 1 else 0), nr
-            qin = qi[i + 1] if i + 1 < nl else 0
-            recs += struct.pack("<10i", types[i], acts[i], qk[i], qi[i], qb[i], 0, kb, rb, bc, qin)
-            for n in (kb, rb):
-                a = rng.integers(-128, 128, n, dtype=np.int8).tobytes()
-                body += a + b"\0" * (-len(a) % 4)
-            a = rng.integers(-32768, 32768, bc, dtype=np.int16).tobytes()
-            body += a + b"\0" * (-len(a) % 4)
-        else:
-            recs += b"\0" * 40
-    return hdr + recs + body
 
 
 def test_text_round_trip_of_the_shipped_models(nb):
