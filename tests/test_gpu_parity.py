@@ -198,3 +198,21 @@ def test_back_to_back_calls_are_pipelined_correctly(nb, oracle):
     for x in d_pcm + d_res:
         x.free()
     b.close()
+
+
+def test_long_call_many_inference_rounds(nb, oracle):
+    """One call of 301 frames (151 inferences): several 16-inference work items per tile in the fc kernels, several
+    staging rounds in the post kernel, a long TMA ring in the scan."""
+    S, T = 19, 301
+    pcm = nb.synth_pcm(S, T, first_stream=77)
+    for nn_id in (0, 2):
+        m = _model(nb, nn_id, False)
+        b = nb.NNSPBatch(m, S)
+        assert b.nn_path == "split"
+        res, taps = b.exec(pcm, taps=True)
+        plain = nb.NNSPBatch(m, S).exec(pcm)
+        m_or = oracle.model(nn_id, False)
+        for s in range(S):
+            _compare_stream(oracle, m_or, pcm[s], res[s], taps, s)
+        assert (plain == res).all()
+        b.close()
