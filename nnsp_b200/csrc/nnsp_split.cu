@@ -230,7 +230,8 @@ seg_kernel(SegArgs a)
     }
     const int XB = 32 * M.pa;                                    /* bytes of one tile-step: [hi|lo][16][pa] */
     uint8_t *wb = smem + a.off_wb + (size_t)warp * a.nbuf * XB;
-    int32_t *wlog = reinterpret_cast<int32_t *>(smem + a.off_log) + warp * 16 * M.no;
+    const int NOP = M.no + 4;                                     /* logits row pitch: (no + 4) words keeps the 8 rows of a store on distinct banks */
+    int32_t *wlog = reinterpret_cast<int32_t *>(smem + a.off_log) + warp * 16 * NOP;
     {   /* activation planes start zeroed: padded k columns must hold defined bytes (they meet zero weights) */
         uint32_t *z = reinterpret_cast<uint32_t *>(smem + a.off_wb);
         for (int i = tid; i < SEG_WARPS * a.nbuf * XB / 4; i += SEG_THREADS) z[i] = 0;
@@ -395,7 +396,7 @@ seg_kernel(SegArgs a)
                                 pre[e] = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e] + (uint32_t)((e & 1) ? b1 : b0)) >> rs;
                             if (act == ACT_LINEAR) {                                            /* activation.c:19-29 */
 #pragma unroll
-                                for (int e = 0; e < 4; e++) { o[e] = 0; wlog[(g + 8 * (e >> 1)) * M.no + nb + (e & 1)] = pre[e]; }
+                                for (int e = 0; e < 4; e++) { o[e] = 0; wlog[(g + 8 * (e >> 1)) * NOP + nb + (e & 1)] = pre[e]; }
                             } else {
                                 if (act == ACT_TANH) {
 #pragma unroll
@@ -409,7 +410,7 @@ seg_kernel(SegArgs a)
                                 }
                                 if (last) {                                                     /* neural_nets.c:160-166 */
 #pragma unroll
-                                    for (int e = 0; e < 4; e++) wlog[(g + 8 * (e >> 1)) * M.no + nb + (e & 1)] = o[e];
+                                    for (int e = 0; e < 4; e++) wlog[(g + 8 * (e >> 1)) * NOP + nb + (e & 1)] = o[e];
                                 } else if (a.tap_act) {
 #pragma unroll
                                     for (int e = 0; e < 4; e++) {
@@ -435,7 +436,7 @@ seg_kernel(SegArgs a)
                 for (int x = lane; x < XB / 16; x += 32) dst[x] = src[x];
             } else {
                 if (lane < nvalid) {
-                    const int32_t *lg = wlog + lane * M.no;
+                    const int32_t *lg = wlog + lane * NOP;
                     int d;
                     if (M.nn_id == NNSP_B200_ID_S2I)
                         d = argmax_last_wins(lg, 7) | (argmax_last_wins(lg + 7, 17) << 8) | (argmax_last_wins(lg + 24, 17) << 16);
@@ -446,7 +447,7 @@ seg_kernel(SegArgs a)
                 if (a.tap_logits)
                     for (int x = lane; x < 16 * M.n_out; x += 32) {
                         const int row = x / M.n_out, n = x - row * M.n_out;
-                        if (row < nvalid) a.tap_logits[((long long)sel_sid(a.sel, tile, row) * T + t) * M.n_out + n] = wlog[row * M.no + n];
+                        if (row < nvalid) a.tap_logits[((long long)sel_sid(a.sel, tile, row) * T + t) * M.n_out + n] = wlog[row * NOP + n];
                     }
             }
             __syncwarp();
@@ -804,7 +805,7 @@ static SegLayout seg_layout(const MmaModel *D, int l0, int l1, bool from_feat)
     s.off_fp = (int)off; if (from_feat) off += 2 * 16 * SEG_PC;
     s.nbuf = (from_feat && l1 - l0 == 1) ? 1 : 2;
     s.off_wb = (int)off; off += (size_t)SEG_WARPS * s.nbuf * 32 * D->pa;
-    s.off_log = (int)off; if (l1 == D->numlayers) off += (size_t)SEG_WARPS * 16 * D->no * 4;
+    s.off_log = (int)off; if (l1 == D->numlayers) off += (size_t)SEG_WARPS * 16 * (D->no + 4) * 4;
     s.total = off;
     return s;
 }
