@@ -45,12 +45,20 @@ constexpr int SEG_PC = SEG_FROWS * 40 + 16;         /* plane pitch: 364 words = 
 constexpr int SCAN_NST = 4;                         /* depth of the input ring of the scan               */
 constexpr int SPLIT_MAX_DYN_SMEM = 227 * 1024 - 256;   /* the kernels also hold 64 B of static shared memory */
 constexpr int LUT2_N = 160;                         /* reachable segments of coeffs_tanh (activation.c:5) */
+/* The LUT is indexed by data, so lanes of a warp collide on banks (ncu: 58 % of the scan's LUT wavefronts were excess).
+ * It is therefore replicated: copy c of entry k sits at [k * COPIES + c] and lane l reads copy l % COPIES, i.e. always
+ * the same bank pair -- with 16 copies a 64-bit load of a half-warp touches every bank exactly once. */
+constexpr int LUT2_COPIES_SCAN = 1;                 /* measured: 16 copies remove the conflicts but not a microsecond (the scan is
+                                                       latency-bound), and the extra shared memory costs seg_kernel a resident CTA */
+constexpr int LUT2_COPIES_SEG = 1;
 
 static_assert((SEG_PC % 16) == 0 && ((SEG_PC / 4) % 8) == 4, "feature plane pitch");
 
 /* ---- tanh LUT as (value, slope) pairs: one 64-bit shared load per evaluation, no unpacking --------------- */
 /* tanh_fix, activation.c:31-69; x == INT32_MIN as in nnsp_device.cuh (-0x7fff). Branch-free so that the
  * evaluations of one epilogue interleave. */
+/* lut2: the calling lane's copy, i.e. base + (lane % COPIES); stride = COPIES */
+template <int COPIES>
 __device__ __forceinline__ int32_t tanh_q15v(int32_t x, const int2 *__restrict__ lut2)
 {
     const uint32_t xi = (x < 0) ? (0u - (uint32_t)x) : (uint32_t)x;
@@ -59,19 +67,24 @@ __device__ __forceinline__ int32_t tanh_q15v(int32_t x, const int2 *__restrict__
     k = k < 0 ? 0 : k;
     k = k > LUT2_N - 1 ? LUT2_N - 1 : k;
     const int32_t dx = t - (k << 10);
-    const int2 e = lut2[k];
+    const int2 e = lut2[k * COPIES];
     int32_t v = e.x + ((int32_t)((uint32_t)dx * (uint32_t)e.y) >> 15);
     v = v > 0 ? v : 0;
     v = (xi >= (5u << 15)) ? 0x7fff : v;
     return x < 0 ? -v : v;
 }
+template <int COPIES>
 __device__ __forceinline__ int32_t sigmoid_q15v(int32_t x, const int2 *__restrict__ lut2)     /* activation.c:72-86 */
 {
-    return (tanh_q15v(x >> 1, lut2) >> 1) + 16384;
+    return (tanh_q15v<COPIES>(x >> 1, lut2) >> 1) + 16384;
 }
+template <int COPIES>
 __device__ __forceinline__ void fill_lut2(int2 *lut2, const DevTables *__restrict__ tb, int tid, int nthr)
 {
-    for (int i = tid; i < LUT2_N; i += nthr) lut2[i] = make_int2((int)tb->tanh_lut[2 * i], (int)tb->tanh_lut[2 * i + 1]);
+    for (int i = tid; i < LUT2_N * COPIES; i += nthr) {
+        const int k = i / COPIES;
+        lut2[i] = make_int2((int)tb->tanh_lut[2 * k], (int)tb->tanh_lut[2 * k + 1]);
+    }
 }
 
 /* ---- decision records: the part of the post-processing that does not depend on earlier frames ---------- */
@@ -203,7 +216,8 @@ seg_kernel(SegArgs a)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     MmaModel &M = *reinterpret_cast<MmaModel *>(smem + 16);
     int32_t *bias32 = reinterpret_cast<int32_t *>(smem + a.off_bias);
-    int2 *lut2 = reinterpret_cast<int2 *>(smem + a.off_lut);
+    int2 *lut2_all = reinterpret_cast<int2 *>(smem + a.off_lut);
+    const int2 *lut2 = lut2_all + (threadIdx.x & (LUT2_COPIES_SEG - 1));
     const uint2 *wsm = reinterpret_cast<const uint2 *>(smem + a.off_w);
     uint8_t *fplanes = smem + a.off_fp;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
@@ -237,7 +251,7 @@ seg_kernel(SegArgs a)
         for (int i = tid; i < SEG_WARPS * a.nbuf * XB / 4; i += SEG_THREADS) z[i] = 0;
     }
     for (int i = tid; i < M.bias_count; i += SEG_THREADS) bias32[i] = a.bias32[i];
-    fill_lut2(lut2, a.tables, tid, SEG_THREADS);
+    fill_lut2<LUT2_COPIES_SEG>(lut2_all, a.tables, tid, SEG_THREADS);
     if (FROM_FEAT)
         for (int e = tid; e < 32 * 4; e += SEG_THREADS)              /* k-step over-read behind the last window */
             *reinterpret_cast<uint32_t *>(fplanes + (e >> 2) * SEG_PC + SEG_FROWS * 40 + (e & 3) * 4) = 0;
@@ -400,10 +414,10 @@ seg_kernel(SegArgs a)
                             } else {
                                 if (act == ACT_TANH) {
 #pragma unroll
-                                    for (int e = 0; e < 4; e++) o[e] = tanh_q15v(pre[e], lut2);
+                                    for (int e = 0; e < 4; e++) o[e] = tanh_q15v<LUT2_COPIES_SEG>(pre[e], lut2);
                                 } else if (act == ACT_SIGMOID) {
 #pragma unroll
-                                    for (int e = 0; e < 4; e++) o[e] = sigmoid_q15v(pre[e], lut2);
+                                    for (int e = 0; e < 4; e++) o[e] = sigmoid_q15v<LUT2_COPIES_SEG>(pre[e], lut2);
                                 } else {
 #pragma unroll
                                     for (int e = 0; e < 4; e++) o[e] = relu6_q12(pre[e]);
@@ -500,8 +514,9 @@ scan_kernel(ScanArgs a)
     uint64_t *hbar = bars + SCAN_NST + 1;
     const int WB = 4 * a.nt * (a.kt + a.ktr) * 256, XB = 32 * a.pa;
     const uint2 *wsm = reinterpret_cast<const uint2 *>(smem + 64);
-    int2 *lut2 = reinterpret_cast<int2 *>(smem + 64 + WB);
-    uint8_t *xs = smem + 64 + WB + LUT2_N * 8;
+    int2 *lut2_all = reinterpret_cast<int2 *>(smem + 64 + WB);
+    const int2 *lut2 = lut2_all + (threadIdx.x & (LUT2_COPIES_SCAN - 1));
+    uint8_t *xs = smem + 64 + WB + LUT2_N * 8 * LUT2_COPIES_SCAN;
     uint8_t *hb = xs + SCAN_NST * XB;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     __shared__ int sids[16];
@@ -521,7 +536,7 @@ scan_kernel(ScanArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 3 * XB / 4; i += nthr) reinterpret_cast<uint32_t *>(hb)[i] = 0;
-    fill_lut2(lut2, a.tables, tid, nthr);
+    fill_lut2<LUT2_COPIES_SCAN>(lut2_all, a.tables, tid, nthr);
     __syncthreads();
     uint8_t *h2 = hb + 2 * XB;                                       /* h before the first inference */
     for (int idx = tid; idx < 16 * H; idx += nthr) {
@@ -614,7 +629,7 @@ scan_kernel(ScanArgs a)
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int32_t pre = (int32_t)(((uint32_t)ach[gt][e] << 8) + (uint32_t)acl[gt][e]) >> rs;
-                    gate[gt][e] = (gt == 1) ? tanh_q15v(pre, lut2) : sigmoid_q15v(pre, lut2);      /* lstm.c:65,78,91,104 */
+                    gate[gt][e] = (gt == 1) ? tanh_q15v<LUT2_COPIES_SCAN>(pre, lut2) : sigmoid_q15v<LUT2_COPIES_SCAN>(pre, lut2);      /* lstm.c:65,78,91,104 */
                 }
             int32_t y[4];
 #pragma unroll
@@ -622,7 +637,7 @@ scan_kernel(ScanArgs a)
                 const int64_t tt = ((int64_t)gate[0][e] * (int64_t)gate[1][e] + (int64_t)gate[2][e] * (int64_t)cst[e]) >> 15;   /* lstm.c:108-109 */
                 const int32_t cn = sat32_dev(tt);
                 cst[e] = cn;
-                int32_t o = (tanh_q15v(cn, lut2) * gate[3][e]) >> 15;                               /* lstm.c:111-115 */
+                int32_t o = (tanh_q15v<LUT2_COPIES_SCAN>(cn, lut2) * gate[3][e]) >> 15;                               /* lstm.c:111-115 */
                 o = o > 32767 ? 32767 : (o < -32768 ? -32768 : o);
                 y[e] = o;
             }
@@ -795,7 +810,7 @@ static SegLayout seg_layout(const MmaModel *D, int l0, int l1, bool from_feat)
     auto a16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     size_t off = a16(16 + sizeof(MmaModel));
     s.off_bias = (int)off; off = a16(off + (size_t)D->bias_count * 4);
-    s.off_lut = (int)off; off += LUT2_N * 8;
+    s.off_lut = (int)off; off += LUT2_N * 8 * LUT2_COPIES_SEG;
     s.w_base = D->layer[l0].w_off;
     long long cnt = 0;
     for (int i = l0; i < l1; i++) cnt += (long long)D->layer[i].nt * D->layer[i].kt * 32;
@@ -811,7 +826,7 @@ static SegLayout seg_layout(const MmaModel *D, int l0, int l1, bool from_feat)
 }
 static size_t scan_smem(const MmaModel *D, const MmaLayer &L)
 {
-    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + LUT2_N * 8 + (size_t)(SCAN_NST + 3) * 32 * D->pa;   /* 64: 6 mbarriers */
+    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + LUT2_N * 8 * LUT2_COPIES_SCAN + (size_t)(SCAN_NST + 3) * 32 * D->pa;   /* 64: 6 mbarriers */
 }
 
 int split_supported(const MmaDeviceModel &mm)
@@ -847,6 +862,7 @@ static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, c
     static bool attr_done[64] = { false };
     if (!attr_done[device]) {
         NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
+        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done[device] = true;
     }
     scan_kernel<NW, MINB><<<ntiles, 32 * NW, smem, st>>>(a);
@@ -864,6 +880,9 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
+        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done[device] = true;
     }
     if (q.n_inf <= 0 || q.max_streams <= 0) return NNSP_B200_OK;

@@ -55,6 +55,9 @@ while i < len(lines):
         hdr = rows[0]
         ca, cs, ci = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
         stall_cols = [(k, h) for k, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+        cx = hdr.index("L1 Wavefronts Shared Excessive") if "L1 Wavefronts Shared Excessive" in hdr else None
+        cw = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
+        exc_line, wav_line = collections.Counter(), collections.Counter()
         norm = lambda x: x.replace("(bool)1", "true").replace("(bool)0", "false").replace("void ", "").replace(" ", "")
         fn = [f for f, d in demangle.items() if norm(d) == norm(kname)]
         fn = fn[0] if fn else None
@@ -66,6 +69,8 @@ while i < len(lines):
             s = int(float(r[cs] or 0)); ie = int(float(r[ci] or 0))
             loc = linemap.get(fn, {}).get(off, (None, ""))[0] if fn else None
             by_line[loc] += s; inst_line[loc] += ie; tot += s; tot_inst += ie
+            if cx is not None:
+                exc_line[loc] += int(float(r[cx] or 0)); wav_line[loc] += int(float(r[cw] or 0))
             for k, h in stall_cols:
                 v = int(float(r[k] or 0))
                 if v: stall_line[loc][h] += v
@@ -74,5 +79,9 @@ while i < len(lines):
             st = ", ".join("%s %d" % (h.replace("stall_", ""), c) for h, c in stall_line[loc].most_common(3))
             print("%6.2f%% samples %6.2f%% inst  %s:%s   [%s]" % (100.0 * v / max(tot, 1), 100.0 * inst_line[loc] / max(tot_inst, 1),
                                                               loc[0] if loc else "?", loc[1] if loc else "?", st))
+        if cx is not None and sum(exc_line.values()):
+            print("   shared-memory wavefronts: %d, of which excessive (bank conflicts) %d; worst lines:" % (sum(wav_line.values()), sum(exc_line.values())))
+            for loc, v in exc_line.most_common(8):
+                if v: print("     %10d excessive of %10d  %s:%s" % (v, wav_line[loc], loc[0] if loc else "?", loc[1] if loc else "?"))
     else:
         i += 1
