@@ -460,19 +460,7 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
         a.t0[s] = t_exit + 1;
         if (t_exit + 1 < T) a.replay_list[a.s0 + atomicAdd(a.replay_count, 1)] = (int)s;
     } else {
-        /* the instance lived through the call: its context is the newest six standardised rows */
-        int16_t nc[240];
-        for (int j = 0; j < 6; j++) {
-            const int f = T - 6 + j;
-            if (f >= 0) {
-                const int32_t *row = cascade_lm_row(a, s, f - d);
-                for (int i = 0; i < 40; i++) nc[j * 40 + i] = standardise(row[i], M.mean[i], M.stdR[i], M.feat_rshift);
-            } else {
-                for (int i = 0; i < 40; i++) nc[j * 40 + i] = ctx[(j + T) * 40 + i];
-            }
-        }
-        for (int i = 0; i < 240; i++) ctx[i] = nc[i];
-        a.t0[s] = T;
+        a.t0[s] = T + 1;                       /* lived through the call: cascade_ctx_kernel rebuilds its context */
     }
     a.st.casc[s * CS_N + CS_CNT_KWS] = (uint16_t)cnt_kws;
     a.st.casc[s * CS_N + CS_CNT_S2I] = (uint16_t)cnt_s2i;
@@ -486,6 +474,35 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
         p[0] = *reinterpret_cast<uint4 *>(&sc[0]);
         p[1] = *reinterpret_cast<uint4 *>(&sc[8]);
     }
+}
+
+/* context of the instances that lived through the call (t0 == T + 1): the newest six standardised rows of
+ * (old rows ++ this call's rows, read with the instance's look-back); a warp per stream */
+__global__ void __launch_bounds__(256) cascade_ctx_kernel(CascadePostArgs a)
+{
+    const int si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (si >= a.ns) return;
+    const long long s = a.s0 + si;
+    const int T = a.T;
+    if (a.t0[s] != T + 1) return;
+    const CascadeDev &cd = a.cd;
+    const int id = cd.seq[a.st.casc[s * CS_N + CS_POS]];
+    const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
+    const MmaModel &M = *a.model[id];
+    int16_t *ctx = a.st.ctx + s * 240;
+    int16_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int e = lane + 32 * k;
+        v[k] = 0;
+        if (e < 240) {
+            const int j = e / 40, i = e - j * 40, f = T - 6 + j;
+            v[k] = (f >= 0) ? standardise(cascade_lm_row(a, s, f - d)[i], M.mean[i], M.stdR[i], M.feat_rshift) : ctx[(j + T) * 40 + i];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const int e = lane + 32 * k; if (e < 240) ctx[e] = v[k]; }
 }
 
 struct ResetModels { const DevModel *m[3]; int seq[CS_MAXSEQ]; };
@@ -665,6 +682,8 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
         p.s0 = s0; p.ns = ns; p.T = T; p.results = results; p.cd = c->cd;
         p.replay_list = c->replay_list; p.replay_count = count + 8;
         cascade_post_kernel<<<(ns + CPOST_THREADS - 1) / CPOST_THREADS, CPOST_THREADS, 0, st>>>(p);
+        NNSP_LAUNCH_CHECK();
+        cascade_ctx_kernel<<<(ns * 32 + 255) / 256, 256, 0, st>>>(p);
         NNSP_LAUNCH_CHECK();
         a.t0 = c->t0;                          /* ... and replay what is left with the sequential kernel */
         a.replay_list = c->replay_list + s0; a.replay_ctl = count + 8;
