@@ -14,8 +14,8 @@
  *                      standardised feature rows, so 16 consecutive inferences share one 36-row plane.
  *   scan_kernel        the LSTM, one CTA per 16-stream tile, one warp per 8-unit group, sequential over the
  *                      inferences: input planes arrive by TMA bulk copies through a 4-deep mbarrier ring,
- *                      Wx.x of step k+1 is issued before the barrier of step k, cell state and biases live
- *                      in registers, h goes back to HBM by one TMA bulk store per step.
+ *                      Wx.x of step k+1 is issued between arriving on and waiting for the h barrier of step k,
+ *                      cell state and biases live in registers, h goes back to HBM by one TMA bulk store per step.
  *   seg_kernel<planes> layers after the LSTM for all rows, logits -> per-row decision record
  *                      (argmax triple or the softmax-threshold flag of binary_post_proc).
  *   post_kernel        the NNSPClass counters / trigger / outputs over the decision records, per stream.
@@ -26,7 +26,9 @@
  * The contraction itself is the exact hi/lo byte-plane IMMA of nnsp_mma.cuh (16 streams x 8 units x 32 k per
  * mma.sync.m16n8k32, s8/u8 x s8, int32). Activation planes between kernels: [tile][inference][hi|lo][16][pa]
  * bytes, so one tile-step is a contiguous, 16-byte aligned block (bulk-copyable, conflict-free as A operand).
- * Only models whose every layer has the exact 32-bit finish (MmaLayer.fast) take this path. */
+ * Only models whose every layer has the exact 32-bit finish (MmaLayer.fast) take this path.
+ * The kernels work on a stream selection (StreamSel): a contiguous range for the batched NNSPClass, or a device-side
+ * list for the cascade, whose stage-sorted pass (nnsp_cascade.cu) runs them once per (model, phase) group. */
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,8 +48,8 @@ constexpr int SCAN_NST = 4;                         /* depth of the input ring o
 constexpr int SPLIT_MAX_DYN_SMEM = 227 * 1024 - 256;   /* the kernels also hold 64 B of static shared memory */
 constexpr int LUT2_N = 160;                         /* reachable segments of coeffs_tanh (activation.c:5) */
 /* The LUT is indexed by data, so lanes of a warp collide on banks (ncu: 58 % of the scan's LUT wavefronts were excess).
- * It is therefore replicated: copy c of entry k sits at [k * COPIES + c] and lane l reads copy l % COPIES, i.e. always
- * the same bank pair -- with 16 copies a 64-bit load of a half-warp touches every bank exactly once. */
+ * It can be replicated: copy c of entry k sits at [k * COPIES + c] and lane l reads copy l % COPIES, i.e. always the same
+ * bank pair -- with 16 copies a 64-bit load of a half-warp touches every bank exactly once. */
 constexpr int LUT2_COPIES_SCAN = 1;                 /* measured: 16 copies remove the conflicts but not a microsecond (the scan is
                                                        latency-bound), and the extra shared memory costs seg_kernel a resident CTA */
 constexpr int LUT2_COPIES_SEG = 1;
