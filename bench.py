@@ -49,6 +49,15 @@ def measured_traffic(kernel):
         return None
 
 
+def measured_counts(kernel):
+    """warp instructions executed by one launch of `kernel` on the bench workload (committed ncu capture), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[kernel]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -285,6 +294,17 @@ def main():
         ipk = nb.int_peak(device)
         imad, mixed = ipk["imad"], ipk["mixed"]
         int_ach = ALGO_INTOPS_PER_FRAME_FEATURE * frames_per_launch / (feat_ms * 1e-3) / 1e9
+        cnt = measured_counts("feat_kernel") or {}
+        winst = cnt.get("warp_instructions_per_launch")
+        sm_mhz = clocks.get("sm_mhz") or 1965
+        issue_peak = 4.0 * 148 * sm_mhz * 1e6                      # one warp instruction per clock per SM sub-partition
+        issue = None if not winst else {
+            "kernel": "feat_kernel", "warp_instructions_per_launch": winst,
+            "achieved_ginst_s": winst / (feat_ms * 1e-3) / 1e9, "peak_ginst_s": issue_peak / 1e9,
+            "frac": winst / (feat_ms * 1e-3) / issue_peak,
+            "pipe_fmaheavy_pct": cnt.get("pipe_fmaheavy_pct"), "pipe_alu_pct": cnt.get("pipe_alu_pct"),
+            "note": "the binding resource of this integer kernel: issue slots and the FMA-heavy pipe (IMAD.WIDE = 4 cycles); "
+                    "instruction and pipe counts from the committed ncu capture (profiles/traffic.json), duration measured live"}
         line = {
             "metric": "audio-sec/sec (16 kHz streams, VAD, FeatureClass+NeuralNetClass+NNSPClass)",
             "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -306,6 +326,7 @@ def main():
                         "peak_gops_mixed": mixed, "peak_gops_imad_wide": ipk["imad_wide"], "peak_gops_idp2a": ipk["idp2a"], "frac_of_mixed_peak": int_ach / mixed if mixed else None,
                         "algorithmic_int_ops_per_frame": ALGO_INTOPS_PER_FRAME_FEATURE,
                         "peak_source": "self-measured nnsp_b200_int_peak (register-resident IMAD / IMAD+ALU chains)"},
+            "issue": issue,
             "kernel_ms": {"feat_kernel": feat_ms, "network_kernels": nn_ms,
                           "network_path": "scan-split: seg_kernel<feat> + scan_kernel + seg_kernel<planes> + post_kernel + ctx_kernel"},
         }
