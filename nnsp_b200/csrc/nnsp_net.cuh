@@ -35,7 +35,7 @@ __device__ __forceinline__ void dot_rows(const uint32_t *__restrict__ W, int nro
 {
     const uint2 *x2 = reinterpret_cast<const uint2 *>(x);
     const uint32_t *w = W + r0;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < k4n; k++) {
         const uint2 xx = x2[k];
 #pragma unroll
