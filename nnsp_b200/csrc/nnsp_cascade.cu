@@ -805,6 +805,7 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaMalloc(&c->grp_tile_off, CS_MAX_SLICES * 8 * sizeof(int)));
     TRY(cudaMalloc(&c->t0, S * sizeof(int)));
 #undef TRY
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(NNSP_B200_ERR_CUDA);   /* uploads went through the default stream */
     ResetModels rm{};
     for (int i = 0; i < 3; i++) rm.m[i] = c->dm[i].d;
     for (int i = 0; i < len_seq; i++) rm.seq[i] = seq[i];

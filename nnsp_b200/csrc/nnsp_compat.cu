@@ -146,7 +146,7 @@ static DeviceModel *legacy_model(const NeuralNetClass *net, const int32_t *mean,
     if (nnsp_b200_model_from_net(net, mean ? mean : zeros, stdR ? stdR : zeros, nn_id, &m)) legacy_die("nnsp_b200_model_from_net");
     DeviceModel *dm = new DeviceModel();
     cudaSetDevice(g_lg.device);
-    if (upload_model(m, dm)) legacy_die("model upload");
+    if (upload_model(m, dm) || cudaDeviceSynchronize() != cudaSuccess) legacy_die("model upload");
     nnsp_b200_model_free(m);
     g_lg.models[net] = dm;
     return dm;

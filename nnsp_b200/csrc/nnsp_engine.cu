@@ -100,6 +100,7 @@ int get_device_tables(int device, const DevTables **out)
         DevTables *d = nullptr;
         NNSP_CUDA(cudaMalloc(&d, sizeof h));
         NNSP_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
+        NNSP_CUDA(cudaDeviceSynchronize());      /* pageable source: returned once staged; the engine's streams are non-blocking */
         g_dev_tables[device] = d;
     }
     *out = g_dev_tables[device];
@@ -784,6 +785,7 @@ int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device, 
         TRY(cudaMemcpy(b->norm_dev, norm, sizeof norm, cudaMemcpyHostToDevice));
     }
 #undef TRY
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(NNSP_B200_ERR_CUDA);   /* model / table uploads went through the default stream */
     if ((rc = nnsp_b200_batch_reset(b))) return fail(rc);
     *out = b;
     return NNSP_B200_OK;
@@ -972,6 +974,7 @@ int nnsp_b200_feature_stages(int device, const int16_t *windows, int n, int32_t 
     NNSP_CUDA(cudaMalloc(&dw, (size_t)n * 480 * 2));
     NNSP_CUDA(cudaMalloc(&dbuf, (size_t)n * per * 4));
     NNSP_CUDA(cudaMemcpy(dw, windows, (size_t)n * 480 * 2, cudaMemcpyHostToDevice));
+    NNSP_CUDA(cudaDeviceSynchronize());
     int32_t *d_fi = dbuf, *d_sp = d_fi + (size_t)n * 512, *d_ps = d_sp + (size_t)n * 514, *d_me = d_ps + (size_t)n * 257, *d_lm = d_me + (size_t)n * 40;
     NNSP_CUDA(cudaFuncSetAttribute(feat_stages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem)));
     int blocks = (n + FEAT_WARPS * 2 - 1) / (FEAT_WARPS * 2);
@@ -1081,8 +1084,23 @@ int nnsp_b200_dev_alloc(int device, size_t nbytes, void **ptr)
 int nnsp_b200_dev_free(int device, void *ptr) { NNSP_CUDA(cudaSetDevice(device)); NNSP_CUDA(cudaFree(ptr)); return NNSP_B200_OK; }
 int nnsp_b200_host_alloc_pinned(size_t nbytes, void **ptr) { NNSP_CUDA(cudaMallocHost(ptr, nbytes)); return NNSP_B200_OK; }
 int nnsp_b200_host_free_pinned(void *ptr) { NNSP_CUDA(cudaFreeHost(ptr)); return NNSP_B200_OK; }
-int nnsp_b200_memcpy_h2d(int device, void *dst, const void *src, size_t n) { NNSP_CUDA(cudaSetDevice(device)); NNSP_CUDA(cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice)); return NNSP_B200_OK; }
+/* The engine's streams are cudaStreamNonBlocking, i.e. NOT ordered against the legacy default stream these helpers
+ * use -- and cudaMemcpy from pageable memory returns once the data is staged, cudaMemset is asynchronous to the host.
+ * So each helper drains the default stream before returning: on return the bytes ARE in place for any stream. */
+int nnsp_b200_memcpy_h2d(int device, void *dst, const void *src, size_t n)
+{
+    NNSP_CUDA(cudaSetDevice(device));
+    NNSP_CUDA(cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice));
+    NNSP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    return NNSP_B200_OK;
+}
 int nnsp_b200_memcpy_d2h(int device, void *dst, const void *src, size_t n) { NNSP_CUDA(cudaSetDevice(device)); NNSP_CUDA(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost)); return NNSP_B200_OK; }
-int nnsp_b200_memset(int device, void *dst, int value, size_t n) { NNSP_CUDA(cudaSetDevice(device)); NNSP_CUDA(cudaMemset(dst, value, n)); return NNSP_B200_OK; }
+int nnsp_b200_memset(int device, void *dst, int value, size_t n)
+{
+    NNSP_CUDA(cudaSetDevice(device));
+    NNSP_CUDA(cudaMemset(dst, value, n));
+    NNSP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    return NNSP_B200_OK;
+}
 
 }  /* extern "C" */
