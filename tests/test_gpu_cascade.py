@@ -195,3 +195,37 @@ def test_cascade_back_to_back_calls_are_pipelined_correctly(nb, oracle):
     for x in d_pcm + d_res:
         x.free()
     c.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_cascade_many_pipelined_calls_equal_sequential_one_shot(nb, seed):
+    """30 back-to-back cascade calls of random lengths on 700 streams (stage-sorted pass, pipelined) against one call
+    of the sequential kernel over the same 400 frames."""
+    rng = np.random.default_rng(seed)
+    S, T = 700, 400
+    cuts = np.sort(rng.choice(np.arange(1, T), 29, replace=False))
+    lens = np.diff(np.concatenate([[0], cuts, [T]])).tolist()
+    pcm = nb.synth_pcm(S, T, first_stream=seed * 1000)
+    params = dict(frs_vbufBk_kws=40, frs_vbufBk_s2i=3, thresh_timeout_kws=70, thresh_timeout_s2i=50, thresh_prob_kws=100, thresh_cnts_kws=2)
+    models = _models(nb)
+    ref = nb.Cascade(models, S, params=params)
+    ref.set_path("sequential")
+    want = ref.exec(pcm)
+    ref.close()
+    c = nb.Cascade(models, S, params=params)
+    c.set_path("sorted")
+    d_pcm, d_res, t = [], [], 0
+    for n in lens:
+        d_pcm.append(nb.DeviceArray.from_host(pcm[:, t * 160:(t + n) * 160]))
+        d_res.append(nb.DeviceArray((S, n), nb.CASCADE_RESULT_DT))
+        t += n
+    for k, n in enumerate(lens):
+        c.exec_device(d_pcm[k], n * 160, n, d_res[k])
+    c.sync()
+    got = np.concatenate([r.to_host() for r in d_res], axis=1)
+    for f in got.dtype.names:
+        assert (got[f] == want[f]).all(), f
+    assert len(np.unique(want["stage_id"])) >= 2 and (np.diff(want["pos_after"].astype(int), axis=1) != 0).sum() > 100
+    for x in d_pcm + d_res:
+        x.free()
+    c.close()

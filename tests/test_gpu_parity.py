@@ -216,3 +216,32 @@ def test_long_call_many_inference_rounds(nb, oracle):
             _compare_stream(oracle, m_or, pcm[s], res[s], taps, s)
         assert (plain == res).all()
         b.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_many_pipelined_calls_equal_one_shot(nb, seed):
+    """40 back-to-back calls of random lengths (no sync in between) on 1 000 streams must give exactly what one call
+    over the same 200 frames gives: stresses the two-stream pipeline (buffer reuse, history roll, phase of the gate)."""
+    rng = np.random.default_rng(seed)
+    S, T = 1000, 200
+    cuts = np.sort(rng.choice(np.arange(1, T), 39, replace=False))
+    lens = np.diff(np.concatenate([[0], cuts, [T]])).tolist()
+    pcm = nb.synth_pcm(S, T, first_stream=seed * 100)
+    m = _model(nb, (0, 2, 1)[seed - 1], seed == 2)
+    one = nb.NNSPBatch(m, S)
+    want = one.exec(pcm)
+    one.close()
+    b = nb.NNSPBatch(m, S)
+    d_pcm, d_res, t = [], [], 0
+    for n in lens:
+        d_pcm.append(nb.DeviceArray.from_host(pcm[:, t * 160:(t + n) * 160]))
+        d_res.append(nb.DeviceArray((S, n), nb.RESULT_DT))
+        t += n
+    for k, n in enumerate(lens):
+        b.exec_device(d_pcm[k], n * 160, n, d_res[k])
+    b.sync()
+    got = np.concatenate([r.to_host() for r in d_res], axis=1)
+    assert (got == want).all()
+    for x in d_pcm + d_res:
+        x.free()
+    b.close()
