@@ -245,3 +245,35 @@ def test_many_pipelined_calls_equal_one_shot(nb, seed):
     for x in d_pcm + d_res:
         x.free()
     b.close()
+
+
+@pytest.mark.parametrize("S", [1, 15, 16, 17, 33])
+def test_tile_boundaries_and_strided_input(nb, oracle, S):
+    """Stream counts around the 16-stream tile size, PCM rows with padding between streams (stream_stride > n_frames*160),
+    and one-frame calls (what a real-time caller issues)."""
+    T = 21
+    pcm = nb.synth_pcm(S, T, first_stream=300 + S)
+    wide = np.zeros((S, T * 160 + 96), np.int16)             # 96 samples of padding after every stream's chunk
+    wide[:, :T * 160] = pcm
+    wide[:, T * 160:] = 12345
+    m = _model(nb, 1, False)
+    m_or = oracle.model(1, False)
+    want = np.stack([oracle.nnsp_run(m_or, pcm[s], taps=False)[0] for s in range(S)])
+    b = nb.NNSPBatch(m, S)
+    d = nb.DeviceArray.from_host(wide)
+    r = nb.DeviceArray((S, T), nb.RESULT_DT)
+    b.exec_device(d, wide.shape[1], T, r)                     # strided device input
+    b.sync()
+    assert (r.to_host() == want).all()
+    b.close()
+    b = nb.NNSPBatch(m, S)                                    # (a fresh handle: NNSPClass_reset keeps context row 5)
+    res = np.empty((S, T), nb.RESULT_DT)
+    from nnsp_b200.capi import lib, check
+    import ctypes as C
+    check(lib().nnsp_b200_batch_exec_host(b.h, wide.ctypes.data_as(C.c_void_p), wide.shape[1], T, res.ctypes.data_as(C.c_void_p)))
+    assert (res == want).all()                                # strided host input (2-D copy)
+    b.close()
+    b = nb.NNSPBatch(m, S)
+    one = [b.exec(pcm[:, t * 160:(t + 1) * 160]) for t in range(T)]     # frame by frame
+    assert (np.concatenate(one, axis=1) == want).all()
+    b.close(); d.free(); r.free()
