@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 FRAME = 160
 STREAMS_PER_GPU = 4096
 FRAMES_PER_STEP = 100
+REF_SAMPLE_STREAMS = STREAMS_PER_GPU                 # CPU arms: every stream of one step (~0.5 s on 16 cores per pass)
 MODEL_ID = 1                                     # VAD
 ALGO_BYTES_PER_STREAM_FRAME = 2608               # SURVEY.md section 8(d), VAD, one-frame-per-launch design
 ALGO_INTOPS_PER_FRAME_FEATURE = 17700            # SURVEY.md section 8(d), feature stage
@@ -68,43 +69,82 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process (a sample every 2 ms, so even a
+    13 ms region gets several), nvidia-smi as the fall-back when pynvml is not importable."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device):
         super().__init__(daemon=True)
-        self.device, self.rows, self._stop_evt = device, [], threading.Event()
+        self.device, self.sm, self.mx, self.reasons, self._stop_evt = device, [], [], set(), threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(device))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(device):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip() != ""]
+            if device < len(ids) and ids[device].strip().isdigit():
+                return int(ids[device])
+        return device
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.handle))
+        for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self._physical_index(self.device)), "--query-gpu=" + self.FIELDS,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 6 and parts[0].isdigit():
+            self.sm.append(int(parts[0]))
+            if parts[1].isdigit():
+                self.mx.append(int(parts[1]))
+            for i in range(4):
+                if parts[2 + i].lower().startswith("active"):
+                    self.reasons.add(self.NAMES[i])
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.002 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": int(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's own C implementation on the host cores
 # ---------------------------------------------------------------------------------------------
+_REF_PCM = None          # set before the pool forks: the workers inherit the sample instead of receiving it through a pipe
+
+
 def _ref_worker(args):
-    kind, nn_id, pcm, T = args
+    kind, nn_id, lo, hi, T = args
+    pcm = _REF_PCM[lo:hi]
     sys.path.insert(0, ROOT)
     from oracle import pyoracle
     t0 = time.perf_counter()
@@ -118,16 +158,15 @@ def _ref_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_reference_throughput(pcm, T, cores, pool):
-    """audio-s/s of the reference C over `pcm` ([n, T*160]) split across `cores` forked processes
-    (processes, not threads: the reference keeps global scratch)."""
+def cpu_reference_throughput(n, T, cores, pool):
+    """audio-s/s of the reference C over the first `n` streams of _REF_PCM ([*, T*160]) split across `cores` forked
+    processes (processes, not threads: the reference keeps global scratch)."""
     from oracle import pyoracle
     kind = "reference" if pyoracle.RefLib.available(False) else "port"
-    n = pcm.shape[0]
-    chunks = [pcm[n * k // cores: n * (k + 1) // cores] for k in range(cores)]
-    chunks = [c for c in chunks if len(c)]
+    chunks = [(n * k // cores, n * (k + 1) // cores) for k in range(cores)]
+    chunks = [c for c in chunks if c[1] > c[0]]
     t0 = time.perf_counter()
-    pool.map(_ref_worker, [(kind, MODEL_ID, c, T) for c in chunks])
+    pool.map(_ref_worker, [(kind, MODEL_ID, lo, hi, T) for lo, hi in chunks], chunksize=1)
     dt = time.perf_counter() - t0
     return n * T * AUDIO_S_PER_FRAME / dt, kind, dt
 
@@ -138,16 +177,17 @@ def run_reference_arm(args, rank):
     from nnsp_b200.synth import synth_pcm
     cores = os.cpu_count() or 1
     T = FRAMES_PER_STEP
-    n = min(STREAMS_PER_GPU, max(cores * 24, 64))
-    pcm = synth_pcm(n, T)
+    global _REF_PCM
+    n = REF_SAMPLE_STREAMS
+    _REF_PCM = synth_pcm(n, T)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_reference_throughput(pcm, T, cores, pool)
+            cpu_reference_throughput(n, T, cores, pool)
         t0 = time.perf_counter()
         kind = "port"
         for _ in range(args.steps):
-            _, kind, _ = cpu_reference_throughput(pcm, T, cores, pool)
+            _, kind, _ = cpu_reference_throughput(n, T, cores, pool)
         dt = time.perf_counter() - t0
     value = args.steps * n * T * AUDIO_S_PER_FRAME / dt
     sample = "%d of the %d streams x %d frames per step, %d forked processes, oracle/%s" % (
@@ -208,14 +248,16 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n = min(S, max(cores * 24, 64))
-        sample_pcm = synth_pcm(n, T)
+        global _REF_PCM
+        n = REF_SAMPLE_STREAMS
+        _REF_PCM = synth_pcm(n, T)
         with mp.get_context("fork").Pool(cores) as pool:
-            cpu_reference_throughput(sample_pcm[: max(cores, 8)], T, cores, pool)       # warm the processes
+            cpu_reference_throughput(max(cores, 8), T, cores, pool)                      # warm the processes
             reps, t_total, val, kind = 0, 0.0, 0.0, "port"
-            while t_total < 10.0 and reps < 8:
-                v, kind, dt = cpu_reference_throughput(sample_pcm, T, cores, pool)
+            while (t_total < 1.5 or reps < 3) and reps < 8:                              # ~25 core-seconds on 16 cores
+                v, kind, dt = cpu_reference_throughput(n, T, cores, pool)
                 val, t_total, reps = max(val, v), t_total + dt, reps + 1
+        _REF_PCM = None
         cpu_baseline = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": kind,
                         "sample": "%d of the %d streams x %d frames, best of %d passes, %d forked processes, %s" % (
                             n, S, T, reps, cores, "oracle/_ref = unmodified reference C (gcc -O2)" if kind == "reference" else "oracle/nnsp_oracle.c port")}
@@ -273,10 +315,15 @@ def main():
     for i in range(2):
         batch.exec_host(pin[i & 1].array, pin_res.array)
     barrier()
+    sampler = ClockSampler(device)
+    sampler.start()
     t0 = time.perf_counter()
     for i in range(args.steps):
         batch.exec_host(pin[i & 1].array, pin_res.array)
     e2e_s = time.perf_counter() - t0
+    clocks_e2e = sampler.stop()
+    clocks["e2e"] = {k: clocks_e2e[k] for k in ("sm_mhz", "reasons", "samples")}
+    clocks["reasons"] = sorted(set(clocks["reasons"]) | set(clocks_e2e["reasons"]))
     barrier()
 
     if dist is not None:
