@@ -202,14 +202,15 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, n_bound=0):
     return {"workload": "VAD model (def_nn1_vad, acc64) x %d streams per GPU x %d frames (%.1f s audio) per step; "
                         "FeatureClass -> NeuralNetClass -> NNSPClass post-proc, bit-exact vs reference C" %
                         (STREAMS_PER_GPU, FRAMES_PER_STEP, FRAMES_PER_STEP * AUDIO_S_PER_FRAME),
             "streams_per_gpu": STREAMS_PER_GPU, "frames_per_step": FRAMES_PER_STEP, "total_streams": STREAMS_PER_GPU * n_gpus,
             "partition": "streams block-partitioned over GPUs, no data-path collective",
             "cache": "two alternating %d MB PCM buffers per GPU (larger than the 126 MB L2)" %
-                     (STREAMS_PER_GPU * FRAMES_PER_STEP * FRAME * 2 // 1000000)}
+                     (STREAMS_PER_GPU * FRAMES_PER_STEP * FRAME * 2 // 1000000),
+            "host": "rank bound to the %d CPUs local to its GPU (NVML affinity)" % n_bound if n_bound else "rank not bound to a CPU set"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -262,6 +263,12 @@ def main():
                         "sample": "%d of the %d streams x %d frames, best of %d passes, %d forked processes, %s" % (
                             n, S, T, reps, cores, "oracle/_ref = unmodified reference C (gcc -O2)" if kind == "reference" else "oracle/nnsp_oracle.c port")}
 
+    # after the CPU baseline (its workers must keep every core): host thread and pinned buffers next to the GPU
+    bound = set()
+    if os.environ.get("NNSP_BENCH_BIND", "1") != "0":
+        from nnsp_b200.shard import bind_host_to_device
+        bound = bind_host_to_device(device)
+
     model = nb.Model.from_blob(os.path.join(nb.MODEL_DIR, "vad.nnspm"), acc32=False)
     batch = nb.NNSPBatch(model, S, device=device)
     # two distinct PCM sets so consecutive steps never re-read L2-resident input
@@ -307,23 +314,41 @@ def main():
     nn_ms = float(np.mean([k[1] for k in km]))
     barrier()
 
-    # end to end through the host-buffer entry point (pinned host memory -> H2D -> kernels -> D2H)
+    # end to end through the host-buffer entry point (pinned host memory -> H2D -> kernels -> D2H): the serving loop of
+    # INTEGRATION.md -- two pinned PCM/result buffer pairs, call i queued while the results of call i-1 are consumed
     pin = [nb.PinnedArray((S, T * FRAME), np.int16) for _ in range(2)]
     for k in range(2):
         pin[k].array[...] = host_pcm[k]
-    pin_res = nb.PinnedArray((S, T), nb.RESULT_DT)
-    for i in range(2):
-        batch.exec_host(pin[i & 1].array, pin_res.array)
+    pin_res = [nb.PinnedArray((S, T), nb.RESULT_DT) for _ in range(2)]
+    trig = [r.array["trigger"] for r in pin_res]
+
+    def e2e_loop(n):
+        fired, prev = 0, None
+        for i in range(n):
+            tk = batch.exec_host_async(pin[i & 1].array, pin_res[i & 1].array)
+            if prev is not None:
+                batch.wait_host(prev)
+                fired += int(np.count_nonzero(trig[(i - 1) & 1]))        # the host reads the step's result
+            prev = tk
+        batch.wait_host(prev)
+        return fired + int(np.count_nonzero(trig[(n - 1) & 1]))
+
+    e2e_loop(3)
     barrier()
     sampler = ClockSampler(device)
     sampler.start()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        batch.exec_host(pin[i & 1].array, pin_res.array)
+    e2e_loop(args.steps)
     e2e_s = time.perf_counter() - t0
     clocks_e2e = sampler.stop()
     clocks["e2e"] = {k: clocks_e2e[k] for k in ("sm_mhz", "reasons", "samples")}
     clocks["reasons"] = sorted(set(clocks["reasons"]) | set(clocks_e2e["reasons"]))
+    barrier()
+    # the same with one blocking call per step (nothing in flight across calls)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        batch.exec_host(pin[i & 1].array, pin_res[i & 1].array)
+    e2e_sync_s = time.perf_counter() - t0
     barrier()
 
     if dist is not None:
@@ -357,9 +382,11 @@ def main():
             "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16 activations x int8 weights, int32/int64 accumulate (bit-exact integer path)",
-            "data": "synthetic", "config": workload_config(world),
+            "data": "synthetic", "config": workload_config(world, len(bound)),
             "e2e": {"value": audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": S * T * FRAME * 2,
-                    "d2h_bytes_per_step": S * T * 8, "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "d2h_bytes_per_step": S * T * 8, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "call": "nnsp_b200_batch_exec_host_async + _wait_host, two pinned buffer pairs, results of every step read on the host",
+                    "blocking_call_value": audio_s / world * 1.0 / e2e_sync_s if world == 1 else None},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "feat_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",

@@ -132,6 +132,14 @@ int nnsp_b200_batch_exec(nnsp_b200_batch *b, const int16_t *pcm_dev, long long s
  * pipelined over stream slices; returns after the results are in `results`.             */
 int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long stream_stride,
                               int n_frames, nnsp_b200_result *results);
+/* The same call without the wait at its end: it returns once the copies and kernels are queued and hands back a
+ * ticket (1, 2, ...). `pcm` and `results` (pinned host memory, or the copies degrade to synchronous ones) belong
+ * to the library until nnsp_b200_batch_wait_host(ticket) -- or any later ticket, or nnsp_b200_batch_sync --
+ * returns. Calls complete in order; with two PCM/result buffer pairs a server keeps one call in flight while it
+ * consumes the previous one, and the host link never idles between calls.                */
+int nnsp_b200_batch_exec_host_async(nnsp_b200_batch *b, const int16_t *pcm, long long stream_stride,
+                                    int n_frames, nnsp_b200_result *results, long long *ticket);
+int nnsp_b200_batch_wait_host(nnsp_b200_batch *b, long long ticket);
 int nnsp_b200_batch_sync(nnsp_b200_batch *b);
 /* Device time (ms) spent in the kernels of the most recent exec call, per kernel:
  * [0] feature kernel, [1] network/post-processing kernel, [2] everything else.          */

@@ -216,6 +216,21 @@ class NNSPBatch:
                                               results.ctypes.data_as(C.c_void_p)), "batch_exec_host")
         return results
 
+    def exec_host_async(self, pcm, results):
+        """exec_host without the final wait: returns a ticket for wait_host. `pcm` and `results` (pinned) must stay
+        untouched until then."""
+        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and pcm.shape[0] == self.S
+        T = pcm.shape[1] // FRAME
+        assert results is None or (results.dtype == RESULT_DT and results.flags.c_contiguous and results.shape == (self.S, T))
+        ticket = C.c_longlong(0)
+        check(lib().nnsp_b200_batch_exec_host_async(self.h, pcm.ctypes.data_as(C.c_void_p), pcm.shape[1], T,
+                                                    results.ctypes.data_as(C.c_void_p) if results is not None else None,
+                                                    C.byref(ticket)), "batch_exec_host_async")
+        return ticket.value
+
+    def wait_host(self, ticket):
+        check(lib().nnsp_b200_batch_wait_host(self.h, ticket), "batch_wait_host")
+
     def last_kernel_ms(self):
         ms = (C.c_float * 3)()
         check(lib().nnsp_b200_batch_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")

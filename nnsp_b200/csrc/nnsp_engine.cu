@@ -574,6 +574,8 @@ feat_stages_kernel(const DevTables *__restrict__ tables, const int16_t *__restri
 /* ======================================================================================== */
 using namespace nnsp;
 
+#define HOST_RING 4
+
 struct nnsp_b200_batch {
     int device = 0, S = 0;
     cudaStream_t stream = nullptr;          /* device-buffer API */
@@ -604,6 +606,10 @@ struct nnsp_b200_batch {
     int nn_ctas_per_sm = 1;
     cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
     bool ev_valid = false;
+    /* asynchronous host-buffer calls: one completion event per pipeline stream, a ring of HOST_RING calls */
+    cudaEvent_t host_ev[HOST_RING][4] = {};
+    long long host_seq = 0;                 /* ticket of the latest asynchronous host call */
+    bool host_inflight = false;
 };
 
 static int batch_nn_path(const nnsp_b200_batch *b);
@@ -724,6 +730,18 @@ static int batch_join_nn(nnsp_b200_batch *b, cudaStream_t st)
     return NNSP_B200_OK;
 }
 
+/* asynchronous host-buffer calls leave work on the pipeline streams: everything else waits for it first */
+static int batch_drain_host(nnsp_b200_batch *b)
+{
+    if (!b->host_inflight) return NNSP_B200_OK;
+    for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    b->host_inflight = false;
+    return NNSP_B200_OK;
+}
+
+static int batch_enqueue_host(nnsp_b200_batch *b, const int16_t *pcm, long long stream_stride, int n_frames,
+                              nnsp_b200_result *results);
+
 extern "C" {
 
 const char *nnsp_b200_version(void) { return "nnsp-b200 0.1 (sm_100a)"; }
@@ -770,6 +788,7 @@ int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device, 
     TRY(cudaEventCreate(&b->ev_nn0));
     for (auto &e : b->ev_feat) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : b->ev_nn) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &r : b->host_ev) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRY(cudaMalloc(&b->st.ctx, S * 240 * sizeof(int16_t)));
     TRY(cudaMemset(b->st.ctx, 0, S * 240 * sizeof(int16_t)));
     TRY(cudaMalloc(&b->st.h, S * HS * sizeof(int16_t)));
@@ -796,6 +815,7 @@ int nnsp_b200_batch_reset(nnsp_b200_batch *b)
     if (!b) return NNSP_B200_ERR_ARG;
     NNSP_CUDA(cudaSetDevice(b->device));
     for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    b->host_inflight = false;
     if (b->nn_stream) NNSP_CUDA(cudaStreamSynchronize(b->nn_stream));
     b->nn_pending[0] = b->nn_pending[1] = false;
     reset_kernel<<<b->S, 128, 0, b->stream>>>(b->dm.d, b->st, b->S, NNSP_B200_FRAME);
@@ -822,6 +842,7 @@ int nnsp_b200_batch_exec(nnsp_b200_batch *b, const int16_t *pcm_dev, long long s
     int rc = check_pcm_args(pcm_dev, stream_stride, n_frames);
     if (rc) return rc;
     NNSP_CUDA(cudaSetDevice(b->device));
+    if ((rc = batch_drain_host(b))) return rc;
     if ((rc = batch_ensure_logmel(b, n_frames))) return rc;
     if ((rc = batch_ensure_split(b, (n_frames + 1) / 2))) return rc;
     if (batch_nn_path(b) == 3 && !taps) {
@@ -843,6 +864,43 @@ int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
                               nnsp_b200_result *results)
 {
     if (!b) return NNSP_B200_ERR_ARG;
+    int rc = batch_enqueue_host(b, pcm, stream_stride, n_frames, results);
+    if (rc) return rc;
+    for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    b->host_inflight = false;
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_batch_exec_host_async(nnsp_b200_batch *b, const int16_t *pcm, long long stream_stride, int n_frames,
+                                    nnsp_b200_result *results, long long *ticket)
+{
+    if (!b) return NNSP_B200_ERR_ARG;
+    int rc = batch_enqueue_host(b, pcm, stream_stride, n_frames, results);
+    if (rc) return rc;
+    const long long t = ++b->host_seq;
+    for (int j = 0; j < 4; j++) NNSP_CUDA(cudaEventRecord(b->host_ev[t % HOST_RING][j], b->xs[j]));
+    if (ticket) *ticket = t;
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_batch_wait_host(nnsp_b200_batch *b, long long ticket)
+{
+    if (!b || ticket <= 0 || ticket > b->host_seq) return NNSP_B200_ERR_ARG;
+    NNSP_CUDA(cudaSetDevice(b->device));
+    /* a slot that has been reused holds the events of a later call on the same streams: waiting for those covers it */
+    for (int j = 0; j < 4; j++) NNSP_CUDA(cudaEventSynchronize(b->host_ev[ticket % HOST_RING][j]));
+    if (ticket == b->host_seq) b->host_inflight = false;
+    return NNSP_B200_OK;
+}
+
+} /* extern "C" */
+
+/* one host-buffer call queued on the four pipeline streams; nothing here waits for it. Slice k always goes to stream
+ * k % 4, so consecutive calls are ordered slice by slice (staging buffers, stream state, result staging) by stream
+ * order alone, and the H2D of call N+1 starts while the last slices of call N are still in their kernels */
+static int batch_enqueue_host(nnsp_b200_batch *b, const int16_t *pcm, long long stream_stride, int n_frames,
+                              nnsp_b200_result *results)
+{
     int rc = check_pcm_args(pcm, stream_stride, n_frames);
     if (rc) return rc;
     NNSP_CUDA(cudaSetDevice(b->device));
@@ -865,6 +923,7 @@ int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
      * is bound by the host link (320 B of PCM per stream-frame), so slices are small enough that the work left
      * after the last H2D -- one slice of kernels and its D2H -- is short, and large enough to fill the GPU */
     const long long dstride = (long long)T * NNSP_B200_FRAME;
+    b->host_inflight = true;
     int nsl = b->S / 256;
     nsl = nsl < 1 ? 1 : (nsl > 16 ? 16 : nsl);
     for (int k = 0; k < nsl; k++) {
@@ -887,10 +946,11 @@ int nnsp_b200_batch_exec_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
             NNSP_CUDA(cudaMemcpyAsync(results + (size_t)s0 * T, b->d_res + (size_t)s0 * T,
                                       (size_t)(s1 - s0) * T * sizeof(nnsp_b200_result), cudaMemcpyDeviceToHost, st));
     }
-    for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
     b->slides = (b->slides + T) % 2;
     return NNSP_B200_OK;
 }
+
+extern "C" {
 
 int nnsp_b200_batch_sync(nnsp_b200_batch *b)
 {
@@ -899,6 +959,7 @@ int nnsp_b200_batch_sync(nnsp_b200_batch *b)
     NNSP_CUDA(cudaStreamSynchronize(b->stream));
     NNSP_CUDA(cudaStreamSynchronize(b->nn_stream));
     for (auto s : b->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    b->host_inflight = false;
     return NNSP_B200_OK;
 }
 
@@ -955,6 +1016,7 @@ void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
     if (b->stream) cudaStreamDestroy(b->stream);
     for (auto s : b->xs) if (s) cudaStreamDestroy(s);
     for (auto e : b->ev) if (e) cudaEventDestroy(e);
+    for (auto &r : b->host_ev) for (auto e : r) if (e) cudaEventDestroy(e);
     delete b;
 }
 

@@ -37,3 +37,39 @@ def gather_results(local, total_streams, group=None):
         blk = outs[r].cpu().numpy()[: b - a]
         full[a:b] = np.frombuffer(blk.tobytes(), local.dtype).reshape(b - a, T)
     return full
+
+
+def _physical_index(device):
+    import os
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [x.strip() for x in vis.split(",") if x.strip() != ""]
+        if device < len(ids) and ids[device].isdigit():
+            return int(ids[device])
+    return device
+
+
+def local_cpus(device):
+    """CPUs on the NUMA node the GPU's PCIe root port hangs off (NVML), restricted to the ones this process may use;
+    empty when NVML cannot tell."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(_physical_index(device))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(os.cpu_count() or 1, 64) + 63) // 64)
+    except Exception:
+        return set()
+    cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+    return cpus & os.sched_getaffinity(0)
+
+
+def bind_host_to_device(device):
+    """One process per GPU: keep the rank's host thread -- and with it the first-touch placement of the pinned PCM and
+    result buffers it allocates next -- on the CPU socket the GPU is attached to, so that the H2D stream of every rank
+    reads local DRAM instead of crossing the inter-socket link. Returns the CPU set bound to (empty = left alone)."""
+    import os
+    cpus = local_cpus(device)
+    if cpus and cpus != os.sched_getaffinity(0):
+        os.sched_setaffinity(0, cpus)
+    return cpus

@@ -200,6 +200,44 @@ def test_back_to_back_calls_are_pipelined_correctly(nb, oracle):
     b.close()
 
 
+def test_async_host_calls_double_buffered(nb, oracle):
+    """nnsp_b200_batch_exec_host_async / _wait_host: a server loop with two pinned PCM/result buffer pairs, one call in
+    flight while the previous one is consumed; odd call lengths flip the stride-2 inference gate between calls; a
+    device-buffer call and a synchronous host call are mixed in behind the asynchronous ones."""
+    S, n = 600, 7                                      # 600 streams -> 2 pipeline slices; 7 frames per call
+    calls = 9
+    T = n * (calls + 2)
+    pcm = nb.synth_pcm(S, T, first_stream=5)
+    for nn_id in (1, 0):
+        b = nb.NNSPBatch(_model(nb, nn_id, False), S)
+        pin = [nb.PinnedArray((S, n * 160), np.int16) for _ in range(2)]
+        pres = [nb.PinnedArray((S, n), nb.RESULT_DT) for _ in range(2)]
+        got, prev = [], None
+        for k in range(calls):
+            pin[k & 1].array[...] = pcm[:, k * n * 160:(k + 1) * n * 160]
+            tk = b.exec_host_async(pin[k & 1].array, pres[k & 1].array)
+            assert tk == k + 1
+            if prev is not None:
+                b.wait_host(prev)
+                got.append(pres[(k - 1) & 1].array.copy())
+            prev = tk
+        b.wait_host(prev)
+        b.wait_host(1)                                 # an old ticket: already complete, returns at once
+        got.append(pres[(calls - 1) & 1].array.copy())
+        got.append(b.exec(pcm[:, calls * n * 160:(calls + 1) * n * 160].copy()))          # device-buffer call
+        got.append(b.exec_host(pcm[:, (calls + 1) * n * 160:].copy()))                    # synchronous host call
+        got = np.concatenate(got, axis=1)
+        m_or = oracle.model(nn_id, False)
+        for s in list(range(0, S, 37)) + [S - 1]:
+            r, _ = oracle.nnsp_run(m_or, pcm[s], taps=False)
+            assert (r == got[s]).all(), "model %d stream %d" % (nn_id, s)
+        with pytest.raises(Exception):
+            b.wait_host(calls + 5)                     # a ticket that was never handed out
+        for x in pin + pres:
+            x.free()
+        b.close()
+
+
 def test_long_call_many_inference_rounds(nb, oracle):
     """One call of 301 frames (151 inferences): several 16-inference work items per tile in the fc kernels, several
     staging rounds in the post kernel, a long TMA ring in the scan."""
