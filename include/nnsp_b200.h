@@ -192,6 +192,10 @@ int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long lo
                            const nnsp_b200_taps *taps);
 int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long long stream_stride,
                                 int n_frames, nnsp_b200_cascade_result *results);
+/* asynchronous twin of the host-buffer call: see nnsp_b200_batch_exec_host_async */
+int nnsp_b200_cascade_exec_host_async(nnsp_b200_cascade *c, const int16_t *pcm, long long stream_stride,
+                                      int n_frames, nnsp_b200_cascade_result *results, long long *ticket);
+int nnsp_b200_cascade_wait_host(nnsp_b200_cascade *c, long long ticket);
 int nnsp_b200_cascade_sync(nnsp_b200_cascade *c);
 int nnsp_b200_cascade_last_kernel_ms(nnsp_b200_cascade *c, float ms[3]);
 void *nnsp_b200_cascade_stream(nnsp_b200_cascade *c);

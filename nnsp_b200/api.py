@@ -314,6 +314,19 @@ class Cascade:
                                                 results.ctypes.data_as(C.c_void_p)), "cascade_exec_host")
         return results
 
+    def exec_host_async(self, pcm, results):
+        """exec_host without the final wait (pinned `pcm` / `results` untouched until wait_host(ticket))."""
+        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and pcm.shape[0] == self.S
+        T = pcm.shape[1] // FRAME
+        assert results.dtype == CASCADE_RESULT_DT and results.flags.c_contiguous and results.shape == (self.S, T)
+        ticket = C.c_longlong(0)
+        check(lib().nnsp_b200_cascade_exec_host_async(self.h, pcm.ctypes.data_as(C.c_void_p), pcm.shape[1], T,
+                                                      results.ctypes.data_as(C.c_void_p), C.byref(ticket)), "cascade_exec_host_async")
+        return ticket.value
+
+    def wait_host(self, ticket):
+        check(lib().nnsp_b200_cascade_wait_host(self.h, ticket), "cascade_wait_host")
+
     def last_kernel_ms(self):
         ms = (C.c_float * 3)()
         check(lib().nnsp_b200_cascade_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")

@@ -537,6 +537,8 @@ __global__ void cascade_reset_kernel(ResetModels rm, StreamState st, int16_t *st
 
 using namespace nnsp;
 
+#define CS_HOST_RING 4
+
 struct nnsp_b200_cascade {
     int device = 0, S = 0;
     cudaStream_t stream = nullptr;
@@ -572,6 +574,10 @@ struct nnsp_b200_cascade {
     int32_t *logmel2 = nullptr;                /* second log-mel buffer */
     int16_t *hist2 = nullptr;                  /* second PCM history buffer */
     cudaEvent_t ev_fork = nullptr, ev_join[CG_GROUPS] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    /* asynchronous host-buffer calls: one completion event per pipeline stream, a ring of CS_HOST_RING calls */
+    cudaEvent_t host_ev[CS_HOST_RING][3] = {};
+    long long host_seq = 0;
+    bool host_inflight = false;
 };
 
 constexpr int CS_MAX_SLICES = 8;
@@ -778,6 +784,7 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaFuncSetAttribute(cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &r : c->host_ev) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : c->ev) TRY(cudaEventCreate(&e));
     for (auto &g : c->gs) TRY(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
     {
@@ -823,6 +830,7 @@ int nnsp_b200_cascade_reset(nnsp_b200_cascade *c)
     NNSP_CUDA(cudaSetDevice(c->device));
     NNSP_CUDA(cudaDeviceSynchronize());
     c->nn_pending[0] = c->nn_pending[1] = false;
+    c->host_inflight = false;
     const int hist_frames = c->cd.dmax + 2, lm_rows = c->cd.dmax > 0 ? c->cd.dmax : 1;
     ResetModels rm{};
     for (int i = 0; i < 3; i++) rm.m[i] = c->dm[i].d;
@@ -851,6 +859,10 @@ int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long lo
     int rc = cascade_check_pcm(pcm_dev, stream_stride, n_frames);
     if (rc) return rc;
     NNSP_CUDA(cudaSetDevice(c->device));
+    if (c->host_inflight) {                             /* asynchronous host-buffer calls still on the pipeline streams */
+        for (auto s : c->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+        c->host_inflight = false;
+    }
     if ((rc = cascade_ensure_logmel(c, n_frames))) return rc;
     if ((rc = cascade_ensure_split(c, n_frames))) return rc;
     if (cascade_use_split(c, taps)) {
@@ -868,10 +880,11 @@ int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long lo
     return cascade_launch(c, pcm_dev, stream_stride, n_frames, 0, c->S, results_dev, taps, c->stream, true);
 }
 
-int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long long stream_stride, int n_frames,
+/* one host-buffer call queued on the pipeline streams (slice k always on stream k % 3: consecutive calls are ordered
+ * slice by slice by stream order alone); nothing here waits for it */
+static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long long stream_stride, int n_frames,
                                 nnsp_b200_cascade_result *results)
 {
-    if (!c) return NNSP_B200_ERR_ARG;
     int rc = cascade_check_pcm(pcm, stream_stride, n_frames);
     if (rc) return rc;
     NNSP_CUDA(cudaSetDevice(c->device));
@@ -891,6 +904,7 @@ int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
     NNSP_CUDA(cudaStreamSynchronize(c->nn_stream));
     c->nn_pending[0] = c->nn_pending[1] = false;
     const long long dstride = (long long)T * NNSP_B200_FRAME;
+    c->host_inflight = true;
     const int nsl = c->S >= 4096 ? 8 : (c->S >= 256 ? 4 : 1);
     for (int k = 0; k < nsl; k++) {
         const int s0 = (int)(((long long)c->S * k / nsl) & ~15LL);
@@ -906,7 +920,39 @@ int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
             NNSP_CUDA(cudaMemcpyAsync(results + (size_t)s0 * T, c->d_res + (size_t)s0 * T,
                                       (size_t)(s1 - s0) * T * sizeof(nnsp_b200_cascade_result), cudaMemcpyDeviceToHost, st));
     }
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_cascade_exec_host(nnsp_b200_cascade *c, const int16_t *pcm, long long stream_stride, int n_frames,
+                                nnsp_b200_cascade_result *results)
+{
+    if (!c) return NNSP_B200_ERR_ARG;
+    int rc = cascade_enqueue_host(c, pcm, stream_stride, n_frames, results);
+    if (rc) return rc;
     for (auto s : c->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    c->host_inflight = false;
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_cascade_exec_host_async(nnsp_b200_cascade *c, const int16_t *pcm, long long stream_stride, int n_frames,
+                                      nnsp_b200_cascade_result *results, long long *ticket)
+{
+    if (!c) return NNSP_B200_ERR_ARG;
+    int rc = cascade_enqueue_host(c, pcm, stream_stride, n_frames, results);
+    if (rc) return rc;
+    const long long t = ++c->host_seq;
+    for (int j = 0; j < 3; j++) NNSP_CUDA(cudaEventRecord(c->host_ev[t % CS_HOST_RING][j], c->xs[j]));
+    if (ticket) *ticket = t;
+    return NNSP_B200_OK;
+}
+
+int nnsp_b200_cascade_wait_host(nnsp_b200_cascade *c, long long ticket)
+{
+    if (!c || ticket <= 0 || ticket > c->host_seq) return NNSP_B200_ERR_ARG;
+    NNSP_CUDA(cudaSetDevice(c->device));
+    /* a reused slot holds the events of a later call on the same streams: waiting for those covers the older one */
+    for (int j = 0; j < 3; j++) NNSP_CUDA(cudaEventSynchronize(c->host_ev[ticket % CS_HOST_RING][j]));
+    if (ticket == c->host_seq) c->host_inflight = false;
     return NNSP_B200_OK;
 }
 
@@ -917,6 +963,7 @@ int nnsp_b200_cascade_sync(nnsp_b200_cascade *c)
     NNSP_CUDA(cudaStreamSynchronize(c->stream));
     NNSP_CUDA(cudaStreamSynchronize(c->nn_stream));
     for (auto s : c->xs) NNSP_CUDA(cudaStreamSynchronize(s));
+    c->host_inflight = false;
     return NNSP_B200_OK;
 }
 
@@ -960,6 +1007,7 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     cudaFree(c->planes[0]); cudaFree(c->planes[1]); cudaFree(c->dec);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto s : c->xs) if (s) cudaStreamDestroy(s);
+    for (auto &r : c->host_ev) for (auto e : r) if (e) cudaEventDestroy(e);
     for (auto e : c->ev) if (e) cudaEventDestroy(e);
     for (auto g : c->gs) if (g) cudaStreamDestroy(g);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);

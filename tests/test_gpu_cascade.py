@@ -115,6 +115,42 @@ def test_cascade_exec_host(nb):
     c.close()
 
 
+@pytest.mark.parametrize("path", ["sorted", "sequential"])
+def test_cascade_async_host_calls_double_buffered(nb, path):
+    """nnsp_b200_cascade_exec_host_async / _wait_host with two pinned buffer pairs against one device-buffer call over the
+    same audio; a blocking host call and a device call follow the asynchronous ones."""
+    S, n, calls = 4100, 40, 6                          # >= 4096 streams: 8 slices over the 3 pipeline streams
+    T = n * (calls + 2)
+    pcm = nb.synth_pcm(S, T, first_stream=11)
+    models = _models(nb)
+    ref = nb.Cascade(models, S)
+    ref.set_path(path)
+    want = ref.exec(pcm)
+    ref.close()
+    c = nb.Cascade(models, S)
+    c.set_path(path)
+    pin = [nb.PinnedArray((S, n * 160), np.int16) for _ in range(2)]
+    pres = [nb.PinnedArray((S, n), nb.CASCADE_RESULT_DT) for _ in range(2)]
+    got, prev = [], None
+    for k in range(calls):
+        pin[k & 1].array[...] = pcm[:, k * n * 160:(k + 1) * n * 160]
+        tk = c.exec_host_async(pin[k & 1].array, pres[k & 1].array)
+        if prev is not None:
+            c.wait_host(prev)
+            got.append(pres[(k - 1) & 1].array.copy())
+        prev = tk
+    c.wait_host(prev)
+    got.append(pres[(calls - 1) & 1].array.copy())
+    got.append(c.exec_host(pcm[:, calls * n * 160:(calls + 1) * n * 160].copy()))
+    got.append(c.exec(pcm[:, (calls + 1) * n * 160:].copy()))
+    got = np.concatenate(got, axis=1)
+    for f in want.dtype.names:
+        assert (want[f] == got[f]).all(), f
+    for x in pin + pres:
+        x.free()
+    c.close()
+
+
 @pytest.mark.parametrize("seq,params,chunks", [
     ((1, 2, 0), None, (100, 100, 37, 1, 2, 160, 300, 100, 100, 100, 100, 100, 100, 100, 100, 100, 100)),
     ((1, 2, 0), dict(frs_vbufBk_kws=99, frs_vbufBk_s2i=1, thresh_timeout_kws=45, thresh_timeout_s2i=30, thresh_prob_kws=100, thresh_cnts_kws=2),

@@ -66,3 +66,18 @@ def test_two_ranks_gloo_equal_single_process(nb, oracle):
     pcm = nb.synth_pcm(total, T)
     _, ref = oracle.batch_run(oracle.model(1, False), pcm, want_results=True)
     assert (got == ref.view(nb.RESULT_DT)).all()
+
+
+def test_host_binding_never_widens_or_empties_the_cpu_set(nb):
+    """bind_host_to_device: the rank ends up on a non-empty subset of the CPUs it was allowed (the GPU's NVML CPU
+    set where NVML answers, untouched otherwise -- this container has no GPU)."""
+    from nnsp_b200.shard import bind_host_to_device, local_cpus
+    before = os.sched_getaffinity(0)
+    try:
+        cpus = bind_host_to_device(0)
+        after = os.sched_getaffinity(0)
+        assert after and after <= before
+        assert cpus == local_cpus(0) or not cpus
+        assert after == (cpus if cpus else before)
+    finally:
+        os.sched_setaffinity(0, before)
