@@ -80,6 +80,20 @@ __device__ __forceinline__ void load_a(const uint8_t *plane, int pitch, int kbyt
     a[3] = *reinterpret_cast<const uint32_t *>(p1 + 16);
 }
 
+/* The same fragment by one ldmatrix.x4. Seen as 8x8 matrices of b16, matrix m covers rows 8(m&1).. and k bytes 16(m>>1)..
+ * of the k-step, and thread (g, q) receives bytes 4q..4q+3 of row g of each: exactly a[0..3] above. Lane l supplies the
+ * address of row l & 15 at k byte 16 (l >> 4); rows must be 16-byte aligned (every plane pitch is a multiple of 16 with
+ * pitch/16 odd, so the eight rows of a matrix fall on distinct bank groups). */
+__device__ __forceinline__ uint32_t ldm_lane_addr(const uint8_t *plane, int pitch, int lane)
+{
+    return (uint32_t)__cvta_generic_to_shared(plane) + (uint32_t)((lane & 15) * pitch + 16 * (lane >> 4));
+}
+__device__ __forceinline__ void load_a_ldm(uint32_t addr, uint32_t (&a)[4])
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr) : "memory");
+}
+
 /* two adjacent units of one stream -> byte pair in the high plane and in the low plane */
 __device__ __forceinline__ void store_pair(uint8_t *hi, uint8_t *lo, int off, int y0, int y1)
 {

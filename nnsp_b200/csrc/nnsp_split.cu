@@ -50,7 +50,10 @@ constexpr int LUT2_N = 160;                         /* reachable segments of coe
 /* The LUT is indexed by data, so lanes of a warp collide on banks (ncu: 58 % of the scan's LUT wavefronts were excess).
  * It can be replicated: copy c of entry k sits at [k * COPIES + c] and lane l reads copy l % COPIES, i.e. always the same
  * bank pair -- with 16 copies a 64-bit load of a half-warp touches every bank exactly once. */
-constexpr int LUT2_COPIES_SCAN = 1;                 /* measured: 16 copies remove the conflicts but not a microsecond (the scan is
+#ifndef NNSP_LUT2_COPIES_SCAN
+#define NNSP_LUT2_COPIES_SCAN 1
+#endif
+constexpr int LUT2_COPIES_SCAN = NNSP_LUT2_COPIES_SCAN;                 /* measured: 16 copies remove the conflicts but not a microsecond (the scan is
                                                        latency-bound), and the extra shared memory costs seg_kernel a resident CTA */
 constexpr int LUT2_COPIES_SEG = 1;
 
@@ -190,10 +193,12 @@ template <int NC>
 __device__ __forceinline__ void fc_tiles(int kt, const uint2 *wf, const uint8_t *in_hi, const uint8_t *in_lo,
                                          int pitch, int g, int q, int (&ch)[4][4], int (&cl)[4][4])
 {
+    const int lane = 4 * g + q;
+    const uint32_t ah = ldm_lane_addr(in_hi, pitch, lane), al = ldm_lane_addr(in_lo, pitch, lane);
     for (int ks = 0; ks < kt; ks++) {
         uint32_t fh[4], fl[4];
-        load_a(in_hi, pitch, 32 * ks, g, q, fh);
-        load_a(in_lo, pitch, 32 * ks, g, q, fl);
+        load_a_ldm(ah + 32 * ks, fh);
+        load_a_ldm(al + 32 * ks, fl);
 #pragma unroll
         for (int j = 0; j < NC; j++) {
             const uint2 b = wf[(j * kt + ks) * 32];
@@ -390,7 +395,13 @@ seg_kernel(SegArgs a)
                 uint8_t *oh = wb + pp * XB, *ol = oh + 16 * M.pa;
                 for (int n0 = 0; n0 < L.nt; n0 += 4) {
                     const int nc = min(4, L.nt - n0);
-                    int ch[4][4] = {}, cl[4][4] = {};
+                    int ch[4][4] = {}, cl[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {                    /* the bias rides in the low-plane accumulator */
+                        const int nb = (n0 + (j < nc ? j : 0)) * 8 + 2 * q;
+                        const int32_t b0 = B[nb], b1 = B[nb + 1];
+                        cl[j][0] = b0; cl[j][1] = b1; cl[j][2] = b0; cl[j][3] = b1;
+                    }
                     const uint2 *wf = wsm + (L.w_off - a.w_base) + n0 * kt * 32 + lane;
                     switch (nc) {
                     case 4: fc_tiles<4>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
@@ -405,11 +416,10 @@ seg_kernel(SegArgs a)
                              * exact 32-bit finish (MmaLayer.fast): affine.c:190-249 without reachable clamps; units past
                              * L.rows are computed too (zero weights), they only ever meet zero weights downstream */
                             const int nb = (n0 + j) * 8 + 2 * q;
-                            const int32_t b0 = B[nb], b1 = B[nb + 1];
                             int32_t pre[4], o[4];
 #pragma unroll
                             for (int e = 0; e < 4; e++)
-                                pre[e] = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e] + (uint32_t)((e & 1) ? b1 : b0)) >> rs;
+                                pre[e] = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e]) >> rs;
                             if (act == ACT_LINEAR) {                                            /* activation.c:19-29 */
 #pragma unroll
                                 for (int e = 0; e < 4; e++) { o[e] = 0; wlog[(g + 8 * (e >> 1)) * NOP + nb + (e & 1)] = pre[e]; }
@@ -584,10 +594,11 @@ scan_kernel(ScanArgs a)
             for (int e = 0; e < 4; e++) { ach[gt][e] = 0; acl[gt][e] = bz[gt][e & 1]; }
     };
     auto half = [&](const uint8_t *plane, const uint2 *w, int nk) {          /* acc += W . plane (rc_Krows_8x16) */
+        const uint32_t ah = ldm_lane_addr(plane, pa, lane), al = ah + 16 * pa;
         for (int ks = 0; ks < nk; ks++) {
             uint32_t fh[4], fl[4];
-            load_a(plane, pa, 32 * ks, g, q, fh);
-            load_a(plane + 16 * pa, pa, 32 * ks, g, q, fl);
+            load_a_ldm(ah + 32 * ks, fh);
+            load_a_ldm(al + 32 * ks, fl);
 #pragma unroll
             for (int gt = 0; gt < 4; gt++) {
                 const uint2 b = w[(gt * nk + ks) * 32];
