@@ -256,6 +256,7 @@ int upload_model_mma(const nnsp_b200_model *m, MmaDeviceModel *out)
         foff += (long long)(is_lstm ? 4 : 1) * G.nt * G.kt * 32;
         G.wh_off = (int)foff;
         foff += (long long)(is_lstm ? 4 : 0) * G.nt * G.ktr * 32;
+        boff = (boff + 1) & ~1;                            /* even: the fc finish reads bias pairs with one 64-bit load */
         G.bias_off = boff; boff += (is_lstm ? 4 : 1) * L.rows;
         if (i < m->numlayers - 1) D->act_stride += L.rows;
         if (i > 0 && G.kt * 32 > width) width = G.kt * 32;

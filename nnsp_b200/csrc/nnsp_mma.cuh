@@ -97,8 +97,8 @@ __device__ __forceinline__ void load_a_ldm(uint32_t addr, uint32_t (&a)[4])
 /* two adjacent units of one stream -> byte pair in the high plane and in the low plane */
 __device__ __forceinline__ void store_pair(uint8_t *hi, uint8_t *lo, int off, int y0, int y1)
 {
-    *reinterpret_cast<uint16_t *>(hi + off) = (uint16_t)(((y0 >> 8) & 0xff) | (((y1 >> 8) & 0xff) << 8));
-    *reinterpret_cast<uint16_t *>(lo + off) = (uint16_t)((y0 & 0xff) | ((y1 & 0xff) << 8));
+    *reinterpret_cast<uint16_t *>(hi + off) = (uint16_t)__byte_perm((uint32_t)y0, (uint32_t)y1, 0x0051);   /* y0.b1 | y1.b1 << 8 */
+    *reinterpret_cast<uint16_t *>(lo + off) = (uint16_t)__byte_perm((uint32_t)y0, (uint32_t)y1, 0x0040);   /* y0.b0 | y1.b0 << 8 */
 }
 
 /* byte offsets of the tile's buffers from the tile base in shared memory (offsets, not pointers, so that

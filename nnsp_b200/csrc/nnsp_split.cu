@@ -189,12 +189,31 @@ struct SegArgs {
     int16_t thresh_prob;
 };
 
+/* Where the outputs of one fc layer of one (tile, inference) row block go. */
+struct FcOut {
+    uint8_t *oh, *ol;               /* output planes [16][pa] (not written by the model's last layer) */
+    int32_t *wlog;                  /* logits rows [16][nop] (linear layers and the model's last layer) */
+    const int2 *lut2;
+    int pa, nop, rs, act;
+    bool last;
+};
+
+/* NC (1..4) column tiles of 8 units starting at unit 8*n0 for the warp's 16 rows: both byte-plane products, then the
+ * layer's finish. Everything that depends on NC or the lane is resolved at compile time or hoisted, the activation is
+ * chosen once per group, so the 4*NC evaluations of a group are straight-line code that interleaves.
+ * exact 32-bit finish (MmaLayer.fast): affine.c:190-249 without reachable clamps; the bias (pre-shifted) rides in the
+ * low-plane accumulator; units past the layer's rows are computed too (zero weights) and only ever meet zero weights. */
 template <int NC>
-__device__ __forceinline__ void fc_tiles(int kt, const uint2 *wf, const uint8_t *in_hi, const uint8_t *in_lo,
-                                         int pitch, int g, int q, int (&ch)[4][4], int (&cl)[4][4])
+__device__ __forceinline__ void fc_group(int kt, const uint2 *__restrict__ wf, uint32_t ah, uint32_t al,
+                                         const int32_t *__restrict__ B, int n0, int g, int q, const FcOut &o)
 {
-    const int lane = 4 * g + q;
-    const uint32_t ah = ldm_lane_addr(in_hi, pitch, lane), al = ldm_lane_addr(in_lo, pitch, lane);
+    int ch[NC][4], cl[NC][4];
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const int2 b = *reinterpret_cast<const int2 *>(B + (n0 + j) * 8 + 2 * q);
+        ch[j][0] = ch[j][1] = ch[j][2] = ch[j][3] = 0;
+        cl[j][0] = b.x; cl[j][1] = b.y; cl[j][2] = b.x; cl[j][3] = b.y;
+    }
     for (int ks = 0; ks < kt; ks++) {
         uint32_t fh[4], fl[4];
         load_a_ldm(ah + 32 * ks, fh);
@@ -204,6 +223,51 @@ __device__ __forceinline__ void fc_tiles(int kt, const uint2 *wf, const uint8_t 
             const uint2 b = wf[(j * kt + ks) * 32];
             imma_s8s8(ch[j], fh, b);
             imma_u8s8(cl[j], fl, b);
+        }
+    }
+    int32_t v[NC][4];
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[j][e] = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e]) >> o.rs;
+    const int r0 = g * o.pa + n0 * 8 + 2 * q, r1 = r0 + 8 * o.pa;           /* plane bytes of rows g, g+8 */
+    int32_t *w0 = o.wlog + g * o.nop + n0 * 8 + 2 * q, *w1 = w0 + 8 * o.nop;  /* logits words of rows g, g+8 */
+    if (o.act == ACT_LINEAR) {                                              /* activation.c:19-29: int32 stays */
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            *reinterpret_cast<int2 *>(w0 + 8 * j) = make_int2(v[j][0], v[j][1]);
+            *reinterpret_cast<int2 *>(w1 + 8 * j) = make_int2(v[j][2], v[j][3]);
+            if (!o.last) { store_pair(o.oh, o.ol, r0 + 8 * j, 0, 0); store_pair(o.oh, o.ol, r1 + 8 * j, 0, 0); }
+        }
+        return;
+    }
+    if (o.act == ACT_RELU6) {
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[j][e] = relu6_q12(v[j][e]);
+    } else if (o.act == ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[j][e] = tanh_q15v<LUT2_COPIES_SEG>(v[j][e], o.lut2);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[j][e] = sigmoid_q15v<LUT2_COPIES_SEG>(v[j][e], o.lut2);
+    }
+    if (o.last) {                                                           /* neural_nets.c:160-166 */
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            *reinterpret_cast<int2 *>(w0 + 8 * j) = make_int2(v[j][0], v[j][1]);
+            *reinterpret_cast<int2 *>(w1 + 8 * j) = make_int2(v[j][2], v[j][3]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            store_pair(o.oh, o.ol, r0 + 8 * j, v[j][0], v[j][1]);
+            store_pair(o.oh, o.ol, r1 + 8 * j, v[j][2], v[j][3]);
         }
     }
 }
@@ -252,6 +316,7 @@ seg_kernel(SegArgs a)
     const int XB = 32 * M.pa;                                    /* bytes of one tile-step: [hi|lo][16][pa] */
     uint8_t *wb = smem + a.off_wb + (size_t)warp * a.nbuf * XB;
     const int NOP = M.no + 4;                                     /* logits row pitch: (no + 4) words keeps the 8 rows of a store on distinct banks */
+    const int pa = M.pa, nlayers = M.numlayers, act_stride = M.act_stride;
     int32_t *wlog = reinterpret_cast<int32_t *>(smem + a.off_log) + warp * 16 * NOP;
     {   /* activation planes start zeroed: padded k columns must hold defined bytes (they meet zero weights) */
         uint32_t *z = reinterpret_cast<uint32_t *>(smem + a.off_wb);
@@ -389,72 +454,32 @@ seg_kernel(SegArgs a)
             int pp = 0, ao = a.ao0;
             for (int li = a.l0; li < a.l1; li++) {
                 const MmaLayer &L = M.layer[li];
-                const bool last = (li == M.numlayers - 1);
+                const int kt = L.kt, nt = L.nt, rows = L.rows;
                 const int32_t *B = bias32 + L.bias_off;
-                const int rs = -L.sh_out, act = L.act, kt = L.kt;
-                uint8_t *oh = wb + pp * XB, *ol = oh + 16 * M.pa;
-                for (int n0 = 0; n0 < L.nt; n0 += 4) {
-                    const int nc = min(4, L.nt - n0);
-                    int ch[4][4] = {}, cl[4][4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {                    /* the bias rides in the low-plane accumulator */
-                        const int nb = (n0 + (j < nc ? j : 0)) * 8 + 2 * q;
-                        const int32_t b0 = B[nb], b1 = B[nb + 1];
-                        cl[j][0] = b0; cl[j][1] = b1; cl[j][2] = b0; cl[j][3] = b1;
-                    }
-                    const uint2 *wf = wsm + (L.w_off - a.w_base) + n0 * kt * 32 + lane;
-                    switch (nc) {
-                    case 4: fc_tiles<4>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
-                    case 3: fc_tiles<3>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
-                    case 2: fc_tiles<2>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
-                    default: fc_tiles<1>(kt, wf, in_hi, in_lo, in_pitch, g, q, ch, cl); break;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (j < nc) {
-                            /* the lane's 2 rows x 2 units of this tile, branch-free so the four evaluations interleave.
-                             * exact 32-bit finish (MmaLayer.fast): affine.c:190-249 without reachable clamps; units past
-                             * L.rows are computed too (zero weights), they only ever meet zero weights downstream */
-                            const int nb = (n0 + j) * 8 + 2 * q;
-                            int32_t pre[4], o[4];
-#pragma unroll
-                            for (int e = 0; e < 4; e++)
-                                pre[e] = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e]) >> rs;
-                            if (act == ACT_LINEAR) {                                            /* activation.c:19-29 */
-#pragma unroll
-                                for (int e = 0; e < 4; e++) { o[e] = 0; wlog[(g + 8 * (e >> 1)) * NOP + nb + (e & 1)] = pre[e]; }
-                            } else {
-                                if (act == ACT_TANH) {
-#pragma unroll
-                                    for (int e = 0; e < 4; e++) o[e] = tanh_q15v<LUT2_COPIES_SEG>(pre[e], lut2);
-                                } else if (act == ACT_SIGMOID) {
-#pragma unroll
-                                    for (int e = 0; e < 4; e++) o[e] = sigmoid_q15v<LUT2_COPIES_SEG>(pre[e], lut2);
-                                } else {
-#pragma unroll
-                                    for (int e = 0; e < 4; e++) o[e] = relu6_q12(pre[e]);
-                                }
-                                if (last) {                                                     /* neural_nets.c:160-166 */
-#pragma unroll
-                                    for (int e = 0; e < 4; e++) wlog[(g + 8 * (e >> 1)) * NOP + nb + (e & 1)] = o[e];
-                                } else if (a.tap_act) {
-#pragma unroll
-                                    for (int e = 0; e < 4; e++) {
-                                        const int row = g + 8 * (e >> 1), n = nb + (e & 1);
-                                        if (row < nvalid && n < L.rows)
-                                            a.tap_act[((long long)sel_sid(a.sel, tile, row) * T + t) * M.act_stride + ao + n] = (int16_t)o[e];
-                                    }
-                                }
-                            }
-                            store_pair(oh, ol, g * M.pa + nb, o[0], o[1]);
-                            store_pair(oh, ol, (g + 8) * M.pa + nb, o[2], o[3]);
-                        }
-                    }
+                FcOut out;
+                out.oh = wb + pp * XB; out.ol = out.oh + 16 * pa; out.wlog = wlog; out.lut2 = lut2;
+                out.pa = pa; out.nop = NOP; out.rs = -L.sh_out; out.act = L.act; out.last = (li == nlayers - 1);
+                const uint32_t ah = ldm_lane_addr(in_hi, in_pitch, lane), al = ldm_lane_addr(in_lo, in_pitch, lane);
+                const uint2 *wl = wsm + (L.w_off - a.w_base) + lane;
+                int n0 = 0;
+                for (; n0 + 4 <= nt; n0 += 4) fc_group<4>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, out);
+                switch (nt - n0) {
+                case 3: fc_group<3>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, out); break;
+                case 2: fc_group<2>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, out); break;
+                case 1: fc_group<1>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, out); break;
+                default: break;
                 }
                 __syncwarp();
-                in_hi = oh; in_lo = ol; in_pitch = M.pa;
+                if (a.tap_act && !out.last && out.act != ACT_LINEAR) {        /* debug tap: the layer's int16 outputs back from the planes */
+                    for (int x = lane; x < nvalid * rows; x += 32) {
+                        const int row = x / rows, n = x - row * rows;
+                        a.tap_act[((long long)sel_sid(a.sel, tile, row) * T + t) * act_stride + ao + n] =
+                            (int16_t)(((int)(int8_t)out.oh[row * pa + n] << 8) | out.ol[row * pa + n]);
+                    }
+                }
+                in_hi = out.oh; in_lo = out.ol; in_pitch = pa;
                 pp ^= 1;
-                if (!last) ao += L.rows;
+                if (!out.last) ao += rows;
             }
             if (a.l1 < M.numlayers) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(wb + (pp ^ 1) * XB);
