@@ -69,6 +69,21 @@ __device__ __forceinline__ void imma_u8s8(int (&c)[4], const uint32_t (&a)[4], u
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
+/* first k-step of an accumulation: D = A.B + C with C given apart from D (zeros, or the bias pair of the lane's two
+ * columns repeated for its two rows), so no accumulator has to be initialised by moves */
+__device__ __forceinline__ void imma_s8s8_first(int (&d)[4], const uint32_t (&a)[4], uint2 b)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "r"(0));
+}
+__device__ __forceinline__ void imma_u8s8_first(int (&d)[4], const uint32_t (&a)[4], uint2 b, int c0, int c1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "r"(c0), "r"(c1));
+}
+
 /* A fragment of one byte plane: rows g and g+8, k bytes 4q..4q+3 and 16+4q..16+4q+3 of the k-step */
 __device__ __forceinline__ void load_a(const uint8_t *plane, int pitch, int kbyte, int g, int q, uint32_t (&a)[4])
 {

@@ -203,26 +203,49 @@ struct FcOut {
  * chosen once per group, so the 4*NC evaluations of a group are straight-line code that interleaves.
  * exact 32-bit finish (MmaLayer.fast): affine.c:190-249 without reachable clamps; the bias (pre-shifted) rides in the
  * low-plane accumulator; units past the layer's rows are computed too (zero weights) and only ever meet zero weights. */
-template <int NC>
-__device__ __forceinline__ void fc_group(int kt, const uint2 *__restrict__ wf, uint32_t ah, uint32_t al,
+template <int NC, int KT>           /* KT: k-steps of the layer when known at compile time (fully unrolled), 0 = run-time kt */
+__device__ __forceinline__ void fc_group(int kt_rt, const uint2 *__restrict__ wf, uint32_t ah, uint32_t al,
                                          const int32_t *__restrict__ B, int n0, int g, int q, const FcOut &o)
 {
+    const int kt = KT ? KT : kt_rt;
     int ch[NC][4], cl[NC][4];
-#pragma unroll
-    for (int j = 0; j < NC; j++) {
-        const int2 b = *reinterpret_cast<const int2 *>(B + (n0 + j) * 8 + 2 * q);
-        ch[j][0] = ch[j][1] = ch[j][2] = ch[j][3] = 0;
-        cl[j][0] = b.x; cl[j][1] = b.y; cl[j][2] = b.x; cl[j][3] = b.y;
-    }
-    for (int ks = 0; ks < kt; ks++) {
+    {                                                                       /* k-step 0 starts the accumulators */
         uint32_t fh[4], fl[4];
-        load_a_ldm(ah + 32 * ks, fh);
-        load_a_ldm(al + 32 * ks, fl);
+        load_a_ldm(ah, fh);
+        load_a_ldm(al, fl);
 #pragma unroll
         for (int j = 0; j < NC; j++) {
-            const uint2 b = wf[(j * kt + ks) * 32];
-            imma_s8s8(ch[j], fh, b);
-            imma_u8s8(cl[j], fl, b);
+            const int2 bias = *reinterpret_cast<const int2 *>(B + (n0 + j) * 8 + 2 * q);
+            const uint2 b = wf[(j * kt) * 32];
+            imma_s8s8_first(ch[j], fh, b);
+            imma_u8s8_first(cl[j], fl, b, bias.x, bias.y);
+        }
+    }
+    if (KT) {
+#pragma unroll
+        for (int ks = 1; ks < (KT ? KT : 1); ks++) {
+            uint32_t fh[4], fl[4];
+            load_a_ldm(ah + 32 * ks, fh);
+            load_a_ldm(al + 32 * ks, fl);
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const uint2 b = wf[(j * KT + ks) * 32];
+                imma_s8s8(ch[j], fh, b);
+                imma_u8s8(cl[j], fl, b);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int ks = 1; ks < kt; ks++) {
+            uint32_t fh[4], fl[4];
+            load_a_ldm(ah + 32 * ks, fh);
+            load_a_ldm(al + 32 * ks, fl);
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const uint2 b = wf[(j * kt + ks) * 32];
+                imma_s8s8(ch[j], fh, b);
+                imma_u8s8(cl[j], fl, b);
+            }
         }
     }
     int32_t v[NC][4];
@@ -269,6 +292,21 @@ __device__ __forceinline__ void fc_group(int kt, const uint2 *__restrict__ wf, u
             store_pair(o.oh, o.ol, r0 + 8 * j, v[j][0], v[j][1]);
             store_pair(o.oh, o.ol, r1 + 8 * j, v[j][2], v[j][3]);
         }
+    }
+}
+
+/* all nt column tiles of one fc layer for the warp's 16 rows, in groups of four */
+template <int KT>
+__device__ __forceinline__ void fc_layer(int kt, int nt, const uint2 *__restrict__ wl, uint32_t ah, uint32_t al,
+                                         const int32_t *__restrict__ B, int g, int q, const FcOut &o)
+{
+    int n0 = 0;
+    for (; n0 + 4 <= nt; n0 += 4) fc_group<4, KT>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, o);
+    switch (nt - n0) {
+    case 3: fc_group<3, KT>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, o); break;
+    case 2: fc_group<2, KT>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, o); break;
+    case 1: fc_group<1, KT>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, o); break;
+    default: break;
     }
 }
 
@@ -461,13 +499,12 @@ seg_kernel(SegArgs a)
                 out.pa = pa; out.nop = NOP; out.rs = -L.sh_out; out.act = L.act; out.last = (li == nlayers - 1);
                 const uint32_t ah = ldm_lane_addr(in_hi, in_pitch, lane), al = ldm_lane_addr(in_lo, in_pitch, lane);
                 const uint2 *wl = wsm + (L.w_off - a.w_base) + lane;
-                int n0 = 0;
-                for (; n0 + 4 <= nt; n0 += 4) fc_group<4>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, out);
-                switch (nt - n0) {
-                case 3: fc_group<3>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, out); break;
-                case 2: fc_group<2>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, out); break;
-                case 1: fc_group<1>(kt, wl + n0 * kt * 32, ah, al, B, n0, g, q, out); break;
-                default: break;
+                switch (kt) {                                             /* the shipped models: 1 (VAD), 2 (KWS), 3 and 8 (S2I, layer 0) */
+                case 1: fc_layer<1>(kt, nt, wl, ah, al, B, g, q, out); break;
+                case 2: fc_layer<2>(kt, nt, wl, ah, al, B, g, q, out); break;
+                case 3: fc_layer<3>(kt, nt, wl, ah, al, B, g, q, out); break;
+                case 8: fc_layer<8>(kt, nt, wl, ah, al, B, g, q, out); break;
+                default: fc_layer<0>(kt, nt, wl, ah, al, B, g, q, out); break;
                 }
                 __syncwarp();
                 if (a.tap_act && !out.last && out.act != ACT_LINEAR) {        /* debug tap: the layer's int16 outputs back from the planes */
