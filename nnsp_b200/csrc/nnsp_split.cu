@@ -578,8 +578,58 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-/* NW = warps per CTA (>= unit groups of the layer), MINB = CTAs per SM the register budget is sized for */
-template <int NW, int MINB>
+/* one half of a gate pre-activation for the warp's four gate tiles (rc_Krows_8x16, affine.c:348-407): acc (+)= W . plane.
+ * NK = k-steps when known at compile time (0 = run time); FIRST: the accumulators start here, from the bias (low plane)
+ * and zero (high plane), handed to the first k-step as its C operand */
+template <int NK, bool FIRST>
+__device__ __forceinline__ void scan_half(int nk_rt, const uint8_t *plane, int pa, int lane, const uint2 *__restrict__ w,
+                                          int (&ach)[4][4], int (&acl)[4][4], const int32_t (&bz)[4][2])
+{
+    const int nk = NK ? NK : nk_rt;
+    const uint32_t ah = ldm_lane_addr(plane, pa, lane), al = ah + 16 * pa;
+    if (FIRST) {
+        uint32_t fh[4], fl[4];
+        load_a_ldm(ah, fh);
+        load_a_ldm(al, fl);
+#pragma unroll
+        for (int gt = 0; gt < 4; gt++) {
+            const uint2 b = w[(gt * nk) * 32];
+            imma_s8s8_first(ach[gt], fh, b);
+            imma_u8s8_first(acl[gt], fl, b, bz[gt][0], bz[gt][1]);
+        }
+    }
+    if (NK) {
+#pragma unroll
+        for (int ks = FIRST ? 1 : 0; ks < (NK ? NK : 1); ks++) {
+            uint32_t fh[4], fl[4];
+            load_a_ldm(ah + 32 * ks, fh);
+            load_a_ldm(al + 32 * ks, fl);
+#pragma unroll
+            for (int gt = 0; gt < 4; gt++) {
+                const uint2 b = w[(gt * NK + ks) * 32];
+                imma_s8s8(ach[gt], fh, b);
+                imma_u8s8(acl[gt], fl, b);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int ks = FIRST ? 1 : 0; ks < nk; ks++) {
+            uint32_t fh[4], fl[4];
+            load_a_ldm(ah + 32 * ks, fh);
+            load_a_ldm(al + 32 * ks, fl);
+#pragma unroll
+            for (int gt = 0; gt < 4; gt++) {
+                const uint2 b = w[(gt * nk + ks) * 32];
+                imma_s8s8(ach[gt], fh, b);
+                imma_u8s8(acl[gt], fl, b);
+            }
+        }
+    }
+}
+
+/* NW = warps per CTA (>= unit groups of the layer), MINB = CTAs per SM the register budget is sized for;
+ * KT = k-steps of both the input and the recurrent half when they are equal and known (0 = run time) */
+template <int NW, int MINB, int KT>
 __global__ void __launch_bounds__(32 * NW, MINB)
 scan_kernel(ScanArgs a)
 {
@@ -649,26 +699,6 @@ scan_kernel(ScanArgs a)
     const uint2 *wx = wsm + (size_t)warp * 4 * a.kt * 32 + lane;
     const uint2 *wh = wsm + (size_t)a.nt * 4 * a.kt * 32 + (size_t)warp * 4 * a.ktr * 32 + lane;
     int ach[4][4], acl[4][4];
-    auto init_acc = [&]() {                                           /* the bias rides in the low-plane accumulator */
-#pragma unroll
-        for (int gt = 0; gt < 4; gt++)
-#pragma unroll
-            for (int e = 0; e < 4; e++) { ach[gt][e] = 0; acl[gt][e] = bz[gt][e & 1]; }
-    };
-    auto half = [&](const uint8_t *plane, const uint2 *w, int nk) {          /* acc += W . plane (rc_Krows_8x16) */
-        const uint32_t ah = ldm_lane_addr(plane, pa, lane), al = ah + 16 * pa;
-        for (int ks = 0; ks < nk; ks++) {
-            uint32_t fh[4], fl[4];
-            load_a_ldm(ah + 32 * ks, fh);
-            load_a_ldm(al + 32 * ks, fl);
-#pragma unroll
-            for (int gt = 0; gt < 4; gt++) {
-                const uint2 b = w[(gt * nk + ks) * 32];
-                imma_s8s8(ach[gt], fh, b);
-                imma_u8s8(acl[gt], fl, b);
-            }
-        }
-    };
     auto tap_state = [&](const uint8_t *hp, int t) {                         /* debug taps only */
         if (a.tap_h)
             for (int idx = tid; idx < nvalid * H; idx += nthr) {
@@ -685,8 +715,7 @@ scan_kernel(ScanArgs a)
     };
 
     mbar_wait(bars + 0, 0);
-    init_acc();
-    if (active) half(xs, wx, a.kt);                                   /* Wx . x of inference 0 */
+    if (active) scan_half<KT, true>(a.kt, xs, pa, lane, wx, ach, acl, bz);   /* b + Wx . x of inference 0 */
     if (a.first == 1) tap_state(h2, 0);                               /* frame 0 ran no inference */
 
     /* per inference: recurrent half + cell on the accumulators that already hold Wx.x + b; the warp then ARRIVES
@@ -697,7 +726,7 @@ scan_kernel(ScanArgs a)
         uint8_t *hn = hb + (k % 3) * XB;
         const int t = a.first + 2 * k;
         if (active) {
-            half(hp, wh, a.ktr);                                      /* + Wh . h_old (lstm.c:54-104 all read the old h) */
+            scan_half<KT, false>(a.ktr, hp, pa, lane, wh, ach, acl, bz);   /* + Wh . h_old (lstm.c:54-104 all read the old h) */
             int32_t gate[4][4];
 #pragma unroll
             for (int gt = 0; gt < 4; gt++)
@@ -731,8 +760,7 @@ scan_kernel(ScanArgs a)
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(hbar)) : "memory");
             if (k + 1 < n_inf) {                                      /* Wx . x of the next inference, off the recurrence */
                 mbar_wait(bars + ((k + 1) % SCAN_NST), (uint32_t)(((k + 1) / SCAN_NST) & 1));
-                init_acc();
-                half(xs + ((k + 1) % SCAN_NST) * XB, wx, a.kt);
+                scan_half<KT, true>(a.kt, xs + ((k + 1) % SCAN_NST) * XB, pa, lane, wx, ach, acl, bz);
             }
         }
         mbar_wait(hbar, (uint32_t)(k & 1));                           /* every slice of h(k) is in hn */
@@ -931,16 +959,16 @@ size_t split_plane_bytes(const MmaDeviceModel &mm, int n_streams, int n_inf)
     return (size_t)((n_streams + 15) / 16) * (size_t)n_inf * 32 * mm.h->pa;
 }
 
-template <int NW, int MINB>
+template <int NW, int MINB, int KT>
 static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, cudaStream_t st)
 {
     static bool attr_done[64] = { false };
     if (!attr_done[device]) {
-        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
-        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
+        NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB, KT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done[device] = true;
     }
-    scan_kernel<NW, MINB><<<ntiles, 32 * NW, smem, st>>>(a);
+    scan_kernel<NW, MINB, KT><<<ntiles, 32 * NW, smem, st>>>(a);
     NNSP_LAUNCH_CHECK();
     return NNSP_B200_OK;
 }
@@ -1008,9 +1036,12 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
             a.xin = cur_in; a.hout = bufs[which]; a.h = q.h; a.c = q.c;
             a.tap_act = tp.act; a.tap_h = tp.hstate; a.tap_c = tp.cstate;
             const size_t smem = scan_smem(D, L);
-            if (L.nt <= 4) rc = launch_scan<4, 4>(a, ntiles, smem, device, st);
-            else if (L.nt <= 9) rc = launch_scan<9, 2>(a, ntiles, smem, device, st);
-            else rc = launch_scan<16, 1>(a, ntiles, smem, device, st);
+            /* the shipped layers get their k-step counts compiled in: VAD 28 -> 28 (1 k-step), KWS 64 -> 64 (2), S2I 72 -> 72 (3) */
+            const int kq = (L.kt == L.ktr) ? L.kt : 0;
+            if (L.nt <= 4) rc = (kq == 1) ? launch_scan<4, 4, 1>(a, ntiles, smem, device, st) : launch_scan<4, 4, 0>(a, ntiles, smem, device, st);
+            else if (L.nt <= 9) rc = (kq == 2) ? launch_scan<9, 2, 2>(a, ntiles, smem, device, st)
+                                   : (kq == 3) ? launch_scan<9, 2, 3>(a, ntiles, smem, device, st) : launch_scan<9, 2, 0>(a, ntiles, smem, device, st);
+            else rc = launch_scan<16, 1, 0>(a, ntiles, smem, device, st);
             if (rc) return rc;
             cur_in = bufs[which]; which ^= 1;
             ao += L.rows; ho += L.rows;
