@@ -1,6 +1,6 @@
 #!/bin/bash
 # Host topology of a multi-GPU box and the e2e leg of bench.py with and without NUMA-local host binding.
-# usage (on the GPU box): bash tools/scale_probe.sh "8 4 2" > gpurun_out/scale_probe.log
+# usage (on the GPU box): bash tools/scale_probe.sh "8 4 2" ["0 1"] > gpurun_out/scale_probe.log
 mkdir -p gpurun_out
 nvidia-smi topo -m
 lscpu | grep -i -E "numa|socket|^CPU\(s\)|model name"
@@ -15,7 +15,7 @@ for d in range(nb.device_count()):
 PY
 port=29611
 for n in $1; do
-  for bind in 0 1; do
+  for bind in ${2:-0 1}; do
     port=$((port+1))
     NNSP_BENCH_BIND=$bind python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
         bench.py --gpus $n --steps 20 --warmup 3 2>gpurun_out/scale_err_${n}_${bind}.log | tail -1 > gpurun_out/scale_${n}_${bind}.json
