@@ -27,7 +27,10 @@
 
 namespace nnsp {
 
-constexpr int CS_WARPS = 8;
+#ifndef NNSP_CS_WARPS
+#define NNSP_CS_WARPS 8
+#endif
+constexpr int CS_WARPS = NNSP_CS_WARPS;
 constexpr int CS_THREADS = CS_WARPS * 32;
 constexpr int CS_MAXSEQ = 3;
 constexpr int LOGMEL_OF_ZERO = 0x2688 * -15;     /* log10_q15(0): fixlog10.c:39-47 with x -> 1 */
