@@ -250,7 +250,7 @@ int upload_model_mma(const nnsp_b200_model *m, MmaDeviceModel *out)
         if (is_lstm && (ho & 3)) return NNSP_B200_ERR_UNSUPPORTED;
         /* exact 32-bit finish: no clamp of the reference can fire and every shift is an arithmetic right shift */
         const double macs = (double)(L.cols + (is_lstm ? L.rows : 0)) * 128.0 * 32768.0;
-        const bool shifts_ok = (G.sh_x == 0 && G.sh_bias >= 0 && G.sh_bias <= 15 && G.sh_out <= 0);
+        const bool shifts_ok = (G.sh_x == 0 && G.sh_bias >= 0 && G.sh_bias <= 15 && G.sh_out <= 0 && G.sh_out >= -28);   /* -28: the relu6 finish shifts by 3 more */
         G.fast = shifts_ok && (L.acc32 || macs + 32768.0 * (double)(1 << G.sh_bias) < 2147483647.0);
         G.w_off = (int)foff;
         foff += (long long)(is_lstm ? 4 : 1) * G.nt * G.kt * 32;

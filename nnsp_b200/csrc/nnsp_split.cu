@@ -248,11 +248,13 @@ __device__ __forceinline__ void fc_group(int kt_rt, const uint2 *__restrict__ wf
             }
         }
     }
+    /* relu6_fix (activation.c:6-17) starts with x >> 3: two arithmetic right shifts compose exactly, so its layers shift once */
+    const int rs = o.rs + (o.act == ACT_RELU6 ? 3 : 0);
     int32_t v[NC][4];
 #pragma unroll
     for (int j = 0; j < NC; j++)
 #pragma unroll
-        for (int e = 0; e < 4; e++) v[j][e] = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e]) >> o.rs;
+        for (int e = 0; e < 4; e++) v[j][e] = (int32_t)(((uint32_t)ch[j][e] << 8) + (uint32_t)cl[j][e]) >> rs;
     const int r0 = g * o.pa + n0 * 8 + 2 * q, r1 = r0 + 8 * o.pa;           /* plane bytes of rows g, g+8 */
     int32_t *w0 = o.wlog + g * o.nop + n0 * 8 + 2 * q, *w1 = w0 + 8 * o.nop;  /* logits words of rows g, g+8 */
     if (o.act == ACT_LINEAR) {                                              /* activation.c:19-29: int32 stays */
@@ -268,7 +270,7 @@ __device__ __forceinline__ void fc_group(int kt_rt, const uint2 *__restrict__ wf
 #pragma unroll
         for (int j = 0; j < NC; j++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) v[j][e] = relu6_q12(v[j][e]);
+            for (int e = 0; e < 4; e++) v[j][e] = min(max(v[j][e], 0), 6 << 12);
     } else if (o.act == ACT_TANH) {
 #pragma unroll
         for (int j = 0; j < NC; j++)
