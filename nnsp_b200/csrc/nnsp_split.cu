@@ -1016,7 +1016,7 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
             a.out_planes = (l1 < D->numlayers) ? bufs[which] : nullptr;
             a.dec = q.dec; a.tap_act = tp.act; a.tap_logits = tp.logits; a.ao0 = ao; a.thresh_prob = q.thresh_prob;
             int per_sm = (int)((227 * 1024) / (lay.total + 1024));
-            per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);     /* __launch_bounds__(256, 2) */
+            per_sm = per_sm < 1 ? 1 : (per_sm > SEG_MINB ? SEG_MINB : per_sm);     /* __launch_bounds__(256, SEG_MINB) */
             int grid = sm_count(device) * per_sm;
             if (grid > nchunks * ntiles) grid = nchunks * ntiles;
             if (!from_feat) seg_kernel<0><<<grid, SEG_THREADS, lay.total, st>>>(a);
