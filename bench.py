@@ -82,8 +82,8 @@ class ClockSampler(threading.Thread):
         self.nvml = self.handle = None
         try:
             import pynvml
-            pynvml.nvmlInit()
-            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(device))
+            from nnsp_b200.shard import nvml_handle
+            self.nvml, self.handle = pynvml, nvml_handle(device)      # the GPU the kernels run on, by PCI bus id
         except Exception:
             self.nvml = None
 

@@ -247,6 +247,9 @@ int nnsp_b200_int_peak(int device, double gops[4]);
 
 /* Device utilities so that C callers need no CUDA headers. */
 int nnsp_b200_device_count(void);
+/* PCI bus id ("0000:1b:00.0") of CUDA device `device`: the key by which NVML / nvidia-smi name the same GPU whatever
+ * CUDA_VISIBLE_DEVICES says */
+int nnsp_b200_device_pci_bus_id(int device, char *buf, int len);
 int nnsp_b200_dev_alloc(int device, size_t nbytes, void **ptr);
 int nnsp_b200_dev_free(int device, void *ptr);
 int nnsp_b200_host_alloc_pinned(size_t nbytes, void **ptr);

@@ -397,6 +397,15 @@ class Event:
         return ms.value
 
 
+def device_pci_bus_id(device=0):
+    """PCI bus id of CUDA device `device` (how NVML / nvidia-smi address the same GPU)."""
+    buf = C.create_string_buffer(32)
+    L = lib()
+    L.nnsp_b200_device_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
+    check(L.nnsp_b200_device_pci_bus_id(device, buf, 32), "device_pci_bus_id")
+    return buf.value.decode()
+
+
 def int_peak(device=0):
     """dict of self-measured integer-pipe peaks (giga lane-instructions/s): imad, mixed, imad_wide, idp2a."""
     g = (C.c_double * 4)()

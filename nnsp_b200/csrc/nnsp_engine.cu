@@ -753,6 +753,13 @@ int nnsp_b200_device_count(void)
     return (cudaGetDeviceCount(&n) == cudaSuccess) ? n : 0;
 }
 
+int nnsp_b200_device_pci_bus_id(int device, char *buf, int len)
+{
+    if (!buf || len < 16) return NNSP_B200_ERR_ARG;
+    NNSP_CUDA(cudaDeviceGetPCIBusId(buf, len, device));
+    return NNSP_B200_OK;
+}
+
 int nnsp_b200_batch_create(const nnsp_b200_model *m, int n_streams, int device, int16_t thresh_prob,
                            int16_t th_count_trigger, nnsp_b200_batch **out)
 {

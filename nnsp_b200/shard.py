@@ -49,14 +49,25 @@ def _physical_index(device):
     return device
 
 
+def nvml_handle(device):
+    """NVML handle of CUDA device `device`: by PCI bus id when the CUDA runtime is there to ask (exact under any
+    CUDA_VISIBLE_DEVICES, UUID entries included), else by the index CUDA_VISIBLE_DEVICES implies."""
+    import pynvml
+    pynvml.nvmlInit()
+    try:
+        from .api import device_pci_bus_id
+        return pynvml.nvmlDeviceGetHandleByPciBusId(device_pci_bus_id(device).encode())
+    except Exception:
+        return pynvml.nvmlDeviceGetHandleByIndex(_physical_index(device))
+
+
 def local_cpus(device):
     """CPUs on the NUMA node the GPU's PCIe root port hangs off (NVML), restricted to the ones this process may use;
     empty when NVML cannot tell."""
     import os
     try:
         import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(_physical_index(device))
+        h = nvml_handle(device)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(os.cpu_count() or 1, 64) + 63) // 64)
     except Exception:
         return set()
