@@ -267,8 +267,14 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
      * (higher-priority, latency-bound) network kernels of the previous call find room on every SM while this
      * kernel streams through (the table prologue is ~2 % of such a CTA) */
     const long long cap = (long long)sm_count(device) * FEAT_CTAS_PER_SM;
-    const long long chunked = (blocks + FEAT_ITERS - 1) / FEAT_ITERS;
-    if (blocks > cap) blocks = chunked > cap ? chunked : cap;
+    /* rounds per CTA: FEAT_ITERS for about eight waves, up to four times that on larger calls (the table prologue
+     * amortises further: S2I x 32 768 -0.6 %; 8 is best for the 4 096-stream call) */
+    long long iters = blocks / (cap * 8);
+    iters = iters < FEAT_ITERS ? FEAT_ITERS : (iters > 4 * FEAT_ITERS ? 4 * FEAT_ITERS : iters);
+    const long long chunked = (blocks + iters - 1) / iters;
+    /* a whole number of resident waves: every CTA slot then runs the same number of CTAs and the slots finish within one
+     * round of each other instead of one CTA lifetime (3 200 CTAs on 444 slots left the last wave 20 % full) */
+    if (blocks > cap) blocks = chunked > cap ? ((chunked + cap / 2) / cap) * cap : cap;
     feat_kernel<<<(unsigned)blocks, FEAT_THREADS, sizeof(FeatSmem), st>>>(tb, a.pcm, a.stride, a.hist, a.hist_frames,
                                                                             a.s0, a.ns, a.T, a.logmel, a.norm, a.feat16);
     NNSP_LAUNCH_CHECK();
