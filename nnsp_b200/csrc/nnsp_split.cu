@@ -380,7 +380,11 @@ seg_kernel(SegArgs a)
     __syncthreads();
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int chunk = item % a.nchunks, tile = item / a.nchunks;
+        /* chunk-major order: the last chunk of every tile is a short one (n_inf = 50: 16, 16, 16, 2), and with the tile-major
+         * order a CTA met the same chunk index over and over (grid 296 is a multiple of 4 chunks): a quarter of the CTAs
+         * got nothing but short items. Now every CTA walks through all chunk indices and the short items come last. */
+        const int ntl = (nsel + 15) >> 4;
+        const int chunk = item / ntl, tile = item - chunk * ntl;
         const int k0 = chunk * SEG_KC;
         const int nvalid = min(16, nsel - 16 * tile);
         const size_t tile_abs = tile_base + tile;
