@@ -316,6 +316,34 @@ __global__ void cascade_offsets_kernel(int *count, int *tile_off)
     for (int g = 0; g < CG_GROUPS; g++) { tile_off[g] = o; o += (count[g] + 15) >> 4; }
 }
 
+/* The replay is latency-bound -- one warp walks one stream frame by frame, so the kernel lasts at least as long as the
+ * longest remainder. Handing the streams out longest-first (earliest t0 first) keeps a long one from being started
+ * last: a counting sort of the replay list by t0, one CTA. */
+constexpr int CSORT_THREADS = 1024, CSORT_BUCKETS = 1024;
+__global__ void __launch_bounds__(CSORT_THREADS) cascade_sort_replay_kernel(const int *__restrict__ list_in, int *__restrict__ list_out,
+                                                                           const int *__restrict__ ctl, const int *__restrict__ t0, int T)
+{
+    __shared__ int hist[CSORT_BUCKETS];
+    const int n = ctl[0];
+    for (int i = threadIdx.x; i < CSORT_BUCKETS; i += CSORT_THREADS) hist[i] = 0;
+    __syncthreads();
+    auto bucket = [&](int s) { const long long b = (long long)t0[s] * CSORT_BUCKETS / (T + 1); return (int)(b < 0 ? 0 : (b >= CSORT_BUCKETS ? CSORT_BUCKETS - 1 : b)); };
+    for (int i = threadIdx.x; i < n; i += CSORT_THREADS) atomicAdd(&hist[bucket(list_in[i])], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {                                            /* exclusive scan of 1024 counts by one warp */
+        int carry = 0;
+        for (int base = 0; base < CSORT_BUCKETS; base += 32) {
+            const int v = hist[base + threadIdx.x];
+            int x = v;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((int)threadIdx.x >= o) x += y; }
+            hist[base + threadIdx.x] = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += CSORT_THREADS) { const int s = list_in[i]; list_out[atomicAdd(&hist[bucket(s)], 1)] = s; }
+}
+
 struct CascadePostArgs {
     const MmaModel *model[3];        /* statistics and silence rows of each model */
     StreamState st;
@@ -563,7 +591,7 @@ struct nnsp_b200_cascade {
     bool split_ok = false;
     int path = 0;                              /* 0 auto, 1 sequential kernel only, 2 stage-sorted pass + replay */
     int pa_max = 0;
-    int *grp_list = nullptr, *grp_count = nullptr, *grp_tile_off = nullptr, *t0 = nullptr, *replay_list = nullptr;
+    int *grp_list = nullptr, *grp_count = nullptr, *grp_tile_off = nullptr, *t0 = nullptr, *replay_list = nullptr, *replay_sorted = nullptr;
     uint8_t *planes[2] = { nullptr, nullptr };
     int32_t *dec = nullptr;
     long long split_cap_T = 0;
@@ -694,8 +722,10 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
         NNSP_LAUNCH_CHECK();
         cascade_ctx_kernel<<<(ns * 32 + 255) / 256, 256, 0, st>>>(p);
         NNSP_LAUNCH_CHECK();
-        a.t0 = c->t0;                          /* ... and replay what is left with the sequential kernel */
-        a.replay_list = c->replay_list + s0; a.replay_ctl = count + 8;
+        a.t0 = c->t0;                          /* ... and replay what is left with the sequential kernel, longest remainder first */
+        cascade_sort_replay_kernel<<<1, CSORT_THREADS, 0, st>>>(c->replay_list + s0, c->replay_sorted + s0, count + 8, c->t0, T);
+        NNSP_LAUNCH_CHECK();
+        a.replay_list = c->replay_sorted + s0; a.replay_ctl = count + 8;
     }
     int blocks = (ns + CS_WARPS - 1) / CS_WARPS;
     const int cap = sm_count(c->device);
@@ -812,6 +842,7 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaMalloc(&c->grp_list, (size_t)CG_GROUPS * S * sizeof(int)));
     TRY(cudaMalloc(&c->grp_count, CS_MAX_SLICES * 16 * sizeof(int)));
     TRY(cudaMalloc(&c->replay_list, S * sizeof(int)));
+    TRY(cudaMalloc(&c->replay_sorted, S * sizeof(int)));
     TRY(cudaMalloc(&c->grp_tile_off, CS_MAX_SLICES * 8 * sizeof(int)));
     TRY(cudaMalloc(&c->t0, S * sizeof(int)));
 #undef TRY
@@ -1006,7 +1037,7 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     for (auto e : c->ev_feat) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_nn) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) free_model_mma(&c->mm[i]);
-    cudaFree(c->replay_list); cudaFree(c->grp_list); cudaFree(c->grp_count); cudaFree(c->grp_tile_off); cudaFree(c->t0);
+    cudaFree(c->replay_list); cudaFree(c->replay_sorted); cudaFree(c->grp_list); cudaFree(c->grp_count); cudaFree(c->grp_tile_off); cudaFree(c->t0);
     cudaFree(c->planes[0]); cudaFree(c->planes[1]); cudaFree(c->dec);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto s : c->xs) if (s) cudaStreamDestroy(s);
