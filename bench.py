@@ -84,6 +84,7 @@ class ClockSampler(threading.Thread):
             import pynvml
             from nnsp_b200.shard import nvml_handle
             self.nvml, self.handle = pynvml, nvml_handle(device)      # the GPU the kernels run on, by PCI bus id
+            self.mx.append(int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
         except Exception:
             self.nvml = None
 
@@ -99,7 +100,8 @@ class ClockSampler(threading.Thread):
     def _sample_nvml(self):
         n = self.nvml
         self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-        self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        if not self.mx:                                  # a property of the board: asked once, the loop stays short
+            self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
         get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
         r = int(get(self.handle))
         for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
@@ -127,7 +129,7 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.002 if self.nvml is not None else 0.2)
+            self._stop_evt.wait(0.0005 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
