@@ -15,6 +15,7 @@
  *                    dataBuffer -- recompute it on the spot; standardise, network, post-processing,
  *                    controller transition, reset-on-exit
  *   hist kernels   : newest d_max+2 PCM frames and d_max log-mel rows for the next call */
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <new>
 #include <string.h>
@@ -27,11 +28,13 @@
 
 namespace nnsp {
 
-#ifndef NNSP_CS_WARPS
-#define NNSP_CS_WARPS 8
-#endif
-constexpr int CS_WARPS = NNSP_CS_WARPS;
-constexpr int CS_THREADS = CS_WARPS * 32;
+/* Two shapes of the sequential kernel. WIDE: any model the engine accepts, 8 warps per CTA, a front-end scratch per warp.
+ * NARROW (all models at most 80 wide, 48 outputs -- the shipped three): the per-stream scratch shrinks to 2.1 KB and the
+ * front-end scratch, needed only for the two frames after an instance reset, is a pool of 4 per CTA behind a lock, so
+ * 16 warps fit next to the three weight images. The kernel is latency-bound (one warp walks one stream), so the
+ * resident warps are what it runs on. */
+struct CsWide   { using WS = WarpScratch;            static constexpr int WARPS = 8,  NFS = 8; static constexpr bool POOL = false; };
+struct CsNarrow { using WS = WarpScratchT<80, 48>;   static constexpr int WARPS = 16, NFS = 4; static constexpr bool POOL = true;  };
 constexpr int CS_MAXSEQ = 3;
 constexpr int LOGMEL_OF_ZERO = 0x2688 * -15;     /* log10_q15(0): fixlog10.c:39-47 with x -> 1 */
 
@@ -60,19 +63,24 @@ struct CascadeArgs {
     int *replay_ctl;                  /* ... [0] = how many, [1] = cursor                                         */
 };
 
+template <class V>
 struct CascadeSmem {
     FeatSmemTables ft;
     int16_t tanh_lut[384];
     DevModel model[3];
-    FrameScratch fs[CS_WARPS];
-    WarpScratch ws[CS_WARPS];
+    FrameScratch fs[V::NFS];
+    typename V::WS ws[V::WARPS];
+    int fs_lock[V::NFS];
 };
 
-__global__ void __launch_bounds__(CS_THREADS, 1)
+template <class V>
+__global__ void __launch_bounds__(32 * V::WARPS, 1)
 cascade_kernel(CascadeArgs a, int off_w, int off_b)
 {
+    constexpr int CS_WARPS = V::WARPS, CS_THREADS = 32 * V::WARPS;
+    using WS = typename V::WS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    CascadeSmem &sm = *reinterpret_cast<CascadeSmem *>(smem_raw + 16);
+    CascadeSmem<V> &sm = *reinterpret_cast<CascadeSmem<V> *>(smem_raw + 16);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *wimg = reinterpret_cast<uint32_t *>(smem_raw + off_w);
     int16_t *bimg = reinterpret_cast<int16_t *>(smem_raw + off_b);
@@ -80,6 +88,7 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
 
     load_feat_tables(&sm.ft, a.tables, threadIdx.x, CS_THREADS);
     for (int i = threadIdx.x; i < 384; i += CS_THREADS) sm.tanh_lut[i] = a.tables->tanh_lut[i];
+    if (threadIdx.x < V::NFS) sm.fs_lock[threadIdx.x] = 0;
     for (int k = 0; k < cd.len_seq; k++) {
         const int id = cd.seq[k];
         const int *src = reinterpret_cast<const int *>(a.model[id]);
@@ -122,9 +131,8 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, L16 = lane & 15;
-    WarpScratch *ws = &sm.ws[warp];
-    FrameScratch &fs = sm.fs[warp];
-    const int T = a.T, HS = NNSP_B200_MAX_WIDTH;
+    WS *ws = &sm.ws[warp];
+    const int T = a.T, HS = NNSP_B200_MAX_WIDTH, HW = WS::WIDTH;      /* HS: stride of the state in global memory, HW: what the scratch holds */
     const int hist_frames = cd.dmax + 2, hist_len = hist_frames * NNSP_B200_FRAME;
 
     for (int it = 0;; it++) {
@@ -143,7 +151,7 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
         const int t_begin = a.t0 ? a.t0[s] : 0;                       /* frames before it were done by the stage-sorted pass */
         if (t_begin >= a.T) continue;
         for (int i = lane; i < 240; i += 32) ws->ctx[i] = a.st.ctx[(long long)s * 240 + i];
-        for (int i = lane; i < HS; i += 32) { ws->h[i] = a.st.h[(long long)s * HS + i]; ws->c[i] = a.st.c[(long long)s * HS + i]; }
+        for (int i = lane; i < HW; i += 32) { ws->h[i] = a.st.h[(long long)s * HS + i]; ws->c[i] = a.st.c[(long long)s * HS + i]; }
         if (lane < SC_N) ws->scal[lane] = a.st.scal[(long long)s * SC_N + lane];
         int pos = a.st.casc[(long long)s * CS_N + CS_POS];
         int cnt_kws = a.st.casc[(long long)s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[(long long)s * CS_N + CS_CNT_S2I];
@@ -177,8 +185,19 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
                     const int16_t *q = (g < 0) ? (hs + g) : (ps + g);
                     return *reinterpret_cast<const unsigned int *>(q);
                 };
-                frame_logmel<false>(sm.ft, fs, L16, load_pair, ws->logits, lane < 16, FeatDump{});   /* logits[] doubles as a 40-int scratch row */
+                int slot = warp;
+                if (V::POOL) {                                       /* borrow a front-end scratch from the CTA's pool */
+                    slot = -1;
+                    if (lane == 0) {
+                        for (int probe = warp; slot < 0; probe++)
+                            if (atomicCAS(&sm.fs_lock[probe % V::NFS], 0, 1) == 0) slot = probe % V::NFS;
+                        __threadfence_block();
+                    }
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                }
+                frame_logmel<false>(sm.ft, sm.fs[slot], L16, load_pair, ws->logits, lane < 16, FeatDump{});   /* logits[] doubles as a 40-int scratch row */
                 __syncwarp();
+                if (V::POOL && lane == 0) { __threadfence_block(); atomicExch(&sm.fs_lock[slot], 0); }
                 lm0 = ws->logits[lane];
                 lm1 = (lane < 8) ? ws->logits[32 + lane] : 0;
                 __syncwarp();
@@ -268,7 +287,7 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
         }
         __syncwarp();
         for (int i = lane; i < 240; i += 32) a.st.ctx[(long long)s * 240 + i] = ws->ctx[i];
-        for (int i = lane; i < HS; i += 32) { a.st.h[(long long)s * HS + i] = ws->h[i]; a.st.c[(long long)s * HS + i] = ws->c[i]; }
+        for (int i = lane; i < HW; i += 32) { a.st.h[(long long)s * HS + i] = ws->h[i]; a.st.c[(long long)s * HS + i] = ws->c[i]; }
         if (lane < SC_N) a.st.scal[(long long)s * SC_N + lane] = ws->scal[lane];
         if (lane == 0) {
             a.st.casc[(long long)s * CS_N + CS_POS] = (uint16_t)pos;
@@ -584,6 +603,7 @@ struct nnsp_b200_cascade {
     int16_t *d_pcm = nullptr; long long d_pcm_frames = 0;
     nnsp_b200_cascade_result *d_res = nullptr;
     size_t smem_total = 0; int off_w = 0, off_b = 0;
+    bool narrow = false;                      /* which shape of the sequential kernel (CsNarrow / CsWide) */
     cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
     bool ev_valid = false;
     /* stage-sorted pass (scan-split kernels per (model, phase) group + replay) */
@@ -727,10 +747,12 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
         NNSP_LAUNCH_CHECK();
         a.replay_list = c->replay_sorted + s0; a.replay_ctl = count + 8;
     }
-    int blocks = (ns + CS_WARPS - 1) / CS_WARPS;
+    const int cs_warps = c->narrow ? CsNarrow::WARPS : CsWide::WARPS;
+    int blocks = (ns + cs_warps - 1) / cs_warps;
     const int cap = sm_count(c->device);
     if (blocks > cap) blocks = cap;
-    cascade_kernel<<<blocks, CS_THREADS, c->smem_total, st>>>(a, c->off_w, c->off_b);
+    if (c->narrow) cascade_kernel<CsNarrow><<<blocks, 32 * CsNarrow::WARPS, c->smem_total, st>>>(a, c->off_w, c->off_b);
+    else cascade_kernel<CsWide><<<blocks, 32 * CsWide::WARPS, c->smem_total, st>>>(a, c->off_w, c->off_b);
     NNSP_LAUNCH_CHECK();
     if (timed) { NNSP_CUDA(cudaEventRecord(c->ev[2], st)); c->ev_valid = true; c->last_piped = piped; }
     if (!piped && (rc = launch_hist_update(pcm, stride / 2, c->st.hist, hist_frames, NNSP_B200_FRAME / 2, s0, ns, T, st))) return rc;
@@ -807,14 +829,26 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
         if (!split_supported(c->mm[id])) c->split_ok = false;
         if (c->mm[id].h && c->mm[id].h->pa > c->pa_max) c->pa_max = c->mm[id].h->pa;
     }
-    c->off_w = (int)((16 + sizeof(CascadeSmem) + 127) & ~(size_t)127);
+    /* the narrow shape of the sequential kernel when every model fits its scratch */
+    c->narrow = true;
+    for (int id = 0; id < 3; id++) {
+        if (!seen[id]) continue;
+        const DevModel &D = c->dm[id].h;
+        if (D.h_stride > CsNarrow::WS::WIDTH || D.n_out > 48) c->narrow = false;
+        for (int i = 0; i < D.numlayers; i++)
+            if (D.layer[i].rows > CsNarrow::WS::WIDTH || (i > 0 && ((D.layer[i].cols + 3) & ~3) > CsNarrow::WS::WIDTH)) c->narrow = false;
+    }
+    { const char *e = getenv("NNSP_B200_CASCADE_WIDE"); if (e && e[0] == '1') c->narrow = false; }   /* A/B switch for measurements */
+    const size_t smem_struct = c->narrow ? sizeof(CascadeSmem<CsNarrow>) : sizeof(CascadeSmem<CsWide>);
+    c->off_w = (int)((16 + smem_struct + 127) & ~(size_t)127);
     c->off_b = (int)(c->off_w + wtot);
     c->smem_total = (size_t)c->off_b + btot * 2 + 16;
     if (c->smem_total > 227 * 1024) { nnsp_set_error("cascade needs %zu bytes of shared memory (> 227 KB)", c->smem_total); return fail(NNSP_B200_ERR_UNSUPPORTED); }
     const size_t S = (size_t)n_streams, HS = NNSP_B200_MAX_WIDTH;
     const int hist_frames = c->cd.dmax + 2, lm_rows = c->cd.dmax > 0 ? c->cd.dmax : 1;
 #define TRY(x) do { if ((x) != cudaSuccess) { nnsp_set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); return fail(NNSP_B200_ERR_CUDA); } } while (0)
-    TRY(cudaFuncSetAttribute(cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TRY(cudaFuncSetAttribute(cascade_kernel<CsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TRY(cudaFuncSetAttribute(cascade_kernel<CsNarrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &r : c->host_ev) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

@@ -18,15 +18,20 @@
 
 namespace nnsp {
 
-struct WarpScratch {
+/* One stream's working set in shared memory. W = widest layer / LSTM state it can hold, NOUT = widest final layer;
+ * the functions below take any instantiation (the cascade uses a narrow one to fit twice the warps per CTA). */
+template <int W, int NOUT>
+struct WarpScratchT {
+    static constexpr int WIDTH = W;
     alignas(16) int16_t ctx[240];      /* normFeatContext, 6 rows x 40 (feature_module.h:12)      */
-    alignas(16) int16_t buf[2][NNSP_B200_MAX_WIDTH];   /* ping-pong layer I/O (neural_nets.c:9-10) */
-    alignas(16) int16_t h[NNSP_B200_MAX_WIDTH];
-    int32_t c[NNSP_B200_MAX_WIDTH];
-    int16_t gates[4 * NNSP_B200_MAX_WIDTH];
-    int32_t logits[NNSP_B200_MAX_OUT];
+    alignas(16) int16_t buf[2][W];     /* ping-pong layer I/O (neural_nets.c:9-10)                */
+    alignas(16) int16_t h[W];
+    int32_t c[W];
+    int16_t gates[4 * W];
+    int32_t logits[NOUT];
     int16_t scal[SC_N];
 };
+using WarpScratch = WarpScratchT<NNSP_B200_MAX_WIDTH, NNSP_B200_MAX_OUT>;
 
 /* acc[i] += W[row r0 + 32 i] . x for NR rows per lane; x is int16, 8-byte aligned */
 template <int NR>
@@ -98,9 +103,10 @@ __device__ __forceinline__ int32_t activate16(int act, int32_t pre, const int16_
 
 /* One network evaluation for the warp's stream. ws->ctx is the input; LSTM state in ws->h/c.
  * tap_act / tap_logits (global, may be null) receive the layer outputs of this frame. */
+template <class WS>
 __device__ __forceinline__ void net_forward(const DevModel &M, const uint32_t *__restrict__ wimg,
                                             const int16_t *__restrict__ bimg,
-                                            const int16_t *__restrict__ tanh_lut, WarpScratch *ws,
+                                            const int16_t *__restrict__ tanh_lut, WS *ws,
                                             int lane, int16_t *tap_act, int32_t *tap_logits)
 {
     const int16_t *x = ws->ctx;
@@ -218,10 +224,11 @@ __device__ __forceinline__ void post_binary(int16_t *sc, const int32_t *logits, 
 }
 
 /* NNSPClass_reset for the warp's scratch copy of a stream (nn_speech.c:57-72) */
-__device__ __forceinline__ void reset_stream_scratch(const DevModel &M, WarpScratch *ws, int lane)
+template <class WS>
+__device__ __forceinline__ void reset_stream_scratch(const DevModel &M, WS *ws, int lane)
 {
     for (int i = lane; i < 200; i += 32) ws->ctx[i] = M.silence[i % 40];     /* feature_module.c:32-43: rows 0..4 only, row 5 stays */
-    for (int i = lane; i < NNSP_B200_MAX_WIDTH; i += 32) { ws->h[i] = 0; ws->c[i] = 0; }   /* neural_nets.c:27-42 */
+    for (int i = lane; i < WS::WIDTH; i += 32) { ws->h[i] = 0; ws->c[i] = 0; }   /* neural_nets.c:27-42 */
     if (lane < SC_N) {
         /* counts_category[7] survives a reset in the reference (nn_speech.c:64-65 clears 7 of 8);
          * nothing ever writes it, so it is always 0 */
