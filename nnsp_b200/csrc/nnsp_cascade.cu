@@ -301,6 +301,219 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
 
 
 /* ======================================================================================================== */
+/* cascade_replay_kernel: the replay after the stage-sorted pass, four warps per stream                        */
+/* ======================================================================================================== */
+/* Same per-frame semantics as cascade_kernel (see there for the reference lines), narrow models only, no taps (a call
+ * with taps never takes the stage-sorted pass). The replay lasts as long as its longest remainder, so the chain per
+ * stream is what counts: a group of four warps shares one stream (net_forward_group), 4 groups per CTA next to the
+ * three weight images; streams are handed out to groups dynamically, longest remainder first. */
+#ifndef NNSP_CR_GW
+#define NNSP_CR_GW 2
+#endif
+constexpr int CR_GW = NNSP_CR_GW, CR_GT = 32 * CR_GW, CR_GROUPS = 16 / CR_GW, CR_THREADS = 512;   /* warps, threads per group */
+struct ReplaySmem {
+    FeatSmemTables ft;
+    int16_t tanh_lut[384];
+    DevModel model[3];
+    FrameScratch fs[CR_GROUPS];
+    CsNarrow::WS ws[CR_GROUPS];
+    int slot[CR_GROUPS];
+};
+
+__global__ void __launch_bounds__(CR_THREADS, 1)
+cascade_replay_kernel(CascadeArgs a, int off_w, int off_b)
+{
+    using WS = CsNarrow::WS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ReplaySmem &sm = *reinterpret_cast<ReplaySmem *>(smem_raw + 16);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *wimg = reinterpret_cast<uint32_t *>(smem_raw + off_w);
+    int16_t *bimg = reinterpret_cast<int16_t *>(smem_raw + off_b);
+    const CascadeDev &cd = a.cd;
+
+    load_feat_tables(&sm.ft, a.tables, threadIdx.x, CR_THREADS);
+    for (int i = threadIdx.x; i < 384; i += CR_THREADS) sm.tanh_lut[i] = a.tables->tanh_lut[i];
+    for (int k = 0; k < cd.len_seq; k++) {
+        const int id = cd.seq[k];
+        const int *src = reinterpret_cast<const int *>(a.model[id]);
+        int *dst = reinterpret_cast<int *>(&sm.model[id]);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += CR_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    for (int k = 0; k < cd.len_seq; k++) {
+        const int id = cd.seq[k];
+        for (int i = threadIdx.x; i < sm.model[id].bias_count; i += CR_THREADS) bimg[cd.boff[id] + i] = a.bimg[id][i];
+    }
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int k = 0; k < cd.len_seq; k++) total += (uint32_t)cd.wbytes[cd.seq[k]];
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
+        for (int k = 0; k < cd.len_seq; k++) {
+            const int id = cd.seq[k];
+            uint32_t off = 0;
+            const uint32_t bytes = (uint32_t)cd.wbytes[id];
+            while (off < bytes) {
+                const uint32_t n = (bytes - off) > 32768u ? 32768u : (bytes - off);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32((char *)(wimg + cd.woff_words[id]) + off)), "l"((const char *)a.wimg[id] + off), "r"(n), "r"(smem_u32(bar)) : "memory");
+                off += n;
+            }
+        }
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, L16 = lane & 15;
+    const int grp = warp / CR_GW, wg = warp % CR_GW, gt = threadIdx.x % CR_GT, bid = 1 + grp;      /* barrier 0 is __syncthreads */
+    WS *ws = &sm.ws[grp];
+    FrameScratch &fs = sm.fs[grp];
+    const int T = a.T, HS = NNSP_B200_MAX_WIDTH, HW = WS::WIDTH;
+    const int hist_frames = cd.dmax + 2, hist_len = hist_frames * NNSP_B200_FRAME;
+
+    for (;;) {
+        if (gt == 0) sm.slot[grp] = atomicAdd(a.replay_ctl + 1, 1);
+        group_sync<CR_GW>(bid);
+        const int idx = sm.slot[grp];
+        group_sync<CR_GW>(bid);                                              /* everyone has read the slot before it is rewritten */
+        if (idx >= a.replay_ctl[0]) break;
+        const int s = a.replay_list[idx];
+        const int t_begin = a.t0[s];
+        if (t_begin >= T) continue;
+        for (int i = gt; i < 240; i += CR_GT) ws->ctx[i] = a.st.ctx[(long long)s * 240 + i];
+        for (int i = gt; i < HW; i += CR_GT) { ws->h[i] = a.st.h[(long long)s * HS + i]; ws->c[i] = a.st.c[(long long)s * HS + i]; }
+        if (gt < SC_N) ws->scal[gt] = a.st.scal[(long long)s * SC_N + gt];
+        int pos = a.st.casc[(long long)s * CS_N + CS_POS];
+        int cnt_kws = a.st.casc[(long long)s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[(long long)s * CS_N + CS_CNT_S2I];
+        int age = a.st.casc[(long long)s * CS_N + CS_AGE];
+        group_sync<CR_GW>(bid);
+        const int16_t *ps = a.pcm + (long long)s * a.stride;
+        const int16_t *hs = a.st.hist + (long long)s * hist_len + hist_len;
+        const int32_t *lm_now = a.logmel + (long long)s * T * NNSP_B200_NMEL;
+        const int32_t *lm_old = a.st.lmhist + ((long long)s * cd.dmax + cd.dmax) * NNSP_B200_NMEL;
+
+        for (int t = t_begin; t < T; t++) {
+            const long long ft = (long long)s * T + t;
+            const int id = cd.seq[pos];
+            const DevModel &M = sm.model[id];
+            const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
+            const int tf = t - d;
+            /* ---- FeatureClass_execute of the live instance: log-mel value of feature gt (gt < 40) ---- */
+            int32_t lmv = 0;
+            if (age >= 2) {
+                const int32_t *row = (tf >= 0) ? (lm_now + (long long)tf * NNSP_B200_NMEL) : (lm_old + (long long)tf * NNSP_B200_NMEL);
+                if (gt < 40) lmv = row[gt];
+            } else {
+                if (wg == 0) {                                       /* the first warp recomputes the frame (zeros in the STFT buffer) */
+                    const int base = (tf - 2) * NNSP_B200_FRAME;
+                    const int first_live = (2 - age) * NNSP_B200_FRAME;
+                    auto load_pair = [&](int, int p) -> uint32_t {
+                        if (2 * p < first_live) return 0u;
+                        const int g = base + 2 * p;
+                        const int16_t *q = (g < 0) ? (hs + g) : (ps + g);
+                        return *reinterpret_cast<const unsigned int *>(q);
+                    };
+                    frame_logmel<false>(sm.ft, fs, L16, load_pair, ws->logits, lane < 16, FeatDump{});
+                }
+                group_sync<CR_GW>(bid);
+                if (gt < 40) lmv = ws->logits[gt];
+                group_sync<CR_GW>(bid);
+            }
+            /* context rows up by one, the new row standardised with the instance's statistics */
+            constexpr int NMV = (200 + CR_GT - 1) / CR_GT;
+            int16_t mv[NMV];
+#pragma unroll
+            for (int j = 0; j < NMV; j++) { const int i = gt + CR_GT * j; mv[j] = (i < 200) ? ws->ctx[i + 40] : (int16_t)0; }
+            group_sync<CR_GW>(bid);
+#pragma unroll
+            for (int j = 0; j < NMV; j++) { const int i = gt + CR_GT * j; if (i < 200) ws->ctx[i] = mv[j]; }
+            if (gt < 40) ws->ctx[200 + gt] = standardise(lmv, M.mean[gt], M.stdR[gt], M.feat_rshift);
+            group_sync<CR_GW>(bid);
+            /* ---- NNSPClass_exec tail ------------------------------------------------------------------ */
+            const bool ran = (ws->scal[SC_SLIDES] == 1);
+            const int16_t th_prob = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_prob_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_prob_kws : cd.P.thresh_prob_s2i);
+            const int16_t th_cnt = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_cnts_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_cnts_kws : cd.P.thresh_cnts_s2i);
+            group_sync<CR_GW>(bid);                                          /* everyone has read slides before it changes */
+            if (ran) {
+                net_forward_group<CR_GW>(M, wimg + cd.woff_words[id], bimg + cd.boff[id], sm.tanh_lut, ws, wg, lane, bid);
+                if (gt == 0) {
+                    if (id == NNSP_B200_ID_S2I) post_s2i(ws->scal, ws->logits, th_cnt);
+                    else post_binary(ws->scal, ws->logits, th_prob, th_cnt);
+                }
+            }
+            if (gt == 0) ws->scal[SC_SLIDES] = (int16_t)((ws->scal[SC_SLIDES] + 1) % 2);
+            group_sync<CR_GW>(bid);
+            /* ---- controller (nnCntrlClass.c:172-269), evaluated redundantly by every thread of the group ---- */
+            const int detected = ws->scal[SC_TRIGGER];
+            int next_pos = pos, do_reset = 0, cnt_out = 0;
+            if (id == NNSP_B200_ID_S2I) {
+                cnt_s2i = (cnt_s2i + 1) % cd.P.thresh_timeout_s2i;
+                if (detected || cnt_s2i == cd.P.thresh_timeout_s2i - 1) {
+                    next_pos = (pos + 1) % cd.len_seq;
+                    if (detected || cd.seq[next_pos] != id) { cnt_s2i = 0; do_reset = 1; }
+                }
+                cnt_out = cnt_s2i;
+            } else if (id == NNSP_B200_ID_KWS) {
+                cnt_kws = (cnt_kws + 1) % cd.P.thresh_timeout_kws;
+                if (detected || cnt_kws == cd.P.thresh_timeout_kws - 1) {
+                    if (detected) next_pos = (pos + 1) % cd.len_seq;
+                    else { next_pos = (pos - 1) % cd.len_seq; if (next_pos < 0) next_pos += cd.len_seq; }
+                    if (detected || cd.seq[next_pos] != id) { cnt_kws = 0; do_reset = 1; }
+                }
+                cnt_out = cnt_kws;
+            } else if (detected) {
+                next_pos = (pos + 1) % cd.len_seq;
+                do_reset = 1;
+            }
+            if (gt == 0 && a.results) {
+                nnsp_b200_cascade_result r;
+                r.stage_id = (int8_t)id; r.pos_after = (int8_t)next_pos; r.detected = (int16_t)detected;
+                r.outputs[0] = ws->scal[SC_OUT0]; r.outputs[1] = ws->scal[SC_OUT0 + 1]; r.outputs[2] = ws->scal[SC_OUT0 + 2];
+                r.cnt_timeout = (uint16_t)cnt_out;
+                a.results[ft] = r;
+            }
+            group_sync<CR_GW>(bid);
+            if (do_reset) {
+                int16_t *stale = a.stale + ((long long)s * 3 + id) * 40;
+                if (gt < 40) stale[gt] = ws->ctx[200 + gt];
+                group_sync<CR_GW>(bid);
+                const int nid = cd.seq[next_pos];
+                const DevModel &N = sm.model[nid];
+                for (int i = gt; i < 200; i += CR_GT) ws->ctx[i] = N.silence[i % 40];             /* reset_stream_scratch, group-wide */
+                for (int i = gt; i < HW; i += CR_GT) { ws->h[i] = 0; ws->c[i] = 0; }
+                if (gt < SC_N) ws->scal[gt] = (gt == SC_SLIDES) ? 1 : 0;
+                const int16_t *st2 = a.stale + ((long long)s * 3 + nid) * 40;
+                if (gt < 40) ws->ctx[200 + gt] = st2[gt];
+                age = 0;
+            } else {
+                age = age < 2 ? age + 1 : 2;
+            }
+            pos = next_pos;
+            group_sync<CR_GW>(bid);
+        }
+        for (int i = gt; i < 240; i += CR_GT) a.st.ctx[(long long)s * 240 + i] = ws->ctx[i];
+        for (int i = gt; i < HW; i += CR_GT) { a.st.h[(long long)s * HS + i] = ws->h[i]; a.st.c[(long long)s * HS + i] = ws->c[i]; }
+        if (gt < SC_N) a.st.scal[(long long)s * SC_N + gt] = ws->scal[gt];
+        if (gt == 0) {
+            a.st.casc[(long long)s * CS_N + CS_POS] = (uint16_t)pos;
+            a.st.casc[(long long)s * CS_N + CS_CNT_KWS] = (uint16_t)cnt_kws;
+            a.st.casc[(long long)s * CS_N + CS_CNT_S2I] = (uint16_t)cnt_s2i;
+            a.st.casc[(long long)s * CS_N + CS_AGE] = (uint16_t)age;
+        }
+        group_sync<CR_GW>(bid);
+    }
+}
+
+/* ======================================================================================================== */
 /* stage-sorted pass: the scan-split network kernels (nnsp_split.cu) over the streams of each (stage, phase)   */
 /* ======================================================================================================== */
 /* Within a call most streams stay in the stage they are in. Streams are therefore sorted by (live model, phase of
@@ -604,6 +817,8 @@ struct nnsp_b200_cascade {
     nnsp_b200_cascade_result *d_res = nullptr;
     size_t smem_total = 0; int off_w = 0, off_b = 0;
     bool narrow = false;                      /* which shape of the sequential kernel (CsNarrow / CsWide) */
+    bool replay_coop = true;                  /* replay by cascade_replay_kernel (four warps per stream); NNSP_B200_REPLAY_COOP=0: one warp per stream */
+    size_t smem_replay = 0; int off_w_replay = 0;
     cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
     bool ev_valid = false;
     /* stage-sorted pass (scan-split kernels per (model, phase) group + replay) */
@@ -751,7 +966,12 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
     int blocks = (ns + cs_warps - 1) / cs_warps;
     const int cap = sm_count(c->device);
     if (blocks > cap) blocks = cap;
-    if (c->narrow) cascade_kernel<CsNarrow><<<blocks, 32 * CsNarrow::WARPS, c->smem_total, st>>>(a, c->off_w, c->off_b);
+    if (a.replay_list && c->narrow && c->replay_coop) {
+        /* replay: four warps per stream; as many CTAs as the worst case needs (ns streams), at most one per SM */
+        int rb = (ns + CR_GROUPS - 1) / CR_GROUPS;
+        if (rb > cap) rb = cap;
+        cascade_replay_kernel<<<rb, CR_THREADS, c->smem_replay, st>>>(a, c->off_w_replay, c->off_w_replay + (c->off_b - c->off_w));
+    } else if (c->narrow) cascade_kernel<CsNarrow><<<blocks, 32 * CsNarrow::WARPS, c->smem_total, st>>>(a, c->off_w, c->off_b);
     else cascade_kernel<CsWide><<<blocks, 32 * CsWide::WARPS, c->smem_total, st>>>(a, c->off_w, c->off_b);
     NNSP_LAUNCH_CHECK();
     if (timed) { NNSP_CUDA(cudaEventRecord(c->ev[2], st)); c->ev_valid = true; c->last_piped = piped; }
@@ -843,12 +1063,16 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     c->off_w = (int)((16 + smem_struct + 127) & ~(size_t)127);
     c->off_b = (int)(c->off_w + wtot);
     c->smem_total = (size_t)c->off_b + btot * 2 + 16;
+    c->off_w_replay = (int)((16 + sizeof(ReplaySmem) + 127) & ~(size_t)127);
+    c->smem_replay = (size_t)c->off_w_replay + wtot + btot * 2 + 16;
+    { const char *e = getenv("NNSP_B200_REPLAY_COOP"); c->replay_coop = !(e && e[0] == '0'); }        /* A/B switch for measurements */
     if (c->smem_total > 227 * 1024) { nnsp_set_error("cascade needs %zu bytes of shared memory (> 227 KB)", c->smem_total); return fail(NNSP_B200_ERR_UNSUPPORTED); }
     const size_t S = (size_t)n_streams, HS = NNSP_B200_MAX_WIDTH;
     const int hist_frames = c->cd.dmax + 2, lm_rows = c->cd.dmax > 0 ? c->cd.dmax : 1;
 #define TRY(x) do { if ((x) != cudaSuccess) { nnsp_set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); return fail(NNSP_B200_ERR_CUDA); } } while (0)
     TRY(cudaFuncSetAttribute(cascade_kernel<CsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TRY(cudaFuncSetAttribute(cascade_kernel<CsNarrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TRY(cudaFuncSetAttribute(cascade_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &r : c->host_ev) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

@@ -179,6 +179,86 @@ __device__ __forceinline__ void net_forward(const DevModel &M, const uint32_t *_
     }
 }
 
+/* net_forward by a group of GW warps that share one stream: the 32-row rounds of every layer are dealt
+ * out to the warps in contiguous runs, the LSTM cell and the copies go over all threads of the group, and a named barrier
+ * (`bar_id`, 32 GW threads) separates the phases. Same arithmetic, same order per row: bit-exact with net_forward. A stream
+ * that one warp walks frame by frame is latency-bound; this shortens the chain per inference about threefold. */
+template <int GW>
+__device__ __forceinline__ void group_sync(int bar_id) { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * GW) : "memory"); }
+
+template <int GW, class WS>
+__device__ __forceinline__ void net_forward_group(const DevModel &M, const uint32_t *__restrict__ wimg,
+                                                  const int16_t *__restrict__ bimg, const int16_t *__restrict__ tanh_lut,
+                                                  WS *ws, int wg, int lane, int bar_id)
+{
+    const int gt = wg * 32 + lane;
+    const int16_t *x = ws->ctx;
+    int pp = 0, ho = 0;
+    for (int li = 0; li < M.numlayers; li++) {
+        const DevLayer &L = M.layer[li];
+        int16_t *y = ws->buf[pp];
+        const uint32_t *W = wimg + L.w_off;
+        const int16_t *B = bimg + L.bias_off;
+        const bool last = (li == M.numlayers - 1);
+        const int rounds = L.nrows_pad >> 5;
+        const int per = (rounds + GW - 1) / GW, rs = wg * per, re = min(rounds, rs + per);      /* this warp's run of rounds */
+        if (L.type == LAYER_LSTM) {
+            const uint32_t *Wr = wimg + L.wrec_off;
+            const int16_t *hh = ws->h + ho;
+            for (int r = rs; r < re; r += 4) {
+                const int nr = min(4, re - r), r0 = r * 32 + lane;
+                int32_t ax[4] = { 0, 0, 0, 0 }, ah[4] = { 0, 0, 0, 0 };
+                dot_rows_n(nr, W, L.nrows_pad, L.k4, x, r0, ax);
+                dot_rows_n(nr, Wr, L.nrows_pad, L.k4rec, hh, r0, ah);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int n = r0 + 32 * i;
+                    if (i < nr && n < L.nrows) {
+                        const int32_t pre = finish_gate(L, ax[i], ah[i], B[n]);
+                        const int g = (n >= L.rows) + (n >= 2 * L.rows) + (n >= 3 * L.rows);
+                        ws->gates[n] = (int16_t)((g == 1) ? tanh_q15(pre, tanh_lut) : sigmoid_q15(pre, tanh_lut));   /* lstm.c:65,78,91,104 */
+                    }
+                }
+            }
+            group_sync<GW>(bar_id);                                        /* every gate of the layer is in place; all read the old h */
+            const int H = L.rows;
+            for (int u = gt; u < H; u += 32 * GW) {
+                const int32_t gi = ws->gates[u], gj = ws->gates[H + u], gf = ws->gates[2 * H + u], go = ws->gates[3 * H + u];
+                const int64_t t = ((int64_t)gi * (int64_t)gj + (int64_t)gf * (int64_t)ws->c[ho + u]) >> 15;   /* lstm.c:108-109 */
+                const int32_t cn = sat32_dev(t);
+                ws->c[ho + u] = cn;
+                int32_t o = (tanh_q15(cn, tanh_lut) * go) >> 15;                                              /* lstm.c:111-115 */
+                o = o > 32767 ? 32767 : (o < -32768 ? -32768 : o);
+                y[u] = (int16_t)o;
+                ws->h[ho + u] = (int16_t)o;
+            }
+            ho += H;
+        } else {
+            for (int r = rs; r < re; r += 4) {
+                const int nr = min(4, re - r), r0 = r * 32 + lane;
+                int32_t ax[4] = { 0, 0, 0, 0 };
+                dot_rows_n(nr, W, L.nrows_pad, L.k4, x, r0, ax);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int n = r0 + 32 * i;
+                    if (i < nr && n < L.nrows) {
+                        const int32_t pre = finish_fc(L, ax[i], B[n]);
+                        if (L.act == ACT_LINEAR) ws->logits[n] = pre;          /* linear_fix keeps int32 (activation.c:19-29) */
+                        else y[n] = (int16_t)activate16(L.act, pre, tanh_lut);
+                    }
+                }
+            }
+        }
+        group_sync<GW>(bar_id);
+        if (last && !(L.type == LAYER_FC && L.act == ACT_LINEAR)) {    /* neural_nets.c:152-167 */
+            for (int n = gt; n < L.rows; n += 32 * GW) ws->logits[n] = y[n];
+            group_sync<GW>(bar_id);
+        }
+        x = y;
+        pp ^= 1;
+    }
+}
+
 /* s2i_post_proc, nn_speech.c:146-189 (run by one lane; sc = NNSPClass scalars) */
 __device__ __forceinline__ void post_s2i(int16_t *sc, const int32_t *est, int16_t th_count)
 {
