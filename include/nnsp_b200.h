@@ -123,8 +123,13 @@ int nnsp_b200_batch_reset(nnsp_b200_batch *b);
  *   results  device pointer [n_streams][n_frames] (may be NULL)
  * Asynchronous: the call returns once the work is queued. On the default network path consecutive calls are
  * pipelined over two CUDA streams (front end of call N+1 while the network kernels of call N finish), so results
- * and state are complete only after nnsp_b200_batch_sync; the PCM buffer of a call may be reused once the next
- * call has been issued or after a sync.                                                   */
+ * and state are complete only after nnsp_b200_batch_sync.
+ * Ownership: `pcm_dev` and `results_dev` belong to the library from the call until nnsp_b200_batch_sync returns.
+ * The engine's streams are non-blocking, so a refill through cudaMemcpy / nnsp_b200_memcpy_h2d (legacy stream) or
+ * through a stream of the caller is NOT ordered against them. The one exception: work the caller enqueues on
+ * nnsp_b200_batch_stream() AFTER the next exec call has been issued is ordered behind every reader of this call's
+ * PCM (the feature and history kernels run on that stream); a serving loop that wants no sync therefore rotates
+ * three PCM buffers and fills buffer k+1 on that stream.                                   */
 int nnsp_b200_batch_exec(nnsp_b200_batch *b, const int16_t *pcm_dev, long long stream_stride,
                          int n_frames, nnsp_b200_result *results_dev,
                          const nnsp_b200_taps *taps);
@@ -185,8 +190,9 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
                              nnsp_b200_cascade **out);
 int nnsp_b200_cascade_reset(nnsp_b200_cascade *c);
 /* Asynchronous and pipelined like nnsp_b200_batch_exec: results, state and the PCM buffer of a call are settled
- * after nnsp_b200_cascade_sync (the replay of stage changes reads the call's PCM while the next call's front end
- * already runs). */
+ * only after nnsp_b200_cascade_sync -- the kernels that handle the first frames after a stage change read the call's
+ * PCM on an internal stream while the next call's front end already runs, so there is NO stream of the caller's on
+ * which a refill of that buffer would be ordered. Rotate buffers and sync before reusing one. */
 int nnsp_b200_cascade_exec(nnsp_b200_cascade *c, const int16_t *pcm_dev, long long stream_stride,
                            int n_frames, nnsp_b200_cascade_result *results_dev,
                            const nnsp_b200_taps *taps);
@@ -217,6 +223,23 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c);
  * Any output pointer may be NULL. */
 int nnsp_b200_feature_stages(int device, const int16_t *windows, int n, int32_t *fft_in,
                              int32_t *spec, int32_t *pspec, int32_t *mel, int32_t *logmel);
+
+/* ------------------------------------------------------------------------------------ */
+/* One network evaluation on explicit inputs (parity tool)                              */
+/* ------------------------------------------------------------------------------------ */
+/* NeuralNetClass_exe(net, input, output, -1) (ns-nnsp/src/neural_nets.c:44-168) for n independent evaluations on the
+ * network kernels of `nn_path` (0 automatic, 1 dp2a, 2 IMMA in the time loop, 3 scan-split; see
+ * nnsp_b200_batch_set_nn_path), no front end involved. Host pointers:
+ *   x      [n][240] int16   the 6 x 40 context the network reads (normFeatContext)
+ *   h0, c0 [n][h_stride]    LSTM state of all lstm layers back to back before the evaluation (NULL = zeros)
+ *   act    [n][act_stride]  outputs of layers 0..L-2 back to back          (may be NULL)
+ *   logits [n][n_out]       final layer (int32; int16 values when it is not linear, neural_nets.c:152-167)
+ *   h1, c1 [n][h_stride]    LSTM state after the evaluation                (may be NULL)
+ * act_stride / h_stride / n_out as reported by nnsp_b200_batch_dims. This is how adversarial inputs and states
+ * (full-scale x, saturated c, wrap-around under ACC32BIT_OPT) reach every CUDA network path. */
+int nnsp_b200_net_eval(const nnsp_b200_model *m, int device, int nn_path, int n, const int16_t *x,
+                       const int16_t *h0, const int32_t *c0, int16_t *act, int32_t *logits,
+                       int16_t *h1, int32_t *c1);
 
 /* ------------------------------------------------------------------------------------ */
 /* Ingest: the application's PCM conditioning in front of the path                      */

@@ -15,7 +15,7 @@
  *   NNSPClass .................. ns-nnsp/includes-api/nn_speech.h:12-25
  *   NNSP_ID .................... ns-nnsp/includes-api/nnsp_identification.h:3-9
  *   constants .................. ns-nnsp/includes-api/ambiq_nnsp_const.h:3-10, s2i_const.h:3-4
- * tests/test_abi_layout.py checks sizeof/offsetof of every struct against the reference
+ * tests/test_abi.py checks sizeof/offsetof of every struct against the reference
  * headers whenever /root/reference is present.
  */
 #ifndef NNSP_B200_LEGACY_API_H

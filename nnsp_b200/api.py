@@ -372,6 +372,29 @@ def ingest_audadc(raw, device=0):
     return out
 
 
+def net_eval(model, x, h0=None, c0=None, nn_path="auto", device=0):
+    """NeuralNetClass_exe on explicit inputs: x int16 [n, 240], h0 int16 / c0 int32 [n, h_stride] (None = zeros).
+    Returns (act [n, act_stride], logits [n, n_out], h1, c1) computed by the CUDA network kernels of `nn_path`."""
+    x = np.ascontiguousarray(x, np.int16)
+    n = x.shape[0]
+    assert x.shape == (n, 240)
+    sz = model.size_layer
+    b = NNSPBatch(model, 1, device)                    # only for the strides the engine reports
+    a_s, h_s, n_o = b.act_stride, b.h_stride, b.n_out
+    b.close()
+    hs = max(h_s, 1)
+    h0 = np.zeros((n, hs), np.int16) if h0 is None else np.ascontiguousarray(h0, np.int16)
+    c0 = np.zeros((n, hs), np.int32) if c0 is None else np.ascontiguousarray(c0, np.int32)
+    assert h0.shape == (n, hs) and c0.shape == (n, hs), (h0.shape, c0.shape, hs, sz)
+    act = np.zeros((n, max(a_s, 1)), np.int16)
+    logits = np.zeros((n, n_o), np.int32)
+    h1, c1 = np.zeros((n, hs), np.int16), np.zeros((n, hs), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().nnsp_b200_net_eval(model.h, device, NNSPBatch.NN_PATH[nn_path], n, p(x), p(h0), p(c0), p(act), p(logits),
+                                   p(h1), p(c1)), "net_eval")
+    return act[:, :a_s], logits, h1[:, :h_s], c1[:, :h_s]
+
+
 def table(name):
     p, eb = C.c_void_p(), C.c_int()
     n = lib().nnsp_b200_table(name.encode(), C.byref(p), C.byref(eb))

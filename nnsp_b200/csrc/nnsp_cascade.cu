@@ -844,6 +844,7 @@ struct nnsp_b200_cascade {
     cudaEvent_t host_ev[CS_HOST_RING][3] = {};
     long long host_seq = 0;
     bool host_inflight = false;
+    int host_last_T = 0;                       /* frames per stream of the latest host-buffer call */
 };
 
 constexpr int CS_MAX_SLICES = 8;
@@ -1195,6 +1196,13 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
     NNSP_CUDA(cudaStreamSynchronize(c->stream));
     NNSP_CUDA(cudaStreamSynchronize(c->nn_stream));
     c->nn_pending[0] = c->nn_pending[1] = false;
+    /* every per-call scratch array is laid out [stream][T] (or by n_inf_max = (T + 1) / 2): a slice owns the same bytes in
+     * consecutive calls only while T stays the same. When it changes with an asynchronous call still in flight, every
+     * pipeline stream first waits for all streams of that call. */
+    if (c->host_inflight && c->host_seq > 0 && c->host_last_T != T)
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) NNSP_CUDA(cudaStreamWaitEvent(c->xs[j], c->host_ev[c->host_seq % CS_HOST_RING][k], 0));
+    c->host_last_T = T;
     const long long dstride = (long long)T * NNSP_B200_FRAME;
     c->host_inflight = true;
     const int nsl = c->S >= 4096 ? 8 : (c->S >= 256 ? 4 : 1);

@@ -13,7 +13,7 @@ enum { ACT_RELU6 = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_LINEAR = 3 };
 /* (a*b) >> 15 with a 64-bit intermediate and floor: the ">>= 15" of complex.c:66-69. The
  * int32 saturation that follows in the reference cannot fire for int16 PCM input: with the
  * shipped window sum|fft_in| <= 8 175 452, so every FFT intermediate stays below 2^24
- * (DESIGN.md "Why the FFT clamps are elided"; tests/test_feature_bounds.py). */
+ * (DESIGN.md "Why the FFT clamps are elided"; tests/test_tables_and_format.py::test_window_bound_behind_the_elided_fft_clamps). */
 __device__ __forceinline__ int32_t mul_q15(int32_t a, int32_t b)
 {
     return (int32_t)(((int64_t)a * (int64_t)b) >> 15);

@@ -40,6 +40,7 @@ int select_device(int device)
     }
     if (device < 0 || device >= n || device >= 64) { nnsp_set_error("device %d out of range (have %d)", device, n); return NNSP_B200_ERR_ARG; }
     NNSP_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_mu);
     if (!g_sm_count[device]) {
         cudaDeviceProp p;
         NNSP_CUDA(cudaGetDeviceProperties(&p, device));
@@ -256,10 +257,13 @@ feat_kernel(const DevTables *__restrict__ tables, const int16_t *__restrict__ pc
 int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStream_t st)
 {
     static bool attr_set[64] = { false };
+    static std::mutex attr_mu;                         /* host threads may drive separate handles on one device */
+    std::unique_lock<std::mutex> attr_lk(attr_mu);
     if (!attr_set[device]) {
         NNSP_CUDA(cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem)));
         attr_set[device] = true;
     }
+    attr_lk.unlock();
     const long long F = (long long)a.ns * a.T;
     if (F <= 0) return NNSP_B200_OK;
     long long blocks = (F + FEAT_WARPS * 2 - 1) / (FEAT_WARPS * 2);
@@ -364,6 +368,7 @@ struct NNArgs {
     nnsp_b200_result *results;      /* [S][T] or null */
     nnsp_b200_taps taps;
     int16_t thresh_prob, th_count;
+    int raw_ctx;                    /* nnsp_b200_net_eval: the stored context IS the network input (no slide, no new row) */
 };
 
 struct NNSmemLayout { size_t bar, w, b, lut, model, scratch, total; };
@@ -415,23 +420,26 @@ nn_kernel(NNArgs a, int off_b, int off_lut, int off_model, int off_scratch)
         if (lane < SC_N) ws->scal[lane] = a.st.scal[(long long)s * SC_N + lane];
         __syncwarp();
         const int32_t *lm = a.logmel + (long long)s * T * NNSP_B200_NMEL;
-        int32_t lm0 = lm[lane], lm1 = (lane < 8) ? lm[32 + lane] : 0;
+        int32_t lm0 = 0, lm1 = 0;
+        if (!a.raw_ctx) { lm0 = lm[lane]; lm1 = (lane < 8) ? lm[32 + lane] : 0; }
         for (int t = 0; t < T; t++) {
             const long long ft = (long long)s * T + t;
             /* FeatureClass_execute tail: slide the context (feature_module.c:54-57), standardise (:67-73) */
-            int16_t mv[7];
+            if (!a.raw_ctx) {
+                int16_t mv[7];
 #pragma unroll
-            for (int j = 0; j < 7; j++) { const int i = lane + 32 * j; mv[j] = (i < 200) ? ws->ctx[i + 40] : (int16_t)0; }
-            __syncwarp();
+                for (int j = 0; j < 7; j++) { const int i = lane + 32 * j; mv[j] = (i < 200) ? ws->ctx[i + 40] : (int16_t)0; }
+                __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 7; j++) { const int i = lane + 32 * j; if (i < 200) ws->ctx[i] = mv[j]; }
-            const int16_t f0 = standardise(lm0, M.mean[lane], M.stdR[lane], M.feat_rshift);
-            ws->ctx[200 + lane] = f0;
-            int16_t f1 = 0;
-            if (lane < 8) { f1 = standardise(lm1, M.mean[32 + lane], M.stdR[32 + lane], M.feat_rshift); ws->ctx[232 + lane] = f1; }
-            if (a.taps.logmel) { a.taps.logmel[ft * 40 + lane] = lm0; if (lane < 8) a.taps.logmel[ft * 40 + 32 + lane] = lm1; }
-            if (a.taps.feat) { a.taps.feat[ft * 40 + lane] = f0; if (lane < 8) a.taps.feat[ft * 40 + 32 + lane] = f1; }
-            if (t + 1 < T) { lm0 = lm[(t + 1) * 40 + lane]; lm1 = (lane < 8) ? lm[(t + 1) * 40 + 32 + lane] : 0; }   /* prefetch */
+                for (int j = 0; j < 7; j++) { const int i = lane + 32 * j; if (i < 200) ws->ctx[i] = mv[j]; }
+                const int16_t f0 = standardise(lm0, M.mean[lane], M.stdR[lane], M.feat_rshift);
+                ws->ctx[200 + lane] = f0;
+                int16_t f1 = 0;
+                if (lane < 8) { f1 = standardise(lm1, M.mean[32 + lane], M.stdR[32 + lane], M.feat_rshift); ws->ctx[232 + lane] = f1; }
+                if (a.taps.logmel) { a.taps.logmel[ft * 40 + lane] = lm0; if (lane < 8) a.taps.logmel[ft * 40 + 32 + lane] = lm1; }
+                if (a.taps.feat) { a.taps.feat[ft * 40 + lane] = f0; if (lane < 8) a.taps.feat[ft * 40 + 32 + lane] = f1; }
+                if (t + 1 < T) { lm0 = lm[(t + 1) * 40 + lane]; lm1 = (lane < 8) ? lm[(t + 1) * 40 + 32 + lane] : 0; }   /* prefetch */
+            }
             __syncwarp();
             const bool ran = (ws->scal[SC_SLIDES] == 1);                                  /* nn_speech.c:84 */
             if (ran) {
@@ -616,6 +624,7 @@ struct nnsp_b200_batch {
     cudaEvent_t host_ev[HOST_RING][4] = {};
     long long host_seq = 0;                 /* ticket of the latest asynchronous host call */
     bool host_inflight = false;
+    int host_last_T = 0;                    /* frames per stream of the latest host-buffer call */
 };
 
 static int batch_nn_path(const nnsp_b200_batch *b);
@@ -702,7 +711,7 @@ static int batch_launch(nnsp_b200_batch *b, const int16_t *pcm, long long stride
         l.tables = b->tables; l.st = b->st; l.logmel = b->logmel; l.s0 = s0; l.ns = ns; l.T = T; l.results = results;
         if (taps) l.taps = *taps;
         l.thresh_prob = b->thresh_prob; l.th_count = b->th_count;
-        if ((rc = launch_nn_split(b->mm, l, feat16, first, n_inf, b->sp_planes[0], b->sp_planes[1], b->sp_dec, b->device, st))) return rc;
+        if ((rc = launch_nn_split(b->mm, l, feat16, first, n_inf, b->sp_planes[0], b->sp_planes[1], b->sp_dec, (int)b->sp_cap_inf, b->device, st))) return rc;
     } else if (path == 2) {
         if (!b->mma_ok) { nnsp_set_error("this model has no IMMA formulation"); return NNSP_B200_ERR_UNSUPPORTED; }
         NNLaunch l{};
@@ -932,6 +941,14 @@ static int batch_enqueue_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
     NNSP_CUDA(cudaStreamSynchronize(b->stream));
     NNSP_CUDA(cudaStreamSynchronize(b->nn_stream));
     b->nn_pending[0] = b->nn_pending[1] = false;
+    /* The per-call scratch (feature rows, staged PCM, result records) is laid out [stream][T]: a slice owns the same bytes
+     * in consecutive calls only while T stays the same. When T changes and an asynchronous call is still in flight, every
+     * pipeline stream first waits for ALL streams of that call (stream order alone covers equal-length calls; the
+     * inference-dependent buffers are strided by their capacity and never move). */
+    if (b->host_inflight && b->host_seq > 0 && b->host_last_T != T)
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 4; k++) NNSP_CUDA(cudaStreamWaitEvent(b->xs[j], b->host_ev[b->host_seq % HOST_RING][k], 0));
+    b->host_last_T = T;
     /* slices of streams pipelined over four CUDA streams: H2D(k+1) overlaps kernels(k) overlaps D2H(k-1). The call
      * is bound by the host link (320 B of PCM per stream-frame), so slices are small enough that the work left
      * after the last H2D -- one slice of kernels and its D2H -- is short, and large enough to fill the GPU */
@@ -1031,6 +1048,89 @@ void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
     for (auto e : b->ev) if (e) cudaEventDestroy(e);
     for (auto &r : b->host_ev) for (auto e : r) if (e) cudaEventDestroy(e);
     delete b;
+}
+
+/* ---- one network evaluation on explicit inputs and explicit LSTM state (parity tool) ------------------ */
+/* NeuralNetClass_exe (neural_nets.c:44-168) for n independent (input, state) pairs on the network kernels of the chosen
+ * path: the stored context / the staged feature rows are loaded with x as it stands, no front end runs. */
+int nnsp_b200_net_eval(const nnsp_b200_model *m, int device, int nn_path, int n, const int16_t *x, const int16_t *h0,
+                       const int32_t *c0, int16_t *act, int32_t *logits, int16_t *h1, int32_t *c1)
+{
+    if (!m || !x || n <= 0 || nn_path < 0 || nn_path > 3) { nnsp_set_error("net_eval: bad arguments"); return NNSP_B200_ERR_ARG; }
+    nnsp_b200_batch *b = nullptr;
+    int rc = nnsp_b200_batch_create(m, n, device, 16383, 4, &b);
+    if (rc) return rc;
+    int16_t *t_act = nullptr, *t_h = nullptr, *xs = nullptr;
+    int32_t *t_logits = nullptr, *t_c = nullptr;
+    auto done = [&](int code) {
+        cudaFree(t_act); cudaFree(t_logits); cudaFree(t_h); cudaFree(t_c);
+        free(xs);
+        nnsp_b200_batch_destroy(b);
+        return code;
+    };
+#define NE_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { nnsp_set_error("%s failed: %s", #expr, cudaGetErrorString(e__)); return done(NNSP_B200_ERR_CUDA); } } while (0)
+    if (nn_path && (rc = nnsp_b200_batch_set_nn_path(b, nn_path))) return done(rc);
+    const int path = batch_nn_path(b);
+    const DevModel &D = b->dm.h;
+    const int HS = D.h_stride, AS = D.act_stride > 0 ? D.act_stride : 1, NO = D.n_out;
+    const size_t N = (size_t)n;
+    NE_CUDA(cudaMalloc(&t_act, N * AS * sizeof(int16_t)));
+    NE_CUDA(cudaMalloc(&t_logits, N * NO * sizeof(int32_t)));
+    NE_CUDA(cudaMalloc(&t_h, N * (HS > 0 ? HS : 1) * sizeof(int16_t)));
+    NE_CUDA(cudaMalloc(&t_c, N * (HS > 0 ? HS : 1) * sizeof(int32_t)));
+    NE_CUDA(cudaMemset(t_act, 0, N * AS * sizeof(int16_t)));
+    if (HS > 0) {
+        if (h0) NE_CUDA(cudaMemcpy(b->st.h, h0, N * HS * sizeof(int16_t), cudaMemcpyHostToDevice));
+        if (c0) NE_CUDA(cudaMemcpy(b->st.c, c0, N * HS * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    nnsp_b200_taps tp{};
+    tp.act = t_act; tp.logits = t_logits;
+    if (HS > 0) { tp.hstate = t_h; tp.cstate = t_c; }
+    if (path == 3) {
+        /* the scan-split kernels take the window as (context rows 1..5 carried, row of frame 0 staged): feed x that way */
+        if ((rc = batch_ensure_logmel(b, 1)) || (rc = batch_ensure_split(b, 1))) return done(rc);
+        xs = (int16_t *)calloc(N * 240 + N * 40, sizeof(int16_t));
+        if (!xs) return done(NNSP_B200_ERR_NOMEM);
+        int16_t *row5 = xs + N * 240;
+        for (size_t i = 0; i < N; i++) {
+            memcpy(xs + i * 240 + 40, x + i * 240, 200 * sizeof(int16_t));
+            memcpy(row5 + i * 40, x + i * 240 + 200, 40 * sizeof(int16_t));
+        }
+        NE_CUDA(cudaMemcpy(b->st.ctx, xs, N * 240 * sizeof(int16_t), cudaMemcpyHostToDevice));
+        NE_CUDA(cudaMemcpy(b->feat16[0], row5, N * 40 * sizeof(int16_t), cudaMemcpyHostToDevice));
+        NE_CUDA(cudaDeviceSynchronize());
+        NNLaunch l{};
+        l.tables = b->tables; l.st = b->st; l.s0 = 0; l.ns = n; l.T = 1; l.taps = tp;
+        l.thresh_prob = b->thresh_prob; l.th_count = b->th_count;
+        if ((rc = launch_nn_split(b->mm, l, b->feat16[0], 0, 1, b->sp_planes[0], b->sp_planes[1], b->sp_dec, (int)b->sp_cap_inf, b->device, b->stream))) return done(rc);
+    } else {
+        NE_CUDA(cudaMemcpy(b->st.ctx, x, N * 240 * sizeof(int16_t), cudaMemcpyHostToDevice));
+        NE_CUDA(cudaDeviceSynchronize());
+        if (path == 2) {
+            NNLaunch l{};
+            l.tables = b->tables; l.st = b->st; l.s0 = 0; l.ns = n; l.T = 1; l.taps = tp; l.raw_ctx = 1;
+            l.thresh_prob = b->thresh_prob; l.th_count = b->th_count;
+            if ((rc = launch_nn_mma(b->mm, l, b->device, b->stream))) return done(rc);
+        } else {
+            NNArgs a{};
+            a.model = b->dm.d; a.wimg = b->dm.wimg; a.bimg = b->dm.bimg; a.tables = b->tables; a.st = b->st;
+            a.s0 = 0; a.ns = n; a.T = 1; a.taps = tp; a.raw_ctx = 1;
+            a.thresh_prob = b->thresh_prob; a.th_count = b->th_count;
+            int blocks = (n + NN_WARPS - 1) / NN_WARPS;
+            const int cap = sm_count(b->device) * b->nn_ctas_per_sm;
+            if (blocks > cap) blocks = cap;
+            nn_kernel<<<blocks, NN_THREADS, b->lay.total, b->stream>>>(a, (int)b->lay.b, (int)b->lay.lut, (int)b->lay.model, (int)b->lay.scratch);
+            g_launches.fetch_add(1);
+            NE_CUDA(cudaGetLastError());
+        }
+    }
+    NE_CUDA(cudaStreamSynchronize(b->stream));
+    if (act && D.act_stride > 0) NE_CUDA(cudaMemcpy(act, t_act, N * D.act_stride * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    if (logits) NE_CUDA(cudaMemcpy(logits, t_logits, N * NO * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (h1 && HS > 0) NE_CUDA(cudaMemcpy(h1, t_h, N * HS * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    if (c1 && HS > 0) NE_CUDA(cudaMemcpy(c1, t_c, N * HS * sizeof(int32_t), cudaMemcpyDeviceToHost));
+#undef NE_CUDA
+    return done(NNSP_B200_OK);
 }
 
 /* ---- stage-by-stage front-end tap -------------------------------------------------------- */

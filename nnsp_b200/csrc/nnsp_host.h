@@ -80,6 +80,7 @@ void free_model_mma(MmaDeviceModel *mm);
 struct NNLaunch {
     const DevTables *tables; StreamState st; const int32_t *logmel;
     int s0, ns, T; nnsp_b200_result *results; nnsp_b200_taps taps; int16_t thresh_prob, th_count;
+    int raw_ctx = 0;              /* nnsp_b200_net_eval: the stored context is the network input as it stands */
 };
 int launch_nn_mma(const MmaDeviceModel &mm, const NNLaunch &a, int device, cudaStream_t st);
 
@@ -109,6 +110,6 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
 int split_supported(const MmaDeviceModel &mm);
 size_t split_plane_bytes(const MmaDeviceModel &mm, int n_streams, int n_inf);
 int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *feat16, int first, int n_inf,
-                    uint8_t *planes0, uint8_t *planes1, int32_t *dec, int device, cudaStream_t st);
+                    uint8_t *planes0, uint8_t *planes1, int32_t *dec, int cap_inf, int device, cudaStream_t st);
 
 }  // namespace nnsp

@@ -2,7 +2,7 @@
  * tables store in NeuralNetClass.layer_func[] / act_func[] (evb/src/def_nn1_vad.c:61-84).
  *
  * In nnsp-b200 the per-layer arithmetic runs inside the fused CUDA network kernel
- * (nnsp_kernels.cu), never one layer at a time on the host, so these symbols exist to be
+ * (nnsp_engine.cu, nnsp_split.cu, nnsp_compat.cu), never one layer at a time on the host, so these symbols exist to be
  * compared against (nnsp_model_net.c) and to let unmodified def_nn*.c objects link. Calling
  * one directly is a usage error: they report it and compute nothing (no CPU fallback). */
 #include "nnsp_compat/nnsp_legacy_api.h"

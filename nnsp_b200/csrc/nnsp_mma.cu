@@ -1,6 +1,7 @@
 /* nnsp_mma.cu -- host packing + kernel of the tensor-core network path (see nnsp_mma.cuh).
  * nn_mma_kernel: one CTA (4 warps) = one tile of 16 streams, all T frames of the call in order. */
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -23,6 +24,7 @@ struct MmaArgs {
     nnsp_b200_result *results;
     nnsp_b200_taps taps;
     int16_t thresh_prob, th_count;
+    int raw_ctx;
 };
 
 __global__ void __launch_bounds__(MMA_THREADS, 4)
@@ -89,12 +91,14 @@ nn_mma_kernel(MmaArgs a, int off_lut, int off_model, int off_tile, int smem_tota
         const int32_t *lmrow = a.logmel + ((long long)(sb + (srv ? sr : 0)) * T) * NNSP_B200_NMEL + f0;
         int nxt[5];
 #pragma unroll
-        for (int j = 0; j < 5; j++) nxt[j] = srv ? __ldg(lmrow + j) : 0;
+        for (int j = 0; j < 5; j++) nxt[j] = (srv && !a.raw_ctx) ? __ldg(lmrow + j) : 0;
 
         for (int t = 0; t < T; t++) {
             /* FeatureClass_execute tail (feature_module.c:54-73): the window slides one ring row */
-            int newrow;
-            if (base == MMA_RING_ROWS - 6) {
+            int newrow = 0;
+            if (a.raw_ctx) {
+                /* nnsp_b200_net_eval: rows 0..5 of the ring are the network input as loaded */
+            } else if (base == MMA_RING_ROWS - 6) {
                 /* rows base+1 .. base+5 back to rows 0..4 (200 bytes per plane row, 50 words, 32 plane rows) */
                 __syncthreads();                  /* the previous frame's new row may have been written without a barrier */
                 for (int idx = tid; idx < 1600; idx += MMA_THREADS) {
@@ -112,11 +116,11 @@ nn_mma_kernel(MmaArgs a, int off_lut, int off_model, int off_tile, int smem_tota
             int lm[5];
 #pragma unroll
             for (int j = 0; j < 5; j++) lm[j] = nxt[j];
-            if (t + 1 < T) {
+            if (t + 1 < T && !a.raw_ctx) {
 #pragma unroll
                 for (int j = 0; j < 5; j++) nxt[j] = srv ? __ldg(lmrow + (long long)(t + 1) * NNSP_B200_NMEL + j) : 0;
             }
-            {
+            if (!a.raw_ctx) {
                 const long long ft = (long long)(sb + sr) * T + t;
                 const int o = sr * MMA_PC + newrow * 40 + f0;
 #pragma unroll
@@ -336,14 +340,17 @@ int launch_nn_mma(const MmaDeviceModel &mm, const NNLaunch &l, int device, cudaS
 {
     const size_t smem = mm.smem_base + mm.smem_warp;
     static bool attr_done[64] = { false };
+    static std::mutex attr_mu;                         /* host threads may drive separate handles on one device */
+    std::unique_lock<std::mutex> attr_lk(attr_mu);
     if (!attr_done[device]) {
         NNSP_CUDA(cudaFuncSetAttribute(nn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done[device] = true;
     }
+    attr_lk.unlock();
     MmaArgs a{};
     a.model = mm.d; a.frag = (const uint2 *)mm.frag; a.bias32 = mm.bias32; a.tables = l.tables; a.st = l.st;
     a.logmel = l.logmel; a.s0 = l.s0; a.ns = l.ns; a.T = l.T; a.results = l.results; a.taps = l.taps;
-    a.thresh_prob = l.thresh_prob; a.th_count = l.th_count;
+    a.thresh_prob = l.thresh_prob; a.th_count = l.th_count; a.raw_ctx = l.raw_ctx;
     int blocks = (l.ns + 15) / 16;
     /* leave L1 room for the weight image: the B fragments are read through the read-only L1 path */
     const size_t frag_bytes = (size_t)mm.h->frag_count * 8;

@@ -30,6 +30,7 @@
  * The kernels work on a stream selection (StreamSel): a contiguous range for the batched NNSPClass, or a device-side
  * list for the cascade, whose stage-sorted pass (nnsp_cascade.cu) runs them once per (model, phase) group. */
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -806,7 +807,7 @@ constexpr int POST_THREADS = 64;                    /* streams per CTA */
 constexpr int POST_KCH = 64;                        /* decision records staged per round */
 
 struct PostArgs {
-    int nn_id, s0, ns, T, first, n_inf;
+    int nn_id, s0, ns, T, first, n_inf, dec_stride;
     const int32_t *dec;
     int16_t *scal;
     nnsp_b200_result *results;
@@ -858,7 +859,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostArgs a)
         __syncthreads();
         for (int e = threadIdx.x; e < nstr * nk; e += POST_THREADS) {
             const int rr = e / nk, kk = e - rr * nk;
-            dsm[rr][kk] = a.dec[(size_t)(a.s0 + si0 + rr) * a.n_inf + kc + kk];
+            dsm[rr][kk] = a.dec[(size_t)(a.s0 + si0 + rr) * a.dec_stride + kc + kk];
         }
         __syncthreads();
         if (valid) {
@@ -969,11 +970,14 @@ template <int NW, int MINB, int KT>
 static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, cudaStream_t st)
 {
     static bool attr_done[64] = { false };
+    static std::mutex attr_mu;                         /* host threads may drive separate handles on one device */
+    std::unique_lock<std::mutex> attr_lk(attr_mu);
     if (!attr_done[device]) {
         NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
         NNSP_CUDA(cudaFuncSetAttribute(scan_kernel<NW, MINB, KT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done[device] = true;
     }
+    attr_lk.unlock();
     scan_kernel<NW, MINB, KT><<<ntiles, 32 * NW, smem, st>>>(a);
     NNSP_LAUNCH_CHECK();
     return NNSP_B200_OK;
@@ -985,6 +989,8 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
 {
     const MmaModel *D = mm.h;
     static bool attr_done[64] = { false };
+    static std::mutex attr_mu;                         /* host threads may drive separate handles on one device */
+    std::unique_lock<std::mutex> attr_lk(attr_mu);
     if (!attr_done[device]) {
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_MAX_DYN_SMEM));
@@ -994,6 +1000,7 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done[device] = true;
     }
+    attr_lk.unlock();
     if (q.n_inf <= 0 || q.max_streams <= 0) return NNSP_B200_OK;
     StreamSel sel{};
     sel.list = q.list; sel.count = q.count; sel.tile_off = q.tile_off; sel.s0 = q.s0; sel.ns = q.ns; sel.tile0 = q.tile0;
@@ -1058,8 +1065,12 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
 }
 
 int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *feat16, int first, int n_inf,
-                    uint8_t *planes0, uint8_t *planes1, int32_t *dec, int device, cudaStream_t st)
+                    uint8_t *planes0, uint8_t *planes1, int32_t *dec, int cap_inf, int device, cudaStream_t st)
 {
+    /* cap_inf: the inference capacity the plane / decision buffers were allocated for. Strides follow the capacity, not
+     * this call's n_inf, so that a stream slice owns the same bytes in every call (calls of different lengths may be in
+     * flight on different CUDA streams of the host-buffer pipeline) */
+    if (cap_inf < n_inf) cap_inf = n_inf;
     const MmaModel *D = mm.h;
     if (l.ns <= 0 || l.T <= 0) return NNSP_B200_OK;
     if ((l.s0 & 15) != 0) { nnsp_set_error("stream slices of the split path must start at a multiple of 16"); return NNSP_B200_ERR_ARG; }
@@ -1080,7 +1091,7 @@ int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *
         q.tables = l.tables; q.s0 = l.s0; q.ns = l.ns; q.tile0 = l.s0 >> 4; q.max_streams = l.ns;
         q.T = T; q.first = first; q.n_inf = n_inf; q.mode = 1; q.feat16 = feat16; q.ctx = l.st.ctx;
         q.h = l.st.h; q.c = l.st.c; q.h_stride = D->h_stride; q.planes0 = planes0; q.planes1 = planes1;
-        q.dec = dec; q.dec_stride = n_inf; q.thresh_prob = l.thresh_prob; q.taps = tp;
+        q.dec = dec; q.dec_stride = cap_inf; q.tile_bytes = (long long)cap_inf * 32 * D->pa; q.thresh_prob = l.thresh_prob; q.taps = tp;
         if ((rc = launch_split_layers(mm, q, device, st))) return rc;
     } else if ((tp.hstate || tp.cstate) && D->h_stride > 0) {
         /* a call without any inference (one frame, slides == 0): the state taps repeat the stored state */
@@ -1092,7 +1103,7 @@ int launch_nn_split(const MmaDeviceModel &mm, const NNLaunch &l, const int16_t *
     }
     {
         PostArgs p{};
-        p.nn_id = D->nn_id; p.s0 = l.s0; p.ns = l.ns; p.T = T; p.first = first; p.n_inf = n_inf;
+        p.nn_id = D->nn_id; p.s0 = l.s0; p.ns = l.ns; p.T = T; p.first = first; p.n_inf = n_inf; p.dec_stride = cap_inf;
         p.dec = dec; p.scal = l.st.scal; p.results = l.results; p.tap_post = tp.post; p.th_count = l.th_count;
         post_kernel<<<(l.ns + POST_THREADS - 1) / POST_THREADS, POST_THREADS, 0, st>>>(p);
         NNSP_LAUNCH_CHECK();

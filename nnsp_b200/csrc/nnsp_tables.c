@@ -222,7 +222,7 @@ uint64_t nnsp_tables_fingerprint(const nnsp_tables *t)
 }
 
 /* Fingerprint of the tables when they equal the reference's (verified against the reference
- * objects by tests/test_tables.py). */
+ * objects by tests/test_tables_and_format.py). */
 #define NNSP_TABLES_EXPECTED_FNV 0x64c7c19ae737264dULL
 
 static nnsp_tables g_tables;

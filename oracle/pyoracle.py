@@ -15,7 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-MODEL_DIR = os.path.join(ROOT, "tests", "golden", "models")
+MODEL_DIR = os.path.join(ROOT, "nnsp_b200", "models")
 
 S2I, VAD, KWS = 0, 1, 2
 MODEL_FILES = {S2I: "s2i.nnspm", VAD: "vad.nnspm", KWS: "kws_galaxy.nnspm"}
@@ -291,3 +291,66 @@ class RefLib:
         if rc:
             raise RuntimeError("ref_cascade_run rc=%d" % rc)
         return res, tp, valid
+
+    # -- synthetic models: a NeuralNetClass built over an NNSPM1 container (ref_glue.c ref_net_eval_blob) ------------
+    def net_eval_blob(self, blob, acc32, x, h, c, act_stride, n_out):
+        x = np.ascontiguousarray(x, np.int16)
+        h = np.ascontiguousarray(h, np.int16).copy()
+        c = np.ascontiguousarray(c, np.int32).copy()
+        hh, cc = np.zeros(1024, np.int16), np.zeros(1024, np.int32)     # the glue reads / writes whole state rows
+        hh[: len(h)] = h
+        cc[: len(c)] = c
+        act = np.zeros(max(act_stride, 1) + 512, np.int16)
+        logits = np.zeros(n_out + 512, np.int32)
+        buf = C.create_string_buffer(bytes(blob), len(blob))
+        self.lib.ref_net_eval_blob.argtypes = [C.c_void_p, C.c_longlong, C.c_int] + [C.c_void_p] * 5
+        rc = self.lib.ref_net_eval_blob(buf, len(blob), int(bool(acc32)), _p(x), _p(hh), _p(cc), _p(act), _p(logits))
+        if rc:
+            raise RuntimeError("ref_net_eval_blob rc=%d" % rc)
+        return act[:act_stride], logits[:n_out], hh[: len(h)], cc[: len(c)]
+
+    # -- many streams through the one controller, per-stream state swapped in and out (CPU arms of bench.py) ---------
+    def cascade_state_bytes(self):
+        self.lib.ref_cascade_state_bytes.restype = C.c_longlong
+        return int(self.lib.ref_cascade_state_bytes())
+
+    def cascade_batch(self, pcm2d, states, fresh, seq=(VAD, KWS, S2I), params=None, want_results=False, stage_frames=None):
+        """pcm2d int16 [n, T*160]; states uint8 [n, cascade_state_bytes()] (kept by the caller between calls)."""
+        pcm2d = np.ascontiguousarray(pcm2d, np.int16)
+        n, ns = pcm2d.shape
+        T = ns // 160
+        seq_a = np.asarray(seq, np.int32)
+        par = None if params is None else np.ascontiguousarray(params, np.int16)
+        res = np.zeros((n, T), CASCADE_RESULT_DT) if want_results else None
+        self.lib.ref_cascade_batch.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong,
+                                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.lib.ref_cascade_batch(int(bool(fresh)), _p(seq_a), len(seq_a), _p(par), n, _p(pcm2d), ns, T, _p(states),
+                                        _p(res), _p(stage_frames))
+        if rc:
+            raise RuntimeError("ref_cascade_batch rc=%d" % rc)
+        return res
+
+
+class RefS2ICtrl:
+    """oracle/_ref/libnnsp_ref_s2ictrl.so: the reference's S2I-only controller (evb/src/s2iCntrlClass.c), unmodified."""
+
+    PATH = os.path.join(HERE, "_ref", "libnnsp_ref_s2ictrl.so")
+
+    def __init__(self):
+        if not os.path.exists(self.PATH):
+            raise FileNotFoundError(self.PATH)
+        self.lib = C.CDLL(self.PATH)
+        self.lib.ref_s2ictrl_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH)
+
+    def run(self, pcm, reset=1, thresh_prob=-1, thresh_cnts=-1):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        T = len(pcm) // 160
+        res = np.zeros(T, CASCADE_RESULT_DT)
+        rc = self.lib.ref_s2ictrl_run(int(reset), thresh_prob, thresh_cnts, _p(pcm), T, _p(res))
+        if rc:
+            raise RuntimeError("ref_s2ictrl_run rc=%d" % rc)
+        return res

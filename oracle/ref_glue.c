@@ -17,6 +17,10 @@
 #include "feature_module.h"
 #include "neural_nets.h"
 #include "nnsp_identification.h"
+#include "affine.h"
+#include "affine_acc32b.h"
+#include "lstm.h"
+#include "activation.h"
 #ifndef GLUE_DROPIN          /* internals of the reference's front end: not part of the public interface */
 #include "spectrogram_module.h"
 #include "melSpecProc.h"
@@ -61,7 +65,7 @@ int ref_model(int nn_id, void **net, const int32_t **mean, const int32_t **stdR)
 }
 
 #ifndef GLUE_DROPIN
-/* the reference's constant tables, for tests/test_tables.py */
+/* the reference's constant tables, for tests/test_tables_and_format.py */
 int ref_table(const char *name, const void **p, int *elem_bytes)
 {
     if (!strcmp(name, "stft_win")) { *p = stft_win_coeff;   *elem_bytes = 2; return 480; }
@@ -190,6 +194,56 @@ int ref_net_eval(int nn_id, const int16_t *input, int16_t *h, int32_t *c, int16_
     NeuralNetClass_exe(net, in, out, -1);            /* the real evaluation advances the state */
     save_hc(net, h, c);
     load_hc(net, hl, cl);
+    return 0;
+}
+
+/* ---- the same on a model the glue builds from an NNSPM1 container --------------------------------- */
+/* The container (nnsp_b200_model_to_blob; tests/common.py make_blob) stores every table in the layout of def_nn*.c, so a
+ * NeuralNetClass literal pointing straight into it is what the converter would have emitted. This is how the unmodified
+ * reference evaluates SYNTHETIC layer stacks (Q-format spreads, odd widths, two LSTMs, crafted weights) for the fixtures
+ * of tests/golden/make_golden_nets.py. acc32: 0 = fc_8x16 / lstm_8x16, 1 = the _acc32b twins. */
+int ref_net_eval_blob(const void *blob, long long nbytes, int acc32, const int16_t *input, int16_t *h, int32_t *c,
+                      int16_t *act, int32_t *logits)
+{
+    static NeuralNetClass net;
+    static int16_t hstate[10][1024]; static int32_t cstate[10][1024];
+    static int16_t in[512];
+    static int32_t out[512];
+    const unsigned char *p = (const unsigned char *)blob;
+    int32_t nl, rec[10];
+    int i;
+    size_t off = 8 + 8 + 24 + 320 + 400;
+    if (nbytes < (long long)off || memcmp(p, "NNSPM1\0\0", 8) != 0) return -1;
+    memcpy(&nl, p + 12, 4);
+    if (nl < 1 || nl > 10) return -1;
+    memset(&net, 0, sizeof net);
+    net.numlayers = (int8_t)nl;
+    memcpy(net.size_layer, p + 16, 22);
+    for (i = 0; i < nl; i++) {
+        memcpy(rec, p + 360 + 40 * i, 40);
+        const int is_lstm = rec[0] == 1;
+        net.net_layer_type[i] = is_lstm ? lstm : fc;
+        net.qbit_kernel[i] = (int8_t)rec[2]; net.qbit_input[i] = (int8_t)rec[3]; net.qbit_bias[i] = (int8_t)rec[4];
+        if (i + 1 < 10) net.qbit_input[i + 1] = (int8_t)rec[9];        /* neural_nets.c:108 reads qbit_input[i+1] */
+        switch (rec[1]) {
+        case 0: net.activation_type[i] = relu6;   net.act_func[i] = (void *(*)(void *, int32_t *, int))&relu6_fix; break;
+        case 1: net.activation_type[i] = ftanh;   net.act_func[i] = (void *(*)(void *, int32_t *, int))&tanh_fix; break;
+        case 2: net.activation_type[i] = sigmoid; net.act_func[i] = (void *(*)(void *, int32_t *, int))&sigmoid_fix; break;
+        default: net.activation_type[i] = linear; net.act_func[i] = (void *(*)(void *, int32_t *, int))&linear_fix; break;
+        }
+        if (is_lstm) net.layer_func[i] = acc32 ? (int *(*)())&lstm_8x16_acc32b : (int *(*)())&lstm_8x16;
+        else         net.layer_func[i] = acc32 ? (int *(*)())&fc_8x16_acc32b : (int *(*)())&fc_8x16;
+        net.pt_kernel[i] = (int8_t *)(p + off);     off += ((size_t)rec[6] + 3) & ~(size_t)3;
+        net.pt_kernel_rec[i] = (int8_t *)(p + off); off += ((size_t)rec[7] + 3) & ~(size_t)3;
+        net.pt_bias[i] = (int16_t *)(p + off);      off += ((size_t)rec[8] * 2 + 3) & ~(size_t)3;
+        net.pt_hstate[i] = hstate[i]; net.pt_cstate[i] = cstate[i];
+        if ((long long)off > nbytes) return -1;
+    }
+    memcpy(in, input, net.size_layer[0] * sizeof(int16_t));
+    shadow_layers(&net, in, h, c, act, logits);
+    load_hc(&net, h, c);
+    NeuralNetClass_exe(&net, in, out, -1);
+    save_hc(&net, h, c);
     return 0;
 }
 
@@ -333,3 +387,93 @@ int ref_cascade_run(int do_reset, const int *seq, int len_seq, const int16_t *pa
     }
     return 0;
 }
+
+/* ---- many streams through ONE controller: per-stream state saved and restored around each chunk ------------ */
+/* The reference is single-instance, so a process that serves several streams in turn has to
+ * swap the controller's whole state in and out: the controller struct, the three NNSPClass / FeatureClass instances,
+ * the PCM ring, and the LSTM state arrays of the three model tables. bench.py's CPU arms use this to keep every sampled
+ * stream in the same steady state as the GPU's (which stage it is in, its time-out counters), step after step. */
+#ifndef GLUE_DROPIN
+extern PcmBufClass pcmbuf_inst;
+extern int16_t PCM_BUFFER[];
+#define GLUE_RING_SAMPLES (160 * 100)           /* PcmBufClass.c:6-7 */
+#define GLUE_HC 128
+
+typedef struct {
+    nnCntrlClass cntrl;
+    NNSPClass insts[3];
+    FeatureClass feats[3];
+    PcmBufClass ring;
+    int16_t pcm[GLUE_RING_SAMPLES];
+    int16_t h[3][GLUE_HC];
+    int32_t c[3][GLUE_HC];
+} glue_cascade_state;
+
+long long ref_cascade_state_bytes(void) { return (long long)sizeof(glue_cascade_state); }
+
+void ref_cascade_state_save(void *buf)
+{
+    glue_cascade_state *s = (glue_cascade_state *)buf;
+    int id;
+    s->cntrl = g_cntrl;
+    memcpy(s->insts, NNSP_INSTS, sizeof s->insts);
+    memcpy(s->feats, FEAT_INSTS, sizeof s->feats);
+    s->ring = pcmbuf_inst;
+    memcpy(s->pcm, PCM_BUFFER, sizeof s->pcm);
+    for (id = 0; id < 3; id++) {
+        void *netv; const int32_t *m, *sd;
+        ref_model(id, &netv, &m, &sd);
+        memset(s->h[id], 0, sizeof s->h[id]); memset(s->c[id], 0, sizeof s->c[id]);
+        save_hc((NeuralNetClass *)netv, s->h[id], s->c[id]);
+    }
+}
+
+void ref_cascade_state_load(const void *buf)
+{
+    const glue_cascade_state *s = (const glue_cascade_state *)buf;
+    int id;
+    g_cntrl = s->cntrl;
+    memcpy(NNSP_INSTS, s->insts, sizeof s->insts);
+    memcpy(FEAT_INSTS, s->feats, sizeof s->feats);
+    pcmbuf_inst = s->ring;
+    memcpy(PCM_BUFFER, s->pcm, sizeof s->pcm);
+    for (id = 0; id < 3; id++) {
+        void *netv; const int32_t *m, *sd;
+        ref_model(id, &netv, &m, &sd);
+        load_hc((NeuralNetClass *)netv, s->h[id], s->c[id]);
+    }
+}
+
+/* n_streams streams, n_frames each, through nnCntrlClass_exec; states: n_streams blobs of ref_cascade_state_bytes()
+ * (fresh != 0: every stream starts from a new controller). stage_frames[3] (may be null) counts frames per NNSP id. */
+int ref_cascade_batch(int fresh, const int *seq, int len_seq, const int16_t *params10, int n_streams,
+                      const int16_t *pcm, long long stream_stride, int n_frames, void *states,
+                      glue_cascade_result *results, long long *stage_frames)
+{
+    int s;
+    const long long sb = ref_cascade_state_bytes();
+    for (s = 0; s < n_streams; s++) {
+        char *st = (char *)states + (size_t)s * sb;
+        const int16_t *x = pcm + (size_t)s * stream_stride;
+        int rc;
+        if (fresh) rc = ref_cascade_run(1, seq, len_seq, params10, x, 0, 0, 0, 0, 0, 0, 0, 0);
+        else { ref_cascade_state_load(st); rc = 0; }
+        if (rc) return rc;
+        if (results || stage_frames) {
+            static glue_cascade_result tmp[4096];
+            int t0;
+            for (t0 = 0; t0 < n_frames; t0 += 4096) {
+                const int n = (n_frames - t0) < 4096 ? (n_frames - t0) : 4096;
+                int t;
+                glue_cascade_result *r = results ? results + (size_t)s * n_frames + t0 : tmp;
+                ref_cascade_run(0, seq, len_seq, params10, x + (size_t)t0 * 160, n, r, 0, 0, 0, 0, 0, 0);
+                if (stage_frames) for (t = 0; t < n; t++) stage_frames[r[t].stage_id]++;
+            }
+        } else {
+            ref_cascade_run(0, seq, len_seq, params10, x, n_frames, 0, 0, 0, 0, 0, 0, 0);
+        }
+        ref_cascade_state_save(st);
+    }
+    return 0;
+}
+#endif

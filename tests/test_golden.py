@@ -3,7 +3,8 @@ Runs anywhere (no reference sources, no GPU)."""
 import numpy as np
 import pytest
 
-from common import MODEL_NAME, TAP_NAMES, golden, res4, sha
+from common import (GOLDEN_NETS, MODEL_NAME, NET_CASES, NET_CRAFTED, TAP_NAMES, golden, net_case_blob, net_case_dims,
+                    res4, sha)
 
 G = golden()
 
@@ -82,3 +83,22 @@ def test_cascade(oracle, nb):
         assert [sha(tp.feat), sha(tp.c), sha(tp.post), sha(tp.logmel)] == list(G["casc_sha"][s])
     stages = np.unique(G["casc_res"][:, :, 0])
     assert set(stages.tolist()) == {0, 1, 2}
+
+
+@pytest.mark.parametrize("acc32", [False, True])
+@pytest.mark.parametrize("case", NET_CASES + NET_CRAFTED, ids=[c[0] for c in NET_CASES + NET_CRAFTED])
+def test_synthetic_and_crafted_networks(oracle, case, acc32):
+    """NeuralNetClass_exe of the unmodified reference on synthetic / crafted layer stacks (tests/golden/make_golden_nets.py):
+    Q-format spreads, odd widths, two LSTMs, shift_32b saturation, bias << 30 wrap, tanh_fix past 5.0, cell sat32."""
+    import hashlib
+    N = np.load(GOLDEN_NETS)
+    blob = net_case_blob(case, acc32)
+    key = "%s_%s" % (case[0], "acc32" if acc32 else "acc64")
+    assert hashlib.sha256(blob).hexdigest() == str(N[key + "_blob_sha"][0]), "make_blob changed: regenerate the fixture"
+    a_s, h_s, n_o = net_case_dims(case)
+    m = oracle.load_model(blob, acc32)
+    for i, x in enumerate(N["x"]):
+        act, logits, h, c = oracle.net_eval(m, x, N[key + "_h0"][i, :max(h_s, 1)], N[key + "_c0"][i, :max(h_s, 1)])
+        assert (act == N[key + "_act"][i]).all() and (logits == N[key + "_logits"][i]).all(), (key, i)
+        if h_s:
+            assert (h[:h_s] == N[key + "_h1"][i]).all() and (c[:h_s] == N[key + "_c1"][i]).all(), (key, i)

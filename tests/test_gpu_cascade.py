@@ -265,3 +265,25 @@ def test_cascade_many_pipelined_calls_equal_sequential_one_shot(nb, seed):
     for x in d_pcm + d_res:
         x.free()
     c.close()
+
+
+def test_s2i_only_controller_on_the_gpu(nb):
+    """evb/src/s2iCntrlClass.c (unmodified reference, oracle/_ref/libnnsp_ref_s2ictrl.so) == nnsp_b200_cascade with
+    seq = {s2i}, frs_vbufBk_s2i = 0 -- both cascade paths, detections and the resets that follow them included."""
+    from oracle.pyoracle import RefS2ICtrl
+    if not RefS2ICtrl.available():
+        pytest.skip("oracle/_ref/libnnsp_ref_s2ictrl.so not built")
+    R = RefS2ICtrl()
+    x = np.concatenate([nb.synth_pcm(12, 700, first_stream=17), nb.synth_pcm(1, 700, first_stream=5)])
+    models = _models(nb)
+    for th_cnt in (4, 1):
+        want = [R.run(x[s], reset=1, thresh_cnts=th_cnt) for s in range(len(x))]
+        assert sum(int(w["detected"].sum()) for w in want) > 0
+        for path in ("sorted", "sequential"):
+            c = nb.Cascade(models, len(x), seq=(0,), params=dict(frs_vbufBk_s2i=0, thresh_cnts_s2i=th_cnt))
+            c.set_path(path)
+            got = np.concatenate([c.exec(x[:, :300 * 160]), c.exec(x[:, 300 * 160:])], axis=1)
+            c.close()
+            for s in range(len(x)):
+                for f in ("stage_id", "pos_after", "detected", "outputs"):
+                    assert (got[s][f] == want[s][f]).all(), (path, th_cnt, s, f)

@@ -5,23 +5,13 @@ else IMMA in the time loop, else dp2a -- so the fallbacks are exercised too."""
 import numpy as np
 import pytest
 
-from common import make_blob
+from common import NET_CASES, make_blob
 
 pytestmark = pytest.mark.gpu
 TAPS = ["feat", "act", "logits", "hstate", "cstate", "post"]
 ORACLE_TAP = dict(feat="feat", act="act", logits="logits", hstate="h", cstate="c", post="post")
 
-CASES = [
-    # nn_id, sizes, types (0 fc, 1 lstm), acts (0 relu6 1 tanh 2 sigmoid 3 linear), qk, qi, qb
-    ("fc_only", 1, (240, 33, 17, 2), (0, 0, 0), (1, 0, 3), (7, 5, 6), (8, 15, 12), (14, 15, 15)),
-    ("two_lstm", 2, (240, 24, 20, 12, 9, 2), (0, 1, 0, 1, 0), (1, 1, 2, 1, 3), (6, 5, 5, 5, 6), (8, 15, 15, 15, 15), (13, 13, 15, 14, 15)),
-    ("lstm_wide", 0, (240, 40, 100, 41), (0, 1, 0), (0, 1, 3), (7, 4, 5), (8, 15, 15), (14, 14, 14)),        # 13 unit groups
-    ("lstm_requant", 0, (240, 40, 100, 41), (0, 1, 0), (0, 1, 3), (7, 4, 5), (8, 12, 15), (14, 14, 14)),     # qbit_input_rec != qbit_input
-    ("lstm_last_fc_sigmoid", 1, (240, 10, 6, 2), (0, 1, 0), (2, 1, 3), (7, 6, 7), (8, 15, 15), (15, 12, 15)),
-    ("odd_widths", 2, (240, 7, 5, 3, 2), (0, 1, 0, 0), (1, 1, 0, 3), (7, 5, 5, 7), (8, 15, 15, 12), (14, 13, 15, 15)),
-    ("big_shifts", 1, (240, 16, 16, 2), (0, 1, 0), (1, 1, 3), (3, 7, 2), (8, 15, 15), (6, 15, 4)),
-    ("bias_shift_18", 1, (240, 16, 16, 2), (0, 1, 0), (1, 1, 3), (12, 7, 2), (8, 15, 15), (2, 15, 4)),  # layer 0 needs the 64-bit finish
-]
+CASES = NET_CASES
 
 
 @pytest.mark.parametrize("acc32", [False, True])

@@ -72,7 +72,7 @@ def test_text_reader_rejects_malformed_tables(nb):
 @pytest.mark.skipif(not have_reference_tree(), reason="needs /root/reference")
 def test_reference_table_files_parse_to_the_compiled_models(nb):
     """The three shipped def_nn*.c files, read as text, equal the models obtained by COMPILING them
-    (tests/golden/models/*.nnspm were exported from the compiled reference objects); s2i and kws ship with
+    (nnsp_b200/models/*.nnspm were exported from the compiled reference objects); s2i and kws ship with
     CRLF line ends and stray blank lines. The VAD file is reproduced byte for byte (modulo CRLF) by the writer."""
     nb = nb
     for name, (src, nn_id, blob) in FILES.items():

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from common import TAP_NAMES, have_reference_tree
-from oracle.pyoracle import RefLib
+from oracle.pyoracle import RefLib, RefS2ICtrl
 
 pytestmark = pytest.mark.skipif(not RefLib.available(False), reason="oracle/_ref not built (needs /root/reference)")
 WAVS = "/root/reference/python/test_wavs"
@@ -89,3 +89,60 @@ def test_reset_of_a_live_instance(oracle, nb):
     R.nnsp_run(1, x[:50 * 160], reset=1, taps=False)
     r2, t2 = R.nnsp_run(1, x[50 * 160:], reset=2)
     assert (r1 == r2).all() and not _same(t1, t2)
+
+
+@pytest.mark.skipif(not RefS2ICtrl.available(), reason="oracle/_ref/libnnsp_ref_s2ictrl.so not built")
+def test_s2i_only_controller_is_the_single_stage_cascade(oracle, nb):
+    """evb/src/s2iCntrlClass.c:92-122 (compiled unmodified) == nnCntrlClass semantics with seq = {s2i}, look-back 0:
+    the equivalence INTEGRATION.md claims, pinned frame by frame (detections, outputs, resets on detection)."""
+    R = RefS2ICtrl()
+    x = np.concatenate([nb.synth_pcm(12, 700, first_stream=17), nb.synth_pcm(1, 700, first_stream=5)])   # 27, 28 and 5 detect
+    par = oracle.default_params()
+    par[2] = 0                       # frs_vbufBk_s2i: the S2I-only controller reads the newest frame (s2iCntrlClass.c:105-109)
+    om = [oracle.model(i) for i in range(3)]
+    detections = 0
+    for th_cnt in (4, 1):
+        par[5] = th_cnt              # thresh_cnts_s2i
+        for s in range(len(x)):
+            want = R.run(x[s], reset=1, thresh_cnts=th_cnt)
+            got, _, _ = oracle.cascade_run(om, x[s], seq=(0,), params=par, taps=False)
+            for f in ("stage_id", "pos_after", "detected", "outputs"):
+                assert (got[f] == want[f]).all(), (s, f)
+            detections += int(want["detected"].sum())
+    assert detections > 0            # the controller really reset instances on the way
+
+
+def test_controller_state_swap_keeps_streams_apart(nb):
+    """ref_cascade_batch (the CPU arm of bench.py): streams served in turn by the one reference controller, state swapped
+    in and out per chunk, give exactly what each stream gives alone in one go."""
+    R = RefLib(False)
+    S, T = 5, 260
+    x = nb.synth_pcm(S, T, first_stream=18)
+    states = np.zeros((S, R.cascade_state_bytes()), np.uint8)
+    parts = [R.cascade_batch(x[:, :100 * 160], states, fresh=True, want_results=True),
+             R.cascade_batch(x[:, 100 * 160:101 * 160], states, fresh=False, want_results=True),
+             R.cascade_batch(x[:, 101 * 160:], states, fresh=False, want_results=True)]
+    got = np.concatenate(parts, axis=1)
+    for s in range(S):
+        want, _, _ = R.cascade_run(x[s], taps=False)
+        assert (got[s] == want).all(), s
+
+
+@pytest.mark.parametrize("acc32", [False, True])
+def test_synthetic_network_through_the_reference(oracle, acc32):
+    """restatement == unmodified reference on a synthetic two-LSTM stack, fresh random inputs (not the fixture's)."""
+    from common import NET_CASES, NET_CRAFTED, net_case_blob, net_case_dims
+    R = RefLib(False)
+    rng = np.random.default_rng(99)
+    for case in (NET_CASES[1], NET_CRAFTED[0], NET_CRAFTED[2]):
+        blob = net_case_blob(case, acc32)
+        a_s, h_s, n_o = net_case_dims(case)
+        m = oracle.load_model(blob, acc32)
+        for k in range(6):
+            x = rng.integers(-32768, 32768, 240).astype(np.int16)
+            h = rng.integers(-32768, 32768, h_s).astype(np.int16)
+            c = rng.integers(-2 ** 31, 2 ** 31, h_s).astype(np.int32)
+            a = oracle.net_eval(m, x, h, c)
+            b = R.net_eval_blob(blob, acc32, x, h, c, a_s, n_o)
+            for u, v in zip(a, b):
+                assert (u[: len(v)] == v).all(), (case[0], k)
