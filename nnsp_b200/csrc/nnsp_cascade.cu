@@ -85,6 +85,7 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
     uint32_t *wimg = reinterpret_cast<uint32_t *>(smem_raw + off_w);
     int16_t *bimg = reinterpret_cast<int16_t *>(smem_raw + off_b);
     const CascadeDev &cd = a.cd;
+    if (a.replay_list && a.replay_ctl[0] == 0) return;            /* fallback after the stage-sorted rounds: nothing left */
 
     load_feat_tables(&sm.ft, a.tables, threadIdx.x, CS_THREADS);
     for (int i = threadIdx.x; i < 384; i += CS_THREADS) sm.tanh_lut[i] = a.tables->tanh_lut[i];
@@ -301,12 +302,13 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
 
 
 /* ======================================================================================================== */
-/* cascade_replay_kernel: the replay after the stage-sorted pass, four warps per stream                        */
+/* cascade_replay_kernel: what is left after the stage-sorted rounds, NNSP_CR_GW (two) warps per stream          */
 /* ======================================================================================================== */
 /* Same per-frame semantics as cascade_kernel (see there for the reference lines), narrow models only, no taps (a call
  * with taps never takes the stage-sorted pass). The replay lasts as long as its longest remainder, so the chain per
- * stream is what counts: a group of four warps shares one stream (net_forward_group), 4 groups per CTA next to the
- * three weight images; streams are handed out to groups dynamically, longest remainder first. */
+ * stream is what counts: a group of NNSP_CR_GW warps (two; four leave too few streams in flight) shares one stream
+ * (net_forward_group), 16 / NNSP_CR_GW groups per CTA next to the three weight images; streams are handed out to groups
+ * dynamically, longest remainder first. */
 #ifndef NNSP_CR_GW
 #define NNSP_CR_GW 2
 #endif
@@ -330,6 +332,7 @@ cascade_replay_kernel(CascadeArgs a, int off_w, int off_b)
     uint32_t *wimg = reinterpret_cast<uint32_t *>(smem_raw + off_w);
     int16_t *bimg = reinterpret_cast<int16_t *>(smem_raw + off_b);
     const CascadeDev &cd = a.cd;
+    if (a.replay_ctl[0] == 0) return;                             /* nothing left after the stage-sorted rounds */
 
     load_feat_tables(&sm.ft, a.tables, threadIdx.x, CR_THREADS);
     for (int i = threadIdx.x; i < 384; i += CR_THREADS) sm.tanh_lut[i] = a.tables->tanh_lut[i];
@@ -514,49 +517,148 @@ cascade_replay_kernel(CascadeArgs a, int off_w, int off_b)
 }
 
 /* ======================================================================================================== */
-/* stage-sorted pass: the scan-split network kernels (nnsp_split.cu) over the streams of each (stage, phase)   */
+/* stage-sorted rounds: the scan-split network kernels (nnsp_split.cu) over the streams of each live model      */
 /* ======================================================================================================== */
-/* Within a call most streams stay in the stage they are in. Streams are therefore sorted by (live model, phase of
- * the stride-2 gate) on the device, each group runs through the batched scan-split kernels as if nothing changed,
- * and cascade_post_kernel then walks every stream's frames through the controller (nnCntrlClass.c:172-269). At
- * the first frame where the controller leaves the instance, that instance is reset -- which is all the reference
- * keeps of it (plus context row 5) -- the speculative rest is dropped, and the stream's remaining frames are
- * replayed by cascade_kernel from t0[s]. Streams whose instance is younger than two frames (its STFT buffer
- * still holds zeros) take the sequential kernel for the whole call. */
-constexpr int CG_GROUPS = 6;                        /* group = id * 2 + first inference frame (0 or 1) */
+/* Within a call most streams stay in the stage they are in. Round 0 sorts the streams by live model on the device,
+ * runs every group through the batched scan-split kernels as if nothing changed, and cascade_post_kernel then walks
+ * every stream's frames through the controller (nnCntrlClass.c:172-269). At the first frame where the controller
+ * leaves the instance, that instance is reset -- which is all the reference keeps of it (plus context row 5) -- the
+ * speculative rest is dropped, and the stream is queued for the NEXT ROUND with the instance it enters: round r + 1 is
+ * the same three kernels over the queued streams, each starting at its own frame (tstart[s]; the kernels take per-row
+ * start frames and inference counts). A stream takes one round per stage change inside the call; what is still queued
+ * after the last round (CS_MAX_ROUNDS) goes to the sequential kernel. The first two frames of a fresh instance see a
+ * partly zero STFT buffer (spectrogram_module.c:25-31): cascade_fix_kernel computes those log-mel rows on the side. */
+constexpr int CG_GROUPS = 6;                        /* plane tiles reserved per slice beyond S/16 (one partial tile per group + slack) */
 constexpr int CPOST_THREADS = 64, CPOST_KCH = 64;
+constexpr int CS_MAX_ROUNDS = 4;
+/* per-slice control block (ints, zeroed at the start of a call): round r at CTL_ROUND * r */
+constexpr int CTL_ROUND = 12;                       /* [0..2] group sizes by model id, [3..5] first plane tile of the group, */
+constexpr int CTL_NEXT = 6, CTL_FIX = 7;            /* [6] streams queued for the next round, [7] streams that need fix rows */
+constexpr int CTL_REPLAY = CTL_ROUND * CS_MAX_ROUNDS;   /* [0] streams left for the sequential kernel, [1] its cursor          */
+constexpr int CTL_INTS = 64;
 
-__global__ void cascade_classify_kernel(StreamState st, CascadeDev cd, int s0, int ns, int S, int *list, int *count, int *t0,
-                                        int *replay_list)
+struct RoundArrays {                  /* per stream, valid during one call */
+    int *t0;                          /* -1: live in the current round; T + 1: lived through the call (context rebuild);
+                                         else: first frame the sequential kernel still has to process                   */
+    int *tstart, *tb, *age0;          /* see SplitGroup */
+    int32_t *lmfix;                   /* [S][2][40] */
+};
+
+__global__ void cascade_classify_kernel(StreamState st, CascadeDev cd, int s0, int ns, int S, int *list, int *ctl, RoundArrays ra,
+                                        int *fix_list)
 {
     const int si = blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= ns) return;
     const long long s = s0 + si;
     const int pos = st.casc[s * CS_N + CS_POS], age = st.casc[s * CS_N + CS_AGE];
-    if (age < 2) { t0[s] = 0; replay_list[s0 + atomicAdd(&count[8], 1)] = (int)s; return; }
     const int id = cd.seq[pos];
-    const int first = (st.scal[s * SC_N + SC_SLIDES] == 1) ? 0 : 1;
-    const int g = id * 2 + first;
-    const int idx = atomicAdd(&count[g], 1);
-    list[(long long)g * S + s0 + idx] = (int)s;
-    t0[s] = -1;
+    ra.tb[s] = 0;
+    ra.tstart[s] = (st.scal[s * SC_N + SC_SLIDES] == 1) ? 0 : 1;     /* nn_speech.c:84: the stride-2 gate */
+    ra.age0[s] = age;
+    ra.t0[s] = -1;
+    list[(long long)id * S + s0 + atomicAdd(&ctl[id], 1)] = (int)s;
+    if (age < 2) fix_list[s0 + atomicAdd(&ctl[CTL_FIX], 1)] = (int)s;
 }
-__global__ void cascade_offsets_kernel(int *count, int *tile_off)
+__global__ void cascade_offsets_kernel(int *ctl)
 {
-    count[9] = 0;                                                     /* replay cursor */
     int o = 0;
-    for (int g = 0; g < CG_GROUPS; g++) { tile_off[g] = o; o += (count[g] + 15) >> 4; }
+    for (int g = 0; g < 3; g++) { ctl[3 + g] = o; o += (ctl[g] + 15) >> 4; }
+}
+
+/* round r >= 1: the streams queued by the previous round's walk, sorted by (model they entered, start frame) so that a
+ * 16-stream tile holds streams of similar length; one CTA, counting sort over 3 x 256 buckets */
+constexpr int CSORT_THREADS = 1024, CSORT_BUCKETS = 1024, CRG_NB = 256;
+__global__ void __launch_bounds__(CSORT_THREADS) cascade_regroup_kernel(StreamState st, CascadeDev cd, const int *__restrict__ pend,
+                                                                       const int *__restrict__ ctl_prev, int *ctl, int *list, int S, int s0,
+                                                                       RoundArrays ra, int T)
+{
+    __shared__ int hist[3 * CRG_NB];
+    __shared__ int gstart[4];
+    const int n = ctl_prev[CTL_NEXT];
+    if (n == 0) return;                                               /* (ctl of this round stays zero: every kernel of the round leaves at once) */
+    for (int i = threadIdx.x; i < 3 * CRG_NB; i += CSORT_THREADS) hist[i] = 0;
+    __syncthreads();
+    auto bucket = [&](int s) {
+        const int id = cd.seq[st.casc[(long long)s * CS_N + CS_POS]];
+        const long long b = (long long)ra.tstart[s] * CRG_NB / (T + 1);
+        return id * CRG_NB + (int)(b < 0 ? 0 : (b >= CRG_NB ? CRG_NB - 1 : b));
+    };
+    for (int i = threadIdx.x; i < n; i += CSORT_THREADS) atomicAdd(&hist[bucket(pend[i])], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {                                            /* exclusive scan of the 768 counts by one warp */
+        int carry = 0;
+        for (int base = 0; base < 3 * CRG_NB; base += 32) {
+            if ((base % CRG_NB) == 0 && threadIdx.x == 0) gstart[base / CRG_NB] = carry;
+            const int v = hist[base + threadIdx.x];
+            int x = v;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((int)threadIdx.x >= o) x += y; }
+            hist[base + threadIdx.x] = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (threadIdx.x == 0) {
+            gstart[3] = carry;
+            int o = 0;
+            for (int g = 0; g < 3; g++) { const int c = gstart[g + 1] - gstart[g]; ctl[g] = c; ctl[3 + g] = o; o += (c + 15) >> 4; }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += CSORT_THREADS) {
+        const int s = pend[i], b = bucket(s), id = b / CRG_NB;
+        list[(long long)id * S + s0 + (atomicAdd(&hist[b], 1) - gstart[id])] = s;
+    }
+}
+
+/* log-mel rows of the first two frames of a fresh instance: window = [0, (second frame ? raw frame tf-1 : 0), raw frame tf]
+ * with tf = t - look-back. One half-warp per (stream, life frame); streams from a device-side list. */
+struct FixArgs {
+    const DevTables *tables;
+    StreamState st;
+    const int16_t *pcm; long long stride;
+    const int *list, *count;
+    RoundArrays ra;
+    CascadeDev cd;
+    int T;
+};
+struct FixSmem { FeatSmemTables ft; FrameScratch fs[16]; };
+__global__ void __launch_bounds__(256) cascade_fix_kernel(FixArgs a)
+{
+    __shared__ FixSmem sm;
+    const int n = *a.count;
+    if ((int)blockIdx.x * 8 >= n) return;                             /* a warp takes both life frames of one stream */
+    load_feat_tables(&sm.ft, a.tables, threadIdx.x, 256);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, la = lane >> 4, L = lane & 15;
+    const CascadeDev &cd = a.cd;
+    const int hist_len = (cd.dmax + 2) * NNSP_B200_FRAME;
+    for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+        const long long s = a.list[i];
+        const int id = cd.seq[a.st.casc[s * CS_N + CS_POS]];
+        const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
+        const int t = a.ra.tb[s] + la - a.ra.age0[s];                 /* frame of the call with life index la */
+        const bool valid = la >= a.ra.age0[s] && t < a.T;
+        const int tf = t - d, base = (tf - 2) * NNSP_B200_FRAME, first_live = (2 - la) * NNSP_B200_FRAME;
+        const int16_t *ps = a.pcm + s * a.stride;
+        const int16_t *hs = a.st.hist + s * hist_len + hist_len;       /* hs[g], g < 0: frames before the call */
+        auto load_pair = [&](int, int p) -> uint32_t {
+            if (!valid || 2 * p < first_live) return 0u;
+            const int g = base + 2 * p;
+            return *reinterpret_cast<const unsigned int *>((g < 0) ? (hs + g) : (ps + g));
+        };
+        frame_logmel<false>(sm.ft, sm.fs[warp * 2 + la], L, load_pair, a.ra.lmfix + (s * 2 + la) * NNSP_B200_NMEL, valid, FeatDump{});
+    }
 }
 
 /* The replay is latency-bound -- one warp walks one stream frame by frame, so the kernel lasts at least as long as the
  * longest remainder. Handing the streams out longest-first (earliest t0 first) keeps a long one from being started
- * last: a counting sort of the replay list by t0, one CTA. */
-constexpr int CSORT_THREADS = 1024, CSORT_BUCKETS = 1024;
+ * last: a counting sort of the list by t0, one CTA. */
 __global__ void __launch_bounds__(CSORT_THREADS) cascade_sort_replay_kernel(const int *__restrict__ list_in, int *__restrict__ list_out,
-                                                                           const int *__restrict__ ctl, const int *__restrict__ t0, int T)
+                                                                           const int *__restrict__ count_in, int *__restrict__ ctl_out,
+                                                                           const int *__restrict__ t0, int T)
 {
     __shared__ int hist[CSORT_BUCKETS];
-    const int n = ctl[0];
+    const int n = *count_in;
+    if (threadIdx.x == 0) { ctl_out[0] = n; ctl_out[1] = 0; }
+    if (n == 0) return;
     for (int i = threadIdx.x; i < CSORT_BUCKETS; i += CSORT_THREADS) hist[i] = 0;
     __syncthreads();
     auto bucket = [&](int s) { const long long b = (long long)t0[s] * CSORT_BUCKETS / (T + 1); return (int)(b < 0 ? 0 : (b >= CSORT_BUCKETS ? CSORT_BUCKETS - 1 : b)); };
@@ -583,15 +685,19 @@ struct CascadePostArgs {
     const int32_t *logmel;
     const int32_t *dec;
     int dec_stride;
-    int *t0;
-    int *replay_list, *replay_count;
+    RoundArrays ra;
+    const int *list, *count;         /* the round's streams (null: the range s0 .. s0 + ns - 1, round 0) */
+    int *next_list, *next_count;     /* streams that change stage are queued here for the next round */
     int s0, ns, T;
     nnsp_b200_cascade_result *results;
     CascadeDev cd;
 };
 
-__device__ __forceinline__ const int32_t *cascade_lm_row(const CascadePostArgs &a, long long s, int fr)
+/* log-mel row the instance of stream s reads at frame f of the call (f >= its tb): a fix row during its first two frames */
+__device__ __forceinline__ const int32_t *cascade_lm_row(const CascadePostArgs &a, long long s, int f, int d, int tb, int age0)
 {
+    const int la = f - tb + age0, fr = f - d;
+    if (la < 2) return a.ra.lmfix + (s * 2 + la) * NNSP_B200_NMEL;
     return (fr >= 0) ? a.logmel + (s * a.T + fr) * NNSP_B200_NMEL
                      : a.st.lmhist + (s * a.cd.dmax + a.cd.dmax + fr) * NNSP_B200_NMEL;
 }
@@ -599,11 +705,17 @@ __device__ __forceinline__ const int32_t *cascade_lm_row(const CascadePostArgs &
 __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePostArgs a)
 {
     __shared__ int32_t dsm[CPOST_THREADS][CPOST_KCH + 1];
+    __shared__ int ssid[CPOST_THREADS];
     const CascadeDev &cd = a.cd;
+    const int nsel = a.list ? *a.count : a.ns;
     const int si0 = blockIdx.x * CPOST_THREADS, si = si0 + threadIdx.x;
-    const long long s = a.s0 + (si < a.ns ? si : 0);
-    bool live = si < a.ns && a.t0[s] < 0;                             /* took part in the stage-sorted pass */
+    if (si0 >= nsel) return;
+    const bool mine = si < nsel;
+    const long long s = a.list ? a.list[mine ? si : si0] : (long long)a.s0 + (mine ? si : si0);
+    ssid[threadIdx.x] = (int)s;
+    bool live = mine;
     const int T = a.T;
+    const int tb = a.ra.tb[s], ts = a.ra.tstart[s], age0 = a.ra.age0[s];
     int pos = a.st.casc[s * CS_N + CS_POS];
     int cnt_kws = a.st.casc[s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[s * CS_N + CS_CNT_S2I];
     const int id = cd.seq[pos];
@@ -621,27 +733,27 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
         for (int i = 0; i < 8; i++) cnt[i] = sc[SC_CNT0 + i];
         last = sc[SC_ARGMAX_LAST]; slides = sc[SC_SLIDES];
     }
-    const int first = (slides == 1) ? 0 : 1;
-    const int n_inf = (T > first) ? (T - first + 1) / 2 : 0;
+    const int n_inf = (ts < T) ? (T - ts + 1) >> 1 : 0;               /* inferences of this stream's round: frames ts, ts + 2, ... */
     const int n_inf_max = (T + 1) / 2;
-    const int nstr = min(CPOST_THREADS, a.ns - si0);
-    int t = 0, t_exit = -1, next_pos_exit = 0;
+    const int nstr = min(CPOST_THREADS, nsel - si0);
+    int t = tb, t_exit = -1, next_pos_exit = 0;
+    __syncthreads();
 
     for (int kc = 0; kc == 0 || kc < n_inf_max; kc += CPOST_KCH) {
         const int nk = min(CPOST_KCH, n_inf_max - kc);
         __syncthreads();
         for (int e = threadIdx.x; e < nstr * nk; e += CPOST_THREADS) {
             const int rr = e / nk, kk = e - rr * nk;
-            dsm[rr][kk] = a.dec[(size_t)(a.s0 + si0 + rr) * a.dec_stride + kc + kk];
+            dsm[rr][kk] = a.dec[(size_t)ssid[rr] * a.dec_stride + kc + kk];
         }
         __syncthreads();
-        /* frames whose inference index lies in this round */
-        const int t_end = (kc + CPOST_KCH < n_inf) ? first + 2 * (kc + CPOST_KCH) : T;
+        /* frames whose inference index lies in this round of the staging loop */
+        const int t_end = (kc + CPOST_KCH < n_inf) ? ts + 2 * (kc + CPOST_KCH) : T;
         if (live) {
             for (; t < t_end; t++) {
-                const bool ran = (t >= first) && (((t - first) & 1) == 0);                 /* nn_speech.c:84 */
+                const bool ran = (t >= ts) && (((t - ts) & 1) == 0);                       /* nn_speech.c:84 */
                 if (ran) {
-                    const int dv = dsm[threadIdx.x][((t - first) >> 1) - kc];
+                    const int dv = dsm[threadIdx.x][((t - ts) >> 1) - kc];
                     if (id == NNSP_B200_ID_S2I) {                                           /* s2i_post_proc, nn_speech.c:146-189 */
                         const int ai = dv & 0xff;
                         trig = 0; out0 = 0; out1 = 0; out2 = 0;
@@ -699,13 +811,13 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
         }
         if (nk <= 0) break;
     }
-    if (si >= a.ns || a.t0[s] >= 0) return;                           /* sequential-only stream */
+    if (!mine) return;
     const MmaModel &M = *a.model[id];
     int16_t *ctx = a.st.ctx + s * 240;
     if (t_exit >= 0) {
         /* NNSPClass_reset of the instance the controller leaves (nn_speech.c:57-72): its newest context row stays
          * behind as that instance's stale row 5 (feature_module.c:39-42) ... */
-        const int32_t *row = cascade_lm_row(a, s, t_exit - d);
+        const int32_t *row = cascade_lm_row(a, s, t_exit, d, tb, age0);
         int16_t *stale = a.stale + (s * 3 + id) * 40;
         for (int i = 0; i < 40; i++) stale[i] = standardise(row[i], M.mean[i], M.stdR[i], M.feat_rshift);
         /* ... and the instance entered starts from ITS reset state plus ITS stale row */
@@ -720,10 +832,13 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
         for (int i = 0; i < 8; i++) cnt[i] = 0;
         a.st.casc[s * CS_N + CS_POS] = (uint16_t)next_pos_exit;
         a.st.casc[s * CS_N + CS_AGE] = 0;
-        a.t0[s] = t_exit + 1;
-        if (t_exit + 1 < T) a.replay_list[a.s0 + atomicAdd(a.replay_count, 1)] = (int)s;
+        a.ra.t0[s] = t_exit + 1;
+        a.ra.tb[s] = t_exit + 1; a.ra.tstart[s] = t_exit + 1; a.ra.age0[s] = 0;       /* a fresh instance: slides == 1 (nn_speech.c:62) */
+        if (t_exit + 1 < T) a.next_list[a.s0 + atomicAdd(a.next_count, 1)] = (int)s;
     } else {
-        a.t0[s] = T + 1;                       /* lived through the call: cascade_ctx_kernel rebuilds its context */
+        a.ra.t0[s] = T + 1;                    /* lived through the call: cascade_ctx_kernel rebuilds its context */
+        const int age = age0 + (T - tb);
+        a.st.casc[s * CS_N + CS_AGE] = (uint16_t)(age < 2 ? age : 2);
     }
     a.st.casc[s * CS_N + CS_CNT_KWS] = (uint16_t)cnt_kws;
     a.st.casc[s * CS_N + CS_CNT_S2I] = (uint16_t)cnt_s2i;
@@ -739,18 +854,20 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
     }
 }
 
-/* context of the instances that lived through the call (t0 == T + 1): the newest six standardised rows of
- * (old rows ++ this call's rows, read with the instance's look-back); a warp per stream */
+/* context of the instances that lived through the call (t0 == T + 1): the newest six standardised rows of (the rows the
+ * instance had when its life in this call began ++ the rows of its frames tb .. T-1, read with its look-back); a warp
+ * per stream */
 __global__ void __launch_bounds__(256) cascade_ctx_kernel(CascadePostArgs a)
 {
     const int si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (si >= a.ns) return;
     const long long s = a.s0 + si;
     const int T = a.T;
-    if (a.t0[s] != T + 1) return;
+    if (a.ra.t0[s] != T + 1) return;
     const CascadeDev &cd = a.cd;
     const int id = cd.seq[a.st.casc[s * CS_N + CS_POS]];
     const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
+    const int tb = a.ra.tb[s], age0 = a.ra.age0[s];
     const MmaModel &M = *a.model[id];
     int16_t *ctx = a.st.ctx + s * 240;
     int16_t v[8];
@@ -760,7 +877,8 @@ __global__ void __launch_bounds__(256) cascade_ctx_kernel(CascadePostArgs a)
         v[k] = 0;
         if (e < 240) {
             const int j = e / 40, i = e - j * 40, f = T - 6 + j;
-            v[k] = (f >= 0) ? standardise(cascade_lm_row(a, s, f - d)[i], M.mean[i], M.stdR[i], M.feat_rshift) : ctx[(j + T) * 40 + i];
+            v[k] = (f >= tb) ? standardise(cascade_lm_row(a, s, f, d, tb, age0)[i], M.mean[i], M.stdR[i], M.feat_rshift)
+                             : ctx[(6 + f - tb) * 40 + i];
         }
     }
     __syncwarp();
@@ -817,7 +935,7 @@ struct nnsp_b200_cascade {
     nnsp_b200_cascade_result *d_res = nullptr;
     size_t smem_total = 0; int off_w = 0, off_b = 0;
     bool narrow = false;                      /* which shape of the sequential kernel (CsNarrow / CsWide) */
-    bool replay_coop = true;                  /* replay by cascade_replay_kernel (four warps per stream); NNSP_B200_REPLAY_COOP=0: one warp per stream */
+    bool replay_coop = true;                  /* what the rounds leave goes to cascade_replay_kernel (NNSP_CR_GW warps per stream); NNSP_B200_REPLAY_COOP=0: one warp per stream */
     size_t smem_replay = 0; int off_w_replay = 0;
     cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
     bool ev_valid = false;
@@ -826,11 +944,13 @@ struct nnsp_b200_cascade {
     bool split_ok = false;
     int path = 0;                              /* 0 auto, 1 sequential kernel only, 2 stage-sorted pass + replay */
     int pa_max = 0;
-    int *grp_list = nullptr, *grp_count = nullptr, *grp_tile_off = nullptr, *t0 = nullptr, *replay_list = nullptr, *replay_sorted = nullptr;
+    int *grp_list = nullptr, *ctl = nullptr, *fix_list = nullptr, *pend[2] = { nullptr, nullptr }, *replay_sorted = nullptr;
+    RoundArrays ra{};
+    int rounds = 3;                            /* stage-sorted rounds per call (1 .. CS_MAX_ROUNDS); NNSP_B200_CASCADE_ROUNDS */
     uint8_t *planes[2] = { nullptr, nullptr };
     int32_t *dec = nullptr;
     long long split_cap_T = 0;
-    cudaStream_t gs[CG_GROUPS] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* one per (model, phase) group */
+    cudaStream_t gs[4][3] = {};                /* per pipeline stream (3 host-call streams + the device-call stream): one per model group */
     /* device-buffer calls are pipelined like the batched path: front end + PCM history roll of call N+1 on `stream`,
      * controller / network work of call N on `nn_stream`; log-mel rows and PCM history are double buffered */
     cudaStream_t nn_stream = nullptr;
@@ -839,7 +959,7 @@ struct nnsp_b200_cascade {
     unsigned pipe = 0;
     int32_t *logmel2 = nullptr;                /* second log-mel buffer */
     int16_t *hist2 = nullptr;                  /* second PCM history buffer */
-    cudaEvent_t ev_fork = nullptr, ev_join[CG_GROUPS] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev_fork[4] = {}, ev_join[4][3] = {};
     /* asynchronous host-buffer calls: one completion event per pipeline stream, a ring of CS_HOST_RING calls */
     cudaEvent_t host_ev[CS_HOST_RING][3] = {};
     long long host_seq = 0;
@@ -914,61 +1034,83 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
     a.s0 = s0; a.ns = ns; a.T = T; a.results = results; a.cd = c->cd;
     if (taps) a.taps = *taps;
     if (cascade_use_split(c, taps)) {
-        /* stage-sorted pass: sort the slice's streams by (live model, inference phase) on the device ... */
-        int *count = c->grp_count + slice * 16, *toff = c->grp_tile_off + slice * 8;   /* count[8], [9]: replay length, cursor */
-        NNSP_CUDA(cudaMemsetAsync(count, 0, 16 * sizeof(int), st));
-        cascade_classify_kernel<<<(ns + 255) / 256, 256, 0, st>>>(c->st, c->cd, s0, ns, c->S, c->grp_list, count, c->t0, c->replay_list);
-        NNSP_LAUNCH_CHECK();
-        cascade_offsets_kernel<<<1, 1, 0, st>>>(count, toff);
-        NNSP_LAUNCH_CHECK();
-        /* ... run every group through the scan-split kernels, the groups side by side on their own CUDA streams
-         * (their chains are independent and the scans are latency-bound) ... */
+        /* stage-sorted rounds (see the kernels above). Everything is sized for the worst case and reads its true size
+         * from the slice's control block on the device: no host round trip between the rounds. */
+        int *ctl = c->ctl + slice * CTL_INTS;
+        const int lane_set = piped ? 3 : slice % 3;     /* group streams / events of this pipeline stream */
         const int n_inf_max = (T + 1) / 2;
-        NNSP_CUDA(cudaEventRecord(c->ev_fork, st));
-        for (int k = 0; k < c->cd.len_seq; k++) {
-            const int id = c->cd.seq[k];
-            for (int first = 0; first < 2; first++) {
-                const int g = id * 2 + first;
+        const int cap = sm_count(c->device);
+        NNSP_CUDA(cudaMemsetAsync(ctl, 0, CTL_INTS * sizeof(int), st));
+        cascade_classify_kernel<<<(ns + 255) / 256, 256, 0, st>>>(c->st, c->cd, s0, ns, c->S, c->grp_list, ctl, c->ra, c->fix_list);
+        NNSP_LAUNCH_CHECK();
+        cascade_offsets_kernel<<<1, 1, 0, st>>>(ctl);
+        NNSP_LAUNCH_CHECK();
+        CascadePostArgs p{};
+        for (int i = 0; i < 3; i++) p.model[i] = c->mm[i].d;
+        p.st = c->st; p.stale = c->stale; p.logmel = logmel; p.dec = c->dec; p.dec_stride = n_inf_max; p.ra = c->ra;
+        p.s0 = s0; p.ns = ns; p.T = T; p.results = results; p.cd = c->cd;
+        for (int r = 0; r < c->rounds; r++) {
+            int *ctl_r = ctl + CTL_ROUND * r, *ctl_prev = ctl + CTL_ROUND * (r - 1);
+            const int *queued = r ? c->pend[r & 1] + s0 : nullptr;        /* streams the previous round's walk queued */
+            if (r) {
+                cascade_regroup_kernel<<<1, CSORT_THREADS, 0, st>>>(c->st, c->cd, queued, ctl_prev, ctl_r, c->grp_list, c->S, s0, c->ra, T);
+                NNSP_LAUNCH_CHECK();
+            }
+            {   /* log-mel rows of the first two frames of fresh instances */
+                FixArgs f{};
+                f.tables = c->tables; f.st = c->st; f.pcm = pcm; f.stride = stride; f.ra = c->ra; f.cd = c->cd; f.T = T;
+                f.list = r ? queued : c->fix_list + s0;
+                f.count = r ? ctl_prev + CTL_NEXT : ctl + CTL_FIX;
+                int fb = (ns + 7) / 8;
+                if (fb > 4 * cap) fb = 4 * cap;
+                cascade_fix_kernel<<<fb, 256, 0, st>>>(f);
+                NNSP_LAUNCH_CHECK();
+            }
+            /* every model's group through the scan-split kernels, side by side on their own CUDA streams (independent
+             * chains, and the scans are latency-bound) */
+            NNSP_CUDA(cudaEventRecord(c->ev_fork[lane_set], st));
+            for (int k = 0; k < c->cd.len_seq; k++) {
+                const int id = c->cd.seq[k];
                 SplitGroup q{};
                 q.tables = c->tables;
-                q.list = c->grp_list + (size_t)g * c->S + s0; q.count = count + g; q.tile_off = toff + g;
+                q.list = c->grp_list + (size_t)id * c->S + s0; q.count = ctl_r + id; q.tile_off = ctl_r + 3 + id;
                 q.tile0 = (s0 >> 4) + (CG_GROUPS + 1) * slice; q.max_streams = ns;
                 q.tile_bytes = (long long)n_inf_max * 32 * c->pa_max;
-                q.T = T; q.first = first; q.n_inf = (T > first) ? (T - first + 1) / 2 : 0;
+                q.T = T; q.first = 0; q.n_inf = n_inf_max;
                 q.mode = 2; q.logmel = logmel; q.lmhist = c->st.lmhist; q.dmax = c->cd.dmax;
                 q.dback = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? c->cd.P.frs_vbufBk_kws : c->cd.P.frs_vbufBk_s2i);
                 q.ctx = c->st.ctx; q.h = c->st.h; q.c = c->st.c; q.h_stride = NNSP_B200_MAX_WIDTH;
                 q.planes0 = c->planes[0]; q.planes1 = c->planes[1];
                 q.dec = c->dec; q.dec_stride = n_inf_max;
                 q.thresh_prob = (id == NNSP_B200_ID_VAD) ? c->cd.P.thresh_prob_vad : (id == NNSP_B200_ID_KWS ? c->cd.P.thresh_prob_kws : c->cd.P.thresh_prob_s2i);
-                if (q.n_inf <= 0) continue;
-                NNSP_CUDA(cudaStreamWaitEvent(c->gs[g], c->ev_fork, 0));
-                if ((rc = launch_split_layers(c->mm[id], q, c->device, c->gs[g]))) return rc;
-                NNSP_CUDA(cudaEventRecord(c->ev_join[g], c->gs[g]));
-                NNSP_CUDA(cudaStreamWaitEvent(st, c->ev_join[g], 0));
+                q.tstart = c->ra.tstart; q.tb = c->ra.tb; q.age0 = c->ra.age0; q.lmfix = c->ra.lmfix;
+                cudaStream_t gs = c->gs[lane_set][k];
+                NNSP_CUDA(cudaStreamWaitEvent(gs, c->ev_fork[lane_set], 0));
+                if ((rc = launch_split_layers(c->mm[id], q, c->device, gs))) return rc;
+                NNSP_CUDA(cudaEventRecord(c->ev_join[lane_set][k], gs));
+                NNSP_CUDA(cudaStreamWaitEvent(st, c->ev_join[lane_set][k], 0));
             }
+            /* walk the controller over the decisions; a stream that changes stage is cut there and queued for the next round */
+            p.list = queued; p.count = r ? ctl_prev + CTL_NEXT : nullptr;
+            p.next_list = c->pend[(r + 1) & 1]; p.next_count = ctl_r + CTL_NEXT;
+            cascade_post_kernel<<<(ns + CPOST_THREADS - 1) / CPOST_THREADS, CPOST_THREADS, 0, st>>>(p);
+            NNSP_LAUNCH_CHECK();
         }
-        /* ... walk the controller over the decisions, cut at the first stage change ... */
-        CascadePostArgs p{};
-        for (int i = 0; i < 3; i++) p.model[i] = c->mm[i].d;
-        p.st = c->st; p.stale = c->stale; p.logmel = logmel; p.dec = c->dec; p.dec_stride = n_inf_max; p.t0 = c->t0;
-        p.s0 = s0; p.ns = ns; p.T = T; p.results = results; p.cd = c->cd;
-        p.replay_list = c->replay_list; p.replay_count = count + 8;
-        cascade_post_kernel<<<(ns + CPOST_THREADS - 1) / CPOST_THREADS, CPOST_THREADS, 0, st>>>(p);
-        NNSP_LAUNCH_CHECK();
         cascade_ctx_kernel<<<(ns * 32 + 255) / 256, 256, 0, st>>>(p);
         NNSP_LAUNCH_CHECK();
-        a.t0 = c->t0;                          /* ... and replay what is left with the sequential kernel, longest remainder first */
-        cascade_sort_replay_kernel<<<1, CSORT_THREADS, 0, st>>>(c->replay_list + s0, c->replay_sorted + s0, count + 8, c->t0, T);
+        /* what is still queued after the last round goes to the sequential kernel, longest remainder first */
+        a.t0 = c->ra.t0;
+        cascade_sort_replay_kernel<<<1, CSORT_THREADS, 0, st>>>(c->pend[c->rounds & 1] + s0, c->replay_sorted + s0,
+                                                                ctl + CTL_ROUND * (c->rounds - 1) + CTL_NEXT, ctl + CTL_REPLAY, c->ra.t0, T);
         NNSP_LAUNCH_CHECK();
-        a.replay_list = c->replay_sorted + s0; a.replay_ctl = count + 8;
+        a.replay_list = c->replay_sorted + s0; a.replay_ctl = ctl + CTL_REPLAY;
     }
     const int cs_warps = c->narrow ? CsNarrow::WARPS : CsWide::WARPS;
     int blocks = (ns + cs_warps - 1) / cs_warps;
     const int cap = sm_count(c->device);
     if (blocks > cap) blocks = cap;
     if (a.replay_list && c->narrow && c->replay_coop) {
-        /* replay: four warps per stream; as many CTAs as the worst case needs (ns streams), at most one per SM */
+        /* NNSP_CR_GW warps per stream; as many CTAs as the worst case needs (ns streams), at most one per SM */
         int rb = (ns + CR_GROUPS - 1) / CR_GROUPS;
         if (rb > cap) rb = cap;
         cascade_replay_kernel<<<rb, CR_THREADS, c->smem_replay, st>>>(a, c->off_w_replay, c->off_w_replay + (c->off_b - c->off_w));
@@ -1067,6 +1209,8 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     c->off_w_replay = (int)((16 + sizeof(ReplaySmem) + 127) & ~(size_t)127);
     c->smem_replay = (size_t)c->off_w_replay + wtot + btot * 2 + 16;
     { const char *e = getenv("NNSP_B200_REPLAY_COOP"); c->replay_coop = !(e && e[0] == '0'); }        /* A/B switch for measurements */
+    if (c->smem_replay > 227 * 1024) c->replay_coop = false;      /* the one-warp-per-stream shape fits whenever create succeeds */
+    { const char *e = getenv("NNSP_B200_CASCADE_ROUNDS"); if (e && e[0] >= '1' && e[0] <= '0' + CS_MAX_ROUNDS) c->rounds = e[0] - '0'; }
     if (c->smem_total > 227 * 1024) { nnsp_set_error("cascade needs %zu bytes of shared memory (> 227 KB)", c->smem_total); return fail(NNSP_B200_ERR_UNSUPPORTED); }
     const size_t S = (size_t)n_streams, HS = NNSP_B200_MAX_WIDTH;
     const int hist_frames = c->cd.dmax + 2, lm_rows = c->cd.dmax > 0 ? c->cd.dmax : 1;
@@ -1078,7 +1222,7 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &r : c->host_ev) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : c->ev) TRY(cudaEventCreate(&e));
-    for (auto &g : c->gs) TRY(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
+    for (auto &row : c->gs) for (auto &g : row) TRY(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;
         TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1087,8 +1231,8 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaEventCreate(&c->ev_nn0));
     for (auto &e : c->ev_feat) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : c->ev_nn) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    for (auto &e : c->ev_join) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : c->ev_fork) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &row : c->ev_join) for (auto &e : row) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRY(cudaMalloc(&c->st.ctx, S * 240 * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.h, S * HS * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.c, S * HS * sizeof(int32_t)));
@@ -1098,12 +1242,17 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaMalloc(&c->hist2, S * hist_frames * NNSP_B200_FRAME * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.lmhist, S * lm_rows * NNSP_B200_NMEL * sizeof(int32_t)));
     TRY(cudaMalloc(&c->stale, S * 120 * sizeof(int16_t)));
-    TRY(cudaMalloc(&c->grp_list, (size_t)CG_GROUPS * S * sizeof(int)));
-    TRY(cudaMalloc(&c->grp_count, CS_MAX_SLICES * 16 * sizeof(int)));
-    TRY(cudaMalloc(&c->replay_list, S * sizeof(int)));
+    TRY(cudaMalloc(&c->grp_list, (size_t)3 * S * sizeof(int)));
+    TRY(cudaMalloc(&c->ctl, CS_MAX_SLICES * CTL_INTS * sizeof(int)));
+    TRY(cudaMalloc(&c->fix_list, S * sizeof(int)));
+    for (auto &q : c->pend) TRY(cudaMalloc(&q, S * sizeof(int)));
     TRY(cudaMalloc(&c->replay_sorted, S * sizeof(int)));
-    TRY(cudaMalloc(&c->grp_tile_off, CS_MAX_SLICES * 8 * sizeof(int)));
-    TRY(cudaMalloc(&c->t0, S * sizeof(int)));
+    TRY(cudaMalloc(&c->ra.t0, S * sizeof(int)));
+    TRY(cudaMalloc(&c->ra.tstart, S * sizeof(int)));
+    TRY(cudaMalloc(&c->ra.tb, S * sizeof(int)));
+    TRY(cudaMalloc(&c->ra.age0, S * sizeof(int)));
+    TRY(cudaMalloc(&c->ra.lmfix, S * 2 * NNSP_B200_NMEL * sizeof(int32_t)));
+    TRY(cudaMemset(c->ra.lmfix, 0, S * 2 * NNSP_B200_NMEL * sizeof(int32_t)));
 #undef TRY
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(NNSP_B200_ERR_CUDA);   /* uploads went through the default stream */
     ResetModels rm{};
@@ -1303,15 +1452,16 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     for (auto e : c->ev_feat) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_nn) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) free_model_mma(&c->mm[i]);
-    cudaFree(c->replay_list); cudaFree(c->replay_sorted); cudaFree(c->grp_list); cudaFree(c->grp_count); cudaFree(c->grp_tile_off); cudaFree(c->t0);
+    cudaFree(c->replay_sorted); cudaFree(c->grp_list); cudaFree(c->ctl); cudaFree(c->fix_list); cudaFree(c->pend[0]); cudaFree(c->pend[1]);
+    cudaFree(c->ra.t0); cudaFree(c->ra.tstart); cudaFree(c->ra.tb); cudaFree(c->ra.age0); cudaFree(c->ra.lmfix);
     cudaFree(c->planes[0]); cudaFree(c->planes[1]); cudaFree(c->dec);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto s : c->xs) if (s) cudaStreamDestroy(s);
     for (auto &r : c->host_ev) for (auto e : r) if (e) cudaEventDestroy(e);
     for (auto e : c->ev) if (e) cudaEventDestroy(e);
-    for (auto g : c->gs) if (g) cudaStreamDestroy(g);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    for (auto e : c->ev_join) if (e) cudaEventDestroy(e);
+    for (auto &row : c->gs) for (auto g : row) if (g) cudaStreamDestroy(g);
+    for (auto e : c->ev_fork) if (e) cudaEventDestroy(e);
+    for (auto &row : c->ev_join) for (auto e : row) if (e) cudaEventDestroy(e);
     delete c;
 }
 

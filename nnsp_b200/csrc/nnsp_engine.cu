@@ -67,6 +67,14 @@ static bool fill_dev_tables(const nnsp_tables *t, DevTables *d)
         for (int L = 0; L < 16; L++) d->tw1[n][L] = unpack(t->fft_tw[16 * L + 1 + n]);
     for (int m = 0; m < 4; m++)
         for (int n = 0; n < 3; n++) d->tw2[m][n] = unpack(t->fft_tw[64 * m + 1 + n]);
+    {   /* the shapes frame_logmel compiles in for stage 2 (nnsp_feat.cuh, cmul_tw) */
+        auto one = [](int2 w) { return w.x == 0x7fff && w.y == 0; };
+        auto diag = [](int2 w) { return w.x == w.y; };
+        auto adiag = [](int2 w) { return w.y == -(w.x + 1); };
+        if (!(one(d->tw2[0][0]) && one(d->tw2[0][1]) && one(d->tw2[0][2]) && adiag(d->tw2[1][0]) &&
+              d->tw2[2][0].x == 0 && d->tw2[2][0].y == -32768 && adiag(d->tw2[2][1]) && diag(d->tw2[2][2]) && diag(d->tw2[3][0])))
+            ok = false;
+    }
     for (int k = 0; k < 256; k++) d->rtw[k] = unpack(t->rfft_tw[k]);
     d->rtw[256] = make_int2(0, 0);
     {   /* regroup the filterbank: per band, aligned groups of 4 bins with zero taps outside [start, end] */
@@ -97,7 +105,7 @@ int get_device_tables(int device, const DevTables **out)
         const nnsp_tables *t = nnsp_tables_get();
         if (!t) { nnsp_set_error("constant-table self check failed (fingerprint mismatch)"); return NNSP_B200_ERR_ARG; }
         DevTables h;
-        if (!fill_dev_tables(t, &h)) { nnsp_set_error("mel filterbank does not fit the kernel's group bounds"); return NNSP_B200_ERR_ARG; }
+        if (!fill_dev_tables(t, &h)) { nnsp_set_error("constant tables do not have the structure the feature kernel compiles in (mel group bounds, stage-2 twiddles)"); return NNSP_B200_ERR_ARG; }
         DevTables *d = nullptr;
         NNSP_CUDA(cudaMalloc(&d, sizeof h));
         NNSP_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));

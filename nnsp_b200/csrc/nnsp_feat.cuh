@@ -79,6 +79,47 @@ __device__ __forceinline__ void bfly4(int32_t &ar, int32_t &ai, int32_t &cr, int
     }
 }
 
+/* Stage 2 of the 256-point FFT uses the twiddles of k = 0, 16, 32, 48 -- the same for every lane, so their special
+ * shapes can be compiled in (fill_dev_tables verifies that the generated table has them; the values are floor-quantised,
+ * twiddle_fft_dif.c:9):
+ *   TW_ONE   (0x7fff, 0)        the Q15 "one": a + ((-a) >> 15)
+ *   TW_NEGI  (0, -32768)        exactly -j: (re, im) -> (im, -re), no product at all
+ *   TW_DIAG  (c, c)             re = ((a.re - a.im) c) >> 15, im = ((a.re + a.im) c) >> 15: one 64-bit product each
+ *   TW_ADIAG (c, -(c + 1))      re = ((a.re + a.im) c + a.im) >> 15, im = ((a.im - a.re) c - a.re) >> 15
+ *   TW_ANY   the general complex product (complex.c:54-72)
+ * Every form is the reference's (ar wr - ai wi) >> 15, (ar wi + ai wr) >> 15 with the 64-bit sum rearranged exactly. */
+enum { TW_ANY = 0, TW_ONE = 1, TW_NEGI = 2, TW_DIAG = 3, TW_ADIAG = 4 };
+template <int KIND>
+__device__ __forceinline__ void cmul_tw(int32_t or_, int32_t oi, int2 w, int32_t &re, int32_t &im)
+{
+    if (KIND == TW_ONE) { re = mul_one_q15(or_); im = mul_one_q15(oi); }
+    else if (KIND == TW_NEGI) { re = oi; im = -or_; }
+    else if (KIND == TW_DIAG) {
+        re = (int32_t)(((int64_t)(or_ - oi) * (int64_t)w.x) >> 15);
+        im = (int32_t)(((int64_t)(or_ + oi) * (int64_t)w.x) >> 15);
+    } else if (KIND == TW_ADIAG) {
+        re = (int32_t)(((int64_t)(or_ + oi) * (int64_t)w.x + (int64_t)oi) >> 15);
+        im = (int32_t)(((int64_t)(oi - or_) * (int64_t)w.x - (int64_t)or_) >> 15);
+    } else { re = msub_q15(or_, w.x, oi, w.y); im = madd_q15(or_, w.y, oi, w.x); }
+}
+/* bfly4 with the kinds of its three twiddles compiled in */
+template <int K1, int K2, int K3>
+__device__ __forceinline__ void bfly4_tw(int32_t &ar, int32_t &ai, int32_t &cr, int32_t &ci,
+                                         int32_t &br, int32_t &bi, int32_t &dr, int32_t &di,
+                                         int2 w1, int2 w2, int2 w3)
+{
+    const int32_t s1r = cr + dr, s1i = ci + di, d1r = cr - dr, d1i = ci - di;
+    const int32_t o0r = add3(ar, br, s1r), o0i = add3(ai, bi, s1i);
+    const int32_t o1r = add2sub(ar, br, s1r), o1i = add2sub(ai, bi, s1i);
+    const int32_t o2r = sub2add(ar, br, d1i), o2i = sub3(ai, bi, d1r);
+    const int32_t o3r = sub3(ar, br, d1i), o3i = sub2add(ai, bi, d1r);
+    ar = mul_one_q15(o0r);
+    ai = mul_one_q15(o0i);
+    cmul_tw<K1>(o1r, o1i, w1, cr, ci);
+    cmul_tw<K2>(o2r, o2i, w2, br, bi);
+    cmul_tw<K3>(o3r, o3i, w3, dr, di);
+}
+
 __device__ __forceinline__ int xpad(int p) { return p + (p >> 4); }
 
 /* One frame by the 16 lanes of a half-warp (L = lane & 15). `load_pair(a, p)` returns PCM samples
@@ -129,11 +170,12 @@ __device__ __forceinline__ void frame_logmel(const FeatSmemTables &tb, FrameScra
 #pragma unroll
     for (int b = 0; b < 16; b++) { const int2 v = fs.x[xpad(16 * L + b)]; xr[b] = v.x; xi[b] = v.y; }
     __syncwarp();
-    /* stage 2: Nf = 16, q = 4, group g = L, m = 0..3, k = 16m (same for every lane) */
-#pragma unroll
-    for (int m = 0; m < 4; m++)
-        bfly4<false>(xr[m], xi[m], xr[m + 4], xi[m + 4], xr[m + 8], xi[m + 8], xr[m + 12], xi[m + 12],
-                     tb.tw2[m][0], tb.tw2[m][1], tb.tw2[m][2]);
+    /* stage 2: Nf = 16, q = 4, group g = L, m = 0..3, k = 16m (same for every lane): twiddles tw^2k, tw^k, tw^3k of
+     * k = 0 (all ones), 16 (-45 deg, general, general), 32 (-j, -45 deg, -135 deg), 48 (-135 deg, general, general) */
+    bfly4_tw<TW_ONE, TW_ONE, TW_ONE>(xr[0], xi[0], xr[4], xi[4], xr[8], xi[8], xr[12], xi[12], tb.tw2[0][0], tb.tw2[0][1], tb.tw2[0][2]);
+    bfly4_tw<TW_ADIAG, TW_ANY, TW_ANY>(xr[1], xi[1], xr[5], xi[5], xr[9], xi[9], xr[13], xi[13], tb.tw2[1][0], tb.tw2[1][1], tb.tw2[1][2]);
+    bfly4_tw<TW_NEGI, TW_ADIAG, TW_DIAG>(xr[2], xi[2], xr[6], xi[6], xr[10], xi[10], xr[14], xi[14], tb.tw2[2][0], tb.tw2[2][1], tb.tw2[2][2]);
+    bfly4_tw<TW_DIAG, TW_ANY, TW_ANY>(xr[3], xi[3], xr[7], xi[7], xr[11], xi[11], xr[15], xi[15], tb.tw2[3][0], tb.tw2[3][1], tb.tw2[3][2]);
     /* stage 3: Nf = 4, q = 1, k = 0: every twiddle is 0x7fff + 0j */
 #pragma unroll
     for (int g = 0; g < 4; g++)

@@ -105,6 +105,13 @@ struct SplitGroup {
     int32_t *dec = nullptr; int dec_stride = 0;
     int16_t thresh_prob = 0;
     nnsp_b200_taps taps{};
+    /* cascade rounds (null in the batched path): per stream, the first inference frame of this round (inference k of
+     * stream s is frame tstart[s] + 2k, it has (T - tstart[s] + 1) / 2 of them), the frame at which the live instance's
+     * life in this call began (earlier frames of its window come from the stored context), the instance's age (frames
+     * since its reset, capped at 2) at that frame, and the log-mel rows of the instance's first two frames, whose STFT
+     * buffer is still partly zero (spectrogram_module.c:25-31) */
+    const int *tstart = nullptr, *tb = nullptr, *age0 = nullptr;
+    const int32_t *lmfix = nullptr;      /* [S][2][40] */
 };
 int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int device, cudaStream_t st);
 int split_supported(const MmaDeviceModel &mm);

@@ -46,7 +46,7 @@ constexpr int SEG_KC = 16;                          /* inferences per work item 
 constexpr int SEG_FROWS = 2 * SEG_KC + 4;           /* feature rows covering 16 windows of 6, stride 2   */
 constexpr int SEG_PC = SEG_FROWS * 40 + 16;         /* plane pitch: 364 words = 12 mod 32, conflict-free */
 constexpr int SCAN_NST = 4;                         /* depth of the input ring of the scan               */
-constexpr int SPLIT_MAX_DYN_SMEM = 227 * 1024 - 256;   /* the kernels also hold 64 B of static shared memory */
+constexpr int SPLIT_MAX_DYN_SMEM = 227 * 1024 - 512;   /* the kernels also hold up to 276 B of static shared memory */
 constexpr int LUT2_N = 160;                         /* reachable segments of coeffs_tanh (activation.c:5) */
 /* The LUT is indexed by data, so lanes of a warp collide on banks (ncu: 58 % of the scan's LUT wavefronts were excess).
  * It can be replicated: copy c of entry k sits at [k * COPIES + c] and lane l reads copy l % COPIES, i.e. always the same
@@ -188,6 +188,8 @@ struct SegArgs {
     int32_t *tap_logits;            /* [S][T][n_out] or null */
     int ao0;                        /* offset of layer l0's output inside an act row */
     int16_t thresh_prob;
+    const int *tstart, *tb, *age0;  /* cascade rounds: per-stream first inference frame, life begin, age there (SplitGroup) */
+    const int32_t *lmfix;           /* [S][2][40] log-mel rows of an instance's first two frames */
 };
 
 /* Where the outputs of one fc layer of one (tile, inference) row block go. */
@@ -323,8 +325,13 @@ __global__ void __launch_bounds__(SEG_THREADS, SEG_MINB)
 seg_kernel(SegArgs a)
 {
     constexpr bool FROM_FEAT = MODE != 0;
-    __shared__ int sids[16];
+    __shared__ int sids[16], s_ts[16], s_tb[16], s_ag[16], s_ninf;
     extern __shared__ __align__(128) unsigned char smem[];
+    const bool per_row = a.tstart != nullptr;                     /* cascade rounds: every row has its own start frame */
+    {   /* nothing selected (a later round of the cascade, an empty group) or more CTAs than work items: leave before the prologue */
+        const int nsel0 = sel_count(a.sel);
+        if ((int)blockIdx.x >= ((nsel0 + 15) >> 4) * a.nchunks) return;
+    }
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     MmaModel &M = *reinterpret_cast<MmaModel *>(smem + 16);
     int32_t *bias32 = reinterpret_cast<int32_t *>(smem + a.off_bias);
@@ -389,10 +396,23 @@ seg_kernel(SegArgs a)
         const int k0 = chunk * SEG_KC;
         const int nvalid = min(16, nsel - 16 * tile);
         const size_t tile_abs = tile_base + tile;
-        if (FROM_FEAT) {
+        int ninf_tile = a.n_inf;
+        if (FROM_FEAT || per_row) {
             __syncthreads();                                         /* planes of the previous item are free */
-            if (tid < 16) sids[tid] = (tid < nvalid) ? sel_sid(a.sel, tile, tid) : 0;
+            if (tid < 16) {
+                const int sid = (tid < nvalid) ? sel_sid(a.sel, tile, tid) : 0;
+                int ts = a.first, tbv = 0, ag = 2;
+                if (per_row && tid < nvalid) { ts = a.tstart[sid]; tbv = a.tb[sid]; ag = a.age0[sid]; }
+                sids[tid] = sid; s_ts[tid] = ts; s_tb[tid] = tbv; s_ag[tid] = ag;
+                int ni = (tid < nvalid) ? (per_row ? (ts < T ? (T - ts + 1) >> 1 : 0) : a.n_inf) : 0;
+                for (int o = 8; o; o >>= 1) ni = max(ni, __shfl_xor_sync(0x0000ffffu, ni, o));
+                if (tid == 0) s_ninf = ni;
+            }
             __syncthreads();
+            ninf_tile = s_ninf;                                      /* most inferences any row of the tile has */
+        }
+        if (k0 >= ninf_tile) continue;
+        if (FROM_FEAT) {
             /* standardised rows of frames f_first .. f_first+35 as byte planes; frames before the call are the
              * carried context rows 1..5 (feature_module.c:54-57); loads of a batch are issued before its stores */
             const int f_first = a.first + 2 * k0 - 5;
@@ -442,15 +462,17 @@ seg_kernel(SegArgs a)
                         from_ctx[u] = 1;
                         if (e < NQ) {
                             const int r = e / (SEG_FROWS * 10), rem = e - r * (SEG_FROWS * 10), j = rem / 10, x = rem - j * 10;
-                            const int f = f_first + j;
                             if (r < nvalid) {
                                 const long long s = sids[r];
-                                if (f < 0) {
-                                    const uint2 c = *reinterpret_cast<const uint2 *>(a.ctx + s * 240 + (6 + f) * 40 + x * 4);
+                                const int f = s_ts[r] + 2 * k0 - 5 + j;              /* frame of the call */
+                                const int life = f - s_tb[r];                        /* frames since the instance's life in this call began */
+                                if (life < 0) {                                      /* before that: the instance's stored context rows 1..5 */
+                                    const uint2 c = *reinterpret_cast<const uint2 *>(a.ctx + s * 240 + (6 + life) * 40 + x * 4);
                                     v[u] = make_int4((int16_t)(c.x & 0xffff), (int32_t)c.x >> 16, (int16_t)(c.y & 0xffff), (int32_t)c.y >> 16);
                                 } else if (f < T) {
-                                    const int fr = f - a.dback;
-                                    const int32_t *row = (fr >= 0) ? a.logmel + (s * T + fr) * NNSP_B200_NMEL
+                                    const int la = life + s_ag[r], fr = f - a.dback;
+                                    const int32_t *row = (la < 2) ? a.lmfix + (s * 2 + la) * NNSP_B200_NMEL     /* STFT buffer still partly zero */
+                                                       : (fr >= 0) ? a.logmel + (s * T + fr) * NNSP_B200_NMEL
                                                                    : a.lmhist + (s * a.dmax + a.dmax + fr) * NNSP_B200_NMEL;
                                     v[u] = __ldg(reinterpret_cast<const int4 *>(row + x * 4));
                                     from_ctx[u] = 0;
@@ -483,7 +505,7 @@ seg_kernel(SegArgs a)
 
         for (int i = warp; i < SEG_KC; i += SEG_WARPS) {
             const int k = k0 + i;
-            if (k >= a.n_inf) break;
+            if (k >= ninf_tile) break;
             const int t = a.first + 2 * k;                               /* frame of this inference */
             const uint8_t *in_hi, *in_lo;
             int in_pitch;
@@ -568,6 +590,7 @@ struct ScanArgs {
     int32_t *c;
     int16_t *tap_act, *tap_h;
     int32_t *tap_c;
+    const int *tstart;              /* cascade rounds: per-stream first inference frame (null: every row has n_inf inferences) */
 };
 
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
@@ -650,7 +673,7 @@ scan_kernel(ScanArgs a)
     uint8_t *xs = smem + 64 + WB + LUT2_N * 8 * LUT2_COPIES_SCAN;
     uint8_t *hb = xs + SCAN_NST * XB;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-    __shared__ int sids[16];
+    __shared__ int sids[16], s_last[16], s_ninf;
     const int tile = blockIdx.x;
     const int nsel = sel_count(a.sel);
     if (16 * tile >= nsel) return;                                   /* (list launches are sized for the worst case) */
@@ -658,8 +681,22 @@ scan_kernel(ScanArgs a)
     const size_t tile_abs = sel_tile_base(a.sel) + tile;
     const uint8_t *xg = a.xin + tile_abs * (size_t)a.tile_bytes;
     uint8_t *hg = a.hout + tile_abs * (size_t)a.tile_bytes;
-    if (threadIdx.x < 16) sids[threadIdx.x] = ((int)threadIdx.x < nvalid) ? sel_sid(a.sel, tile, threadIdx.x) : 0;
-    const int H = a.H, pa = a.pa, HS = a.hs, T = a.T, n_inf = a.n_inf, rs = a.rs;
+    const bool per_row = a.tstart != nullptr;
+    if (threadIdx.x < 16) {
+        const int r = threadIdx.x;
+        const int sid = (r < nvalid) ? sel_sid(a.sel, tile, r) : 0;
+        sids[r] = sid;
+        /* inferences of this row: the tile runs as many steps as its longest row; a row's state is final after its own
+         * last step and is stored right there (cascade rounds start streams at different frames) */
+        int ni = 0;
+        if (r < nvalid) { ni = a.n_inf; if (per_row) { const int ts = a.tstart[sid]; ni = ts < a.T ? (a.T - ts + 1) >> 1 : 0; } }
+        s_last[r] = ni - 1;
+        for (int o = 8; o; o >>= 1) ni = max(ni, __shfl_xor_sync(0x0000ffffu, ni, o));
+        if (r == 0) s_ninf = ni;
+    }
+    __syncthreads();
+    const int H = a.H, pa = a.pa, HS = a.hs, T = a.T, n_inf = s_ninf, rs = a.rs;
+    if (n_inf <= 0) return;
 
     if (tid == 0) {
         for (int i = 0; i <= SCAN_NST; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
@@ -754,6 +791,16 @@ scan_kernel(ScanArgs a)
             }
             store_pair(hn, hn + 16 * pa, g * pa + u0, y[0], y[1]);
             store_pair(hn, hn + 16 * pa, (g + 8) * pa + u0, y[2], y[3]);
+            if (per_row) {                                            /* a row's last own step: its state goes home now */
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    if (k == s_last[g + 8 * rr]) {                    /* (rows past nvalid have last = -1) */
+                        const long long o = (long long)sids[g + 8 * rr] * HS + a.ho + u0;
+                        if (u0 < H) { a.h[o] = (int16_t)y[2 * rr]; a.c[o] = cst[2 * rr]; }
+                        if (u0 + 1 < H) { a.h[o + 1] = (int16_t)y[2 * rr + 1]; a.c[o + 1] = cst[2 * rr + 1]; }
+                    }
+                }
+            }
             if (a.tap_out && a.tap_act) {
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
@@ -785,6 +832,7 @@ scan_kernel(ScanArgs a)
         }
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (per_row) return;                                             /* every row stored its state after its own last step */
     /* state for the next call */
     const uint8_t *hf = hb + ((n_inf + 2) % 3) * XB;
     for (int idx = tid; idx < nvalid * H; idx += nthr) {
@@ -1026,6 +1074,7 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
             a.ctx = q.ctx; a.in_planes = cur_in;
             a.out_planes = (l1 < D->numlayers) ? bufs[which] : nullptr;
             a.dec = q.dec; a.tap_act = tp.act; a.tap_logits = tp.logits; a.ao0 = ao; a.thresh_prob = q.thresh_prob;
+            a.tstart = q.tstart; a.tb = q.tb; a.age0 = q.age0; a.lmfix = q.lmfix;
             int per_sm = (int)((227 * 1024) / (lay.total + 1024));
             per_sm = per_sm < 1 ? 1 : (per_sm > SEG_MINB ? SEG_MINB : per_sm);     /* __launch_bounds__(256, SEG_MINB) */
             int grid = sm_count(device) * per_sm;
@@ -1047,7 +1096,7 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
             a.ho = ho; a.hs = q.h_stride; a.ao = ao; a.act_stride = D->act_stride; a.tap_out = (li < D->numlayers - 1);
             a.sel = sel; a.T = q.T; a.first = q.first; a.n_inf = q.n_inf; a.tile_bytes = tile_bytes;
             a.xin = cur_in; a.hout = bufs[which]; a.h = q.h; a.c = q.c;
-            a.tap_act = tp.act; a.tap_h = tp.hstate; a.tap_c = tp.cstate;
+            a.tap_act = tp.act; a.tap_h = tp.hstate; a.tap_c = tp.cstate; a.tstart = q.tstart;
             const size_t smem = scan_smem(D, L);
             /* the shipped layers get their k-step counts compiled in: VAD 28 -> 28 (1 k-step), KWS 64 -> 64 (2), S2I 72 -> 72 (3) */
             const int kq = (L.kt == L.ktr) ? L.kt : 0;

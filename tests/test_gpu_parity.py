@@ -238,6 +238,52 @@ def test_async_host_calls_double_buffered(nb, oracle):
         b.close()
 
 
+@pytest.mark.parametrize("kind", ["batch", "cascade"])
+def test_async_host_calls_of_varying_odd_lengths(nb, oracle, kind):
+    """Asynchronous host-buffer calls whose lengths differ from call to call (odd ones flip the inference gate, so the
+    inference count of a call changes even at equal length): consecutive calls run on different pipeline streams, and a
+    stream slice must still own its scratch bytes exclusively. Repeated several times; every stream checked against one
+    device-buffer call over the same audio (which the other tests pin to the oracle)."""
+    lens = [7, 7, 5, 12, 1, 9, 9, 3, 20, 7, 6, 11]
+    S, T = 4200, sum(lens)                           # 16 / 8 slices over the pipeline streams
+    pcm = nb.synth_pcm(S, T, first_stream=3)
+    if kind == "batch":
+        make = lambda: nb.NNSPBatch(_model(nb, 1, False), S)
+        res_dt = nb.RESULT_DT
+    else:
+        models = [nb.Model.from_blob(nb.MODEL_DIR + "/" + f) for f in ("s2i.nnspm", "vad.nnspm", "kws_galaxy.nnspm")]
+        make = lambda: nb.Cascade(models, S, params=dict(thresh_timeout_kws=40, thresh_timeout_s2i=30))
+        res_dt = nb.CASCADE_RESULT_DT
+    ref = make()
+    want = ref.exec(pcm)
+    ref.close()
+    nmax = max(lens)
+    pin = [nb.PinnedArray((S, nmax * 160), np.int16) for _ in range(3)]
+    pres = [nb.PinnedArray((S, nmax), res_dt) for _ in range(3)]
+    for rep in range(3):
+        h = make()
+        got, tickets, t = [], [], 0
+        for k, n in enumerate(lens):
+            if k >= 3:                                  # the buffer pair about to be reused: its call must be over
+                h.wait_host(tickets[k - 3])
+                got.append(pres[k % 3].array.reshape(-1)[: S * lens[k - 3]].reshape(S, lens[k - 3]).copy())
+            pv = pin[k % 3].array.reshape(-1)[: S * n * 160].reshape(S, n * 160)
+            pv[...] = pcm[:, t * 160:(t + n) * 160]
+            rv = pres[k % 3].array.reshape(-1)[: S * n].reshape(S, n)
+            tickets.append(h.exec_host_async(pv, rv))
+            t += n
+        for k in range(len(lens) - 3, len(lens)):
+            h.wait_host(tickets[k])
+            got.append(pres[k % 3].array.reshape(-1)[: S * lens[k]].reshape(S, lens[k]).copy())
+        h.close()
+        got = np.concatenate(got, axis=1)
+        for f in want.dtype.names:
+            bad = np.nonzero((got[f] != want[f]).reshape(S, -1).any(axis=1))[0]
+            assert len(bad) == 0, "%s rep %d: field %s differs on streams %s" % (kind, rep, f, bad[:8].tolist())
+    for x in pin + pres:
+        x.free()
+
+
 def test_long_call_many_inference_rounds(nb, oracle):
     """One call of 301 frames (151 inferences): several 16-inference work items per tile in the fc kernels, several
     staging rounds in the post kernel, a long TMA ring in the scan."""
