@@ -204,12 +204,42 @@ int nnsp_b200_cascade_exec_host_async(nnsp_b200_cascade *c, const int16_t *pcm, 
 int nnsp_b200_cascade_wait_host(nnsp_b200_cascade *c, long long ticket);
 int nnsp_b200_cascade_sync(nnsp_b200_cascade *c);
 int nnsp_b200_cascade_last_kernel_ms(nnsp_b200_cascade *c, float ms[3]);
+/* Device timeline of the last n <= 8 device-buffer calls, oldest first: ms[4 k + 0..3] = front end (feature kernel)
+ * starts / done, controller-and-network chain starts / done, in ms after the oldest call's front end started (CUDA events
+ * on the handle's own streams). Synchronises the handle. */
+int nnsp_b200_cascade_timeline(nnsp_b200_cascade *c, float *ms, int *n_calls);
 void *nnsp_b200_cascade_stream(nnsp_b200_cascade *c);
 /* 0 = automatic, 1 = sequential warp-per-stream kernel only, 2 = stage-sorted pass (the scan-split network kernels
  * over the streams of each (model, phase) group) + replay of the frames after a stage change. Bit-exact either way;
  * calls that request debug taps always take 1. */
 int nnsp_b200_cascade_set_path(nnsp_b200_cascade *c, int path);
 void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c);
+
+/* ------------------------------------------------------------------------------------ */
+/* Several GPUs of one box behind one handle                                            */
+/* ------------------------------------------------------------------------------------ */
+/* The streams are independent (no reference function looks at another instance: nn_speech.c:74-127,
+ * evb/src/nnCntrlClass.c:152-272), so a group block-partitions them over `n_devices` devices -- member k owns streams
+ * [S k / G, S (k + 1) / G) -- with one host thread per device and no inter-GPU traffic. A member is an ordinary
+ * nnsp_b200_batch / nnsp_b200_cascade handle; `devices` may name a device more than once (two members, two threads).
+ * exec_host takes HOST buffers laid out like the single-device calls: pcm[s * stream_stride + t * 160 + i], results
+ * [n_streams][n_frames] records (nnsp_b200_result for a batch group, nnsp_b200_cascade_result for a cascade group).
+ * The asynchronous form returns a ticket; buffers belong to the library until nnsp_b200_group_wait(ticket) (or a later
+ * one) returns. Calls complete in order; with two buffer pairs every device keeps its host link busy across calls. */
+typedef struct nnsp_b200_group nnsp_b200_group;
+int nnsp_b200_group_create_batch(const nnsp_b200_model *m, int n_streams, const int *devices, int n_devices,
+                                 int16_t thresh_prob, int16_t th_count_trigger, nnsp_b200_group **out);
+int nnsp_b200_group_create_cascade(const nnsp_b200_model *const models[3], const int *seq, int len_seq,
+                                   const nnsp_b200_cascade_params *params, int n_streams, const int *devices,
+                                   int n_devices, nnsp_b200_group **out);
+int nnsp_b200_group_size(const nnsp_b200_group *g);
+int nnsp_b200_group_range(const nnsp_b200_group *g, int member, int *device, int *first_stream, int *n_streams);
+int nnsp_b200_group_reset(nnsp_b200_group *g);
+int nnsp_b200_group_exec_host(nnsp_b200_group *g, const int16_t *pcm, long long stream_stride, int n_frames, void *results);
+int nnsp_b200_group_exec_host_async(nnsp_b200_group *g, const int16_t *pcm, long long stream_stride, int n_frames,
+                                    void *results, long long *ticket);
+int nnsp_b200_group_wait(nnsp_b200_group *g, long long ticket);
+void nnsp_b200_group_destroy(nnsp_b200_group *g);
 
 /* ------------------------------------------------------------------------------------ */
 /* Stage-by-stage tap of the feature front end (parity tool)                            */
@@ -249,6 +279,27 @@ int nnsp_b200_net_eval(const nnsp_b200_model *m, int device, int nn_path, int n,
  * pcm_dev: n_frames*160 int16 (device), both 16-byte aligned; frames are consecutive in both, so any
  * [stream][frame] arrangement works. Asynchronous on `stream` (a handle's stream or NULL). */
 int nnsp_b200_ingest_audadc(int device, const uint32_t *raw_dev, int16_t *pcm_dev, long long n_frames, void *stream);
+/* The same conditioning chained in front of the HOST-buffer calls of a handle: with NNSP_B200_HOST_AUDADC the `pcm`
+ * argument of *_exec_host / *_exec_host_async is read as `const uint32_t *` raw AUDADC words (same indexing,
+ * stream_stride still in samples); they cross the link as they are and are conditioned on the device, slice by slice,
+ * right before the feature kernel. Switching the format waits for the handle's work in flight. */
+#define NNSP_B200_HOST_PCM16     0
+#define NNSP_B200_HOST_AUDADC    1
+int nnsp_b200_batch_set_host_format(nnsp_b200_batch *b, int format);
+int nnsp_b200_cascade_set_host_format(nnsp_b200_cascade *c, int format);
+
+/* ------------------------------------------------------------------------------------ */
+/* Audio front door: RIFF/WAVE files -> the [stream][frame][160] PCM layout (host code)  */
+/* ------------------------------------------------------------------------------------ */
+/* Stands where the reference has the AUDADC interrupt (evb/src/main_nnsp.cc:46-74) and, off the device, the Python tools
+ * reading python/test_wavs with soundfile (python/test_s2i.py etc.): 16 kHz, 16-bit integer PCM, any channel count (one
+ * channel is picked), chunks in any order, WAVE_FORMAT_EXTENSIBLE accepted. Other rates are NNSP_B200_ERR_UNSUPPORTED
+ * (the reference has no resampler). Frames past the end of a file are digital silence; frames_read tells how many held
+ * file samples. load_streams fills stream s of a host buffer (pcm[s * stream_stride + t * 160 + i]) from paths[s]. */
+int nnsp_b200_wav_info(const char *path, int *sample_rate, int *channels, int *bits, long long *n_samples);
+int nnsp_b200_wav_read_frames(const char *path, int channel, long long first_frame, int n_frames, int16_t *pcm, int *frames_read);
+int nnsp_b200_wav_load_streams(const char *const *paths, int n_streams, int channel, long long first_frame, int n_frames,
+                               int16_t *pcm, long long stream_stride, int *frames_read);
 
 /* Constant tables the engine generates at load time (host copies; see nnsp_tables.c).
  * name: "stft_win" int16[480], "fft_tw" int32[256], "rfft_tw" int32[256], "bitrev" int16[256],

@@ -206,9 +206,15 @@ class NNSPBatch:
                 v.free()
         return (res, out) if taps else res
 
+    HOST_FORMAT = {"pcm16": 0, "audadc": 1}
+
+    def set_host_format(self, fmt):
+        """'pcm16' (default) or 'audadc': the host-buffer calls then take uint32 raw AUDADC words, conditioned on the device"""
+        check(lib().nnsp_b200_batch_set_host_format(self.h, self.HOST_FORMAT[fmt]), "batch_set_host_format")
+
     def exec_host(self, pcm, results=None):
         """End-to-end call with host buffers (H2D + kernels + D2H inside)."""
-        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and pcm.shape[0] == self.S
+        assert pcm.dtype in (np.int16, np.uint32) and pcm.flags.c_contiguous and pcm.shape[0] == self.S
         T = pcm.shape[1] // FRAME
         if results is None:
             results = np.empty((self.S, T), RESULT_DT)
@@ -306,6 +312,9 @@ class Cascade:
                 v.free()
         return (res, out) if taps else res
 
+    def set_host_format(self, fmt):
+        check(lib().nnsp_b200_cascade_set_host_format(self.h, NNSPBatch.HOST_FORMAT[fmt]), "cascade_set_host_format")
+
     def exec_host(self, pcm, results=None):
         T = pcm.shape[1] // FRAME
         if results is None:
@@ -332,6 +341,13 @@ class Cascade:
         check(lib().nnsp_b200_cascade_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")
         return list(ms)
 
+    def timeline(self):
+        """[[front start, front done, chain start, chain done], ...] in ms for the last <= 8 device-buffer calls"""
+        ms = np.zeros((8, 4), np.float32)
+        n = C.c_int()
+        check(lib().nnsp_b200_cascade_timeline(self.h, ms.ctypes.data_as(C.c_void_p), C.byref(n)), "cascade_timeline")
+        return ms[: n.value].tolist()
+
     @property
     def stream(self):
         return lib().nnsp_b200_cascade_stream(self.h)
@@ -339,6 +355,74 @@ class Cascade:
     def close(self):
         if self.h:
             lib().nnsp_b200_cascade_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """Several GPUs of one box behind one handle (nnsp_b200_group_*): streams block-partitioned over `devices`, one host
+    thread per device inside the library, host buffers in and out. models: one Model (batched NNSPClass) or a list of
+    three indexed by NNSP id (cascade)."""
+
+    def __init__(self, models, n_streams, devices, seq=(VAD, KWS, S2I), params=None, thresh_prob=16383, th_count=4):
+        L = lib()
+        self.S, self.devices = int(n_streams), list(devices)
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        self.h = C.c_void_p()
+        self.is_cascade = isinstance(models, (list, tuple))
+        self.models = models
+        if self.is_cascade:
+            arr = (C.c_void_p * 3)(*[m.h if m is not None else None for m in models])
+            seq_a = (C.c_int * len(seq))(*seq)
+            p = capi.CascadeParams()
+            L.nnsp_b200_cascade_default_params(C.byref(p))
+            for k, v in (params or {}).items():
+                setattr(p, k, v)
+            check(L.nnsp_b200_group_create_cascade(arr, seq_a, len(seq), C.byref(p), self.S, dev, len(self.devices), C.byref(self.h)), "group_create_cascade")
+        else:
+            check(L.nnsp_b200_group_create_batch(models.h, self.S, dev, len(self.devices), thresh_prob, th_count, C.byref(self.h)), "group_create_batch")
+        self.result_dt = CASCADE_RESULT_DT if self.is_cascade else RESULT_DT
+
+    def ranges(self):
+        out = []
+        for k in range(lib().nnsp_b200_group_size(self.h)):
+            d, f, n = C.c_int(), C.c_int(), C.c_int()
+            check(lib().nnsp_b200_group_range(self.h, k, C.byref(d), C.byref(f), C.byref(n)), "group_range")
+            out.append((d.value, f.value, n.value))
+        return out
+
+    def reset(self):
+        check(lib().nnsp_b200_group_reset(self.h), "group_reset")
+
+    def exec_host(self, pcm, results=None):
+        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and pcm.shape[0] == self.S
+        T = pcm.shape[1] // FRAME
+        if results is None:
+            results = np.empty((self.S, T), self.result_dt)
+        check(lib().nnsp_b200_group_exec_host(self.h, pcm.ctypes.data_as(C.c_void_p), pcm.shape[1], T,
+                                              results.ctypes.data_as(C.c_void_p)), "group_exec_host")
+        return results
+
+    def exec_host_async(self, pcm, results):
+        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and pcm.shape[0] == self.S
+        T = pcm.shape[1] // FRAME
+        assert results.dtype == self.result_dt and results.flags.c_contiguous and results.shape == (self.S, T)
+        t = C.c_longlong(0)
+        check(lib().nnsp_b200_group_exec_host_async(self.h, pcm.ctypes.data_as(C.c_void_p), pcm.shape[1], T,
+                                                    results.ctypes.data_as(C.c_void_p), C.byref(t)), "group_exec_host_async")
+        return t.value
+
+    def wait(self, ticket):
+        check(lib().nnsp_b200_group_wait(self.h, ticket), "group_wait")
+
+    def close(self):
+        if self.h:
+            lib().nnsp_b200_group_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):
@@ -393,6 +477,25 @@ def net_eval(model, x, h0=None, c0=None, nn_path="auto", device=0):
     check(lib().nnsp_b200_net_eval(model.h, device, NNSPBatch.NN_PATH[nn_path], n, p(x), p(h0), p(c0), p(act), p(logits),
                                    p(h1), p(c1)), "net_eval")
     return act[:, :a_s], logits, h1[:, :h_s], c1[:, :h_s]
+
+
+def wav_info(path):
+    """(sample_rate, channels, bits, samples per channel) of a RIFF/WAVE file"""
+    r, c, b, n = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+    check(lib().nnsp_b200_wav_info(os.fsencode(path), C.byref(r), C.byref(c), C.byref(b), C.byref(n)), "wav_info")
+    return r.value, c.value, b.value, n.value
+
+
+def wav_load_streams(paths, n_frames, channel=0, first_frame=0):
+    """int16 [len(paths), n_frames * 160]: stream s = frames first_frame.. of paths[s] (16 kHz, 16-bit PCM), zero padded;
+    also returns the number of frames that held file samples, per stream"""
+    n = len(paths)
+    arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    pcm = np.zeros((n, n_frames * FRAME), np.int16)
+    got = np.zeros(n, np.int32)
+    check(lib().nnsp_b200_wav_load_streams(arr, n, channel, first_frame, n_frames, pcm.ctypes.data_as(C.c_void_p),
+                                           n_frames * FRAME, got.ctypes.data_as(C.c_void_p)), "wav_load_streams")
+    return pcm, got
 
 
 def table(name):

@@ -43,7 +43,10 @@ nnsp_b200_cascade_reset nnsp_b200_cascade_exec nnsp_b200_cascade_exec_host nnsp_
 nnsp_b200_cascade_last_kernel_ms nnsp_b200_cascade_stream nnsp_b200_cascade_set_path nnsp_b200_cascade_destroy nnsp_b200_feature_stages
 nnsp_b200_table nnsp_b200_ingest_audadc nnsp_b200_device_count nnsp_b200_device_pci_bus_id nnsp_b200_dev_alloc nnsp_b200_dev_free nnsp_b200_host_alloc_pinned
 nnsp_b200_host_free_pinned nnsp_b200_memcpy_h2d nnsp_b200_memcpy_d2h nnsp_b200_memset nnsp_b200_event_create
-nnsp_b200_event_record nnsp_b200_event_elapsed_ms nnsp_b200_event_destroy nnsp_b200_int_peak nnsp_b200_net_eval""".split()
+nnsp_b200_event_record nnsp_b200_event_elapsed_ms nnsp_b200_event_destroy nnsp_b200_int_peak nnsp_b200_net_eval
+nnsp_b200_group_create_batch nnsp_b200_group_create_cascade nnsp_b200_group_size nnsp_b200_group_range nnsp_b200_group_reset
+nnsp_b200_group_exec_host nnsp_b200_group_exec_host_async nnsp_b200_group_wait nnsp_b200_group_destroy
+nnsp_b200_batch_set_host_format nnsp_b200_cascade_set_host_format nnsp_b200_wav_info nnsp_b200_wav_read_frames nnsp_b200_wav_load_streams nnsp_b200_cascade_timeline""".split()
 
 
 def lib():
@@ -117,6 +120,22 @@ def lib():
     L.nnsp_b200_event_destroy.argtypes = [vp]
     L.nnsp_b200_int_peak.argtypes = [ci, C.POINTER(C.c_double * 4)]
     L.nnsp_b200_net_eval.argtypes = [vp, ci, ci, ci] + [vp] * 7
+    L.nnsp_b200_group_create_batch.argtypes = [vp, ci, C.POINTER(ci), ci, i16, i16, C.POINTER(vp)]
+    L.nnsp_b200_group_create_cascade.argtypes = [C.POINTER(vp), C.POINTER(ci), ci, C.POINTER(CascadeParams), ci, C.POINTER(ci), ci, C.POINTER(vp)]
+    L.nnsp_b200_group_size.argtypes = [vp]
+    L.nnsp_b200_group_range.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+    L.nnsp_b200_group_reset.argtypes = [vp]
+    L.nnsp_b200_group_exec_host.argtypes = [vp, vp, ll, ci, vp]
+    L.nnsp_b200_group_exec_host_async.argtypes = [vp, vp, ll, ci, vp, C.POINTER(ll)]
+    L.nnsp_b200_group_wait.argtypes = [vp, ll]
+    L.nnsp_b200_group_destroy.argtypes = [vp]
+    L.nnsp_b200_group_destroy.restype = None
+    L.nnsp_b200_batch_set_host_format.argtypes = [vp, ci]
+    L.nnsp_b200_cascade_timeline.argtypes = [vp, vp, C.POINTER(ci)]
+    L.nnsp_b200_cascade_set_host_format.argtypes = [vp, ci]
+    L.nnsp_b200_wav_info.argtypes = [C.c_char_p, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ll)]
+    L.nnsp_b200_wav_read_frames.argtypes = [C.c_char_p, ci, ll, ci, vp, C.POINTER(ci)]
+    L.nnsp_b200_wav_load_streams.argtypes = [C.POINTER(C.c_char_p), ci, ci, ll, ci, vp, ll, vp]
     _lib = L
     return L
 

@@ -529,7 +529,7 @@ cascade_replay_kernel(CascadeArgs a, int off_w, int off_b)
  * after the last round (CS_MAX_ROUNDS) goes to the sequential kernel. The first two frames of a fresh instance see a
  * partly zero STFT buffer (spectrogram_module.c:25-31): cascade_fix_kernel computes those log-mel rows on the side. */
 constexpr int CG_GROUPS = 6;                        /* plane tiles reserved per slice beyond S/16 (one partial tile per group + slack) */
-constexpr int CPOST_THREADS = 64, CPOST_KCH = 64;
+constexpr int CPOST_WARPS = 8;                      /* streams per CTA of the controller walk */
 constexpr int CS_MAX_ROUNDS = 4;
 /* per-slice control block (ints, zeroed at the start of a call): round r at CTL_ROUND * r */
 constexpr int CTL_ROUND = 12;                       /* [0..2] group sizes by model id, [3..5] first plane tile of the group, */
@@ -702,21 +702,23 @@ __device__ __forceinline__ const int32_t *cascade_lm_row(const CascadePostArgs &
                      : a.st.lmhist + (s * a.cd.dmax + a.cd.dmax + fr) * NNSP_B200_NMEL;
 }
 
-__global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePostArgs a)
+/* The controller walk of one round, a warp per stream. Between two stage changes the per-frame work of
+ * nnCntrlClass_exec (nnCntrlClass.c:172-269) is closed-form: the time-out counter is (c0 + frames) mod time-out, and no
+ * frame before the exit frame can carry a detection (every detection resets the instance, i.e. IS the exit). So the warp
+ * (every lane redundantly, on broadcast decision records) only steps through the INFERENCES of the round to find the
+ * first detection -- s2i_post_proc / binary_post_proc on the decision records, nn_speech.c:146-227 -- takes the earlier of
+ * that and the first time-out that leaves the instance, and then writes all result records of the round in parallel. */
+__global__ void __launch_bounds__(32 * CPOST_WARPS) cascade_post_kernel(CascadePostArgs a)
 {
-    __shared__ int32_t dsm[CPOST_THREADS][CPOST_KCH + 1];
-    __shared__ int ssid[CPOST_THREADS];
     const CascadeDev &cd = a.cd;
     const int nsel = a.list ? *a.count : a.ns;
-    const int si0 = blockIdx.x * CPOST_THREADS, si = si0 + threadIdx.x;
-    if (si0 >= nsel) return;
-    const bool mine = si < nsel;
-    const long long s = a.list ? a.list[mine ? si : si0] : (long long)a.s0 + (mine ? si : si0);
-    ssid[threadIdx.x] = (int)s;
-    bool live = mine;
+    const int lane = threadIdx.x & 31;
+    const int si = blockIdx.x * CPOST_WARPS + (threadIdx.x >> 5);
+    if (si >= nsel) return;
+    const long long s = a.list ? a.list[si] : (long long)a.s0 + si;
     const int T = a.T;
     const int tb = a.ra.tb[s], ts = a.ra.tstart[s], age0 = a.ra.age0[s];
-    int pos = a.st.casc[s * CS_N + CS_POS];
+    const int pos = a.st.casc[s * CS_N + CS_POS];
     int cnt_kws = a.st.casc[s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[s * CS_N + CS_CNT_S2I];
     const int id = cd.seq[pos];
     const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
@@ -733,85 +735,81 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
         for (int i = 0; i < 8; i++) cnt[i] = sc[SC_CNT0 + i];
         last = sc[SC_ARGMAX_LAST]; slides = sc[SC_SLIDES];
     }
-    const int n_inf = (ts < T) ? (T - ts + 1) >> 1 : 0;               /* inferences of this stream's round: frames ts, ts + 2, ... */
-    const int n_inf_max = (T + 1) / 2;
-    const int nstr = min(CPOST_THREADS, nsel - si0);
-    int t = tb, t_exit = -1, next_pos_exit = 0;
-    __syncthreads();
-
-    for (int kc = 0; kc == 0 || kc < n_inf_max; kc += CPOST_KCH) {
-        const int nk = min(CPOST_KCH, n_inf_max - kc);
-        __syncthreads();
-        for (int e = threadIdx.x; e < nstr * nk; e += CPOST_THREADS) {
-            const int rr = e / nk, kk = e - rr * nk;
-            dsm[rr][kk] = a.dec[(size_t)ssid[rr] * a.dec_stride + kc + kk];
-        }
-        __syncthreads();
-        /* frames whose inference index lies in this round of the staging loop */
-        const int t_end = (kc + CPOST_KCH < n_inf) ? ts + 2 * (kc + CPOST_KCH) : T;
-        if (live) {
-            for (; t < t_end; t++) {
-                const bool ran = (t >= ts) && (((t - ts) & 1) == 0);                       /* nn_speech.c:84 */
-                if (ran) {
-                    const int dv = dsm[threadIdx.x][((t - ts) >> 1) - kc];
-                    if (id == NNSP_B200_ID_S2I) {                                           /* s2i_post_proc, nn_speech.c:146-189 */
-                        const int ai = dv & 0xff;
-                        trig = 0; out0 = 0; out1 = 0; out2 = 0;
-                        if (last == 0 || last == ai) {
-                            int hit = 0;
+    const int st_o0 = out0, st_o1 = out1, st_o2 = out2;              /* outputs[] as the round finds them (binary models never touch them) */
+    /* ---- time-outs (nnCntrlClass.c:186-206, 222-242): the counter of the live model is (c0 + n) mod time-out after n frames */
+    const bool has_to = id != NNSP_B200_ID_VAD;
+    const int timeout = (id == NNSP_B200_ID_S2I) ? cd.P.thresh_timeout_s2i : cd.P.thresh_timeout_kws;
+    const int c0 = (id == NNSP_B200_ID_S2I) ? cnt_s2i : cnt_kws;
+    int to_next = pos, t_to = T;                                      /* first frame whose counter reads time-out - 1 */
+    bool to_exit = false;
+    if (has_to) {
+        int n = timeout - 1 - c0;
+        if (n < 1) n += timeout;
+        t_to = tb + n - 1;
+        if (id == NNSP_B200_ID_S2I) to_next = (pos + 1) % cd.len_seq;
+        else { to_next = (pos - 1) % cd.len_seq; if (to_next < 0) to_next += cd.len_seq; }
+        to_exit = cd.seq[to_next] != id;                              /* otherwise the time-out changes nothing (:198, :234) */
+    }
+    const int t_lim = (to_exit && t_to < T) ? t_to : T - 1;           /* last frame this instance can see in this call */
+    /* ---- first detection: a stale trigger on the frame before the first inference, else the first inference that fires */
+    int t_det = -1;
+    if (ts > tb && tb <= t_lim && trig) t_det = tb;                   /* nn_speech.c:126: odd frames return the previous trigger */
+    if (t_det < 0 && ts <= t_lim) {
+        const int k_lim = ((t_lim - ts) >> 1) + 1;                    /* inferences at frames ts, ts + 2, ... <= t_lim */
+        const int32_t *dec = a.dec + (size_t)s * a.dec_stride;
+        for (int kb = 0; kb < k_lim && t_det < 0; kb += 32) {
+            const int dchunk = (kb + lane < k_lim) ? dec[kb + lane] : 0;
+            const int nk = min(32, k_lim - kb);
+            for (int j = 0; j < nk; j++) {
+                const int dv = __shfl_sync(0xffffffffu, dchunk, j);
+                if (id == NNSP_B200_ID_S2I) {                                               /* s2i_post_proc, nn_speech.c:146-189 */
+                    const int ai = dv & 0xff;
+                    trig = 0; out0 = 0; out1 = 0; out2 = 0;
+                    if (last == 0 || last == ai) {
+                        int hit = 0;
 #pragma unroll
-                            for (int i = 1; i < 7; i++) {
-                                const int c1 = (int)(int16_t)(cnt[i] + 1);
-                                if (ai == i) { cnt[i] = c1; hit = c1 > th_cnt; }
-                            }
-                            if (hit) { trig = 1; out0 = ai; out1 = (dv >> 8) & 0xff; out2 = (dv >> 16) & 0xff; }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 7; i++) cnt[i] = 0;
+                        for (int i = 1; i < 7; i++) {
+                            const int c1 = (int)(int16_t)(cnt[i] + 1);
+                            if (ai == i) { cnt[i] = c1; hit = c1 > th_cnt; }
                         }
-                        last = ai;
-                    } else {                                                                /* binary_post_proc, nn_speech.c:219-226 */
-                        const int c0 = dv ? (int)(int16_t)(cnt[0] + 1) : 0;
-                        cnt[0] = c0;
-                        trig = (c0 >= th_cnt) ? 1 : 0;
+                        if (hit) { trig = 1; out0 = ai; out1 = (dv >> 8) & 0xff; out2 = (dv >> 16) & 0xff; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 7; i++) cnt[i] = 0;
                     }
+                    last = ai;
+                } else {                                                                    /* binary_post_proc, nn_speech.c:219-226 */
+                    const int cc = dv ? (int)(int16_t)(cnt[0] + 1) : 0;
+                    cnt[0] = cc;
+                    trig = (cc >= th_cnt) ? 1 : 0;
                 }
-                slides ^= 1;
-                /* controller, nnCntrlClass.c:172-269 (same code as cascade_kernel) */
-                const int detected = trig;
-                int next_pos = pos, do_reset = 0, cnt_out = 0;
-                if (id == NNSP_B200_ID_S2I) {
-                    cnt_s2i = (cnt_s2i + 1) % cd.P.thresh_timeout_s2i;
-                    if (detected || cnt_s2i == cd.P.thresh_timeout_s2i - 1) {
-                        next_pos = (pos + 1) % cd.len_seq;
-                        if (detected || cd.seq[next_pos] != id) { cnt_s2i = 0; do_reset = 1; }
-                    }
-                    cnt_out = cnt_s2i;
-                } else if (id == NNSP_B200_ID_KWS) {
-                    cnt_kws = (cnt_kws + 1) % cd.P.thresh_timeout_kws;
-                    if (detected || cnt_kws == cd.P.thresh_timeout_kws - 1) {
-                        if (detected) next_pos = (pos + 1) % cd.len_seq;
-                        else { next_pos = (pos - 1) % cd.len_seq; if (next_pos < 0) next_pos += cd.len_seq; }
-                        if (detected || cd.seq[next_pos] != id) { cnt_kws = 0; do_reset = 1; }
-                    }
-                    cnt_out = cnt_kws;
-                } else if (detected) {
-                    next_pos = (pos + 1) % cd.len_seq;
-                    do_reset = 1;
-                }
-                if (a.results) {
-                    nnsp_b200_cascade_result r;
-                    r.stage_id = (int8_t)id; r.pos_after = (int8_t)next_pos; r.detected = (int16_t)detected;
-                    r.outputs[0] = (int16_t)out0; r.outputs[1] = (int16_t)out1; r.outputs[2] = (int16_t)out2;
-                    r.cnt_timeout = (uint16_t)cnt_out;
-                    a.results[s * T + t] = r;
-                }
-                if (do_reset) { t_exit = t; next_pos_exit = next_pos; live = false; break; }
+                if (trig) { t_det = ts + 2 * (kb + j); break; }
             }
         }
-        if (nk <= 0) break;
     }
-    if (!mine) return;
+    /* ---- where the round ends for this stream */
+    int t_exit = -1, next_pos_exit = pos;
+    bool by_det = false;
+    if (t_det >= 0) { t_exit = t_det; by_det = true; next_pos_exit = (pos + 1) % cd.len_seq; }   /* :189-205, :224-228, :256-266 */
+    else if (to_exit && t_to < T) { t_exit = t_to; next_pos_exit = to_next; }
+    const int t_last = (t_exit >= 0) ? t_exit : T - 1;
+    /* ---- result records of frames tb .. t_last, in parallel */
+    if (a.results) {
+        uint32_t *out = reinterpret_cast<uint32_t *>(a.results + s * T);                   /* 12-byte records, 4-byte aligned */
+        const bool zero_outs = id == NNSP_B200_ID_S2I;                                      /* s2i_post_proc clears outputs[] at every inference */
+        for (int t = tb + lane; t <= t_last; t += 32) {
+            const bool ex = t == t_exit;
+            const int det = (ex && by_det) ? trig : 0;
+            int o0 = st_o0, o1 = st_o1, o2 = st_o2;
+            if (zero_outs && t >= ts) { o0 = 0; o1 = 0; o2 = 0; }
+            if (ex && by_det && t >= ts) { o0 = out0; o1 = out1; o2 = out2; }
+            const int ct = (!has_to || ex) ? 0 : (c0 + (t - tb + 1)) % timeout;
+            const int pa = ex ? next_pos_exit : pos;
+            out[3 * t + 0] = (uint32_t)(uint8_t)id | ((uint32_t)(uint8_t)pa << 8) | ((uint32_t)(uint16_t)det << 16);
+            out[3 * t + 1] = (uint32_t)(uint16_t)o0 | ((uint32_t)(uint16_t)o1 << 16);
+            out[3 * t + 2] = (uint32_t)(uint16_t)o2 | ((uint32_t)(uint16_t)ct << 16);
+        }
+    }
     const MmaModel &M = *a.model[id];
     int16_t *ctx = a.st.ctx + s * 240;
     if (t_exit >= 0) {
@@ -819,30 +817,38 @@ __global__ void __launch_bounds__(CPOST_THREADS) cascade_post_kernel(CascadePost
          * behind as that instance's stale row 5 (feature_module.c:39-42) ... */
         const int32_t *row = cascade_lm_row(a, s, t_exit, d, tb, age0);
         int16_t *stale = a.stale + (s * 3 + id) * 40;
-        for (int i = 0; i < 40; i++) stale[i] = standardise(row[i], M.mean[i], M.stdR[i], M.feat_rshift);
+        for (int i = lane; i < 40; i += 32) stale[i] = standardise(row[i], M.mean[i], M.stdR[i], M.feat_rshift);
+        __syncwarp();
         /* ... and the instance entered starts from ITS reset state plus ITS stale row */
         const int nid = cd.seq[next_pos_exit];
         const MmaModel &N = *a.model[nid];
         const int16_t *st2 = a.stale + (s * 3 + nid) * 40;
-        for (int i = 0; i < 200; i++) ctx[i] = N.silence[i % 40];
-        for (int i = 0; i < 40; i++) ctx[200 + i] = st2[i];
-        for (int i = 0; i < NNSP_B200_MAX_WIDTH; i++) { a.st.h[s * NNSP_B200_MAX_WIDTH + i] = 0; a.st.c[s * NNSP_B200_MAX_WIDTH + i] = 0; }
+        for (int i = lane; i < 240; i += 32) ctx[i] = (i < 200) ? N.silence[i % 40] : st2[i - 200];
+        for (int i = lane; i < NNSP_B200_MAX_WIDTH; i += 32) { a.st.h[s * NNSP_B200_MAX_WIDTH + i] = 0; a.st.c[s * NNSP_B200_MAX_WIDTH + i] = 0; }
         trig = out0 = out1 = out2 = last = 0; slides = 1;
 #pragma unroll
         for (int i = 0; i < 8; i++) cnt[i] = 0;
-        a.st.casc[s * CS_N + CS_POS] = (uint16_t)next_pos_exit;
-        a.st.casc[s * CS_N + CS_AGE] = 0;
-        a.ra.t0[s] = t_exit + 1;
-        a.ra.tb[s] = t_exit + 1; a.ra.tstart[s] = t_exit + 1; a.ra.age0[s] = 0;       /* a fresh instance: slides == 1 (nn_speech.c:62) */
-        if (t_exit + 1 < T) a.next_list[a.s0 + atomicAdd(a.next_count, 1)] = (int)s;
+        if (id == NNSP_B200_ID_S2I) cnt_s2i = 0; else if (id == NNSP_B200_ID_KWS) cnt_kws = 0;
+        if (lane == 0) {
+            a.st.casc[s * CS_N + CS_POS] = (uint16_t)next_pos_exit;
+            a.st.casc[s * CS_N + CS_AGE] = 0;
+            a.ra.t0[s] = t_exit + 1;
+            a.ra.tb[s] = t_exit + 1; a.ra.tstart[s] = t_exit + 1; a.ra.age0[s] = 0;   /* a fresh instance: slides == 1 (nn_speech.c:62) */
+            if (t_exit + 1 < T) a.next_list[a.s0 + atomicAdd(a.next_count, 1)] = (int)s;
+        }
     } else {
-        a.ra.t0[s] = T + 1;                    /* lived through the call: cascade_ctx_kernel rebuilds its context */
-        const int age = age0 + (T - tb);
-        a.st.casc[s * CS_N + CS_AGE] = (uint16_t)(age < 2 ? age : 2);
+        const int n = T - tb;                                          /* frames the instance lived in this call */
+        if (has_to) { const int c = (c0 + n) % timeout; if (id == NNSP_B200_ID_S2I) cnt_s2i = c; else cnt_kws = c; }
+        slides ^= n & 1;                                               /* nn_speech.c:125 */
+        if (lane == 0) {
+            a.ra.t0[s] = T + 1;                    /* lived through the call: cascade_ctx_kernel rebuilds its context */
+            const int age = age0 + n;
+            a.st.casc[s * CS_N + CS_AGE] = (uint16_t)(age < 2 ? age : 2);
+        }
     }
-    a.st.casc[s * CS_N + CS_CNT_KWS] = (uint16_t)cnt_kws;
-    a.st.casc[s * CS_N + CS_CNT_S2I] = (uint16_t)cnt_s2i;
-    {
+    if (lane == 0) {
+        a.st.casc[s * CS_N + CS_CNT_KWS] = (uint16_t)cnt_kws;
+        a.st.casc[s * CS_N + CS_CNT_S2I] = (uint16_t)cnt_s2i;
         int16_t sc[SC_N];
         sc[SC_TRIGGER] = (int16_t)trig; sc[SC_OUT0] = (int16_t)out0; sc[SC_OUT0 + 1] = (int16_t)out1; sc[SC_OUT0 + 2] = (int16_t)out2;
 #pragma unroll
@@ -937,7 +943,10 @@ struct nnsp_b200_cascade {
     bool narrow = false;                      /* which shape of the sequential kernel (CsNarrow / CsWide) */
     bool replay_coop = true;                  /* what the rounds leave goes to cascade_replay_kernel (NNSP_CR_GW warps per stream); NNSP_B200_REPLAY_COOP=0: one warp per stream */
     size_t smem_replay = 0; int off_w_replay = 0;
-    cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+    /* CUDA events around the front end and around the controller / network chain of the last CS_TL device-buffer calls:
+     * [0] front end starts, [1] front end done, [2] chain starts, [3] chain done (nnsp_b200_cascade_timeline) */
+    cudaEvent_t tl[8][4] = {};
+    long long tl_count = 0;
     bool ev_valid = false;
     /* stage-sorted pass (scan-split kernels per (model, phase) group + replay) */
     MmaDeviceModel mm[3];
@@ -954,7 +963,7 @@ struct nnsp_b200_cascade {
     /* device-buffer calls are pipelined like the batched path: front end + PCM history roll of call N+1 on `stream`,
      * controller / network work of call N on `nn_stream`; log-mel rows and PCM history are double buffered */
     cudaStream_t nn_stream = nullptr;
-    cudaEvent_t ev_feat[2] = { nullptr, nullptr }, ev_nn[2] = { nullptr, nullptr }, ev_nn0 = nullptr;
+    cudaEvent_t ev_feat[2] = { nullptr, nullptr }, ev_nn[2] = { nullptr, nullptr };
     bool nn_pending[2] = { false, false }, last_piped = false;
     unsigned pipe = 0;
     int32_t *logmel2 = nullptr;                /* second log-mel buffer */
@@ -965,6 +974,8 @@ struct nnsp_b200_cascade {
     long long host_seq = 0;
     bool host_inflight = false;
     int host_last_T = 0;                       /* frames per stream of the latest host-buffer call */
+    int host_fmt = NNSP_B200_HOST_PCM16;       /* int16 PCM or raw 32-bit AUDADC words (conditioned on the device) */
+    uint32_t *d_raw = nullptr;
 };
 
 constexpr int CS_MAX_SLICES = 8;
@@ -1015,10 +1026,11 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
     if (!logmel) logmel = c->logmel;
     const bool piped = st_nn != nullptr;
     FeatLaunch fl{ pcm, stride, c->st.hist, hist_frames, s0, ns, T, logmel };
-    if (timed) NNSP_CUDA(cudaEventRecord(c->ev[0], st));
+    cudaEvent_t *tl = c->tl[c->tl_count % 8];
+    if (timed) NNSP_CUDA(cudaEventRecord(tl[0], st));
     int rc = launch_feature(c->tables, fl, c->device, st);
     if (rc) return rc;
-    if (timed) NNSP_CUDA(cudaEventRecord(c->ev[1], st));
+    if (timed) NNSP_CUDA(cudaEventRecord(tl[1], st));
     if (piped) {
         NNSP_CUDA(cudaEventRecord(ev_feat, st));
         NNSP_CUDA(cudaStreamWaitEvent(st_nn, ev_feat, 0));
@@ -1026,7 +1038,7 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
         if (ev_prev_nn) NNSP_CUDA(cudaStreamWaitEvent(st, ev_prev_nn, 0));
         if ((rc = launch_hist_roll(pcm, stride / 2, c->st.hist, c->hist2, hist_frames, NNSP_B200_FRAME / 2, s0, ns, T, st))) return rc;
         st = st_nn;
-        if (timed) NNSP_CUDA(cudaEventRecord(c->ev_nn0, st));
+        if (timed) NNSP_CUDA(cudaEventRecord(tl[2], st));
     }
     CascadeArgs a{};
     for (int i = 0; i < 3; i++) { a.model[i] = c->dm[i].d; a.wimg[i] = c->dm[i].wimg; a.bimg[i] = c->dm[i].bimg; }
@@ -1093,7 +1105,7 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
             /* walk the controller over the decisions; a stream that changes stage is cut there and queued for the next round */
             p.list = queued; p.count = r ? ctl_prev + CTL_NEXT : nullptr;
             p.next_list = c->pend[(r + 1) & 1]; p.next_count = ctl_r + CTL_NEXT;
-            cascade_post_kernel<<<(ns + CPOST_THREADS - 1) / CPOST_THREADS, CPOST_THREADS, 0, st>>>(p);
+            cascade_post_kernel<<<(ns + CPOST_WARPS - 1) / CPOST_WARPS, 32 * CPOST_WARPS, 0, st>>>(p);
             NNSP_LAUNCH_CHECK();
         }
         cascade_ctx_kernel<<<(ns * 32 + 255) / 256, 256, 0, st>>>(p);
@@ -1117,7 +1129,11 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
     } else if (c->narrow) cascade_kernel<CsNarrow><<<blocks, 32 * CsNarrow::WARPS, c->smem_total, st>>>(a, c->off_w, c->off_b);
     else cascade_kernel<CsWide><<<blocks, 32 * CsWide::WARPS, c->smem_total, st>>>(a, c->off_w, c->off_b);
     NNSP_LAUNCH_CHECK();
-    if (timed) { NNSP_CUDA(cudaEventRecord(c->ev[2], st)); c->ev_valid = true; c->last_piped = piped; }
+    if (timed) {
+        if (!piped) NNSP_CUDA(cudaEventRecord(tl[2], st));      /* one stream: the chain starts where the front end ended */
+        NNSP_CUDA(cudaEventRecord(tl[3], st));
+        c->ev_valid = true; c->last_piped = piped; c->tl_count++;
+    }
     if (!piped && (rc = launch_hist_update(pcm, stride / 2, c->st.hist, hist_frames, NNSP_B200_FRAME / 2, s0, ns, T, st))) return rc;
     if (c->cd.dmax > 0)
         rc = launch_hist_update(logmel, (long long)T * NNSP_B200_NMEL, c->st.lmhist, c->cd.dmax, NNSP_B200_NMEL, s0, ns, T, st);
@@ -1221,14 +1237,13 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &r : c->host_ev) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : c->ev) TRY(cudaEventCreate(&e));
+    for (auto &row : c->tl) for (auto &e : row) TRY(cudaEventCreate(&e));
     for (auto &row : c->gs) for (auto &g : row) TRY(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;
         TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         TRY(cudaStreamCreateWithPriority(&c->nn_stream, cudaStreamNonBlocking, hi));
     }
-    TRY(cudaEventCreate(&c->ev_nn0));
     for (auto &e : c->ev_feat) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : c->ev_nn) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : c->ev_fork) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1337,7 +1352,8 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
         NNSP_CUDA(cudaDeviceSynchronize());
         if (c->d_pcm) cudaFree(c->d_pcm);
         if (c->d_res) cudaFree(c->d_res);
-        c->d_pcm = nullptr; c->d_res = nullptr;
+        if (c->d_raw) cudaFree(c->d_raw);
+        c->d_pcm = nullptr; c->d_res = nullptr; c->d_raw = nullptr;
         NNSP_CUDA(cudaMalloc(&c->d_pcm, (size_t)c->S * T * NNSP_B200_FRAME * sizeof(int16_t)));
         NNSP_CUDA(cudaMalloc(&c->d_res, (size_t)c->S * T * sizeof(nnsp_b200_cascade_result)));
         c->d_pcm_frames = T;
@@ -1353,6 +1369,10 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
             for (int k = 0; k < 3; k++) NNSP_CUDA(cudaStreamWaitEvent(c->xs[j], c->host_ev[c->host_seq % CS_HOST_RING][k], 0));
     c->host_last_T = T;
     const long long dstride = (long long)T * NNSP_B200_FRAME;
+    if (c->host_fmt == NNSP_B200_HOST_AUDADC && !c->d_raw) {
+        NNSP_CUDA(cudaDeviceSynchronize());
+        NNSP_CUDA(cudaMalloc(&c->d_raw, (size_t)c->S * c->d_pcm_frames * NNSP_B200_FRAME * sizeof(uint32_t)));
+    }
     c->host_inflight = true;
     const int nsl = c->S >= 4096 ? 8 : (c->S >= 256 ? 4 : 1);
     for (int k = 0; k < nsl; k++) {
@@ -1360,6 +1380,13 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
         const int s1 = (k == nsl - 1) ? c->S : (int)(((long long)c->S * (k + 1) / nsl) & ~15LL);
         if (s1 <= s0) continue;
         cudaStream_t st = c->xs[k % 3];
+        if (c->host_fmt == NNSP_B200_HOST_AUDADC) {                 /* the application's ingest (main_nnsp.cc:58-65) on the device */
+            const uint32_t *raw = reinterpret_cast<const uint32_t *>(pcm);
+            NNSP_CUDA(cudaMemcpy2DAsync(c->d_raw + (size_t)s0 * dstride, dstride * sizeof(uint32_t),
+                                        raw + (size_t)s0 * stream_stride, stream_stride * sizeof(uint32_t),
+                                        dstride * sizeof(uint32_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
+            if ((rc = launch_ingest(c->d_raw + (size_t)s0 * dstride, c->d_pcm + (size_t)s0 * dstride, (long long)(s1 - s0) * T, c->device, st))) return rc;
+        } else
         NNSP_CUDA(cudaMemcpy2DAsync(c->d_pcm + (size_t)s0 * dstride, dstride * sizeof(int16_t),
                                     pcm + (size_t)s0 * stream_stride, stream_stride * sizeof(int16_t),
                                     dstride * sizeof(int16_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
@@ -1422,13 +1449,41 @@ int nnsp_b200_cascade_last_kernel_ms(nnsp_b200_cascade *c, float ms[3])
     ms[0] = ms[1] = ms[2] = 0.f;
     if (!c->ev_valid) return NNSP_B200_OK;
     NNSP_CUDA(cudaSetDevice(c->device));
-    NNSP_CUDA(cudaEventSynchronize(c->ev[2]));
-    NNSP_CUDA(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
-    NNSP_CUDA(cudaEventElapsedTime(&ms[1], c->last_piped ? c->ev_nn0 : c->ev[1], c->ev[2]));
+    cudaEvent_t *tl = c->tl[(c->tl_count - 1) % 8];
+    NNSP_CUDA(cudaEventSynchronize(tl[3]));
+    NNSP_CUDA(cudaEventElapsedTime(&ms[0], tl[0], tl[1]));
+    NNSP_CUDA(cudaEventElapsedTime(&ms[1], c->last_piped ? tl[2] : tl[1], tl[3]));
+    return NNSP_B200_OK;
+}
+
+/* When, on the device, the front end and the controller / network chain of the last calls ran: for each of the last
+ * n <= 8 device-buffer calls (oldest first) ms[k][0..3] = front end starts / done, chain starts / done, in milliseconds
+ * after the oldest call's front end started. Synchronises the handle. Shows how far consecutive calls overlap. */
+int nnsp_b200_cascade_timeline(nnsp_b200_cascade *c, float *ms, int *n_calls)
+{
+    if (!c || !ms || !n_calls) return NNSP_B200_ERR_ARG;
+    int rc = nnsp_b200_cascade_sync(c);
+    if (rc) return rc;
+    const int n = (int)(c->tl_count < 8 ? c->tl_count : 8);
+    *n_calls = n;
+    if (n == 0) return NNSP_B200_OK;
+    const long long first = c->tl_count - n;
+    for (int k = 0; k < n; k++)
+        for (int j = 0; j < 4; j++)
+            NNSP_CUDA(cudaEventElapsedTime(&ms[4 * k + j], c->tl[first % 8][0], c->tl[(first + k) % 8][j]));
     return NNSP_B200_OK;
 }
 
 void *nnsp_b200_cascade_stream(nnsp_b200_cascade *c) { return c ? (void *)c->stream : nullptr; }
+
+int nnsp_b200_cascade_set_host_format(nnsp_b200_cascade *c, int fmt)
+{
+    if (!c || (fmt != NNSP_B200_HOST_PCM16 && fmt != NNSP_B200_HOST_AUDADC)) return NNSP_B200_ERR_ARG;
+    int rc = nnsp_b200_cascade_sync(c);
+    if (rc) return rc;
+    c->host_fmt = fmt;
+    return NNSP_B200_OK;
+}
 
 int nnsp_b200_cascade_set_path(nnsp_b200_cascade *c, int path)
 {
@@ -1446,9 +1501,8 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     for (int i = 0; i < 3; i++) if (c->have[i]) free_model(&c->dm[i]);
     cudaFree(c->st.ctx); cudaFree(c->st.h); cudaFree(c->st.c); cudaFree(c->st.scal); cudaFree(c->st.casc);
     cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale);
-    cudaFree(c->logmel); cudaFree(c->logmel2); cudaFree(c->hist2); cudaFree(c->d_pcm); cudaFree(c->d_res);
+    cudaFree(c->logmel); cudaFree(c->logmel2); cudaFree(c->hist2); cudaFree(c->d_pcm); cudaFree(c->d_res); cudaFree(c->d_raw);
     if (c->nn_stream) cudaStreamDestroy(c->nn_stream);
-    if (c->ev_nn0) cudaEventDestroy(c->ev_nn0);
     for (auto e : c->ev_feat) if (e) cudaEventDestroy(e);
     for (auto e : c->ev_nn) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) free_model_mma(&c->mm[i]);
@@ -1458,7 +1512,7 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto s : c->xs) if (s) cudaStreamDestroy(s);
     for (auto &r : c->host_ev) for (auto e : r) if (e) cudaEventDestroy(e);
-    for (auto e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &row : c->tl) for (auto e : row) if (e) cudaEventDestroy(e);
     for (auto &row : c->gs) for (auto g : row) if (g) cudaStreamDestroy(g);
     for (auto e : c->ev_fork) if (e) cudaEventDestroy(e);
     for (auto &row : c->ev_join) for (auto e : row) if (e) cudaEventDestroy(e);

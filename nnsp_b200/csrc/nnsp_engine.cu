@@ -287,7 +287,12 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
     /* a whole number of resident waves: every CTA slot then runs the same number of CTAs and the slots finish within one
      * round of each other instead of one CTA lifetime (3 200 CTAs on 444 slots left the last wave 20 % full) */
     if (blocks > cap) blocks = chunked > cap ? ((chunked + cap / 2) / cap) * cap : cap;
-    feat_kernel<<<(unsigned)blocks, FEAT_THREADS, sizeof(FeatSmem), st>>>(tb, a.pcm, a.stride, a.hist, a.hist_frames,
+    static const int pad = [] { const char *e = getenv("NNSP_B200_FEAT_SMEM_PAD"); return e ? atoi(e) : 0; }();   /* measurement knob: fewer resident CTAs */
+    if (pad > 0) {
+        static bool pad_set[64] = { false };
+        if (!pad_set[device]) { NNSP_CUDA(cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeatSmem) + pad)); pad_set[device] = true; }
+    }
+    feat_kernel<<<(unsigned)blocks, FEAT_THREADS, sizeof(FeatSmem) + (pad > 0 ? pad : 0), st>>>(tb, a.pcm, a.stride, a.hist, a.hist_frames,
                                                                             a.s0, a.ns, a.T, a.logmel, a.norm, a.feat16);
     NNSP_LAUNCH_CHECK();
     return NNSP_B200_OK;
@@ -524,6 +529,18 @@ __global__ void __launch_bounds__(256) ingest_audadc_kernel(const uint4 *__restr
     }
 }
 
+int launch_ingest(const uint32_t *raw_dev, int16_t *pcm_dev, long long n_frames, int device, cudaStream_t st)
+{
+    if (n_frames <= 0) return NNSP_B200_OK;
+    const long long groups = n_frames * (NNSP_B200_FRAME / 8);
+    long long blocks = (groups + 255) / 256;
+    const long long cap = (long long)sm_count(device) * 8;
+    if (blocks > cap) blocks = cap;
+    ingest_audadc_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint4 *)raw_dev, (uint4 *)pcm_dev, groups);
+    NNSP_LAUNCH_CHECK();
+    return NNSP_B200_OK;
+}
+
 /* integer-pipe peaks: 8 independent register chains per thread, 16 operations per chain-iteration
  *   mode 0: IMAD (32-bit multiply-add)          mode 1: IMAD + independent ALU ops (add / shift / xor), 1:1
  *   mode 2: IMAD.WIDE (32x32 -> 64 accumulate)  mode 3: IDP.2A (two int16 x int8 MACs per instruction) */
@@ -633,6 +650,8 @@ struct nnsp_b200_batch {
     long long host_seq = 0;                 /* ticket of the latest asynchronous host call */
     bool host_inflight = false;
     int host_last_T = 0;                    /* frames per stream of the latest host-buffer call */
+    int host_fmt = NNSP_B200_HOST_PCM16;    /* what the host-buffer calls are handed: int16 PCM or raw 32-bit AUDADC words */
+    uint32_t *d_raw = nullptr;              /* staging of the raw words, [S][T*160] */
 };
 
 static int batch_nn_path(const nnsp_b200_batch *b);
@@ -941,7 +960,8 @@ static int batch_enqueue_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
         NNSP_CUDA(cudaDeviceSynchronize());
         if (b->d_pcm) cudaFree(b->d_pcm);
         if (b->d_res) cudaFree(b->d_res);
-        b->d_pcm = nullptr; b->d_res = nullptr;
+        if (b->d_raw) cudaFree(b->d_raw);
+        b->d_pcm = nullptr; b->d_res = nullptr; b->d_raw = nullptr;
         NNSP_CUDA(cudaMalloc(&b->d_pcm, (size_t)b->S * T * NNSP_B200_FRAME * sizeof(int16_t)));
         NNSP_CUDA(cudaMalloc(&b->d_res, (size_t)b->S * T * sizeof(nnsp_b200_result)));
         b->d_pcm_frames = T; b->d_res_frames = T;
@@ -957,6 +977,10 @@ static int batch_enqueue_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
         for (int j = 0; j < 4; j++)
             for (int k = 0; k < 4; k++) NNSP_CUDA(cudaStreamWaitEvent(b->xs[j], b->host_ev[b->host_seq % HOST_RING][k], 0));
     b->host_last_T = T;
+    if (b->host_fmt == NNSP_B200_HOST_AUDADC && !b->d_raw) {
+        NNSP_CUDA(cudaDeviceSynchronize());
+        NNSP_CUDA(cudaMalloc(&b->d_raw, (size_t)b->S * b->d_pcm_frames * NNSP_B200_FRAME * sizeof(uint32_t)));
+    }
     /* slices of streams pipelined over four CUDA streams: H2D(k+1) overlaps kernels(k) overlaps D2H(k-1). The call
      * is bound by the host link (320 B of PCM per stream-frame), so slices are small enough that the work left
      * after the last H2D -- one slice of kernels and its D2H -- is short, and large enough to fill the GPU */
@@ -970,7 +994,15 @@ static int batch_enqueue_host(nnsp_b200_batch *b, const int16_t *pcm, long long 
         const int s1 = (k == nsl - 1) ? b->S : (int)(((long long)b->S * (k + 1) / nsl) & ~15LL);
         if (s1 <= s0) continue;
         cudaStream_t st = b->xs[k % 4];
-        if (stream_stride == dstride) {
+        if (b->host_fmt == NNSP_B200_HOST_AUDADC) {
+            /* the application's ingest in front of the path: raw 32-bit words over the link, conditioned on the device
+             * (mask to the 12-bit sample, sample-3 glitch fix: main_nnsp.cc:58-65), then the same kernels */
+            const uint32_t *raw = reinterpret_cast<const uint32_t *>(pcm);
+            NNSP_CUDA(cudaMemcpy2DAsync(b->d_raw + (size_t)s0 * dstride, dstride * sizeof(uint32_t),
+                                        raw + (size_t)s0 * stream_stride, stream_stride * sizeof(uint32_t),
+                                        dstride * sizeof(uint32_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
+            if ((rc = launch_ingest(b->d_raw + (size_t)s0 * dstride, b->d_pcm + (size_t)s0 * dstride, (long long)(s1 - s0) * T, b->device, st))) return rc;
+        } else if (stream_stride == dstride) {
             NNSP_CUDA(cudaMemcpyAsync(b->d_pcm + (size_t)s0 * dstride, pcm + (size_t)s0 * stream_stride,
                                       (size_t)(s1 - s0) * dstride * sizeof(int16_t), cudaMemcpyHostToDevice, st));
         } else {
@@ -1036,6 +1068,15 @@ int nnsp_b200_batch_set_nn_path(nnsp_b200_batch *b, int path)
 
 int nnsp_b200_batch_get_nn_path(const nnsp_b200_batch *b) { return b ? batch_nn_path(b) : NNSP_B200_ERR_ARG; }
 
+int nnsp_b200_batch_set_host_format(nnsp_b200_batch *b, int fmt)
+{
+    if (!b || (fmt != NNSP_B200_HOST_PCM16 && fmt != NNSP_B200_HOST_AUDADC)) return NNSP_B200_ERR_ARG;
+    int rc = nnsp_b200_batch_sync(b);
+    if (rc) return rc;
+    b->host_fmt = fmt;
+    return NNSP_B200_OK;
+}
+
 void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
 {
     if (!b) return;
@@ -1044,7 +1085,7 @@ void nnsp_b200_batch_destroy(nnsp_b200_batch *b)
     free_model(&b->dm);
     free_model_mma(&b->mm);
     cudaFree(b->st.ctx); cudaFree(b->st.h); cudaFree(b->st.c); cudaFree(b->st.scal); cudaFree(b->st.hist);
-    cudaFree(b->logmel); cudaFree(b->d_pcm); cudaFree(b->d_res);
+    cudaFree(b->logmel); cudaFree(b->d_pcm); cudaFree(b->d_res); cudaFree(b->d_raw);
     cudaFree(b->sp_planes[0]); cudaFree(b->sp_planes[1]); cudaFree(b->sp_dec);
     cudaFree(b->feat16[0]); cudaFree(b->feat16[1]); cudaFree(b->norm_dev);
     if (b->nn_stream) cudaStreamDestroy(b->nn_stream);
@@ -1183,14 +1224,7 @@ int nnsp_b200_ingest_audadc(int device, const uint32_t *raw_dev, int16_t *pcm_de
     }
     int rc = select_device(device);
     if (rc) return rc;
-    if (n_frames == 0) return NNSP_B200_OK;
-    const long long groups = n_frames * (NNSP_B200_FRAME / 8);
-    long long blocks = (groups + 255) / 256;
-    const long long cap = (long long)sm_count(device) * 8;
-    if (blocks > cap) blocks = cap;
-    ingest_audadc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4 *)raw_dev, (uint4 *)pcm_dev, groups);
-    NNSP_LAUNCH_CHECK();
-    return NNSP_B200_OK;
+    return launch_ingest(raw_dev, pcm_dev, n_frames, device, (cudaStream_t)stream);
 }
 
 int nnsp_b200_table(const char *name, const void **data, int *elem_bytes)

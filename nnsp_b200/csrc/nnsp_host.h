@@ -64,6 +64,10 @@ int launch_hist_roll(const void *src, long long stride_words, const void *hist_i
                      int words_per_frame, int s0, int ns, int T, cudaStream_t st);
 
 
+/* audio_frame_callback's conditioning (evb/src/main_nnsp.cc:58-65) of n_frames consecutive 160-sample frames, raw 32-bit
+ * AUDADC words -> int16 PCM; both pointers 16-byte aligned */
+int launch_ingest(const uint32_t *raw_dev, int16_t *pcm_dev, long long n_frames, int device, cudaStream_t st);
+
 /* tensor-core (IMMA) network path, nnsp_mma.cu */
 struct MmaModel;
 struct MmaDeviceModel {

@@ -40,7 +40,10 @@
 
 namespace nnsp {
 
-constexpr int SEG_WARPS = 8;
+#ifndef NNSP_SEG_WARPS
+#define NNSP_SEG_WARPS 8
+#endif
+constexpr int SEG_WARPS = NNSP_SEG_WARPS;
 constexpr int SEG_THREADS = SEG_WARPS * 32;
 constexpr int SEG_KC = 16;                          /* inferences per work item                          */
 constexpr int SEG_FROWS = 2 * SEG_KC + 4;           /* feature rows covering 16 windows of 6, stride 2   */
@@ -321,7 +324,11 @@ template <int MODE>
 #ifndef SEG_MINB
 #define SEG_MINB 2
 #endif
+#ifdef SEG_MAXNREG            /* register cap instead of a residency target: a CTA that fits the hole one retiring feat_kernel CTA leaves */
+__global__ void __maxnreg__(SEG_MAXNREG)
+#else
 __global__ void __launch_bounds__(SEG_THREADS, SEG_MINB)
+#endif
 seg_kernel(SegArgs a)
 {
     constexpr bool FROM_FEAT = MODE != 0;
@@ -1101,6 +1108,9 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
             /* the shipped layers get their k-step counts compiled in: VAD 28 -> 28 (1 k-step), KWS 64 -> 64 (2), S2I 72 -> 72 (3) */
             const int kq = (L.kt == L.ktr) ? L.kt : 0;
             if (L.nt <= 4) rc = (kq == 1) ? launch_scan<4, 4, 1>(a, ntiles, smem, device, st) : launch_scan<4, 4, 0>(a, ntiles, smem, device, st);
+#ifdef SCAN_NW8                /* 64-unit layers (KWS): eight unit groups need eight warps, not nine */
+            else if (L.nt <= 8 && kq == 2) rc = launch_scan<8, 2, 2>(a, ntiles, smem, device, st);
+#endif
             else if (L.nt <= 9) rc = (kq == 2) ? launch_scan<9, 2, 2>(a, ntiles, smem, device, st)
                                    : (kq == 3) ? launch_scan<9, 2, 3>(a, ntiles, smem, device, st) : launch_scan<9, 2, 0>(a, ntiles, smem, device, st);
             else rc = launch_scan<16, 1, 0>(a, ntiles, smem, device, st);

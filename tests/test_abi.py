@@ -46,6 +46,10 @@ def test_no_cpu_fallback(nb):
         nb.Cascade([nb.Model.from_blob(os.path.join(nb.MODEL_DIR, f)) for f in ("s2i.nnspm", "vad.nnspm", "kws_galaxy.nnspm")], 8)
     with pytest.raises(nb.NnspError):
         nb.feature_stages(np.zeros((1, 480), np.int16))
+    with pytest.raises(nb.NnspError):
+        nb.Group(m, 64, [0, 0])
+    with pytest.raises(nb.NnspError):
+        nb.net_eval(m, np.zeros((2, 240), np.int16))
 
 
 def test_product_does_not_link_or_import_the_oracle():

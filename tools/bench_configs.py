@@ -33,9 +33,12 @@ def time_handle(h, exec_fn, T, S, steps=8, warm=3):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     paths = ["split", "imma"]
+    cpaths = ["sorted", "sequential"]
     for a in sys.argv[1:]:
         if a.startswith("--paths"):
             paths = a.split("=")[1].split(",")
+        if a.startswith("--cascade-paths"):
+            cpaths = a.split("=")[1].split(",")
     if not args:
         args = ["vad:4096", "kws:16384:acc32", "s2i:32768", "cascade:8192"]
     T = 100
@@ -49,13 +52,13 @@ def main():
         d = [nb.DeviceArray.from_host(pcm), nb.DeviceArray.from_host(np.roll(pcm, 7, axis=0))]
         if name == "cascade":
             models = [nb.Model.from_blob(os.path.join(nb.MODEL_DIR, FILES[k]), acc32=acc32) for k in ("s2i", "vad", "kws")]
-            for cp in ("sorted", "sequential"):
+            for cp in cpaths:
                 h = nb.Cascade(models, S)
                 h.set_path(cp)
                 res = nb.DeviceArray((S, T), nb.CASCADE_RESULT_DT)
                 ms, km = time_handle(h, lambda i: h.exec_device(d[i & 1], T * 160, T, res), T, S, steps=20, warm=10)
                 stage = np.bincount(res.to_host()["stage_id"].ravel().astype(np.int64), minlength=3)
-                print(json.dumps({"config": spec, "kernel": "cascade-" + cp, "ms_per_step": ms, "audio_s_per_s": S * T * 0.01 / (ms * 1e-3),
+                print(json.dumps({"config": spec, "lib": os.path.basename(os.environ.get("NNSP_B200_LIB", "product")), "kernel": "cascade-" + cp, "ms_per_step": ms, "audio_s_per_s": S * T * 0.01 / (ms * 1e-3),
                                   "feat_ms": km[0], "nn_ms": km[1], "stage_frames_last_step": stage.tolist()}), flush=True)
                 h.close()
                 res.free()
@@ -65,7 +68,7 @@ def main():
                 h = nb.NNSPBatch(m, S, nn_path=p)
                 res = nb.DeviceArray((S, T), nb.RESULT_DT)
                 ms, km = time_handle(h, lambda i: h.exec_device(d[i & 1], T * 160, T, res), T, S)
-                print(json.dumps({"config": spec, "kernel": p, "ms_per_step": ms, "audio_s_per_s": S * T * 0.01 / (ms * 1e-3),
+                print(json.dumps({"config": spec, "lib": os.path.basename(os.environ.get("NNSP_B200_LIB", "product")), "kernel": p, "ms_per_step": ms, "audio_s_per_s": S * T * 0.01 / (ms * 1e-3),
                                   "feat_ms": km[0], "nn_ms": km[1]}), flush=True)
                 h.close()
                 res.free()
