@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-configs", action="store_true")
+    ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S, help="repeat the K-step timed region until it adds up to this (profiler runs: 0)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -417,7 +418,7 @@ def main():
 
     sampler = ClockSampler(device)
     sampler.start()
-    ms_total, rep_times = tm.run(casc, step, K, W)
+    ms_total, rep_times = tm.run(casc, step, K, W, min_s=args.min_timed_s)
     clocks = sampler.stop()
     km = []
     for i in range(5):                                  # per-kernel durations: CUDA events the engine records around its launches
@@ -459,7 +460,7 @@ def main():
     sampler = ClockSampler(device)
     sampler.start()
     first = tm.allmax([e2e_once()])[0]
-    e2e_reps = int(min(50, max(1, math.ceil(MIN_TIMED_S / max(first, 1e-6)))))
+    e2e_reps = int(min(50, max(1, math.ceil(args.min_timed_s / max(first, 1e-6)))))
     e2e_times = [first] + tm.allmax([e2e_once() for _ in range(e2e_reps - 1)])
     e2e_s = float(np.median(e2e_times))
     clocks_e2e = sampler.stop()
@@ -499,7 +500,7 @@ def main():
             d = [nb.DeviceArray.from_host(pcm, device), nb.DeviceArray.from_host(np.roll(pcm, 7, axis=0), device)]
             res = nb.DeviceArray((Sg, T), nb.RESULT_DT, device)
             fn = lambda i: b.exec_device(d[i & 1], T * FRAME, T, res)
-            ms, _ = tm.run(b, fn, K, W, min_s=0.25)
+            ms, _ = tm.run(b, fn, K, W, min_s=min(0.25, args.min_timed_s))
             kk = []
             for i in range(3):
                 fn(i); b.sync(); kk.append(b.last_kernel_ms())

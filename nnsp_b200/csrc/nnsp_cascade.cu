@@ -1238,11 +1238,13 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &r : c->host_ev) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &row : c->tl) for (auto &e : row) TRY(cudaEventCreate(&e));
-    for (auto &row : c->gs) for (auto &g : row) TRY(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
     {
-        int lo = 0, hi = 0;
+        int lo = 0, hi = 0;                                /* the controller / network chain outranks the front-end stream */
         TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         TRY(cudaStreamCreateWithPriority(&c->nn_stream, cudaStreamNonBlocking, hi));
+        const char *e = getenv("NNSP_B200_GS_PRIO");       /* measurement knob: 0 = group streams at the default priority */
+        const int gp = (e && e[0] == '0') ? lo : hi;
+        for (auto &row : c->gs) for (auto &g : row) TRY(cudaStreamCreateWithPriority(&g, cudaStreamNonBlocking, gp));
     }
     for (auto &e : c->ev_feat) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : c->ev_nn) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

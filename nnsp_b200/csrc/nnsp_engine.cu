@@ -283,6 +283,8 @@ int launch_feature(const DevTables *tb, const FeatLaunch &a, int device, cudaStr
      * amortises further: S2I x 32 768 -0.6 %; 8 is best for the 4 096-stream call) */
     long long iters = blocks / (cap * 8);
     iters = iters < FEAT_ITERS ? FEAT_ITERS : (iters > 4 * FEAT_ITERS ? 4 * FEAT_ITERS : iters);
+    static const int iters_env = [] { const char *e = getenv("NNSP_B200_FEAT_ITERS"); return e ? atoi(e) : 0; }();   /* measurement knob */
+    if (iters_env > 0) iters = iters_env;
     const long long chunked = (blocks + iters - 1) / iters;
     /* a whole number of resident waves: every CTA slot then runs the same number of CTAs and the slots finish within one
      * round of each other instead of one CTA lifetime (3 200 CTAs on 444 slots left the last wave 20 % full) */

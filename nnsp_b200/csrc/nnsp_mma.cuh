@@ -9,12 +9,14 @@
  * reference's accumulator: exactly for the 64-bit-accumulator models (|sum| < 2^31 because cols <= 480),
  * and modulo 2^32 for ACC32BIT_OPT models, which is what __SMLAD computes (affine_acc32b.c:90-101).
  *
- * Why warp-level IMMA and not tcgen05: the GEMMs are tiny (N <= 288, K <= 256) and the kernel is bound by
- * the element-wise epilogue (LUT activations, LSTM cell) and by latency, not by MMA throughput; a 16-stream
- * tile worked on by the 4 warps of a CTA gives 256 CTAs at the smallest configuration (4 096 streams) where
- * a 128-row tcgen05 tile would leave 32. Measured on B200 (tools/imma_bench.cu): IMMA.16832.S8 has a
- * 98-cycle dependent-issue latency and peaks near 1 470 MAC/clk/SM, so k-steps are split over independent
- * accumulator chains.
+ * Why warp-level IMMA and not tcgen05: the GEMMs are tiny (N <= 288, K <= 256) and the kernels are bound by
+ * the element-wise finish (LUT activations, LSTM cell), by shared-memory traffic and by latency, not by MMA
+ * throughput. tools/tc5_gemm_bench.cu holds both formulations of the layer-0 contraction side by side, bit-exact
+ * against a 64-bit reference: tcgen05.mma kind::i8 (128-row tiles, TMEM accumulators, TMA-fed, warp-specialised)
+ * runs the S2I shape in 283 us where this mma.sync formulation takes 380 us, with the tensor pipe 10 % busy and the
+ * shared-memory pipe 63 % (profiles/r2_tc5_gemm_bench.txt, r2_tc5_ncu.txt); the recurrent scan keeps 16-stream tiles
+ * (256 CTAs at 4 096 streams where 128-row tiles would leave 32). IMMA.16832.S8 has a ~100-cycle dependent-issue
+ * latency, so k-steps are split over independent accumulator chains.
  *
  * Activations live in per-warp shared memory as two byte planes [16 streams][pitch]; an A fragment
  * register is one aligned 32-bit word of a plane (pitch/4 = 4 mod 8 words -> conflict-free), the epilogue

@@ -1,0 +1,634 @@
+/* tools/tc5_gemm_bench.cu -- the layer-0 contraction of NeuralNetClass_exe (fc_8x16, ns-nnsp/src/affine.c:409-490: 240 int16
+ * inputs x int8 weights, bias, shift, tanh_fix) on the 5th-generation tensor cores, next to the warp-level IMMA formulation
+ * the product ships (nnsp_split.cu seg_kernel<feat>). Measurement tool, not part of the library.
+ *
+ *   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o tools/tc5_gemm_bench tools/tc5_gemm_bench.cu
+ *   run  : tools/tc5_gemm_bench [streams] [units N: 72 S2I, 64 KWS, 28 VAD]
+ *   SASS : cuobjdump -sass tools/tc5_gemm_bench | grep -E "UTCIMMA|UTCBAR|LDTM|IMMA"
+ *
+ * Both kernels take what feat_kernel writes -- standardised int16 feature rows [stream][frame][40] -- and produce the int16
+ * activations of layer 0 for every (stream, inference) row: row (s, i) reads frames 2i .. 2i+5 (240 values, the 6 x 40 context).
+ * The int16 x int8 product is exact on int8 tensor cores through x = 256 hi + lo (hi signed, lo unsigned byte):
+ *     acc = (acc_hi << 8) + acc_lo,   two MMAs per k-step, int32 accumulators.
+ *
+ *   tc5_kernel  : tcgen05.mma.cta_group::1.kind::i8, M = 128 rows (8 streams x 16 inferences) x N x K = 256 per tile. The
+ *                 two byte planes of the tile are laid out in shared memory as K-major core matrices (8 rows x 16 bytes, no
+ *                 swizzle), one elected thread issues the 16 MMAs (8 k-steps x {s8 x s8, u8 x s8}) into two TMEM accumulators,
+ *                 tcgen05.commit arrives on an mbarrier, and all 8 warps run the finish out of TMEM (tcgen05.ld 32x32b).
+ *   imma_kernel : mma.sync.m16n8k32 on the same planes (ldmatrix A fragments, B fragments pre-packed), the formulation of
+ *                 seg_kernel<feat>.
+ * Every output of both kernels is compared with a plain int64 reference kernel. */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+constexpr int NMEL = 40, KIN = 240, KP = 256;            /* inputs, padded to 8 k-steps of 32 */
+constexpr int INF_PER_TILE = 16, STR_PER_TILE = 8, TM = 128;
+constexpr int FROWS = 2 * INF_PER_TILE + 4;              /* feature rows covering 16 windows of 6, stride 2 */
+constexpr int PLANE = FROWS * NMEL;                      /* 1440 bytes per stream and byte plane */
+constexpr int LUT_N = 160;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+/* tanh_fix (ns-nnsp/src/activation.c:31-69) on (value, slope) pairs, branch-free: the product's tanh_q15v.
+ * STRIDE > 1: the table is replicated, lut2 already points at the calling lane's copy */
+template <int STRIDE = 1>
+__device__ __forceinline__ int32_t tanh_q15v(int32_t x, const int2 *__restrict__ lut2)
+{
+    const uint32_t xi = (x < 0) ? (0u - (uint32_t)x) : (uint32_t)x;
+    const int32_t t = (int32_t)(xi - 512u);
+    int32_t k = t >> 10;
+    k = k < 0 ? 0 : k;
+    k = k > LUT_N - 1 ? LUT_N - 1 : k;
+    const int32_t dx = t - (k << 10);
+    const int2 e = lut2[k * STRIDE];
+    int32_t v = e.x + ((int32_t)((uint32_t)dx * (uint32_t)e.y) >> 15);
+    v = v > 0 ? v : 0;
+    v = (xi >= (5u << 15)) ? 0x7fff : v;
+    return x < 0 ? -v : v;
+}
+
+/* ---- reference: plain 64-bit arithmetic, one thread per output ------------------------------------------------ */
+__global__ void ref_kernel(const int16_t *__restrict__ feat, int T, int n_inf, const int8_t *__restrict__ W, const int32_t *__restrict__ bias32,
+                           const int2 *__restrict__ lut2, int N, int NPAD, int rs, int16_t *__restrict__ out, long long rows)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * N) return;
+    const long long row = idx / N;
+    const int n = (int)(idx - row * N);
+    const long long s = row / n_inf;
+    const int i = (int)(row - s * n_inf);
+    const int16_t *x = feat + (s * T + 2 * i) * NMEL;
+    long long acc = 0;
+    for (int k = 0; k < KIN; k++) acc += (long long)x[k] * (long long)W[n * KIN + k];
+    const int32_t pre = (int32_t)((acc + bias32[n]) >> rs);
+    out[row * NPAD + n] = (int16_t)tanh_q15v(pre, lut2);
+}
+
+/* ---- staging shared by both kernels: the tile's feature rows as byte planes [8 streams][PLANE] ------------------- */
+__device__ __forceinline__ void stage_planes(uint8_t *ph, uint8_t *pl, const int16_t *__restrict__ feat, int T, long long s0, int f0, int tid, int nthr)
+{
+    constexpr int NQ = STR_PER_TILE * FROWS * 5;          /* 16-byte pieces: 8 features each */
+    for (int e = tid; e < NQ; e += nthr) {
+        const int s = e / (FROWS * 5), rem = e - s * (FROWS * 5), j = rem / 5, x = rem - j * 5;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(feat + ((s0 + s) * T + f0 + j) * NMEL + x * 8));
+        uint2 hi, lo;
+        lo.x = __byte_perm(v.x, v.y, 0x6420); hi.x = __byte_perm(v.x, v.y, 0x7531);
+        lo.y = __byte_perm(v.z, v.w, 0x6420); hi.y = __byte_perm(v.z, v.w, 0x7531);
+        *reinterpret_cast<uint2 *>(ph + s * PLANE + j * NMEL + x * 8) = hi;
+        *reinterpret_cast<uint2 *>(pl + s * PLANE + j * NMEL + x * 8) = lo;
+    }
+}
+
+/* ================================================================================================================== */
+/* tcgen05 kernel                                                                                                       */
+/* ================================================================================================================== */
+/* K-major operand without swizzle: core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes. Element (row r, k byte c)
+ * lives at (r / 8) * SBO + (c / 16) * LBO + (r % 8) * 16 + c % 16. Here [row group][k chunk][8][16]: LBO = 128, SBO = 16 * 128. */
+constexpr uint32_t LBO = 128, SBO = 2048;
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);   /* version 1, SWIZZLE_NONE */
+}
+/* instruction descriptor, kind::i8: D = s32 (bits 4-5 = 2), A format bit 7 (1 = signed), B format bit 10 (signed), both K-major,
+ * N >> 3 at bit 17, M >> 4 at bit 24 */
+__host__ __device__ constexpr uint32_t umma_idesc(int n, bool a_signed) { return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24); }
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+
+constexpr int TC_THREADS = 256, TMEM_COLS = 256, ACC_LO_COL = 128;
+
+template <int NP>      /* units padded to a multiple of 16 (UMMA N) */
+struct TcSmem {
+    alignas(1024) uint8_t a_hi[TM * KP];          /* core-matrix layout */
+    alignas(1024) uint8_t a_lo[TM * KP];
+    alignas(1024) uint8_t w[NP * KP];
+    alignas(16) uint8_t ph[STR_PER_TILE * PLANE + 16];
+    alignas(16) uint8_t pl[STR_PER_TILE * PLANE + 16];
+    int2 lut2[LUT_N];
+    int32_t bias32[NP];
+    alignas(8) uint64_t bar;
+    uint32_t tmem;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+tc5_kernel(const int16_t *__restrict__ feat, int T, int n_inf, const uint8_t *__restrict__ wcm, const int32_t *__restrict__ bias32,
+           const int2 *__restrict__ lut2, int rs, int16_t *__restrict__ out, int n_tiles)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem<NP> &sm = *reinterpret_cast<TcSmem<NP> *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunks = n_inf / INF_PER_TILE;
+
+    if (warp == 0) {                                         /* one warp owns the TMEM allocation */
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    /* weights (already in core-matrix order), biases, LUT: once per persistent CTA */
+    for (int i = tid; i < NP * KP / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sm.w)[i] = __ldg(reinterpret_cast<const uint4 *>(wcm) + i);
+    for (int i = tid; i < NP; i += TC_THREADS) sm.bias32[i] = bias32[i];
+    for (int i = tid; i < LUT_N; i += TC_THREADS) sm.lut2[i] = lut2[i];
+    /* k chunk 15 (bytes 240..255) of every row is padding: zero once */
+    for (int r = tid; r < TM; r += TC_THREADS) {
+        const int off = ((r >> 3) * 16 + 15) * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4 *>(sm.a_hi + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(sm.a_lo + off) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sm.tmem;
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int st = tile / chunks, ch = tile - st * chunks;
+        const long long s0 = (long long)st * STR_PER_TILE;
+        const int k0 = ch * INF_PER_TILE;
+        /* 1. feature rows -> byte planes */
+        stage_planes(sm.ph, sm.pl, feat, T, s0, 2 * k0, tid, TC_THREADS);
+        __syncthreads();
+        /* 2. im2col into the core-matrix layout: row r = 16 s + i reads plane bytes 80 i + 16 j of stream s (j = 0..14).
+         * lane -> (row in group r8 = lane & 7, chunk jj = lane >> 3); a warp writes 512 contiguous bytes per step. */
+        for (int it = warp; it < 16 * 4 * 2; it += TC_THREADS / 32) {        /* (row group, chunk quad, plane) */
+            const int p = it & 1, g = (it >> 1) & 15, jq = it >> 5;
+            const int j = 4 * jq + (lane >> 3), r8 = lane & 7, r = g * 8 + r8;
+            if (j < 15) {
+                const uint8_t *src = (p ? sm.pl : sm.ph) + (r >> 4) * PLANE + 80 * (r & 15) + 16 * j;
+                const uint4 v = *reinterpret_cast<const uint4 *>(src);
+                *reinterpret_cast<uint4 *>((p ? sm.a_lo : sm.a_hi) + (g * 16 + j) * 128 + r8 * 16) = v;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          /* generic-proxy stores -> visible to the tensor core */
+        __syncthreads();
+        /* 3. one thread issues the contraction: 8 k-steps x (hi plane s8 x s8, lo plane u8 x s8) */
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = smem_u32(sm.a_hi), al = smem_u32(sm.a_lo), wb = smem_u32(sm.w);
+#pragma unroll
+            for (int ks = 0; ks < KP / 32; ks++) {
+                const uint64_t db = umma_desc(wb + ks * 256);                 /* two 16-byte k chunks = 2 LBO per k-step */
+                umma_i8(tmem, umma_desc(ah + ks * 256), db, umma_idesc(NP, true), ks > 0);
+                umma_i8(tmem + ACC_LO_COL, umma_desc(al + ks * 256), db, umma_idesc(NP, false), ks > 0);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&sm.bar)) : "memory");
+        }
+        /* 4. finish out of TMEM: warp w reads lanes 32 (w % 4) .. +31 (rows), warps w and w + 4 split the columns */
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&sm.bar)), "r"(phase) : "memory");
+            phase ^= 1;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int r = (warp & 3) * 32 + lane;                                 /* row of the tile = TMEM lane */
+        const long long row = ((s0 + (r >> 4)) * n_inf) + k0 + (r & 15);
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        constexpr int HALF = NP / 2;                                          /* columns per warp: NP / 2 (multiple of 8) */
+        const int c_begin = (warp >> 2) * HALF;
+#pragma unroll
+        for (int c = 0; c < HALF; c += 8) {
+            uint32_t hi[8], lo[8];
+            tmem_ld8(taddr + c_begin + c, hi);
+            tmem_ld8(taddr + ACC_LO_COL + c_begin + c, lo);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const int n = c_begin + c + e;
+                const int32_t p0 = (int32_t)((hi[e] << 8) + lo[e] + (uint32_t)sm.bias32[n]) >> rs;
+                const int32_t p1 = (int32_t)((hi[e + 1] << 8) + lo[e + 1] + (uint32_t)sm.bias32[n + 1]) >> rs;
+                pk[e >> 1] = ((uint32_t)tanh_q15v(p0, sm.lut2) & 0xffffu) | ((uint32_t)tanh_q15v(p1, sm.lut2) << 16);
+            }
+            *reinterpret_cast<uint4 *>(out + row * NP + c_begin + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      /* TMEM reads done before the next tile's MMAs overwrite it */
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)TMEM_COLS) : "memory");
+}
+
+/* ================================================================================================================== */
+/* tcgen05 kernel, warp-specialised and double-buffered                                                                 */
+/* ================================================================================================================== */
+/* One persistent CTA per SM: TP_FW finish warps (warp e reads TMEM lanes 32 (e & 3) .. +31 and the column slice e >> 2),
+ * then four producer warps that stage the next tile (feature rows -> byte planes -> core-matrix im2col) and thread 256 issues its
+ * MMAs. Two A buffers and two TMEM accumulator pairs: while the finish drains tile n, tile n + 1 is staged and multiplied.
+ *   mma_done[b]   : tcgen05.commit of the MMAs that read A[b] / wrote TMEM stage b   (finish waits; producers wait before refilling A[b])
+ *   tmem_free[b]  : the eight finish warps have read TMEM stage b                    (the issuer waits before overwriting it) */
+#ifndef TP_FW
+#define TP_FW 8                                           /* finish warps: TP_FW / 4 per TMEM lane quarter, each a slice of the columns */
+#endif
+constexpr int TP_FINISH_WARPS = TP_FW, TP_PROD_THREADS = 128, TP_THREADS = TP_FINISH_WARPS * 32 + TP_PROD_THREADS;
+#ifndef LUT_COPIES
+#define LUT_COPIES 1                                        /* 16 removes the LUT bank conflicts; measured neutral (profiles/r2_tc5_gemm_bench.txt) */
+#endif
+constexpr int RAW_ROW = FROWS * NMEL;                    /* 1440 int16 = 2880 contiguous bytes per stream: one bulk copy */
+constexpr int RAW_PITCH = RAW_ROW + 8;                   /* 2896 B: consecutive streams start 16 B apart modulo 128 */
+
+template <int NP>
+struct TpSmem {
+    alignas(1024) uint8_t a_hi[2][TM * KP];
+    alignas(1024) uint8_t a_lo[2][TM * KP];
+    alignas(1024) uint8_t w[NP * KP];
+    alignas(128) int16_t raw[2][STR_PER_TILE][RAW_PITCH];       /* feature rows of the tile as feat_kernel wrote them: TMA bulk copies */
+    int2 lut2[LUT_N * LUT_COPIES];                               /* copy c of entry k at [k * COPIES + c]; lane l reads copy l % COPIES: no bank conflicts */
+    int32_t bias32[NP];
+    alignas(8) uint64_t mma_done[2], tmem_free[2], raw_full[2];
+    uint32_t tmem;
+};
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int NP>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+tc5p_kernel(const int16_t *__restrict__ feat, int T, int n_inf, const uint8_t *__restrict__ wcm, const int32_t *__restrict__ bias32,
+            const int2 *__restrict__ lut2, int rs, int16_t *__restrict__ out, int n_tiles)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TpSmem<NP> &sm = *reinterpret_cast<TpSmem<NP> *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunks = n_inf / INF_PER_TILE;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int b = 0; b < 2; b++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.mma_done[b])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.raw_full[b])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.tmem_free[b])), "r"((uint32_t)TP_FINISH_WARPS));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < NP * KP / 16; i += TP_THREADS) reinterpret_cast<uint4 *>(sm.w)[i] = __ldg(reinterpret_cast<const uint4 *>(wcm) + i);
+    for (int i = tid; i < NP; i += TP_THREADS) sm.bias32[i] = bias32[i];
+    for (int i = tid; i < LUT_N * LUT_COPIES; i += TP_THREADS) sm.lut2[i] = lut2[i / LUT_COPIES];
+    for (int r = tid; r < 2 * TM; r += TP_THREADS) {                           /* k chunk 15 of both A buffers: padding */
+        const int b = r / TM, rr = r - b * TM, off = ((rr >> 3) * 16 + 15) * 128 + (rr & 7) * 16;
+        *reinterpret_cast<uint4 *>(sm.a_hi[b] + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(sm.a_lo[b] + off) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sm.tmem;
+
+    if (warp >= TP_FINISH_WARPS) {
+        /* ---------------- producers: warps 8..11 ---------------- */
+        const int ptid = tid - TP_FINISH_WARPS * 32, pwarp = ptid >> 5;
+        /* raw feature rows of a tile: 8 TMA bulk copies of 2880 contiguous bytes (36 frames x 40 int16 of one stream) */
+        auto fetch = [&](int tile, int rb) {
+            const int st = tile / chunks, ch = tile - st * chunks;
+            const int16_t *src = feat + (((long long)st * STR_PER_TILE) * T + 2 * ch * INF_PER_TILE) * NMEL;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&sm.raw_full[rb])), "r"((uint32_t)(STR_PER_TILE * RAW_ROW * 2)) : "memory");
+            for (int q = 0; q < STR_PER_TILE; q++)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(&sm.raw[rb][q][0])), "l"(src + (long long)q * T * NMEL), "r"((uint32_t)(RAW_ROW * 2)), "r"(smem_u32(&sm.raw_full[rb])) : "memory");
+        };
+        if (ptid == 0 && (int)blockIdx.x < n_tiles) fetch(blockIdx.x, 0);
+        int n = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n++) {
+            const int b = n & 1;
+            /* the raw buffer of tile n + 1 was last read by the conversion of tile n - 1, which every producer finished
+             * before the second named barrier of that iteration */
+            if (ptid == 0 && tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x, b ^ 1);
+            if (n >= 2) mbar_wait_parity(&sm.mma_done[b], (uint32_t)(((n - 2) >> 1) & 1));   /* the MMAs that read A[b] are complete */
+            mbar_wait_parity(&sm.raw_full[b], (uint32_t)((n >> 1) & 1));
+            /* int16 rows -> the two byte planes, straight into the core-matrix layout: row r = 16 s + i, k chunk j takes the
+             * 16 values 40 (2 i) + 16 j .. of stream s. lane -> (row in group r8 = lane & 7, chunk jj = lane >> 3). */
+            for (int it = pwarp; it < 16 * 4; it += TP_PROD_THREADS / 32) {
+                const int g = it & 15, jq = it >> 4;
+                const int j = 4 * jq + (lane >> 3), r8 = lane & 7, r = g * 8 + r8;
+                if (j < 15) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(&sm.raw[b][r >> 4][80 * (r & 15) + 16 * j]);
+                    const uint4 v0 = src[0], v1 = src[1];
+                    uint4 hi, lo;
+                    lo.x = __byte_perm(v0.x, v0.y, 0x6420); hi.x = __byte_perm(v0.x, v0.y, 0x7531);
+                    lo.y = __byte_perm(v0.z, v0.w, 0x6420); hi.y = __byte_perm(v0.z, v0.w, 0x7531);
+                    lo.z = __byte_perm(v1.x, v1.y, 0x6420); hi.z = __byte_perm(v1.x, v1.y, 0x7531);
+                    lo.w = __byte_perm(v1.z, v1.w, 0x6420); hi.w = __byte_perm(v1.z, v1.w, 0x7531);
+                    const int off = (g * 16 + j) * 128 + r8 * 16;
+                    *reinterpret_cast<uint4 *>(sm.a_hi[b] + off) = hi;
+                    *reinterpret_cast<uint4 *>(sm.a_lo[b] + off) = lo;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");                     /* A[b] complete, raw[b] consumed */
+            if (ptid == 0) {
+                if (n >= 2) mbar_wait_parity(&sm.tmem_free[b], (uint32_t)(((n - 2) >> 1) & 1));   /* the finish has drained TMEM stage b */
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ah = smem_u32(sm.a_hi[b]), al = smem_u32(sm.a_lo[b]), wb = smem_u32(sm.w), td = tmem + 256u * b;
+#pragma unroll
+                for (int ks = 0; ks < KP / 32; ks++) {
+                    const uint64_t db = umma_desc(wb + ks * 256);
+                    umma_i8(td, umma_desc(ah + ks * 256), db, umma_idesc(NP, true), ks > 0);
+                    umma_i8(td + ACC_LO_COL, umma_desc(al + ks * 256), db, umma_idesc(NP, false), ks > 0);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&sm.mma_done[b])) : "memory");
+            }
+        }
+    } else {
+        /* ---------------- finish warps ---------------- */
+        constexpr int SLICES = TP_FINISH_WARPS / 4, COLS = NP / SLICES;        /* columns per warp (multiple of 4) */
+        static_assert(NP % SLICES == 0 && COLS % 4 == 0, "column slices");
+        const int c_begin = (warp >> 2) * COLS;
+        const int r = (warp & 3) * 32 + lane;
+        int n = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n++) {
+            const int b = n & 1;
+            const int st = tile / chunks, ch = tile - st * chunks;
+            mbar_wait_parity(&sm.mma_done[b], (uint32_t)((n >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem + 256u * b + ((uint32_t)((warp & 3) * 32) << 16) + c_begin;
+            const long long row = (((long long)st * STR_PER_TILE + (r >> 4)) * n_inf) + ch * INF_PER_TILE + (r & 15);
+            const int2 *lut = sm.lut2 + (lane & (LUT_COPIES - 1));
+            constexpr int G = (COLS % 8 == 0) ? 8 : 4;                          /* columns per TMEM load / per global store */
+#pragma unroll
+            for (int c = 0; c < COLS; c += G) {
+                uint32_t hi[G], lo[G], pk[G / 2];
+                if (G == 8) { tmem_ld8(taddr + c, reinterpret_cast<uint32_t (&)[8]>(hi)); tmem_ld8(taddr + ACC_LO_COL + c, reinterpret_cast<uint32_t (&)[8]>(lo)); }
+                else {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]) : "r"(taddr + c));
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]) : "r"(taddr + ACC_LO_COL + c));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < G; e += 2) {
+                    const int nn = c_begin + c + e;
+                    const int32_t p0 = (int32_t)((hi[e] << 8) + lo[e] + (uint32_t)sm.bias32[nn]) >> rs;
+                    const int32_t p1 = (int32_t)((hi[e + 1] << 8) + lo[e + 1] + (uint32_t)sm.bias32[nn + 1]) >> rs;
+                    pk[e >> 1] = ((uint32_t)tanh_q15v<LUT_COPIES>(p0, lut) & 0xffffu) | ((uint32_t)tanh_q15v<LUT_COPIES>(p1, lut) << 16);
+                }
+                if (G == 8) *reinterpret_cast<uint4 *>(out + row * NP + c_begin + c) = make_uint4(pk[0], pk[1], pk[G / 2 - 2], pk[G / 2 - 1]);
+                else *reinterpret_cast<uint2 *>(out + row * NP + c_begin + c) = make_uint2(pk[0], pk[1]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&sm.tmem_free[b])) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+/* ================================================================================================================== */
+/* warp-level IMMA kernel (the product's formulation)                                                                   */
+/* ================================================================================================================== */
+constexpr int IM_THREADS = 256, PC = FROWS * NMEL + 16;      /* plane pitch 1456 = 91 x 16: odd multiple of 16, conflict-free ldmatrix */
+
+__device__ __forceinline__ void imma(int (&c)[4], const uint32_t (&a)[4], uint2 b, bool a_signed)
+{
+    if (a_signed)
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+    else
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ void ldm4(uint32_t addr, uint32_t (&a)[4])
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr) : "memory");
+}
+
+template <int NP>
+__global__ void __launch_bounds__(IM_THREADS, 2)
+imma_kernel(const int16_t *__restrict__ feat, int T, int n_inf, const uint2 *__restrict__ wfrag, const int32_t *__restrict__ bias32,
+            const int2 *__restrict__ lut2, int rs, int16_t *__restrict__ out, int n_tiles)
+{
+    constexpr int NT = NP / 8;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint2 *wsm = reinterpret_cast<uint2 *>(smem_raw);                                  /* [NT][8 k-steps][32 lanes] */
+    uint8_t *ph = smem_raw + NT * 8 * 32 * 8;                                          /* [8 streams][PC] */
+    uint8_t *pl = ph + STR_PER_TILE * PC;
+    int2 *slut = reinterpret_cast<int2 *>(pl + STR_PER_TILE * PC);
+    int32_t *sb = reinterpret_cast<int32_t *>(slut + LUT_N);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int chunks = n_inf / INF_PER_TILE;
+    for (int i = tid; i < NT * 8 * 32; i += IM_THREADS) wsm[i] = wfrag[i];
+    for (int i = tid; i < NP; i += IM_THREADS) sb[i] = bias32[i];
+    for (int i = tid; i < LUT_N; i += IM_THREADS) slut[i] = lut2[i];
+    for (int i = tid; i < 2 * STR_PER_TILE * 4; i += IM_THREADS)                       /* k-step over-read behind the last window */
+        *reinterpret_cast<uint32_t *>(ph + (i >> 2) * PC + FROWS * NMEL + (i & 3) * 4) = 0;
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int st = tile / chunks, ch = tile - st * chunks;
+        const long long s0 = (long long)st * STR_PER_TILE;
+        const int k0 = ch * INF_PER_TILE;
+        __syncthreads();
+        {   /* planes with pitch PC: stage_planes writes with pitch PLANE, so inline the pitch here */
+            constexpr int NQ = STR_PER_TILE * FROWS * 5;
+            for (int e = tid; e < NQ; e += IM_THREADS) {
+                const int s = e / (FROWS * 5), rem = e - s * (FROWS * 5), j = rem / 5, x = rem - j * 5;
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(feat + ((s0 + s) * T + 2 * k0 + j) * NMEL + x * 8));
+                uint2 hi, lo;
+                lo.x = __byte_perm(v.x, v.y, 0x6420); hi.x = __byte_perm(v.x, v.y, 0x7531);
+                lo.y = __byte_perm(v.z, v.w, 0x6420); hi.y = __byte_perm(v.z, v.w, 0x7531);
+                *reinterpret_cast<uint2 *>(ph + s * PC + j * NMEL + x * 8) = hi;
+                *reinterpret_cast<uint2 *>(pl + s * PC + j * NMEL + x * 8) = lo;
+            }
+        }
+        __syncthreads();
+        /* warp w: stream w of the tile, its 16 inferences = the 16 rows of the MMA; A row i starts at plane byte 80 i */
+        const uint32_t ah = smem_u32(ph + warp * PC) + (uint32_t)((lane & 15) * 80 + 16 * (lane >> 4));
+        const uint32_t al = smem_u32(pl + warp * PC) + (uint32_t)((lane & 15) * 80 + 16 * (lane >> 4));
+        const long long row0 = (s0 + warp) * n_inf + k0;
+#pragma unroll 1
+        for (int n0 = 0; n0 < NT; n0 += 4) {
+            int chh[4][4] = {}, cll[4][4] = {};
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+                uint32_t fh[4], fl[4];
+                ldm4(ah + 32 * ks, fh);
+                ldm4(al + 32 * ks, fl);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (n0 + j < NT) {
+                        const uint2 b = wsm[((n0 + j) * 8 + ks) * 32 + lane];
+                        imma(chh[j], fh, b, true);
+                        imma(cll[j], fl, b, false);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (n0 + j < NT) {
+                    const int n = (n0 + j) * 8 + 2 * q;
+                    int32_t v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        v[e] = tanh_q15v((int32_t)(((uint32_t)chh[j][e] << 8) + (uint32_t)cll[j][e] + (uint32_t)sb[n + (e & 1)]) >> rs, slut);
+                    *reinterpret_cast<uint32_t *>(out + (row0 + g) * NP + n) = ((uint32_t)v[0] & 0xffffu) | ((uint32_t)v[1] << 16);
+                    *reinterpret_cast<uint32_t *>(out + (row0 + g + 8) * NP + n) = ((uint32_t)v[2] & 0xffffu) | ((uint32_t)v[3] << 16);
+                }
+            }
+        }
+    }
+}
+
+/* ================================================================================================================== */
+template <int NP>
+static int run(int S, int N)
+{
+    const int n_inf = 48, T = 2 * n_inf + 4;                   /* 100 frames per stream: 48 inferences of 6-frame windows, stride 2 */
+    const long long rows = (long long)S * n_inf;
+    const int n_tiles = (S / STR_PER_TILE) * (n_inf / INF_PER_TILE);
+    const int rs = 7;                                          /* layer 0 of the shipped models: Q8 x Q7 -> Q15 */
+    std::vector<int16_t> feat((size_t)S * T * NMEL);
+    std::vector<int8_t> W((size_t)N * KIN);
+    std::vector<int32_t> bias(NP, 0);
+    std::vector<int2> lut(LUT_N);
+    uint64_t z = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { z ^= z << 13; z ^= z >> 7; z ^= z << 17; return (uint32_t)(z >> 11); };
+    for (auto &v : feat) { const uint32_t r = rnd(); v = (r & 15) == 0 ? (int16_t)(r >> 8) : (int16_t)((int)((r >> 8) & 0x1fff) - 4096); }   /* mostly moderate, some full scale */
+    for (auto &v : W) v = (int8_t)rnd();
+    for (int n = 0; n < N; n++) bias[n] = (int32_t)((int16_t)rnd()) << 1;                                          /* bias << (15 - qbit_bias) */
+    for (int k = 0; k < LUT_N; k++) { lut[k].x = (int)(32767.0 * (1.0 - 1.0 / (1.0 + k * 0.2))); lut[k].y = (int)(20000.0 / (1.0 + k)); }   /* any monotone table does */
+    /* weights: core-matrix order for the UMMA B operand; B-fragment order for mma.sync (nnsp_mma.cu pack_tile) */
+    std::vector<uint8_t> wcm((size_t)NP * KP, 0);
+    for (int n = 0; n < N; n++)
+        for (int k = 0; k < KIN; k++) wcm[(size_t)((n >> 3) * 16 + (k >> 4)) * 128 + (n & 7) * 16 + (k & 15)] = (uint8_t)W[(size_t)n * KIN + k];
+    std::vector<uint2> wfrag((size_t)(NP / 8) * 8 * 32);
+    auto pack4 = [&](int n, int k0) { uint32_t v = 0; for (int i = 0; i < 4; i++) { const int k = k0 + i; const uint8_t b = (n < N && k < KIN) ? (uint8_t)W[(size_t)n * KIN + k] : 0; v |= (uint32_t)b << (8 * i); } return v; };
+    for (int nt = 0; nt < NP / 8; nt++)
+        for (int ks = 0; ks < 8; ks++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int gg = lane >> 2, qq = lane & 3;
+                wfrag[((size_t)nt * 8 + ks) * 32 + lane] = make_uint2(pack4(nt * 8 + gg, 32 * ks + 4 * qq), pack4(nt * 8 + gg, 32 * ks + 16 + 4 * qq));
+            }
+    int16_t *d_feat, *d_ref, *d_out;
+    int8_t *d_W; uint8_t *d_wcm; uint2 *d_wfrag; int32_t *d_bias; int2 *d_lut;
+    CK(cudaMalloc(&d_feat, feat.size() * 2)); CK(cudaMalloc(&d_ref, (size_t)rows * NP * 2)); CK(cudaMalloc(&d_out, (size_t)rows * NP * 2));
+    CK(cudaMalloc(&d_W, W.size())); CK(cudaMalloc(&d_wcm, wcm.size())); CK(cudaMalloc(&d_wfrag, wfrag.size() * 8));
+    CK(cudaMalloc(&d_bias, NP * 4)); CK(cudaMalloc(&d_lut, LUT_N * 8));
+    CK(cudaMemcpy(d_feat, feat.data(), feat.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_W, W.data(), W.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_wcm, wcm.data(), wcm.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_wfrag, wfrag.data(), wfrag.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_bias, bias.data(), NP * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_lut, lut.data(), LUT_N * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_ref, 0, (size_t)rows * NP * 2));
+    {
+        const long long n = rows * N;
+        ref_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_feat, T, n_inf, d_W, d_bias, d_lut, N, NP, rs, d_ref, rows);
+        CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+    }
+    std::vector<int16_t> h_ref((size_t)rows * NP), h_out((size_t)rows * NP);
+    CK(cudaMemcpy(h_ref.data(), d_ref, h_ref.size() * 2, cudaMemcpyDeviceToHost));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    auto check = [&](const char *name) {
+        CK(cudaMemcpy(h_out.data(), d_out, h_out.size() * 2, cudaMemcpyDeviceToHost));
+        long long bad = 0, first = -1;
+        for (long long r = 0; r < rows; r++)
+            for (int n = 0; n < N; n++)
+                if (h_out[(size_t)r * NP + n] != h_ref[(size_t)r * NP + n]) { if (first < 0) first = r * NP + n; bad++; }
+        printf("  %-12s %s", name, bad ? "MISMATCH" : "bit-exact");
+        if (bad) printf(" (%lld of %lld outputs differ, first at row %lld unit %lld: got %d want %d)", bad, rows * N, first / NP, first % NP, h_out[first], h_ref[first]);
+        printf("\n");
+        return bad == 0;
+    };
+    auto time_it = [&](auto launch) {
+        for (int i = 0; i < 3; i++) launch();
+        CK(cudaDeviceSynchronize());
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; rep++) {
+            CK(cudaEventRecord(e0));
+            for (int i = 0; i < 10; i++) launch();
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (ms / 10 < best) best = ms / 10;
+        }
+        return best;
+    };
+    const double macs = (double)rows * N * KIN;
+    printf("%d streams x %d inferences = %lld rows, K = %d, N = %d (padded %d): %.2f GMAC\n", S, n_inf, rows, KIN, N, NP, macs * 1e-9);
+    bool ok = true;
+    {
+        const size_t smem = sizeof(TcSmem<NP>) + 1024;
+        CK(cudaFuncSetAttribute(tc5_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
+        CK(cudaMemset(d_out, 0x55, (size_t)rows * NP * 2));
+        auto launch = [&]() { tc5_kernel<NP><<<grid, TC_THREADS, smem>>>(d_feat, T, n_inf, d_wcm, d_bias, d_lut, rs, d_out, n_tiles); };
+        launch(); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+        ok &= check("tcgen05");
+        const float ms = time_it(launch);
+        printf("  tcgen05 kind::i8 : %8.1f us  %.1f TMAC/s (int16 x int8; twice that in int8 tensor-core MACs)  grid %d x %d threads, %zu B smem\n", ms * 1e3, macs / (ms * 1e-3) * 1e-12, grid, TC_THREADS, smem);
+    }
+    {
+        const size_t smem = sizeof(TpSmem<NP>) + 1024;
+        CK(cudaFuncSetAttribute(tc5p_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = n_tiles < sms ? n_tiles : sms;
+        CK(cudaMemset(d_out, 0x55, (size_t)rows * NP * 2));
+        auto launch = [&]() { tc5p_kernel<NP><<<grid, TP_THREADS, smem>>>(d_feat, T, n_inf, d_wcm, d_bias, d_lut, rs, d_out, n_tiles); };
+        launch(); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+        ok &= check("tcgen05 piped");
+        const float ms = time_it(launch);
+        printf("  tcgen05 pipelined: %8.1f us  %.1f TMAC/s  grid %d x %d threads (%d finish warps, 4 producer warps fed by TMA bulk copies, 2 A buffers, 2 TMEM stages), %zu B smem\n", ms * 1e3, macs / (ms * 1e-3) * 1e-12, grid, TP_THREADS, TP_FINISH_WARPS, smem);
+    }
+    {
+        const size_t smem = (size_t)(NP / 8) * 8 * 32 * 8 + 2 * STR_PER_TILE * PC + LUT_N * 8 + NP * 4 + 64;
+        CK(cudaFuncSetAttribute(imma_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
+        CK(cudaMemset(d_out, 0x55, (size_t)rows * NP * 2));
+        auto launch = [&]() { imma_kernel<NP><<<grid, IM_THREADS, smem>>>(d_feat, T, n_inf, d_wfrag, d_bias, d_lut, rs, d_out, n_tiles); };
+        launch(); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+        ok &= check("mma.sync");
+        const float ms = time_it(launch);
+        printf("  mma.sync m16n8k32: %8.1f us  %.1f TMAC/s  grid %d x %d threads, %zu B smem\n", ms * 1e3, macs / (ms * 1e-3) * 1e-12, grid, IM_THREADS, smem);
+    }
+    cudaFree(d_feat); cudaFree(d_ref); cudaFree(d_out); cudaFree(d_W); cudaFree(d_wcm); cudaFree(d_wfrag); cudaFree(d_bias); cudaFree(d_lut);
+    return ok ? 0 : 1;
+}
+
+int main(int argc, char **argv)
+{
+    const int S = argc > 1 ? atoi(argv[1]) : 32768, N = argc > 2 ? atoi(argv[2]) : 72;
+    if (S % STR_PER_TILE) { fprintf(stderr, "streams must be a multiple of %d\n", STR_PER_TILE); return 2; }
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, 0));
+    printf("%s, sm_%d%d, %d SMs\n", p.name, p.major, p.minor, p.multiProcessorCount);
+    if (N == 72) return run<80>(S, 72);
+    if (N == 64) return run<64>(S, 64);
+    if (N == 28) return run<32>(S, 28);
+    fprintf(stderr, "units: 72, 64 or 28\n");
+    return 2;
+}
