@@ -1108,9 +1108,9 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
             /* the shipped layers get their k-step counts compiled in: VAD 28 -> 28 (1 k-step), KWS 64 -> 64 (2), S2I 72 -> 72 (3) */
             const int kq = (L.kt == L.ktr) ? L.kt : 0;
             if (L.nt <= 4) rc = (kq == 1) ? launch_scan<4, 4, 1>(a, ntiles, smem, device, st) : launch_scan<4, 4, 0>(a, ntiles, smem, device, st);
-#ifdef SCAN_NW8                /* 64-unit layers (KWS): eight unit groups need eight warps, not nine */
+            /* 64-unit layers (KWS): eight unit groups take eight warps, not nine (-2 % of the network time; capping the
+             * registers for three CTAs per SM spills and gains nothing: profiles/r2_cascade_overlap.txt) */
             else if (L.nt <= 8 && kq == 2) rc = launch_scan<8, 2, 2>(a, ntiles, smem, device, st);
-#endif
             else if (L.nt <= 9) rc = (kq == 2) ? launch_scan<9, 2, 2>(a, ntiles, smem, device, st)
                                    : (kq == 3) ? launch_scan<9, 2, 3>(a, ntiles, smem, device, st) : launch_scan<9, 2, 0>(a, ntiles, smem, device, st);
             else rc = launch_scan<16, 1, 0>(a, ntiles, smem, device, st);
