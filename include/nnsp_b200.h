@@ -59,6 +59,8 @@ const char *nnsp_b200_strerror(int code);
 const char *nnsp_b200_last_error(void);
 /* number of CUDA kernels launched by this library since load (all handles) */
 long long nnsp_b200_kernel_launches(void);
+/* how many of them were the tcgen05 (5th-generation tensor core) layer-0 kernel of the batched network path */
+long long nnsp_b200_tc5_launches(void);
 
 /* ------------------------------------------------------------------------------------ */
 /* Models                                                                               */

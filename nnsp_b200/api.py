@@ -545,3 +545,7 @@ def device_count():
 
 def kernel_launches():
     return lib().nnsp_b200_kernel_launches()
+
+
+def tc5_launches():
+    return lib().nnsp_b200_tc5_launches()

@@ -21,7 +21,7 @@
 
 namespace nnsp {
 
-std::atomic<long long> g_launches{0};
+std::atomic<long long> g_launches{0}, g_tc5_launches{0};
 
 /* ======================================================================================== */
 /* device bookkeeping                                                                         */
@@ -699,7 +699,7 @@ static int batch_ensure_split(nnsp_b200_batch *b, int n_inf)
     if (b->sp_dec) { cudaFree(b->sp_dec); b->sp_dec = nullptr; }
     b->sp_cap_inf = 0;
     const size_t pb = split_plane_bytes(b->mm, b->S, n_inf);
-    for (auto &p : b->sp_planes) NNSP_CUDA(cudaMalloc(&p, pb));
+    for (auto &p : b->sp_planes) { NNSP_CUDA(cudaMalloc(&p, pb)); NNSP_CUDA(cudaMemset(p, 0, pb)); }   /* columns no layer writes are read (against zero weights) */
     NNSP_CUDA(cudaMalloc(&b->sp_dec, (size_t)((b->S + 15) & ~15) * n_inf * sizeof(int32_t)));
     b->sp_cap_inf = n_inf;
     return NNSP_B200_OK;
@@ -790,6 +790,7 @@ extern "C" {
 
 const char *nnsp_b200_version(void) { return "nnsp-b200 0.1 (sm_100a)"; }
 long long nnsp_b200_kernel_launches(void) { return g_launches.load(); }
+long long nnsp_b200_tc5_launches(void) { return g_tc5_launches.load(); }
 
 int nnsp_b200_device_count(void)
 {

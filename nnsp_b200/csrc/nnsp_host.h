@@ -10,7 +10,7 @@
 
 namespace nnsp {
 
-extern std::atomic<long long> g_launches;
+extern std::atomic<long long> g_launches, g_tc5_launches;
 
 #define NNSP_CUDA(expr)                                                                       \
     do {                                                                                      \
@@ -75,6 +75,8 @@ struct MmaDeviceModel {
     MmaModel *d = nullptr;
     void     *frag = nullptr;     /* uint2 fragment image */
     int32_t  *bias32 = nullptr;
+    uint8_t  *tc5 = nullptr;      /* layer 0 for the tcgen05 kernel (nnsp_tc5.cuh): 8 x tc5_np x 32 weight bytes + tc5_np biases; null when not eligible */
+    int       tc5_np = 0;
     size_t    smem_base = 0, smem_warp = 0;
     int       off_bias = 0, off_lut = 0, off_model = 0, off_warps = 0;
 };

@@ -222,6 +222,46 @@ static void pack_tile(uint2 *dst, const int8_t *w, int nrows_total, int cols, in
     }
 }
 
+/* Layer 0 in the operand layout of seg0_tc5_kernel (nnsp_tc5.cuh), when the layer qualifies: fc 240 -> rows <= 80, tanh,
+ * exact 32-bit finish, an LSTM behind it. Eight K = 32 instructions per byte plane; instruction j, 16-byte chunk c2, byte bb
+ * is weight (frame f of the window, feature k):
+ *   j 0..3: f = 2 c2 + (j >> 1), k = 16 (j & 1) + bb      j 4, 5: f = 4 + (j - 4), k = 16 c2 + bb
+ *   j 6:    f = 2 c2 + (bb >> 3), k = 32 + (bb & 7)        j 7:    c2 = 0: f = 4 + (bb >> 3), k = 32 + (bb & 7); c2 = 1: zero
+ * stored K-major without swizzle: [j][unit / 8][c2][unit % 8][16]. The biases follow, shifted as for the IMMA finish. */
+static int upload_layer0_tc5(const nnsp_b200_model *m, MmaDeviceModel *out)
+{
+    const MmaModel *D = out->h;
+    const nnsp_layer &L = m->layer[0];
+    const MmaLayer &G = D->layer[0];
+    if (m->numlayers < 2 || L.type != NNSP_LAYER_FC || m->layer[1].type != NNSP_LAYER_LSTM || L.cols != 240 || L.act != NNSP_ACT_TANH ||
+        !G.fast || L.rows > 80)
+        return NNSP_B200_OK;
+    const int np = (L.rows + 15) & ~15;
+    const size_t wbytes = (size_t)8 * np * 32, total = wbytes + (size_t)np * 4;
+    uint8_t *img = (uint8_t *)calloc(1, total);
+    if (!img) return NNSP_B200_ERR_NOMEM;
+    for (int n = 0; n < L.rows; n++) {
+        for (int j = 0; j < 8; j++)
+            for (int c2 = 0; c2 < 2; c2++)
+                for (int bb = 0; bb < 16; bb++) {
+                    int f, k;
+                    if (j < 4) { f = 2 * c2 + (j >> 1); k = 16 * (j & 1) + bb; }
+                    else if (j < 6) { f = 4 + (j - 4); k = 16 * c2 + bb; }
+                    else if (j == 6) { f = 2 * c2 + (bb >> 3); k = 32 + (bb & 7); }
+                    else { if (c2) continue; f = 4 + (bb >> 3); k = 32 + (bb & 7); }
+                    img[(size_t)j * np * 32 + (size_t)(n >> 3) * 256 + c2 * 128 + (n & 7) * 16 + bb] = (uint8_t)L.w[(size_t)n * 240 + f * 40 + k];
+                }
+        const int32_t b = (int32_t)((uint32_t)(int32_t)L.bias[n] << G.sh_bias);
+        memcpy(img + wbytes + (size_t)n * 4, &b, 4);
+    }
+    cudaError_t e = cudaMalloc(&out->tc5, total);
+    if (e == cudaSuccess) e = cudaMemcpy(out->tc5, img, total, cudaMemcpyHostToDevice);
+    free(img);
+    if (e != cudaSuccess) { nnsp_set_error("tcgen05 layer image upload failed: %s", cudaGetErrorString(e)); return NNSP_B200_ERR_CUDA; }
+    out->tc5_np = np;
+    return NNSP_B200_OK;
+}
+
 int upload_model_mma(const nnsp_b200_model *m, MmaDeviceModel *out)
 {
     MmaModel *D = (MmaModel *)calloc(1, sizeof(MmaModel));
@@ -324,7 +364,7 @@ int upload_model_mma(const nnsp_b200_model *m, MmaDeviceModel *out)
         nnsp_set_error("IMMA model upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
         return NNSP_B200_ERR_CUDA;
     }
-    return NNSP_B200_OK;
+    return upload_layer0_tc5(m, out);
 }
 
 void free_model_mma(MmaDeviceModel *mm)
@@ -332,7 +372,9 @@ void free_model_mma(MmaDeviceModel *mm)
     if (mm->frag) cudaFree(mm->frag);
     if (mm->bias32) cudaFree(mm->bias32);
     if (mm->d) cudaFree(mm->d);
+    if (mm->tc5) cudaFree(mm->tc5);
     free(mm->h);
+    mm->tc5 = nullptr; mm->tc5_np = 0;
     mm->frag = nullptr; mm->bias32 = nullptr; mm->d = nullptr; mm->h = nullptr;
 }
 

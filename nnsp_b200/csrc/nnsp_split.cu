@@ -167,6 +167,10 @@ __device__ __forceinline__ int sel_count(const StreamSel &q) { return q.list ? *
 __device__ __forceinline__ size_t sel_tile_base(const StreamSel &q) { return (size_t)q.tile0 + (q.list ? (size_t)*q.tile_off : 0); }
 __device__ __forceinline__ int sel_sid(const StreamSel &q, int tile, int row) { return q.list ? q.list[16 * tile + row] : q.s0 + 16 * tile + row; }
 
+}   /* namespace nnsp */
+#include "nnsp_tc5.cuh"
+namespace nnsp {
+
 struct SegArgs {
     const MmaModel *model;
     const uint2 *frag;              /* fragment image of the whole model */
@@ -1038,6 +1042,12 @@ static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, c
     return NNSP_B200_OK;
 }
 
+static bool tc5_enabled()
+{
+    static const bool on = []() { const char *e = getenv("NNSP_B200_TC5"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 /* the fc runs and lstm scans of one model over one stream selection (launch_nn_split: a range of a batch;
  * cascade: a device-side list). mode: 1 = feat16 input, 2 = log-mel input with look-back. Returns through *dec. */
 int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int device, cudaStream_t st)
@@ -1053,6 +1063,7 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         NNSP_CUDA(cudaFuncSetAttribute(seg_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        NNSP_CUDA(cudaFuncSetAttribute(seg0_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc5Smem) + 1024));
         attr_done[device] = true;
     }
     attr_lk.unlock();
@@ -1068,6 +1079,24 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
     while (li < D->numlayers) {
         int l1 = li;
         while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
+        if (l1 > li && from_feat && l1 == 1 && q.mode == 1 && mm.tc5 && !q.list && !q.tstart && !tp.act && tc5_enabled()) {
+            /* layer 0 of the batched path on the tcgen05 tensor cores (nnsp_tc5.cuh) */
+            Tc5Args a{};
+            a.img = mm.tc5; a.tables = q.tables; a.np = mm.tc5_np; a.rs = -D->layer[0].sh_out;
+            a.s0 = q.s0; a.ns = q.ns; a.tile0 = q.tile0;
+            a.T = q.T; a.first = q.first; a.n_inf = q.n_inf; a.nchunks = (q.n_inf + TC5_KC - 1) / TC5_KC;
+            a.pa = D->pa; a.tile_bytes = tile_bytes;
+            a.feat16 = q.feat16; a.ctx = q.ctx; a.out_planes = bufs[which];
+            const int nitems = ((q.ns + 1) / 2) * a.nchunks;
+            const int grid = nitems < sm_count(device) ? nitems : sm_count(device);
+            seg0_tc5_kernel<<<grid, TC5_THREADS, sizeof(Tc5Smem) + 1024, st>>>(a);
+            NNSP_LAUNCH_CHECK();
+            g_tc5_launches.fetch_add(1, std::memory_order_relaxed);
+            ao += D->layer[0].rows;
+            cur_in = bufs[which]; which ^= 1;
+            from_feat = false;
+            li = l1;
+        } else
         if (l1 > li) {                                           /* a run of fc layers */
             const SegLayout lay = seg_layout(D, li, l1, from_feat);
             SegArgs a{};

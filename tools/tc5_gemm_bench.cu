@@ -269,8 +269,13 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity)
 {
     uint32_t done = 0;
     while (!done)
+#ifdef TS_TESTWAIT
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#else
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 
 template <int NP>
@@ -409,6 +414,219 @@ tc5p_kernel(const int16_t *__restrict__ feat, int T, int n_inf, const uint8_t *_
 }
 
 /* ================================================================================================================== */
+/* tcgen05 kernel without the window expansion: layer 0 as six shifted K = 40 contractions                               */
+/* ================================================================================================================== */
+/* D[i] = sum over the six context frames f of  F[2 i + f] . W_f^T.  For a fixed f the rows of one stream's consecutive
+ * inferences are its frames f, f + 2, f + 4, ...: keep the byte planes as an EVEN-frame and an ODD-frame array of 16-byte
+ * chunks, [parity][chunk][stream][frame / 2][16], and eight consecutive inferences are 128 contiguous bytes -- a K-major
+ * core matrix exactly where the conversion put the data. The MMA for frame offset f, k-step q reads it through a descriptor
+ * whose start address is shifted by (f >> 1) entries: no thread ever touches the A operand again. A frame's 40 bytes are
+ * padded to 64 (chunk 2 half used, chunk 3 zero) so that a k-step is 32 bytes: 6 x 2 k-steps x 2 planes = 24 MMAs per tile.
+ * Tile = 2 streams x 64 inference slots (up to 62 used: slot i of frame offset f reads entry i + (f >> 1) <= 63 + 2, the
+ * last two slots of a stream would read its neighbour's entries). */
+constexpr int TS_SLOTS = 64, TS_STREAMS = 2, TS_FRAMES = 2 * TS_SLOTS + 4;   /* frames of a stream a tile may read: 132 */
+constexpr int TS_SPITCH = TS_SLOTS * 16;                                   /* 1024 B: a stream's 64 row slots = 8 core matrices */
+constexpr int TS_CH = TS_STREAMS * TS_SPITCH + 64;                         /* chunk array: 2 streams + the 2 (+2 pad) spill-over entries of the last one */
+constexpr int TS_PLANE = 5 * TS_CH;                                        /* arrays (parity 0, bytes 0..15), (0, 16..31), (1, 0..15), (1, 16..31), tails */
+constexpr int TS_LUTC = 16;                                                /* table copies: the half-warp of a 64-bit load never shares a bank */
+#ifndef TS_RING
+#define TS_RING 4
+#endif
+
+#ifndef TS_STAGES
+#define TS_STAGES 3                                                        /* A buffers = TMEM accumulator stages in flight */
+#endif
+template <int NP>
+struct TsSmem {
+    alignas(1024) uint8_t a[TS_STAGES][2][TS_PLANE];               /* [stage][hi|lo][array][stream][entry][16] */
+    alignas(1024) uint8_t w[8 * NP * 32];                          /* [MMA j][n / 8][2 chunks][8][16] */
+    alignas(128) int16_t raw[TS_RING][TS_STREAMS][TS_FRAMES * NMEL + 8];   /* TMA ring: tiles n + 1 .. n + TS_RING - 1 in flight */
+    int2 lut2[LUT_N * TS_LUTC];
+    int32_t bias32[NP];
+    alignas(8) uint64_t mma_done[TS_STAGES], tmem_free[TS_STAGES], a_full[TS_STAGES], raw_full[TS_RING];
+    uint32_t tmem;
+};
+constexpr int TS_THREADS = TP_THREADS + 32;                                /* finish warps, four conversion warps, one warp whose lane 0 issues the MMAs */
+__device__ __forceinline__ uint64_t umma_desc2(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+/* Three tiles in flight (conversion -> MMAs -> finish is a latency chain of several microseconds: with two stages the
+ * period is half of it, whatever the stages' own times). The finish warps work in groups of four (one warp per TMEM lane
+ * quarter, all columns): group g takes the tiles n = g (mod groups), so a group has `groups` periods for one tile. */
+template <int NP>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+tc5s_kernel(const int16_t *__restrict__ feat, int T, int n_inf, const uint8_t *__restrict__ wsh, const int32_t *__restrict__ bias32,
+            const int2 *__restrict__ lut2, int rs, int16_t *__restrict__ out, int n_tiles, long long *prof)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TsSmem<NP> &sm = *reinterpret_cast<TsSmem<NP> *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int frames = 2 * n_inf + 4;                                    /* frames of a stream the tile reads (<= TS_FRAMES, <= T) */
+    constexpr int GROUPS = TP_FINISH_WARPS / 4;
+    constexpr uint32_t ST_COLS = 2 * NP;                                 /* TMEM columns of a stage: acc_hi | acc_lo */
+    static_assert(TS_STAGES * 2 * NP <= 512, "TMEM columns");
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int b = 0; b < TS_STAGES; b++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.mma_done[b])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.tmem_free[b])), "r"((uint32_t)TP_FINISH_WARPS));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.a_full[b])));
+        }
+        for (int b = 0; b < TS_RING; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.raw_full[b])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 8 * NP * 32 / 16; i += TS_THREADS) reinterpret_cast<uint4 *>(sm.w)[i] = __ldg(reinterpret_cast<const uint4 *>(wsh) + i);
+    for (int i = tid; i < NP; i += TS_THREADS) sm.bias32[i] = bias32[i];
+    for (int i = tid; i < LUT_N * TS_LUTC; i += TS_THREADS) sm.lut2[i] = lut2[i / TS_LUTC];
+    for (int i = tid; i < (int)(sizeof(sm.a) / 16); i += TS_THREADS) reinterpret_cast<uint4 *>(&sm.a[0][0][0])[i] = make_uint4(0, 0, 0, 0);   /* padding chunks stay zero */
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sm.tmem;
+
+    if (warp == TP_FINISH_WARPS + 4) {
+        /* ---------------- MMA issue: its own warp, because the issue of a queued tcgen05.mma blocks until the tensor core takes it ---------------- */
+        if (lane == 0) {
+            long long pt[6] = { 0, 0, 0, 0, 0, 0 }, tp = clock64();
+#define TS_MARK(i) do { if (prof) { const long long t_ = clock64(); pt[i] += t_ - tp; tp = t_; } } while (0)
+            int n = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n++) {
+                const int b = n % TS_STAGES, use = n / TS_STAGES;
+                mbar_wait_parity(&sm.a_full[b], (uint32_t)(use & 1));                             /* the conversion of tile n is in a[b] */
+                TS_MARK(0);
+                if (use >= 1) mbar_wait_parity(&sm.tmem_free[b], (uint32_t)((use - 1) & 1));   /* its finish group has drained TMEM stage b */
+                TS_MARK(1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ah = smem_u32(sm.a[b][0]), al = smem_u32(sm.a[b][1]), wb = smem_u32(sm.w), td = tmem + ST_COLS * b;
+                /* 15 sixteen-byte K chunks (6 frames x bytes 0..15, 16..31 + 3 tail entries) in 8 K = 32 instructions per plane:
+                 * j 0..3 pair the entries of frames f and f + 2 of one array (second chunk 16 bytes on: LBO = 16), j 4, 5 pair bytes
+                 * 0..15 and 16..31 of frame 4 + parity (LBO = the array stride), j 6, 7 are the tails (the last chunk meets zero weights) */
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t arr = j < 4 ? j : (j < 6 ? 2 * (j - 4) : 4);
+                    const uint32_t aoff = arr * TS_CH + ((j == 4 || j == 5 || j == 7) ? 32 : 0);
+                    const uint32_t lbo = (j == 4 || j == 5) ? TS_CH : 16;
+                    const uint64_t db = umma_desc2(wb + j * NP * 32, 128, 256);
+                    umma_i8(td, umma_desc2(ah + aoff, lbo, 128), db, umma_idesc(NP, true), j ? 1u : 0u);
+                    umma_i8(td + NP, umma_desc2(al + aoff, lbo, 128), db, umma_idesc(NP, false), j ? 1u : 0u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&sm.mma_done[b])) : "memory");
+                TS_MARK(2);
+            }
+            if (prof && blockIdx.x == 0) { for (int i = 0; i < 3; i++) prof[i] = pt[i]; prof[5] = n; }
+        }
+    } else if (warp >= TP_FINISH_WARPS) {
+        /* ---------------- conversion ---------------- */
+        const int ptid = tid - TP_FINISH_WARPS * 32;
+        auto fetch = [&](int tile, int rb) {
+            const int16_t *src = feat + ((long long)tile * TS_STREAMS) * T * NMEL;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&sm.raw_full[rb])), "r"((uint32_t)(TS_STREAMS * frames * NMEL * 2)) : "memory");
+            for (int q = 0; q < TS_STREAMS; q++)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(&sm.raw[rb][q][0])), "l"(src + (long long)q * T * NMEL), "r"((uint32_t)(frames * NMEL * 2)), "r"(smem_u32(&sm.raw_full[rb])) : "memory");
+        };
+        if (ptid == 0)
+            for (int m = 0; m < TS_RING - 1; m++)
+                if ((int)blockIdx.x + m * (int)gridDim.x < n_tiles) fetch(blockIdx.x + m * gridDim.x, m);
+        int n = 0;
+        long long qt[4] = { 0, 0, 0, 0 }, tq = clock64();
+#define TS_MARKQ(i) do { if (prof) { const long long t_ = clock64(); qt[i] += t_ - tq; tq = t_; } } while (0)
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n++) {
+            const int b = n % TS_STAGES, use = n / TS_STAGES, rb = n % TS_RING;
+            /* ring slot (n - 1) % RING was read by the conversion of tile n - 1: every producer is past that iteration's barrier */
+            if (ptid == 0 && tile + (TS_RING - 1) * (int)gridDim.x < n_tiles) fetch(tile + (TS_RING - 1) * gridDim.x, (n + TS_RING - 1) % TS_RING);
+            if (use >= 1) mbar_wait_parity(&sm.mma_done[b], (uint32_t)((use - 1) & 1));      /* the MMAs that read a[b] are complete */
+            TS_MARKQ(0);
+            mbar_wait_parity(&sm.raw_full[rb], (uint32_t)((n / TS_RING) & 1));
+            TS_MARKQ(1);
+            /* one frame per thread-step: 40 int16 -> 40 high bytes + 40 low bytes -> chunks 0, 1, 2 of entry frame / 2 of its parity */
+            for (int e = ptid; e < TS_STREAMS * frames; e += TP_PROD_THREADS) {
+                const int q = e / frames, fr = e - q * frames;
+                const uint4 *src = reinterpret_cast<const uint4 *>(&sm.raw[rb][q][fr * NMEL]);
+                const uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                uint4 h0, l0, h1, l1, h2, l2;
+                l0.x = __byte_perm(v0.x, v0.y, 0x6420); h0.x = __byte_perm(v0.x, v0.y, 0x7531);
+                l0.y = __byte_perm(v0.z, v0.w, 0x6420); h0.y = __byte_perm(v0.z, v0.w, 0x7531);
+                l0.z = __byte_perm(v1.x, v1.y, 0x6420); h0.z = __byte_perm(v1.x, v1.y, 0x7531);
+                l0.w = __byte_perm(v1.z, v1.w, 0x6420); h0.w = __byte_perm(v1.z, v1.w, 0x7531);
+                l1.x = __byte_perm(v2.x, v2.y, 0x6420); h1.x = __byte_perm(v2.x, v2.y, 0x7531);
+                l1.y = __byte_perm(v2.z, v2.w, 0x6420); h1.y = __byte_perm(v2.z, v2.w, 0x7531);
+                l1.z = __byte_perm(v3.x, v3.y, 0x6420); h1.z = __byte_perm(v3.x, v3.y, 0x7531);
+                l1.w = __byte_perm(v3.z, v3.w, 0x6420); h1.w = __byte_perm(v3.z, v3.w, 0x7531);
+                l2.x = __byte_perm(v4.x, v4.y, 0x6420); h2.x = __byte_perm(v4.x, v4.y, 0x7531);
+                l2.y = __byte_perm(v4.z, v4.w, 0x6420); h2.y = __byte_perm(v4.z, v4.w, 0x7531);
+                const int off = q * TS_SPITCH + (fr >> 1) * 16, par = fr & 1;               /* entry frame / 2 of the parity's arrays */
+                uint8_t *ah = sm.a[b][0] + off, *al = sm.a[b][1] + off;
+                *reinterpret_cast<uint4 *>(ah + 2 * par * TS_CH) = h0; *reinterpret_cast<uint4 *>(ah + (2 * par + 1) * TS_CH) = h1;
+                *reinterpret_cast<uint2 *>(ah + 4 * TS_CH + par * 8) = make_uint2(h2.x, h2.y);
+                *reinterpret_cast<uint4 *>(al + 2 * par * TS_CH) = l0; *reinterpret_cast<uint4 *>(al + (2 * par + 1) * TS_CH) = l1;
+                *reinterpret_cast<uint2 *>(al + 4 * TS_CH + par * 8) = make_uint2(l2.x, l2.y);
+            }
+            TS_MARKQ(2);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            TS_MARKQ(3);
+            if (ptid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&sm.a_full[b])) : "memory");
+        }
+        if (prof && blockIdx.x == 0 && ptid == 0) for (int i = 0; i < 4; i++) prof[8 + i] = qt[i];
+    } else {
+        /* ---------------- finish: TMEM lane r = 64 (stream of the tile) + inference slot; the warps of a lane quarter share the column blocks ---------------- */
+        const int grp = warp >> 2;
+        const int r = (warp & 3) * 32 + lane, slot = r & (TS_SLOTS - 1);
+        const int2 *lutl = sm.lut2 + (lane & (TS_LUTC - 1));
+        constexpr int NBLK = NP / 8;
+        int n = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n++) {
+            const int b = n % TS_STAGES, use = n / TS_STAGES;
+            mbar_wait_parity(&sm.mma_done[b], (uint32_t)(use & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem + ST_COLS * b + ((uint32_t)((warp & 3) * 32) << 16);
+            const long long row = ((long long)tile * TS_STREAMS + (r >> 6)) * n_inf + slot;
+#pragma unroll
+            for (int j0 = 0; j0 < NBLK; j0 += GROUPS) {
+                const int j = j0 + grp, c = j * 8;
+                const bool have = j < NBLK, last = j0 + GROUPS >= NBLK;
+                uint32_t hi[8], lo[8], pk[4];
+                if (have) {
+                    tmem_ld8(taddr + c, hi);
+                    tmem_ld8(taddr + NP + c, lo);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
+                if (last) {                                                      /* this warp's share of the stage is in registers: hand it back before the arithmetic */
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&sm.tmem_free[b])) : "memory");
+                }
+                if (have && slot < n_inf) {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const int nn = c + e;
+                        const int32_t p0 = (int32_t)((hi[e] << 8) + lo[e] + (uint32_t)sm.bias32[nn]) >> rs;
+                        const int32_t p1 = (int32_t)((hi[e + 1] << 8) + lo[e + 1] + (uint32_t)sm.bias32[nn + 1]) >> rs;
+#ifdef TS_NOLUT                                                                  /* measurement only: what the table look-ups cost (wrong results) */
+                        pk[e >> 1] = ((uint32_t)max(min(p0, 32767), -32768) & 0xffffu) | ((uint32_t)max(min(p1, 32767), -32768) << 16);
+#else
+                        pk[e >> 1] = ((uint32_t)tanh_q15v<TS_LUTC>(p0, lutl) & 0xffffu) | ((uint32_t)tanh_q15v<TS_LUTC>(p1, lutl) << 16);
+#endif
+                    }
+                    *reinterpret_cast<uint4 *>(out + row * NP + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+/* ================================================================================================================== */
 /* warp-level IMMA kernel (the product's formulation)                                                                   */
 /* ================================================================================================================== */
 constexpr int IM_THREADS = 256, PC = FROWS * NMEL + 16;      /* plane pitch 1456 = 91 x 16: odd multiple of 16, conflict-free ldmatrix */
@@ -532,6 +750,22 @@ static int run(int S, int N)
                 const int gg = lane >> 2, qq = lane & 3;
                 wfrag[((size_t)nt * 8 + ks) * 32 + lane] = make_uint2(pack4(nt * 8 + gg, 32 * ks + 4 * qq), pack4(nt * 8 + gg, 32 * ks + 16 + 4 * qq));
             }
+    /* shifted formulation: W_f, k-step q in core-matrix order [f][q][n / 8][2 chunks][8][16]; a frame's 40 inputs padded to 64 */
+    std::vector<uint8_t> wsh((size_t)8 * NP * 32, 0);
+    for (int n = 0; n < N; n++)
+        for (int j = 0; j < 8; j++)
+            for (int c2 = 0; c2 < 2; c2++)
+                for (int bb = 0; bb < 16; bb++) {
+                    int f, k;
+                    if (j < 4) { f = 2 * c2 + (j >> 1); k = 16 * (j & 1) + bb; }
+                    else if (j < 6) { f = 4 + (j - 4); k = 16 * c2 + bb; }
+                    else if (j == 6) { f = 2 * c2 + (bb >> 3); k = 32 + (bb & 7); }
+                    else { if (c2) continue; f = 4 + (bb >> 3); k = 32 + (bb & 7); }
+                    wsh[(size_t)j * NP * 32 + (size_t)(n >> 3) * 256 + c2 * 128 + (n & 7) * 16 + bb] = (uint8_t)W[(size_t)n * KIN + f * NMEL + k];
+                }
+    uint8_t *d_wsh;
+    CK(cudaMalloc(&d_wsh, wsh.size()));
+    CK(cudaMemcpy(d_wsh, wsh.data(), wsh.size(), cudaMemcpyHostToDevice));
     int16_t *d_feat, *d_ref, *d_out;
     int8_t *d_W; uint8_t *d_wcm; uint2 *d_wfrag; int32_t *d_bias; int2 *d_lut;
     CK(cudaMalloc(&d_feat, feat.size() * 2)); CK(cudaMalloc(&d_ref, (size_t)rows * NP * 2)); CK(cudaMalloc(&d_out, (size_t)rows * NP * 2));
@@ -603,6 +837,30 @@ static int run(int S, int N)
         ok &= check("tcgen05 piped");
         const float ms = time_it(launch);
         printf("  tcgen05 pipelined: %8.1f us  %.1f TMAC/s  grid %d x %d threads (%d finish warps, 4 producer warps fed by TMA bulk copies, 2 A buffers, 2 TMEM stages), %zu B smem\n", ms * 1e3, macs / (ms * 1e-3) * 1e-12, grid, TP_THREADS, TP_FINISH_WARPS, smem);
+    }
+    {
+        const size_t smem = sizeof(TsSmem<NP>) + 1024;
+        CK(cudaFuncSetAttribute(tc5s_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles2 = S / TS_STREAMS;
+        const int grid = tiles2 < sms ? tiles2 : sms;
+        CK(cudaMemset(d_out, 0x55, (size_t)rows * NP * 2));
+        auto launch = [&]() { tc5s_kernel<NP><<<grid, TS_THREADS, smem>>>(d_feat, T, n_inf, d_wsh, d_bias, d_lut, rs, d_out, tiles2, nullptr); };
+        launch(); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+        ok &= check("tcgen05 shift");
+        const float ms = time_it(launch);
+        printf("  tcgen05 shifted  : %8.1f us  %.1f TMAC/s  even / odd frame planes, no window expansion, 8 K = 32 instructions per byte plane; grid %d x %d threads, %zu B smem\n", ms * 1e3, macs / (ms * 1e-3) * 1e-12, grid, TS_THREADS, smem);
+        if (getenv("TC5_PROF")) {                                       /* where the issuing thread of CTA 0 spends a tile's period */
+            long long *d_prof, hp[12];
+            CK(cudaMalloc(&d_prof, 96));
+            tc5s_kernel<NP><<<grid, TS_THREADS, smem>>>(d_feat, T, n_inf, d_wsh, d_bias, d_lut, rs, d_out, tiles2, d_prof);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(hp, d_prof, 96, cudaMemcpyDeviceToHost));
+            const double nt = (double)hp[5];
+            printf("    issuing thread of CTA 0, cycles per tile over %lld tiles: wait for the converted tile %.0f, wait TMEM stage free %.0f, issue 16 MMAs + commit %.0f\n",
+                   hp[5], hp[0] / nt, hp[1] / nt, hp[2] / nt);
+            printf("    conversion thread 0: wait A buffer free %.0f, wait TMA %.0f, convert %.0f, proxy fence + barrier %.0f\n", hp[8] / nt, hp[9] / nt, hp[10] / nt, hp[11] / nt);
+            CK(cudaFree(d_prof));
+        }
     }
     {
         const size_t smem = (size_t)(NP / 8) * 8 * 32 * 8 + 2 * STR_PER_TILE * PC + LUT_N * 8 + NP * 4 + 64;
