@@ -33,7 +33,9 @@ constexpr int TC5_SLOTS = 64, TC5_STREAMS = 2;                               /* 
 constexpr int TC5_KC = TC5_SLOTS - 2;                                        /* usable slots: slot i reads entries i .. i + 2 of its stream's 64 */
 constexpr int TC5_FRAMES = 2 * TC5_KC + 4;                                   /* feature rows a tile reads per stream: 128 */
 constexpr int TC5_SPITCH = TC5_SLOTS * 16;                                   /* a stream's entries in one array */
-constexpr int TC5_CH = TC5_STREAMS * TC5_SPITCH + 64;                        /* one array + the entries the last rows read past it */
+constexpr int TC5_CH = TC5_STREAMS * TC5_SPITCH + 160;                       /* one array + the entries the last rows read past it (64 B); 2208 = 32 mod 128:
+                                                                              * the even- and odd-frame lanes of a conversion store (arrays j, j + 2) take different banks */
+constexpr int TC5_LUTC = 16;                                                 /* tanh table copies: lane l reads copy l % 16, a 64-bit load of a half-warp touches every bank once */
 constexpr int TC5_PLANE = 5 * TC5_CH;
 constexpr int TC5_STAGES = 3, TC5_RING = 4;
 constexpr int TC5_NPMAX = 80;                                                /* 3 stages x 2 x NP TMEM columns <= 512 */
@@ -46,7 +48,7 @@ struct Tc5Smem {
     alignas(1024) uint8_t a[TC5_STAGES][2][TC5_PLANE];             /* [stage][hi|lo][array][stream][entry][16] */
     alignas(1024) uint8_t w[TC5_WBYTES];                           /* [instruction j][unit / 8][2 chunks][8][16] */
     alignas(128) int16_t raw[TC5_RING][TC5_STREAMS][TC5_FRAMES * 40 + 8];
-    int2 lut2[LUT2_N];
+    int2 lut2[LUT2_N * TC5_LUTC];
     int32_t bias[TC5_NPMAX];
     alignas(8) uint64_t mma_done[TC5_STAGES], tmem_free[TC5_STAGES], a_full[TC5_STAGES], raw_full[TC5_RING];
     uint32_t tmem;
@@ -120,7 +122,7 @@ seg0_tc5_kernel(Tc5Args a)
     }
     for (int i = tid; i < 8 * np * 32 / 16; i += TC5_THREADS) reinterpret_cast<uint4 *>(sm.w)[i] = __ldg(reinterpret_cast<const uint4 *>(a.img) + i);
     for (int i = tid; i < np; i += TC5_THREADS) sm.bias[i] = reinterpret_cast<const int32_t *>(a.img + 8 * np * 32)[i];
-    fill_lut2<1>(sm.lut2, a.tables, tid, TC5_THREADS);
+    fill_lut2<TC5_LUTC>(sm.lut2, a.tables, tid, TC5_THREADS);
     /* entries no conversion writes (the slots past a short chunk, the pad behind the last stream) must hold defined bytes:
      * their rows are computed and dropped */
     for (int i = tid; i < (int)(sizeof(sm.a) / 16); i += TC5_THREADS) reinterpret_cast<uint4 *>(&sm.a[0][0][0])[i] = make_uint4(0, 0, 0, 0);
@@ -219,6 +221,7 @@ seg0_tc5_kernel(Tc5Args a)
         const int grp = warp >> 2;
         const int r = (warp & 3) * 32 + lane, q = r >> 6, slot = r & (TC5_SLOTS - 1);
         const int nblk = np >> 4, pa = a.pa, rs = a.rs;
+        const int2 *lutl = sm.lut2 + (lane & (TC5_LUTC - 1));
         const size_t XB = (size_t)32 * pa;
         int n = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, n++) {
@@ -250,7 +253,7 @@ seg0_tc5_kernel(Tc5Args a)
 #pragma unroll
                     for (int e = 0; e < 16; e++) {
                         const int32_t pre = (int32_t)((hi[e] << 8) + lo[e] + (uint32_t)sm.bias[c + e]) >> rs;
-                        const uint32_t y = (uint32_t)tanh_q15v<1>(pre, sm.lut2);
+                        const uint32_t y = (uint32_t)tanh_q15v<TC5_LUTC>(pre, lutl);
                         oh[e >> 2] |= ((y >> 8) & 0xffu) << (8 * (e & 3));
                         ol[e >> 2] |= (y & 0xffu) << (8 * (e & 3));
                     }
