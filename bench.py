@@ -500,7 +500,9 @@ def main():
             d = [nb.DeviceArray.from_host(pcm, device), nb.DeviceArray.from_host(np.roll(pcm, 7, axis=0), device)]
             res = nb.DeviceArray((Sg, T), nb.RESULT_DT, device)
             fn = lambda i: b.exec_device(d[i & 1], T * FRAME, T, res)
+            tc0, kl0 = nb.tc5_launches(), nb.kernel_launches()
             ms, _ = tm.run(b, fn, K, W, min_s=min(0.25, args.min_timed_s))
+            tc5_share = (nb.tc5_launches() - tc0, nb.kernel_launches() - kl0)
             kk = []
             for i in range(3):
                 fn(i); b.sync(); kk.append(b.last_kernel_ms())
@@ -512,6 +514,7 @@ def main():
                          "scaling": scaling, "streams_per_gpu": Sg,
                          "value": world * Sg * T * AUDIO_S_PER_FRAME * K / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms / K,
                          "kernel_ms": {"feat_kernel": f_ms, "network_kernels": n_ms},
+                         "tcgen05_launches": "%d of %d launches (layer 0, seg0_tc5_kernel)" % tc5_share,
                          "roofline_hbm": {"kernel": "feat_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                           "algorithmic_bytes_per_stream_frame": ALGO_BYTES[name]}})
             for x in d:

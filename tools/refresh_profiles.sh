@@ -9,5 +9,6 @@ python bench.py --steps 20 --warmup 5 > $o/${tag}_bench.json 2> $o/${tag}_bench.
 echo "bench rc=$?"
 python tools/bench_configs.py cascade:8192 vad:4096 kws:16384:acc32 s2i:32768 --paths=split > $o/${tag}_configs.jsonl 2>&1
 python tools/casc_timeline.py > $o/${tag}_cascade_timeline.txt 2>&1
-for n in 72 64 28; do tools/tc5_gemm_bench 32768 $n; done > $o/${tag}_tc5_gemm_bench.txt 2>&1
+for n in 72 64 28; do TC5_PROF=1 tools/tc5_gemm_bench 32768 $n; done > $o/${tag}_tc5_gemm_bench.txt 2>&1
+tools/umma_rate > $o/${tag}_umma_rate.txt 2>&1
 python tools/h2d_bw.py 262 > $o/${tag}_h2d_bw.txt 2>&1
