@@ -95,6 +95,33 @@ static bool fill_dev_tables(const nnsp_tables *t, DevTables *d)
     }
     memcpy(d->log_lut, t->log_lut, sizeof d->log_lut);
     memcpy(d->tanh_lut, t->tanh_lut, sizeof d->tanh_lut);
+    /* the folded tanh table: half-segments of 512 (the original segments start at 512 + 1024 k, the clamp region is
+     * [0, 512), the saturation starts at 320 * 512), slope = the segment's, constant = any value of the interval that
+     * makes all 512 points of the half-segment exact. An empty interval would mean coeffs_tanh is not the table this
+     * was derived for: refuse to run rather than approximate. */
+    auto tanh_def = [&](int64_t xi) -> int64_t {                 /* activation.c:31-69 for xi = |x| */
+        if (xi >= (5 << 15)) return 0x7fff;
+        int64_t kx = (xi - 512) >> 10;
+        kx = kx < 0 ? 0 : kx;
+        const int64_t v = (int64_t)t->tanh_lut[2 * kx] + (((xi - 512 - (kx << 10)) * (int64_t)t->tanh_lut[2 * kx + 1]) >> 15);
+        return v > 0 ? v : 0;
+    };
+    for (int w = 0; w < 320; w++) {
+        const int64_t k = w >= 1 ? (w - 1) >> 1 : 0, s = t->tanh_lut[2 * k + 1];
+        int64_t lo = INT64_MIN, hi = INT64_MAX;
+        for (int64_t dd = 0; dd < 512; dd++) {
+            const int64_t y = tanh_def(512 * w + dd);
+            lo = std::max(lo, y * 32768 - dd * s);
+            hi = std::min(hi, (y + 1) * 32768 - dd * s);
+        }
+        if (lo >= hi || lo < 0 || lo + 511 * s > INT32_MAX) ok = false;
+        d->tanh2[w] = make_int2((int)s, (int)lo);
+    }
+    d->tanh2[320] = make_int2(0, 0x7fff << 15);
+    for (int64_t xi = 0; xi < (5 << 15) + 2048 && ok; xi++) {
+        const int64_t w = std::min<int64_t>(xi >> 9, 320), dd = xi - (w << 9);
+        if (((dd * d->tanh2[w].x + d->tanh2[w].y) >> 15) != tanh_def(xi)) ok = false;
+    }
     return ok;
 }
 
@@ -105,7 +132,7 @@ int get_device_tables(int device, const DevTables **out)
         const nnsp_tables *t = nnsp_tables_get();
         if (!t) { nnsp_set_error("constant-table self check failed (fingerprint mismatch)"); return NNSP_B200_ERR_ARG; }
         DevTables h;
-        if (!fill_dev_tables(t, &h)) { nnsp_set_error("constant tables do not have the structure the feature kernel compiles in (mel group bounds, stage-2 twiddles)"); return NNSP_B200_ERR_ARG; }
+        if (!fill_dev_tables(t, &h)) { nnsp_set_error("constant tables do not have the structure the kernels compile in (mel group bounds, stage-2 twiddles, folded tanh table)"); return NNSP_B200_ERR_ARG; }
         DevTables *d = nullptr;
         NNSP_CUDA(cudaMalloc(&d, sizeof h));
         NNSP_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));

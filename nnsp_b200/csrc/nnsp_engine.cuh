@@ -26,6 +26,10 @@ struct DevTables {
     uint32_t mel_meta[40];
     int16_t  log_lut[256];
     int16_t  tanh_lut[384];
+    /* tanh_fix (activation.c:31-69) folded for the vector kernels: for w = min(|x| >> 9, 320), d = |x| - 512 w,
+     * tanh_fix(|x|) = (d * tanh2[w].x + tanh2[w].y) >> 15 -- value, the clamp at 0 and the saturation at 5.0 are in the
+     * constants; fill_dev_tables checks every |x| up to the saturation against the definition */
+    int2     tanh2[321];
 };
 
 /* ---- one layer, GPU layout -------------------------------------------------------------

@@ -50,7 +50,8 @@ constexpr int SEG_FROWS = 2 * SEG_KC + 4;           /* feature rows covering 16 
 constexpr int SEG_PC = SEG_FROWS * 40 + 16;         /* plane pitch: 364 words = 12 mod 32, conflict-free */
 constexpr int SCAN_NST = 4;                         /* depth of the input ring of the scan               */
 constexpr int SPLIT_MAX_DYN_SMEM = 227 * 1024 - 512;   /* the kernels also hold up to 276 B of static shared memory */
-constexpr int LUT2_N = 160;                         /* reachable segments of coeffs_tanh (activation.c:5) */
+constexpr int LUT2_N = 321;                         /* half-segments of coeffs_tanh up to the saturation + the saturated entry (DevTables.tanh2) */
+__host__ __device__ constexpr int lut2_bytes(int copies) { return (LUT2_N * 8 * copies + 127) & ~127; }   /* what follows it in shared memory stays 128-byte aligned */
 /* The LUT is indexed by data, so lanes of a warp collide on banks (ncu: 58 % of the scan's LUT wavefronts were excess).
  * It can be replicated: copy c of entry k sits at [k * COPIES + c] and lane l reads copy l % COPIES, i.e. always the same
  * bank pair -- with 16 copies a 64-bit load of a half-warp touches every bank exactly once. */
@@ -63,23 +64,20 @@ constexpr int LUT2_COPIES_SEG = 1;
 
 static_assert((SEG_PC % 16) == 0 && ((SEG_PC / 4) % 8) == 4, "feature plane pitch");
 
-/* ---- tanh LUT as (value, slope) pairs: one 64-bit shared load per evaluation, no unpacking --------------- */
-/* tanh_fix, activation.c:31-69; x == INT32_MIN as in nnsp_device.cuh (-0x7fff). Branch-free so that the
- * evaluations of one epilogue interleave. */
-/* lut2: the calling lane's copy, i.e. base + (lane % COPIES); stride = COPIES */
+/* ---- tanh LUT as (slope, constant) pairs: one 64-bit shared load and 11 instructions per evaluation ------------ */
+/* tanh_fix, activation.c:31-69, on the folded table DevTables.tanh2: w = min(|x| >> 9, 320), d = |x| - 512 w,
+ * y = (d * slope_w + const_w) >> 15. The reference's value + ((dx * slope) >> 15), its clamp at 0 (which only fires at
+ * x = 0) and the saturation from |x| = 5.0 on are all in the constants (checked for every |x| when the tables are built).
+ * x == INT32_MIN as in nnsp_device.cuh (-0x7fff): |x| = 2^31 as unsigned lands in the saturated entry, whose slope is 0.
+ * Branch-free so that the evaluations of one epilogue interleave.
+ * lut2: the calling lane's copy, i.e. base + (lane % COPIES); stride = COPIES */
 template <int COPIES>
 __device__ __forceinline__ int32_t tanh_q15v(int32_t x, const int2 *__restrict__ lut2)
 {
     const uint32_t xi = (x < 0) ? (0u - (uint32_t)x) : (uint32_t)x;
-    const int32_t t = (int32_t)(xi - 512u);
-    int32_t k = t >> 10;
-    k = k < 0 ? 0 : k;
-    k = k > LUT2_N - 1 ? LUT2_N - 1 : k;
-    const int32_t dx = t - (k << 10);
-    const int2 e = lut2[k * COPIES];
-    int32_t v = e.x + ((int32_t)((uint32_t)dx * (uint32_t)e.y) >> 15);
-    v = v > 0 ? v : 0;
-    v = (xi >= (5u << 15)) ? 0x7fff : v;
+    const uint32_t w = min(xi >> 9, (uint32_t)(LUT2_N - 1));
+    const int2 e = lut2[w * COPIES];
+    const int32_t v = (int32_t)((xi - (w << 9)) * (uint32_t)e.x + (uint32_t)e.y) >> 15;
     return x < 0 ? -v : v;
 }
 template <int COPIES>
@@ -92,7 +90,7 @@ __device__ __forceinline__ void fill_lut2(int2 *lut2, const DevTables *__restric
 {
     for (int i = tid; i < LUT2_N * COPIES; i += nthr) {
         const int k = i / COPIES;
-        lut2[i] = make_int2((int)tb->tanh_lut[2 * k], (int)tb->tanh_lut[2 * k + 1]);
+        lut2[i] = tb->tanh2[k];
     }
 }
 
@@ -681,7 +679,7 @@ scan_kernel(ScanArgs a)
     const uint2 *wsm = reinterpret_cast<const uint2 *>(smem + 64);
     int2 *lut2_all = reinterpret_cast<int2 *>(smem + 64 + WB);
     const int2 *lut2 = lut2_all + (threadIdx.x & (LUT2_COPIES_SCAN - 1));
-    uint8_t *xs = smem + 64 + WB + LUT2_N * 8 * LUT2_COPIES_SCAN;
+    uint8_t *xs = smem + 64 + WB + lut2_bytes(LUT2_COPIES_SCAN);
     uint8_t *hb = xs + SCAN_NST * XB;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     __shared__ int sids[16], s_last[16], s_ninf;
@@ -979,7 +977,7 @@ static SegLayout seg_layout(const MmaModel *D, int l0, int l1, bool from_feat)
     auto a16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     size_t off = a16(16 + sizeof(MmaModel));
     s.off_bias = (int)off; off = a16(off + (size_t)D->bias_count * 4);
-    s.off_lut = (int)off; off += LUT2_N * 8 * LUT2_COPIES_SEG;
+    s.off_lut = (int)off; off += lut2_bytes(LUT2_COPIES_SEG);
     s.w_base = D->layer[l0].w_off;
     long long cnt = 0;
     for (int i = l0; i < l1; i++) cnt += (long long)D->layer[i].nt * D->layer[i].kt * 32;
@@ -995,7 +993,7 @@ static SegLayout seg_layout(const MmaModel *D, int l0, int l1, bool from_feat)
 }
 static size_t scan_smem(const MmaModel *D, const MmaLayer &L)
 {
-    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + LUT2_N * 8 * LUT2_COPIES_SCAN + (size_t)(SCAN_NST + 3) * 32 * D->pa;   /* 64: 6 mbarriers */
+    return 64 + (size_t)4 * L.nt * (L.kt + L.ktr) * 256 + lut2_bytes(LUT2_COPIES_SCAN) + (size_t)(SCAN_NST + 3) * 32 * D->pa;   /* 64: 6 mbarriers */
 }
 
 int split_supported(const MmaDeviceModel &mm)
