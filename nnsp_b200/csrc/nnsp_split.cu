@@ -1040,10 +1040,17 @@ static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, c
     return NNSP_B200_OK;
 }
 
-static bool tc5_enabled()
+/* The tcgen05 layer-0 kernel works on tiles of 2 streams x 64 inference slots; a call with few inferences per stream fills
+ * few of the slots (a 2-frame call: 1 of 64) and the mma.sync kernel, whose cost follows the rows, is faster -- measured
+ * break-even near half-full tiles (4 096 streams x 2 frames: 59 vs 48 us per call; 100-frame calls: 240 vs 395 us).
+ * NNSP_B200_TC5: 0 = never, 2 = whenever the layer qualifies (tests), otherwise by that rule. */
+static bool tc5_wanted(int n_inf)
 {
-    static const bool on = []() { const char *e = getenv("NNSP_B200_TC5"); return !(e && e[0] == '0'); }();
-    return on;
+    const char *e = getenv("NNSP_B200_TC5");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '2') return true;
+    const int nchunks = (n_inf + TC5_KC - 1) / TC5_KC;
+    return 20 * n_inf >= 9 * nchunks * TC5_SLOTS;                 /* slots in use >= 45 % */
 }
 
 /* the fc runs and lstm scans of one model over one stream selection (launch_nn_split: a range of a batch;
@@ -1077,7 +1084,7 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
     while (li < D->numlayers) {
         int l1 = li;
         while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
-        if (l1 > li && from_feat && l1 == 1 && q.mode == 1 && mm.tc5 && !q.list && !q.tstart && !tp.act && tc5_enabled()) {
+        if (l1 > li && from_feat && l1 == 1 && q.mode == 1 && mm.tc5 && D->pa <= TC5_PAMAX && !q.list && !q.tstart && !tp.act && tc5_wanted(q.n_inf)) {
             /* layer 0 of the batched path on the tcgen05 tensor cores (nnsp_tc5.cuh) */
             Tc5Args a{};
             a.img = mm.tc5; a.tables = q.tables; a.np = mm.tc5_np; a.rs = -D->layer[0].sh_out;

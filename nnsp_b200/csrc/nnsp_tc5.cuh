@@ -19,12 +19,13 @@
  *   instruction is either the NEXT entry of the same array (LBO = 16: frames f and f + 2) or the same entry of the
  *   next array (LBO = the array stride): 15 chunks -> 8 instructions per plane, 16 per tile.
  *   Roles (one persistent CTA per SM, 13 warps): 8 finish warps (TMEM lane quarter x share of the 16-unit blocks; TMEM -> registers
- *   -> bias, shift, tanh -> 16-byte stores into the two byte planes), 4 conversion warps (TMA bulk copies of the raw int16 rows through
+ *   -> bias, shift, tanh -> the tile's byte planes assembled in shared memory -> coalesced 16-byte stores), 4 conversion warps (TMA bulk copies of the raw int16 rows through
  *   a 4-deep ring -> byte planes in entry layout), 1 warp whose lane 0 issues the MMAs -- its own warp because the issue of
  *   a queued tcgen05.mma blocks, which would stall the conversion behind it. Three A buffers / TMEM stages in flight.
  * Eligibility (launch_split_layers): a range selection (the batched NNSPClass; the cascade's rounds keep seg_kernel<2>),
  * layer 0 = fc 240 -> rows <= 80 with tanh and the exact 32-bit finish, followed by an LSTM, no activation tap.
- * NNSP_B200_TC5=0 keeps the mma.sync kernel. */
+ * and at least 45 % of the tiles' inference slots in use (tc5_wanted, nnsp_split.cu). NNSP_B200_TC5=0 keeps the mma.sync
+ * kernel, =2 takes this one whenever the layer qualifies. */
 #pragma once
 
 namespace nnsp {
@@ -35,7 +36,8 @@ constexpr int TC5_FRAMES = 2 * TC5_KC + 4;                                   /* 
 constexpr int TC5_SPITCH = TC5_SLOTS * 16;                                   /* a stream's entries in one array */
 constexpr int TC5_CH = TC5_STREAMS * TC5_SPITCH + 160;                       /* one array + the entries the last rows read past it (64 B); 2208 = 32 mod 128:
                                                                               * the even- and odd-frame lanes of a conversion store (arrays j, j + 2) take different banks */
-constexpr int TC5_LUTC = 16;                                                 /* tanh table copies: lane l reads copy l % 16, a 64-bit load of a half-warp touches every bank once */
+constexpr int TC5_LUTC = 4;                                                  /* tanh table copies: lane l reads copy l % 4 (16 would remove every bank conflict; the room goes to the output staging) */
+constexpr int TC5_PAMAX = 128;                                               /* widest plane pitch the output staging holds (2 pa = 16 lanes x 16 bytes) */
 constexpr int TC5_PLANE = 5 * TC5_CH;
 constexpr int TC5_STAGES = 3, TC5_RING = 4;
 constexpr int TC5_NPMAX = 80;                                                /* 3 stages x 2 x NP TMEM columns <= 512 */
@@ -48,6 +50,7 @@ struct Tc5Smem {
     alignas(1024) uint8_t a[TC5_STAGES][2][TC5_PLANE];             /* [stage][hi|lo][array][stream][entry][16] */
     alignas(1024) uint8_t w[TC5_WBYTES];                           /* [instruction j][unit / 8][2 chunks][8][16] */
     alignas(128) int16_t raw[TC5_RING][TC5_STREAMS][TC5_FRAMES * 40 + 8];
+    alignas(128) uint8_t outst[TC5_SLOTS * (4 * TC5_PAMAX + 16)];   /* finished tile: [slot][hi|lo][2 streams][pa] */
     int2 lut2[LUT2_N * TC5_LUTC];
     int32_t bias[TC5_NPMAX];
     alignas(8) uint64_t mma_done[TC5_STAGES], tmem_free[TC5_STAGES], a_full[TC5_STAGES], raw_full[TC5_RING];
@@ -123,6 +126,7 @@ seg0_tc5_kernel(Tc5Args a)
     for (int i = tid; i < 8 * np * 32 / 16; i += TC5_THREADS) reinterpret_cast<uint4 *>(sm.w)[i] = __ldg(reinterpret_cast<const uint4 *>(a.img) + i);
     for (int i = tid; i < np; i += TC5_THREADS) sm.bias[i] = reinterpret_cast<const int32_t *>(a.img + 8 * np * 32)[i];
     fill_lut2<TC5_LUTC>(sm.lut2, a.tables, tid, TC5_THREADS);
+    for (int i = tid; i < (int)(sizeof(sm.outst) / 16); i += TC5_THREADS) reinterpret_cast<uint4 *>(sm.outst)[i] = make_uint4(0, 0, 0, 0);   /* columns np .. pa stay zero */
     /* entries no conversion writes (the slots past a short chunk, the pad behind the last stream) must hold defined bytes:
      * their rows are computed and dropped */
     for (int i = tid; i < (int)(sizeof(sm.a) / 16); i += TC5_THREADS) reinterpret_cast<uint4 *>(&sm.a[0][0][0])[i] = make_uint4(0, 0, 0, 0);
@@ -218,23 +222,32 @@ seg0_tc5_kernel(Tc5Args a)
         }
     } else {
         /* ---------------- finish: TMEM lane r = 64 (stream of the pair) + inference slot; the warps of a lane quarter share the 16-unit blocks ---------------- */
-        const int grp = warp >> 2;
+        /* A thread's 16 bytes of a byte plane are 32 pa bytes away from its lane neighbour's: written straight from the
+         * registers every 16-byte store was its own sector and the L1 store path (one sector per cycle) cost 120 of the
+         * kernel's 266 us. So the tile is assembled in shared memory in the layout of the planes and copied out with lanes
+         * along the 2 pa contiguous bytes that the two streams of a pair share per inference and byte plane (full sectors,
+         * four per cycle). The four warps that own the same 32 slots (two streams x two block shares) synchronise among
+         * themselves only: two 128-thread named barriers per tile. */
+        const int grp = warp >> 2, set = warp & 1;                               /* set: slots 0..31 / 32..63 of both streams */
         const int r = (warp & 3) * 32 + lane, q = r >> 6, slot = r & (TC5_SLOTS - 1);
         const int nblk = np >> 4, pa = a.pa, rs = a.rs;
         const int2 *lutl = sm.lut2 + (lane & (TC5_LUTC - 1));
         const size_t XB = (size_t)32 * pa;
+        const int spitch = 4 * pa + 16;                                          /* staging bytes of a slot: [hi|lo][2 streams][pa], + 16 to spread the banks */
+        uint8_t *stg = sm.outst + (size_t)slot * spitch + q * pa;               /* this row's bytes of the high plane; low plane 2 pa on */
+        const int ctid = (warp >> 1) * 32 + lane;                                /* 0..127 within the set: copy-out role */
+        const int half = ctid >> 4, piece = ctid & 15, npc = pa >> 3;            /* 16 lanes per (slot, plane) run of 2 pa bytes = npc 16-byte pieces */
         int n = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, n++) {
             const int b = n % TC5_STAGES, use = n / TC5_STAGES;
             const int chunk = item / npairs, pair = item - chunk * npairs;
             const int k0 = chunk * TC5_KC, nk = min(TC5_KC, a.n_inf - k0);
-            const int srel = 2 * pair + q;
-            const bool live = slot < nk && srel < a.ns;
-            uint8_t *dst = a.out_planes + (size_t)(a.tile0 + (srel >> 4)) * (size_t)a.tile_bytes + (size_t)(k0 + slot) * XB + (size_t)(srel & 15) * pa;
+            const int nstr = min(TC5_STREAMS, a.ns - 2 * pair);
+            const bool live = slot < nk && q < nstr;
             tc5_wait(&sm.mma_done[b], (uint32_t)(use & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem + st_cols * b + ((uint32_t)((warp & 3) * 32) << 16);
-            for (int j0 = 0; j0 < nblk; j0 += TC5_GROUPS) {                      /* blocks of 16 units: one 16-byte store per byte plane */
+            for (int j0 = 0; j0 < nblk; j0 += TC5_GROUPS) {                      /* blocks of 16 units: one 16-byte piece per byte plane */
                 const int j = j0 + grp, c = j * 16;
                 const bool have = j < nblk, last = j0 + TC5_GROUPS >= nblk;
                 uint32_t hi[16], lo[16];
@@ -257,19 +270,22 @@ seg0_tc5_kernel(Tc5Args a)
                         oh[e >> 2] |= ((y >> 8) & 0xffu) << (8 * (e & 3));
                         ol[e >> 2] |= (y & 0xffu) << (8 * (e & 3));
                     }
-                    *reinterpret_cast<uint4 *>(dst + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-                    *reinterpret_cast<uint4 *>(dst + 16 * pa + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                    *reinterpret_cast<uint4 *>(stg + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                    *reinterpret_cast<uint4 *>(stg + 2 * pa + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
                 }
             }
-            /* the plane columns past the padded units are written too (zeros, as the mma.sync kernel leaves them): a row is then
-             * covered completely and no 32-byte sector of the planes stays partially written (311 -> 288 us for S2I x 32 768).
-             * Assembling the tile in shared memory and writing it with TMA bulk stores (2 pa contiguous bytes per inference and
-             * plane) was slower, 353 us: it needs two barriers over all finish warps per tile. */
-            if (live && grp == TC5_GROUPS - 1)
-                for (int c = np; c < pa; c += 16) {
-                    *reinterpret_cast<uint4 *>(dst + c) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(dst + 16 * pa + c) = make_uint4(0, 0, 0, 0);
-                }
+            asm volatile("bar.sync %0, 128;" :: "r"(2 + set) : "memory");        /* the set's 32 slots are assembled */
+            {   /* copy out: the plane columns past the padded units leave as the zeros the staging buffer was cleared to */
+                uint8_t *gbase = a.out_planes + (size_t)(a.tile0 + ((2 * pair) >> 4)) * (size_t)a.tile_bytes + (size_t)((2 * pair) & 15) * pa + (size_t)piece * 16;
+                const int nrun = 2 * min(32, nk - 32 * set);                     /* (slot, plane) runs of this set; <= 0: nothing */
+                if (piece * 16 < nstr * pa)
+                    for (int run = half; run < nrun; run += 8) {
+                        const int sl = 32 * set + (run >> 1), pl = run & 1;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(sm.outst + (size_t)sl * spitch + pl * 2 * pa + piece * 16);
+                        *reinterpret_cast<uint4 *>(gbase + (size_t)(k0 + sl) * XB + (size_t)pl * 16 * pa) = v;
+                    }
+            }
+            asm volatile("bar.sync %0, 128;" :: "r"(2 + set) : "memory");        /* ... and read: the next tile may overwrite them */
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

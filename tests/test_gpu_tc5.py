@@ -18,6 +18,13 @@ LENS = [1, 1, 2, 7, 100, 129, 3, 257, 64]
 LAST = 9
 
 
+@pytest.fixture(autouse=True)
+def _force_tc5(monkeypatch):
+    """the library takes the kernel on its own only when the tiles are at least 45 % full (calls of >= 58 frames); the
+    small shapes below are forced through it"""
+    monkeypatch.setenv("NNSP_B200_TC5", "2")
+
+
 def _run(nb, oracle, m, m_or, S, first_stream, h_stride=None):
     T = sum(LENS) + LAST
     pcm = nb.synth_pcm(S, T, first_stream=first_stream)
@@ -81,3 +88,15 @@ def test_ineligible_layers_keep_the_mma_sync_kernel(nb, oracle):
             r, _ = oracle.nnsp_run(m_or, pcm[s], h_stride=h_stride, taps=False)
             assert (r == got[s]).all(), (name, s)
         b.close()
+
+
+def test_short_calls_keep_the_mma_sync_kernel(nb, monkeypatch):
+    """the selection rule: tiles of 2 streams x 64 inference slots must be at least 45 % in use"""
+    monkeypatch.delenv("NNSP_B200_TC5")
+    m = nb.Model.from_blob(nb.MODEL_DIR + "/" + MODEL_FILE[1])
+    b = nb.NNSPBatch(m, 8)
+    for frames, want in [(2, 0), (16, 0), (40, 0), (64, 1), (100, 1), (130, 1), (300, 1)]:
+        before = nb.tc5_launches()
+        b.exec(nb.synth_pcm(8, frames, first_stream=1))
+        assert nb.tc5_launches() - before == want, frames
+    b.close()
