@@ -100,3 +100,34 @@ def test_short_calls_keep_the_mma_sync_kernel(nb, monkeypatch):
         b.exec(nb.synth_pcm(8, frames, first_stream=1))
         assert nb.tc5_launches() - before == want, frames
     b.close()
+
+
+def test_async_host_calls_of_bench_shape(nb, oracle, monkeypatch):
+    """the end-to-end loop of bench.py at 100 frames per call: the kernel is chosen by the library's own rule and runs on
+    the pipeline slices of asynchronous host-buffer calls (600 streams = 2 slices; slice starts are multiples of 16)"""
+    monkeypatch.delenv("NNSP_B200_TC5")
+    S, n, calls = 600, 100, 3
+    pcm = nb.synth_pcm(S, n * calls, first_stream=900)
+    m = nb.Model.from_blob(nb.MODEL_DIR + "/" + MODEL_FILE[2], acc32=True)
+    b = nb.NNSPBatch(m, S)
+    pin = [nb.PinnedArray((S, n * 160), np.int16) for _ in range(2)]
+    pres = [nb.PinnedArray((S, n), nb.RESULT_DT) for _ in range(2)]
+    before, got, prev = nb.tc5_launches(), [], None
+    for k in range(calls):
+        pin[k & 1].array[...] = pcm[:, k * n * 160:(k + 1) * n * 160]
+        tk = b.exec_host_async(pin[k & 1].array, pres[k & 1].array)
+        if prev is not None:
+            b.wait_host(prev)
+            got.append(pres[(k - 1) & 1].array.copy())
+        prev = tk
+    b.wait_host(prev)
+    got.append(pres[(calls - 1) & 1].array.copy())
+    assert nb.tc5_launches() - before >= calls
+    got = np.concatenate(got, axis=1)
+    m_or = oracle.model(2, True)
+    for s in list(range(0, S, 41)) + [S - 1]:
+        r, _ = oracle.nnsp_run(m_or, pcm[s], taps=False)
+        assert (r == got[s]).all(), s
+    for x in pin + pres:
+        x.free()
+    b.close()
