@@ -191,6 +191,12 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
                              const nnsp_b200_cascade_params *params, int n_streams, int device,
                              nnsp_b200_cascade **out);
 int nnsp_b200_cascade_reset(nnsp_b200_cascade *c);
+/* ParamCntrlClass belongs to a controller instance (nnCntrlClass.h:12-29), i.e. to a stream: params[i] becomes the
+ * parameter set of stream first_stream + i (thresholds, counts, time-outs; the two look-back depths must equal the
+ * handle's, they size its history buffers). Waits for the handle's work in flight; takes effect with the next call and
+ * survives nnsp_b200_cascade_reset, like the reference's params pointer survives nnCntrlClass_reset. */
+int nnsp_b200_cascade_set_stream_params(nnsp_b200_cascade *c, int first_stream, int n_streams,
+                                        const nnsp_b200_cascade_params *params);
 /* Asynchronous and pipelined like nnsp_b200_batch_exec: results, state and the PCM buffer of a call are settled
  * only after nnsp_b200_cascade_sync -- the kernels that handle the first frames after a stage change read the call's
  * PCM on an internal stream while the next call's front end already runs, so there is NO stream of the caller's on
@@ -237,6 +243,8 @@ int nnsp_b200_group_create_cascade(const nnsp_b200_model *const models[3], const
 int nnsp_b200_group_size(const nnsp_b200_group *g);
 int nnsp_b200_group_range(const nnsp_b200_group *g, int member, int *device, int *first_stream, int *n_streams);
 int nnsp_b200_group_reset(nnsp_b200_group *g);
+/* nnsp_b200_cascade_set_stream_params in the group's stream numbering (cascade groups); waits for the calls issued so far */
+int nnsp_b200_group_set_stream_params(nnsp_b200_group *g, int first_stream, int n_streams, const nnsp_b200_cascade_params *params);
 int nnsp_b200_group_exec_host(nnsp_b200_group *g, const int16_t *pcm, long long stream_stride, int n_frames, void *results);
 int nnsp_b200_group_exec_host_async(nnsp_b200_group *g, const int16_t *pcm, long long stream_stride, int n_frames,
                                     void *results, long long *ticket);

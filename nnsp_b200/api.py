@@ -286,6 +286,11 @@ class Cascade:
     def reset(self):
         check(lib().nnsp_b200_cascade_reset(self.h), "cascade_reset")
 
+    def set_stream_params(self, first_stream, params):
+        """params: [n][10] int16, rows in the field order of ParamCntrlClass (what params_array() returns for the handle)"""
+        p = np.ascontiguousarray(params, np.int16).reshape(-1, len(capi.CascadeParams._fields_))
+        check(lib().nnsp_b200_cascade_set_stream_params(self.h, int(first_stream), len(p), p.ctypes.data_as(C.c_void_p)), "cascade_set_stream_params")
+
     def sync(self):
         check(lib().nnsp_b200_cascade_sync(self.h), "cascade_sync")
 
@@ -398,6 +403,11 @@ class Group:
 
     def reset(self):
         check(lib().nnsp_b200_group_reset(self.h), "group_reset")
+
+    def set_stream_params(self, first_stream, params):
+        """cascade groups: params [n][10] int16 in the field order of ParamCntrlClass, global stream numbering"""
+        p = np.ascontiguousarray(params, np.int16).reshape(-1, len(capi.CascadeParams._fields_))
+        check(lib().nnsp_b200_group_set_stream_params(self.h, int(first_stream), len(p), p.ctypes.data_as(C.c_void_p)), "group_set_stream_params")
 
     def exec_host(self, pcm, results=None):
         assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and pcm.shape[0] == self.S

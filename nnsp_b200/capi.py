@@ -39,12 +39,12 @@ nnsp_b200_model_from_net nnsp_b200_model_from_table_text nnsp_b200_model_to_tabl
 nnsp_b200_model_info nnsp_b200_model_free nnsp_b200_batch_create nnsp_b200_batch_reset nnsp_b200_batch_exec
 nnsp_b200_batch_exec_host nnsp_b200_batch_exec_host_async nnsp_b200_batch_wait_host nnsp_b200_batch_sync nnsp_b200_batch_last_kernel_ms nnsp_b200_batch_dims
 nnsp_b200_batch_stream nnsp_b200_batch_set_nn_path nnsp_b200_batch_get_nn_path nnsp_b200_batch_destroy nnsp_b200_cascade_default_params nnsp_b200_cascade_create
-nnsp_b200_cascade_reset nnsp_b200_cascade_exec nnsp_b200_cascade_exec_host nnsp_b200_cascade_exec_host_async nnsp_b200_cascade_wait_host nnsp_b200_cascade_sync
+nnsp_b200_cascade_reset nnsp_b200_cascade_set_stream_params nnsp_b200_cascade_exec nnsp_b200_cascade_exec_host nnsp_b200_cascade_exec_host_async nnsp_b200_cascade_wait_host nnsp_b200_cascade_sync
 nnsp_b200_cascade_last_kernel_ms nnsp_b200_cascade_stream nnsp_b200_cascade_set_path nnsp_b200_cascade_destroy nnsp_b200_feature_stages
 nnsp_b200_table nnsp_b200_ingest_audadc nnsp_b200_device_count nnsp_b200_device_pci_bus_id nnsp_b200_dev_alloc nnsp_b200_dev_free nnsp_b200_host_alloc_pinned
 nnsp_b200_host_free_pinned nnsp_b200_memcpy_h2d nnsp_b200_memcpy_d2h nnsp_b200_memset nnsp_b200_event_create
 nnsp_b200_event_record nnsp_b200_event_elapsed_ms nnsp_b200_event_destroy nnsp_b200_int_peak nnsp_b200_net_eval
-nnsp_b200_group_create_batch nnsp_b200_group_create_cascade nnsp_b200_group_size nnsp_b200_group_range nnsp_b200_group_reset
+nnsp_b200_group_create_batch nnsp_b200_group_create_cascade nnsp_b200_group_size nnsp_b200_group_range nnsp_b200_group_reset nnsp_b200_group_set_stream_params
 nnsp_b200_group_exec_host nnsp_b200_group_exec_host_async nnsp_b200_group_wait nnsp_b200_group_destroy
 nnsp_b200_batch_set_host_format nnsp_b200_cascade_set_host_format nnsp_b200_wav_info nnsp_b200_wav_read_frames nnsp_b200_wav_load_streams nnsp_b200_cascade_timeline""".split()
 
@@ -94,6 +94,7 @@ def lib():
         L.nnsp_b200_cascade_default_params.restype = None
         L.nnsp_b200_cascade_create.argtypes = [C.POINTER(vp), C.POINTER(ci), ci, C.POINTER(CascadeParams), ci, ci, C.POINTER(vp)]
         L.nnsp_b200_cascade_reset.argtypes = [vp]
+        L.nnsp_b200_cascade_set_stream_params.argtypes = [vp, ci, ci, vp]
         L.nnsp_b200_cascade_exec.argtypes = [vp, vp, ll, ci, vp, C.POINTER(Taps)]
         L.nnsp_b200_cascade_exec_host.argtypes = [vp, vp, ll, ci, vp]
         L.nnsp_b200_cascade_exec_host_async.argtypes = [vp, vp, ll, ci, vp, C.POINTER(ll)]
@@ -126,6 +127,7 @@ def lib():
     L.nnsp_b200_group_size.argtypes = [vp]
     L.nnsp_b200_group_range.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
     L.nnsp_b200_group_reset.argtypes = [vp]
+    L.nnsp_b200_group_set_stream_params.argtypes = [vp, ci, ci, vp]
     L.nnsp_b200_group_exec_host.argtypes = [vp, vp, ll, ci, vp]
     L.nnsp_b200_group_exec_host_async.argtypes = [vp, vp, ll, ci, vp, C.POINTER(ll)]
     L.nnsp_b200_group_wait.argtypes = [vp, ll]

@@ -17,6 +17,7 @@
  *   hist kernels   : newest d_max+2 PCM frames and d_max log-mel rows for the next call */
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include <vector>
 #include <new>
 #include <string.h>
 
@@ -38,9 +39,16 @@ struct CsNarrow { using WS = WarpScratchT<80, 48>;   static constexpr int WARPS 
 constexpr int CS_MAXSEQ = 3;
 constexpr int LOGMEL_OF_ZERO = 0x2688 * -15;     /* log10_q15(0): fixlog10.c:39-47 with x -> 1 */
 
+/* ParamCntrlClass is a member of every nnCntrlClass instance (nnCntrlClass.h:12-29), i.e. per stream: the thresholds and
+ * time-outs of a stream live in a 16-byte device record (nnsp_b200_cascade_set_stream_params); the look-back depths size
+ * the history buffers and stay per handle (CascadeDev.P). prob / cnts are indexed by NNSP id. */
+struct CascThr { int16_t prob[3], cnts[3], timeout_kws, timeout_s2i; };
+static_assert(sizeof(CascThr) == 16, "one 128-bit load per stream");
+
 struct CascadeDev {                   /* small, by value in kernel params */
     int seq[CS_MAXSEQ], len_seq;
-    nnsp_b200_cascade_params P;
+    nnsp_b200_cascade_params P;       /* look-back depths; the thresholds of a stream are thr[stream] */
+    const CascThr *thr;
     int dmax;                         /* max look-back frames over the ids in seq */
     int wbytes[3], woff_words[3], boff[3];   /* per id: weight bytes, word offset of its image in smem, bias offset */
 };
@@ -62,6 +70,13 @@ struct CascadeArgs {
     const int *replay_list;           /* with t0: the streams that still have frames left, handed out dynamically ... */
     int *replay_ctl;                  /* ... [0] = how many, [1] = cursor                                         */
 };
+
+__device__ __forceinline__ CascThr load_thr(const CascadeDev &cd, long long s)
+{
+    CascThr t;
+    *reinterpret_cast<int4 *>(&t) = __ldg(reinterpret_cast<const int4 *>(cd.thr + s));
+    return t;
+}
 
 template <class V>
 struct CascadeSmem {
@@ -157,6 +172,7 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
         int pos = a.st.casc[(long long)s * CS_N + CS_POS];
         int cnt_kws = a.st.casc[(long long)s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[(long long)s * CS_N + CS_CNT_S2I];
         int age = a.st.casc[(long long)s * CS_N + CS_AGE];
+        const CascThr thr = load_thr(cd, s);
         __syncwarp();
         const int16_t *ps = a.pcm + (long long)s * a.stride;
         const int16_t *hs = a.st.hist + (long long)s * hist_len + hist_len;                 /* hs[g], g < 0 */
@@ -216,8 +232,7 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
             __syncwarp();
             /* ---- NNSPClass_exec tail ------------------------------------------------------------------ */
             const bool ran = (ws->scal[SC_SLIDES] == 1);
-            const int16_t th_prob = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_prob_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_prob_kws : cd.P.thresh_prob_s2i);
-            const int16_t th_cnt = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_cnts_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_cnts_kws : cd.P.thresh_cnts_s2i);
+            const int16_t th_prob = thr.prob[id], th_cnt = thr.cnts[id];
             if (ran) {
                 net_forward(M, wimg + cd.woff_words[id], bimg + cd.boff[id], sm.tanh_lut, ws, lane, nullptr, nullptr);
                 if (lane == 0) {
@@ -231,15 +246,15 @@ cascade_kernel(CascadeArgs a, int off_w, int off_b)
             const int detected = ws->scal[SC_TRIGGER];
             int next_pos = pos, do_reset = 0, cnt_out = 0;
             if (id == NNSP_B200_ID_S2I) {
-                cnt_s2i = (cnt_s2i + 1) % cd.P.thresh_timeout_s2i;
-                if (detected || cnt_s2i == cd.P.thresh_timeout_s2i - 1) {
+                cnt_s2i = (cnt_s2i + 1) % thr.timeout_s2i;
+                if (detected || cnt_s2i == thr.timeout_s2i - 1) {
                     next_pos = (pos + 1) % cd.len_seq;
                     if (detected || cd.seq[next_pos] != id) { cnt_s2i = 0; do_reset = 1; }
                 }
                 cnt_out = cnt_s2i;
             } else if (id == NNSP_B200_ID_KWS) {
-                cnt_kws = (cnt_kws + 1) % cd.P.thresh_timeout_kws;
-                if (detected || cnt_kws == cd.P.thresh_timeout_kws - 1) {
+                cnt_kws = (cnt_kws + 1) % thr.timeout_kws;
+                if (detected || cnt_kws == thr.timeout_kws - 1) {
                     if (detected) next_pos = (pos + 1) % cd.len_seq;
                     else { next_pos = (pos - 1) % cd.len_seq; if (next_pos < 0) next_pos += cd.len_seq; }
                     if (detected || cd.seq[next_pos] != id) { cnt_kws = 0; do_reset = 1; }
@@ -398,6 +413,7 @@ cascade_replay_kernel(CascadeArgs a, int off_w, int off_b)
         int pos = a.st.casc[(long long)s * CS_N + CS_POS];
         int cnt_kws = a.st.casc[(long long)s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[(long long)s * CS_N + CS_CNT_S2I];
         int age = a.st.casc[(long long)s * CS_N + CS_AGE];
+        const CascThr thr = load_thr(cd, s);
         group_sync<CR_GW>(bid);
         const int16_t *ps = a.pcm + (long long)s * a.stride;
         const int16_t *hs = a.st.hist + (long long)s * hist_len + hist_len;
@@ -443,8 +459,7 @@ cascade_replay_kernel(CascadeArgs a, int off_w, int off_b)
             group_sync<CR_GW>(bid);
             /* ---- NNSPClass_exec tail ------------------------------------------------------------------ */
             const bool ran = (ws->scal[SC_SLIDES] == 1);
-            const int16_t th_prob = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_prob_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_prob_kws : cd.P.thresh_prob_s2i);
-            const int16_t th_cnt = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_cnts_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_cnts_kws : cd.P.thresh_cnts_s2i);
+            const int16_t th_prob = thr.prob[id], th_cnt = thr.cnts[id];
             group_sync<CR_GW>(bid);                                          /* everyone has read slides before it changes */
             if (ran) {
                 net_forward_group<CR_GW>(M, wimg + cd.woff_words[id], bimg + cd.boff[id], sm.tanh_lut, ws, wg, lane, bid);
@@ -459,15 +474,15 @@ cascade_replay_kernel(CascadeArgs a, int off_w, int off_b)
             const int detected = ws->scal[SC_TRIGGER];
             int next_pos = pos, do_reset = 0, cnt_out = 0;
             if (id == NNSP_B200_ID_S2I) {
-                cnt_s2i = (cnt_s2i + 1) % cd.P.thresh_timeout_s2i;
-                if (detected || cnt_s2i == cd.P.thresh_timeout_s2i - 1) {
+                cnt_s2i = (cnt_s2i + 1) % thr.timeout_s2i;
+                if (detected || cnt_s2i == thr.timeout_s2i - 1) {
                     next_pos = (pos + 1) % cd.len_seq;
                     if (detected || cd.seq[next_pos] != id) { cnt_s2i = 0; do_reset = 1; }
                 }
                 cnt_out = cnt_s2i;
             } else if (id == NNSP_B200_ID_KWS) {
-                cnt_kws = (cnt_kws + 1) % cd.P.thresh_timeout_kws;
-                if (detected || cnt_kws == cd.P.thresh_timeout_kws - 1) {
+                cnt_kws = (cnt_kws + 1) % thr.timeout_kws;
+                if (detected || cnt_kws == thr.timeout_kws - 1) {
                     if (detected) next_pos = (pos + 1) % cd.len_seq;
                     else { next_pos = (pos - 1) % cd.len_seq; if (next_pos < 0) next_pos += cd.len_seq; }
                     if (detected || cd.seq[next_pos] != id) { cnt_kws = 0; do_reset = 1; }
@@ -722,7 +737,8 @@ __global__ void __launch_bounds__(32 * CPOST_WARPS) cascade_post_kernel(CascadeP
     int cnt_kws = a.st.casc[s * CS_N + CS_CNT_KWS], cnt_s2i = a.st.casc[s * CS_N + CS_CNT_S2I];
     const int id = cd.seq[pos];
     const int d = (id == NNSP_B200_ID_VAD) ? 0 : (id == NNSP_B200_ID_KWS ? cd.P.frs_vbufBk_kws : cd.P.frs_vbufBk_s2i);
-    const int th_cnt = (id == NNSP_B200_ID_VAD) ? cd.P.thresh_cnts_vad : (id == NNSP_B200_ID_KWS ? cd.P.thresh_cnts_kws : cd.P.thresh_cnts_s2i);
+    const CascThr thr = load_thr(cd, s);
+    const int th_cnt = thr.cnts[id];
     /* NNSPClass scalars in registers (counters updated by compare-and-add, no dynamically indexed array) */
     int trig, out0, out1, out2, last, slides, cnt[8];
     {
@@ -738,12 +754,12 @@ __global__ void __launch_bounds__(32 * CPOST_WARPS) cascade_post_kernel(CascadeP
     const int st_o0 = out0, st_o1 = out1, st_o2 = out2;              /* outputs[] as the round finds them (binary models never touch them) */
     /* ---- time-outs (nnCntrlClass.c:186-206, 222-242): the counter of the live model is (c0 + n) mod time-out after n frames */
     const bool has_to = id != NNSP_B200_ID_VAD;
-    const int timeout = (id == NNSP_B200_ID_S2I) ? cd.P.thresh_timeout_s2i : cd.P.thresh_timeout_kws;
+    const int timeout = (id == NNSP_B200_ID_S2I) ? thr.timeout_s2i : thr.timeout_kws;
     const int c0 = (id == NNSP_B200_ID_S2I) ? cnt_s2i : cnt_kws;
     int to_next = pos, t_to = T;                                      /* first frame whose counter reads time-out - 1 */
     bool to_exit = false;
     if (has_to) {
-        int n = timeout - 1 - c0;
+        int n = (timeout - 1 - c0) % timeout;                          /* c0 may exceed a time-out that was shortened at run time */
         if (n < 1) n += timeout;
         t_to = tb + n - 1;
         if (id == NNSP_B200_ID_S2I) to_next = (pos + 1) % cd.len_seq;
@@ -934,6 +950,7 @@ struct nnsp_b200_cascade {
     DeviceModel dm[3];
     bool have[3] = { false, false, false };
     CascadeDev cd{};
+    CascThr *thr = nullptr;              /* [S] thresholds and time-outs of every stream (device); cd.thr points here */
     StreamState st{};
     int16_t *stale = nullptr;
     int32_t *logmel = nullptr; long long logmel_frames = 0;
@@ -1094,7 +1111,7 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
                 q.ctx = c->st.ctx; q.h = c->st.h; q.c = c->st.c; q.h_stride = NNSP_B200_MAX_WIDTH;
                 q.planes0 = c->planes[0]; q.planes1 = c->planes[1];
                 q.dec = c->dec; q.dec_stride = n_inf_max;
-                q.thresh_prob = (id == NNSP_B200_ID_VAD) ? c->cd.P.thresh_prob_vad : (id == NNSP_B200_ID_KWS ? c->cd.P.thresh_prob_kws : c->cd.P.thresh_prob_s2i);
+                q.thresh_prob = 0; q.thr_prob = &c->thr->prob[id]; q.thr_stride = (int)(sizeof(CascThr) / sizeof(int16_t));   /* per stream: thr[s].prob[id] */
                 q.tstart = c->ra.tstart; q.tb = c->ra.tb; q.age0 = c->ra.age0; q.lmfix = c->ra.lmfix;
                 cudaStream_t gs = c->gs[lane_set][k];
                 NNSP_CUDA(cudaStreamWaitEvent(gs, c->ev_fork[lane_set], 0));
@@ -1259,6 +1276,12 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaMalloc(&c->hist2, S * hist_frames * NNSP_B200_FRAME * sizeof(int16_t)));
     TRY(cudaMalloc(&c->st.lmhist, S * lm_rows * NNSP_B200_NMEL * sizeof(int32_t)));
     TRY(cudaMalloc(&c->stale, S * 120 * sizeof(int16_t)));
+    TRY(cudaMalloc(&c->thr, S * sizeof(CascThr)));
+    c->cd.thr = c->thr;
+    {
+        std::vector<nnsp_b200_cascade_params> all(S, c->cd.P);              /* every stream starts with the handle's parameters */
+        if ((rc = nnsp_b200_cascade_set_stream_params(c, 0, (int)S, all.data()))) return fail(rc);
+    }
     TRY(cudaMalloc(&c->grp_list, (size_t)3 * S * sizeof(int)));
     TRY(cudaMalloc(&c->ctl, CS_MAX_SLICES * CTL_INTS * sizeof(int)));
     TRY(cudaMalloc(&c->fix_list, S * sizeof(int)));
@@ -1280,6 +1303,34 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     g_launches.fetch_add(1);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { nnsp_set_error("cascade reset kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(NNSP_B200_ERR_CUDA); }
     *out = c;
+    return NNSP_B200_OK;
+}
+
+/* ParamCntrlClass of individual streams (nnCntrlClass.h:12-29 is a member of every controller instance). Thresholds and
+ * time-outs take effect with the next call; a counter that already reads beyond a shortened time-out wraps as the
+ * reference's `(cnt + 1) % timeout` does. The look-back depths size the history buffers and cannot differ from the handle's. */
+int nnsp_b200_cascade_set_stream_params(nnsp_b200_cascade *c, int first_stream, int n_streams, const nnsp_b200_cascade_params *params)
+{
+    if (!c || !params || first_stream < 0 || n_streams < 0 || (long long)first_stream + n_streams > c->S) {
+        nnsp_set_error("cascade_set_stream_params: bad stream range");
+        return NNSP_B200_ERR_ARG;
+    }
+    std::vector<CascThr> h((size_t)n_streams);
+    for (int i = 0; i < n_streams; i++) {
+        const nnsp_b200_cascade_params &P = params[i];
+        if (P.thresh_timeout_kws < 1 || P.thresh_timeout_s2i < 1 || P.frs_vbufBk_kws != c->cd.P.frs_vbufBk_kws || P.frs_vbufBk_s2i != c->cd.P.frs_vbufBk_s2i) {
+            nnsp_set_error("cascade_set_stream_params: stream %d: time-outs must be >= 1 and the look-back depths those of the handle (%d, %d)",
+                           first_stream + i, (int)c->cd.P.frs_vbufBk_kws, (int)c->cd.P.frs_vbufBk_s2i);
+            return NNSP_B200_ERR_ARG;
+        }
+        CascThr &t = h[(size_t)i];
+        t.prob[NNSP_B200_ID_S2I] = P.thresh_prob_s2i; t.prob[NNSP_B200_ID_VAD] = P.thresh_prob_vad; t.prob[NNSP_B200_ID_KWS] = P.thresh_prob_kws;
+        t.cnts[NNSP_B200_ID_S2I] = P.thresh_cnts_s2i; t.cnts[NNSP_B200_ID_VAD] = P.thresh_cnts_vad; t.cnts[NNSP_B200_ID_KWS] = P.thresh_cnts_kws;
+        t.timeout_kws = P.thresh_timeout_kws; t.timeout_s2i = P.thresh_timeout_s2i;
+    }
+    NNSP_CUDA(cudaSetDevice(c->device));
+    NNSP_CUDA(cudaDeviceSynchronize());                          /* calls in flight still read the old records */
+    if (n_streams) NNSP_CUDA(cudaMemcpy(c->thr + first_stream, h.data(), (size_t)n_streams * sizeof(CascThr), cudaMemcpyHostToDevice));
     return NNSP_B200_OK;
 }
 
@@ -1502,7 +1553,7 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     cudaDeviceSynchronize();
     for (int i = 0; i < 3; i++) if (c->have[i]) free_model(&c->dm[i]);
     cudaFree(c->st.ctx); cudaFree(c->st.h); cudaFree(c->st.c); cudaFree(c->st.scal); cudaFree(c->st.casc);
-    cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale);
+    cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale); cudaFree(c->thr);
     cudaFree(c->logmel); cudaFree(c->logmel2); cudaFree(c->hist2); cudaFree(c->d_pcm); cudaFree(c->d_res); cudaFree(c->d_raw);
     if (c->nn_stream) cudaStreamDestroy(c->nn_stream);
     for (auto e : c->ev_feat) if (e) cudaEventDestroy(e);

@@ -239,6 +239,25 @@ int nnsp_b200_group_reset(nnsp_b200_group *g)
     return nnsp_b200_group_wait(g, t);
 }
 
+/* nnsp_b200_cascade_set_stream_params over the group's global stream numbering: every command issued so far completes
+ * first, then each member takes the part of the range it owns (the workers are idle, the handles are the caller's). */
+int nnsp_b200_group_set_stream_params(nnsp_b200_group *g, int first_stream, int n_streams, const nnsp_b200_cascade_params *params)
+{
+    if (!g || !g->is_cascade || !params || first_stream < 0 || n_streams < 0 || (long long)first_stream + n_streams > g->n_streams) {
+        nnsp_set_error("group_set_stream_params: a cascade group and a stream range inside it are required");
+        return NNSP_B200_ERR_ARG;
+    }
+    if (g->seq > 0) { const int rc = nnsp_b200_group_wait(g, g->seq); if (rc) return rc; }
+    for (Member *m : g->members) {
+        const int lo = first_stream > m->first ? first_stream : m->first;
+        const int hi = (first_stream + n_streams) < (m->first + m->count) ? (first_stream + n_streams) : (m->first + m->count);
+        if (hi <= lo) continue;
+        const int rc = nnsp_b200_cascade_set_stream_params(m->cascade, lo - m->first, hi - lo, params + (lo - first_stream));
+        if (rc) return rc;
+    }
+    return NNSP_B200_OK;
+}
+
 void nnsp_b200_group_destroy(nnsp_b200_group *g)
 {
     if (!g) return;

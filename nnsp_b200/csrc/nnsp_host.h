@@ -110,6 +110,7 @@ struct SplitGroup {
     uint8_t *planes0 = nullptr, *planes1 = nullptr;
     int32_t *dec = nullptr; int dec_stride = 0;
     int16_t thresh_prob = 0;
+    const int16_t *thr_prob = nullptr; int thr_stride = 0;   /* cascade: threshold of stream s = thr_prob[s * thr_stride] instead */
     nnsp_b200_taps taps{};
     /* cascade rounds (null in the batched path): per stream, the first inference frame of this round (inference k of
      * stream s is frame tstart[s] + 2k, it has (T - tstart[s] + 1) / 2 of them), the frame at which the live instance's

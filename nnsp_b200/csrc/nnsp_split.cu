@@ -193,6 +193,7 @@ struct SegArgs {
     int32_t *tap_logits;            /* [S][T][n_out] or null */
     int ao0;                        /* offset of layer l0's output inside an act row */
     int16_t thresh_prob;
+    const int16_t *thr_prob; int thr_stride;   /* per-stream thresholds (cascade), else null */
     const int *tstart, *tb, *age0;  /* cascade rounds: per-stream first inference frame, life begin, age there (SplitGroup) */
     const int32_t *lmfix;           /* [S][2][40] log-mel rows of an instance's first two frames */
 };
@@ -567,7 +568,7 @@ seg_kernel(SegArgs a)
                     if (M.nn_id == NNSP_B200_ID_S2I)
                         d = argmax_last_wins(lg, 7) | (argmax_last_wins(lg + 7, 17) << 8) | (argmax_last_wins(lg + 24, 17) << 16);
                     else
-                        d = binary_flag(lg[0], lg[1], a.thresh_prob);
+                        d = binary_flag(lg[0], lg[1], a.thr_prob ? a.thr_prob[(size_t)sel_sid(a.sel, tile, lane) * a.thr_stride] : a.thresh_prob);
                     a.dec[(size_t)sel_sid(a.sel, tile, lane) * a.dec_stride + k] = d;
                 }
                 if (a.tap_logits)
@@ -1114,7 +1115,7 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
             a.feat16 = q.feat16; a.logmel = q.logmel; a.lmhist = q.lmhist; a.dmax = q.dmax; a.dback = q.dback;
             a.ctx = q.ctx; a.in_planes = cur_in;
             a.out_planes = (l1 < D->numlayers) ? bufs[which] : nullptr;
-            a.dec = q.dec; a.tap_act = tp.act; a.tap_logits = tp.logits; a.ao0 = ao; a.thresh_prob = q.thresh_prob;
+            a.dec = q.dec; a.tap_act = tp.act; a.tap_logits = tp.logits; a.ao0 = ao; a.thresh_prob = q.thresh_prob; a.thr_prob = q.thr_prob; a.thr_stride = q.thr_stride;
             a.tstart = q.tstart; a.tb = q.tb; a.age0 = q.age0; a.lmfix = q.lmfix;
             int per_sm = (int)((227 * 1024) / (lay.total + 1024));
             per_sm = per_sm < 1 ? 1 : (per_sm > SEG_MINB ? SEG_MINB : per_sm);     /* __launch_bounds__(256, SEG_MINB) */

@@ -627,6 +627,8 @@ int nnsp_oracle_cascade_run(const nnsp_b200_model *const models[3], nnsp_oracle_
         c->idx_set = 0;
         c->idx_latest = RING_FRAMES - 1;
     } else if (do_reset) cascade_reset(c, models, seq, len_seq, params);
+    else if (params) c->P = *params;    /* a live controller whose Params the application rewrote: the instances read the
+                                         * thresholds through pointers into it (nnCntrlClass.c:100-123), the time-outs directly (:185, :219) */
     for (int t = 0; t < n_frames; t++) {
         int ran = 0, was_reset = 0;
         const int id = cascade_step(c, models, pcm + (size_t)t * 160, results ? &results[t] : NULL, T, &ran, &was_reset);

@@ -173,7 +173,8 @@ class Oracle:
         own = state is None
         st = state or self.lib.nnsp_oracle_cascade_new()
         seq_a = np.asarray(seq, np.int32)
-        par = self.default_params() if params is None else np.ascontiguousarray(params, np.int16)
+        # reset=False with params: the application rewrites the live controller's Params (seen by the next frame); without: kept
+        par = (None if (not reset or reset == 2) else self.default_params()) if params is None else np.ascontiguousarray(params, np.int16)
         res = np.zeros(T, CASCADE_RESULT_DT)
         tp = Taps(T, 1, 128, 1) if taps else None
         valid = np.zeros(T, np.int8)

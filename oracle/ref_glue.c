@@ -350,6 +350,10 @@ int ref_cascade_run(int do_reset, const int *seq, int len_seq, const int16_t *pa
         nnCntrlClass_init(&g_cntrl, (void *)g_seq, (int8_t)len_seq);
         if (params10) memcpy(&g_cntrl.Params, params10, sizeof(ParamCntrlClass));
         nnCntrlClass_reset(&g_cntrl);
+    } else if (params10) {
+        /* the application changes the live controller's parameters: Params is a member of the instance and the NNSPClass
+         * instances hold POINTERS into it (nnCntrlClass.c:100-123), so the next exec already sees the new values */
+        memcpy(&g_cntrl.Params, params10, sizeof(ParamCntrlClass));
     }
     for (t = 0; t < n_frames; t++) {
         const int pos0 = g_cntrl.current_pos_seq, id = g_seq[pos0];

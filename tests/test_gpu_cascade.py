@@ -287,3 +287,47 @@ def test_s2i_only_controller_on_the_gpu(nb):
             for s in range(len(x)):
                 for f in ("stage_id", "pos_after", "detected", "outputs"):
                     assert (got[s][f] == want[s][f]).all(), (path, th_cnt, s, f)
+
+
+@pytest.mark.parametrize("path", ["sorted", "sequential"])
+def test_per_stream_params_changed_at_run_time(nb, oracle, path):
+    """ParamCntrlClass is a member of every nnCntrlClass instance (nnCntrlClass.h:12-29): each stream gets its own
+    thresholds, counts and time-outs (nnsp_b200_cascade_set_stream_params), and a third of the streams get new ones between
+    two calls -- the oracle runs every stream as its own instance with exactly those parameter sets."""
+    S, T1, T2 = 40, 260, 340
+    rng = np.random.default_rng(11)
+    pcm = nb.synth_pcm(S, T1 + T2, first_stream=700)
+    c = nb.Cascade(_models(nb), S)
+    c.set_path(path)
+    base = c.params_array()
+    names = [n for n, _ in nb.capi.CascadeParams._fields_]
+
+    def draw():
+        p = base.copy()
+        for n, lo, hi in [("thresh_timeout_kws", 20, 120), ("thresh_timeout_s2i", 15, 90), ("thresh_cnts_vad", 1, 6), ("thresh_cnts_kws", 1, 5),
+                          ("thresh_cnts_s2i", 1, 5), ("thresh_prob_vad", 2000, 30000), ("thresh_prob_kws", 100, 30000), ("thresh_prob_s2i", 100, 30000)]:
+            p[names.index(n)] = rng.integers(lo, hi + 1)
+        return p
+
+    par1 = np.stack([draw() for _ in range(S)])
+    c.set_stream_params(0, par1)
+    r1 = c.exec(pcm[:, :T1 * 160])
+    par2 = par1.copy()
+    first, n = 13, S // 3
+    par2[first:first + n] = np.stack([draw() for _ in range(n)])
+    c.set_stream_params(first, par2[first:first + n])
+    r2, taps = c.exec(pcm[:, T1 * 160:], taps=True)
+    om = _oracle_models(oracle)
+    for s in range(S):
+        st = oracle.lib.nnsp_oracle_cascade_new()
+        o1, _, _ = oracle.cascade_run(om, pcm[s, :T1 * 160], params=par1[s], state=st, reset=1, taps=False)
+        o2, tp, valid = oracle.cascade_run(om, pcm[s, T1 * 160:], params=par2[s], state=st, reset=0)
+        oracle.lib.nnsp_oracle_cascade_free(st)
+        for f in o1.dtype.names:
+            assert (r1[s][f] == o1[f]).all(), "first call, stream %d, field %s" % (s, f)
+        _check(r2, taps, s, o2, tp, valid)
+    bad = par1[:1].copy()
+    bad[0, names.index("frs_vbufBk_kws")] += 1               # the look-back depth sizes the history: per handle only
+    with pytest.raises(nb.NnspError):
+        c.set_stream_params(0, bad)
+    c.close()

@@ -63,6 +63,39 @@ def test_cascade_group_async_calls(nb):
     g.close()
 
 
+def test_cascade_group_per_stream_params(nb):
+    """nnsp_b200_group_set_stream_params: a range of streams that straddles the members gets its own time-outs after the
+    first call; the group must then behave like one handle that was given the same parameter sets"""
+    S, n = 300, 120
+    pcm = nb.synth_pcm(S, 2 * n, first_stream=2)
+    models = [nb.Model.from_blob(nb.MODEL_DIR + "/" + f) for f in FILES]
+    ref = nb.Cascade(models, S)
+    par = np.tile(ref.params_array(), (170, 1))
+    names = [x for x, _ in nb.capi.CascadeParams._fields_]
+    par[:, names.index("thresh_timeout_kws")] = 25 + np.arange(170) % 40
+    par[:, names.index("thresh_cnts_vad")] = 1 + np.arange(170) % 5
+    w1 = ref.exec_host(pcm[:, :n * 160].copy())
+    ref.set_stream_params(60, par)
+    w2 = ref.exec_host(pcm[:, n * 160:].copy())
+    ref.close()
+    g = nb.Group(models, S, _devices(nb, 3))
+    g1 = g.exec_host(pcm[:, :n * 160].copy())
+    g.set_stream_params(60, par)                          # members own [0,100), [100,200), [200,300): all three are touched
+    g2 = g.exec_host(pcm[:, n * 160:].copy())
+    g.close()
+    for f in w1.dtype.names:
+        assert (g1[f] == w1[f]).all() and (g2[f] == w2[f]).all(), f
+    assert not all((w2[f][60:230] == nb_default_second_call(nb, models, pcm, n)[f][60:230]).all() for f in w2.dtype.names)
+
+
+def nb_default_second_call(nb, models, pcm, n):
+    c = nb.Cascade(models, pcm.shape[0])
+    c.exec_host(pcm[:, :n * 160].copy())
+    r = c.exec_host(pcm[:, n * 160:].copy())
+    c.close()
+    return r
+
+
 def test_group_over_every_device_of_the_box(nb):
     n = nb.device_count()
     if n < 2:

@@ -146,3 +146,30 @@ def test_synthetic_network_through_the_reference(oracle, acc32):
             b = R.net_eval_blob(blob, acc32, x, h, c, a_s, n_o)
             for u, v in zip(a, b):
                 assert (u[: len(v)] == v).all(), (case[0], k)
+
+
+def test_params_rewritten_on_a_live_controller(oracle, nb):
+    """ParamCntrlClass is a member of the controller instance and the NNSPClass instances read the thresholds through
+    pointers into it (nnCntrlClass.c:100-123), the time-outs are read directly (:185, :219): an application that rewrites
+    them between frames is obeyed from the next frame on -- including a time-out shortened below the running counter.
+    The restatement must do the same as the reference itself."""
+    R = RefLib(False)
+    om = [oracle.model(i) for i in range(3)]
+    base = oracle.default_params()
+    names = ["thresh_prob_vad", "thresh_cnts_vad", "frs_vbufBk_s2i", "thresh_timeout_s2i", "thresh_prob_s2i", "thresh_cnts_s2i",
+             "frs_vbufBk_kws", "thresh_timeout_kws", "thresh_prob_kws", "thresh_cnts_kws"]
+    for first in (15, 5, 47):                                    # streams that sit in KWS / S2I when the parameters change
+        x = nb.synth_pcm(1, 700, first_stream=first)[0]
+        p1, p2 = base.copy(), base.copy()
+        p1[names.index("thresh_timeout_kws")] = 400; p1[names.index("thresh_timeout_s2i")] = 300
+        p2[names.index("thresh_timeout_kws")] = 31; p2[names.index("thresh_timeout_s2i")] = 23       # below the counters of the first part
+        p2[names.index("thresh_cnts_vad")] = 2; p2[names.index("thresh_prob_kws")] = 900
+        st = oracle.lib.nnsp_oracle_cascade_new()
+        a1, _, _ = oracle.cascade_run(om, x[:300 * 160], params=p1, state=st, reset=1, taps=False)
+        a2, _, _ = oracle.cascade_run(om, x[300 * 160:], params=p2, state=st, reset=0, taps=False)
+        oracle.lib.nnsp_oracle_cascade_free(st)
+        b1, _, _ = R.cascade_run(x[:300 * 160], params=p1, reset=1, taps=False)
+        b2, _, _ = R.cascade_run(x[300 * 160:], params=p2, reset=0, taps=False)
+        assert (a1 == b1).all() and (a2 == b2).all(), first
+        keep, _, _ = R.cascade_run(np.concatenate([x[:300 * 160], x[300 * 160:]]), params=p1, reset=1, taps=False)
+        assert not (keep[300:] == b2).all(), "stream %d: the rewritten parameters changed nothing, pick another stream" % first
