@@ -954,7 +954,14 @@ struct nnsp_b200_cascade {
     StreamState st{};
     int16_t *stale = nullptr;
     int32_t *logmel = nullptr; long long logmel_frames = 0;
-    int16_t *d_pcm = nullptr; long long d_pcm_frames = 0;
+    int16_t *d_pcm = nullptr; long long d_pcm_frames = 0;   /* host-buffer calls: staged PCM, two buffers of [S][d_pcm_frames][160] used alternately */
+    /* The H2D copies of host-buffer calls go through their own stream, all slices of a call back to back, so that the host
+     * link never waits for a slice's kernels (it bounds the end-to-end rate: 262 MB per 100-frame call of 8 192 streams).
+     * ev_h2d[buffer][slice]: the slice's PCM has arrived; ev_read[buffer][slice]: the kernels that read it are done. */
+    cudaStream_t h2d_stream = nullptr;
+    cudaEvent_t ev_h2d[2][8] = {}, ev_read[2][8] = {};
+    bool read_valid[2][8] = {};
+    long long host_calls = 0;
     nnsp_b200_cascade_result *d_res = nullptr;
     size_t smem_total = 0; int off_w = 0, off_b = 0;
     bool narrow = false;                      /* which shape of the sequential kernel (CsNarrow / CsWide) */
@@ -1254,6 +1261,9 @@ int nnsp_b200_cascade_create(const nnsp_b200_model *const models[3], const int *
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &s : c->xs) TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &r : c->host_ev) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    for (auto &r : c->ev_h2d) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &r : c->ev_read) for (auto &e : r) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &row : c->tl) for (auto &e : row) TRY(cudaEventCreate(&e));
     {
         int lo = 0, hi = 0;                                /* the controller / network chain outranks the front-end stream */
@@ -1407,7 +1417,8 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
         if (c->d_res) cudaFree(c->d_res);
         if (c->d_raw) cudaFree(c->d_raw);
         c->d_pcm = nullptr; c->d_res = nullptr; c->d_raw = nullptr;
-        NNSP_CUDA(cudaMalloc(&c->d_pcm, (size_t)c->S * T * NNSP_B200_FRAME * sizeof(int16_t)));
+        NNSP_CUDA(cudaMalloc(&c->d_pcm, (size_t)2 * c->S * T * NNSP_B200_FRAME * sizeof(int16_t)));
+        for (auto &r : c->read_valid) for (auto &v : r) v = false;
         NNSP_CUDA(cudaMalloc(&c->d_res, (size_t)c->S * T * sizeof(nnsp_b200_cascade_result)));
         c->d_pcm_frames = T;
     }
@@ -1417,9 +1428,13 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
     /* every per-call scratch array is laid out [stream][T] (or by n_inf_max = (T + 1) / 2): a slice owns the same bytes in
      * consecutive calls only while T stays the same. When it changes with an asynchronous call still in flight, every
      * pipeline stream first waits for all streams of that call. */
-    if (c->host_inflight && c->host_seq > 0 && c->host_last_T != T)
+    if (c->host_inflight && c->host_seq > 0 && c->host_last_T != T) {
         for (int j = 0; j < 3; j++)
             for (int k = 0; k < 3; k++) NNSP_CUDA(cudaStreamWaitEvent(c->xs[j], c->host_ev[c->host_seq % CS_HOST_RING][k], 0));
+        /* ... and the copy stream: with another T the slices of the staged PCM are other byte ranges, the per-slice read
+         * events of the earlier calls no longer say when they are free */
+        for (int k = 0; k < 3; k++) NNSP_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->host_ev[c->host_seq % CS_HOST_RING][k], 0));
+    }
     c->host_last_T = T;
     const long long dstride = (long long)T * NNSP_B200_FRAME;
     if (c->host_fmt == NNSP_B200_HOST_AUDADC && !c->d_raw) {
@@ -1428,9 +1443,26 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
     }
     c->host_inflight = true;
     const int nsl = c->S >= 4096 ? 8 : (c->S >= 256 ? 4 : 1);
+    const int buf = (int)(c->host_calls++ & 1);
+    int16_t *dpcm = c->d_pcm + (size_t)buf * c->S * c->d_pcm_frames * NNSP_B200_FRAME;
+    auto slice = [&](int k, int *s0, int *s1) {
+        *s0 = (int)(((long long)c->S * k / nsl) & ~15LL);
+        *s1 = (k == nsl - 1) ? c->S : (int)(((long long)c->S * (k + 1) / nsl) & ~15LL);
+    };
+    if (c->host_fmt != NNSP_B200_HOST_AUDADC)
+        for (int k = 0; k < nsl; k++) {                             /* all copies of the call, in slice order, on the copy stream */
+            int s0, s1;
+            slice(k, &s0, &s1);
+            if (s1 <= s0) continue;
+            if (c->read_valid[buf][k]) NNSP_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_read[buf][k], 0));   /* the call before last has read this buffer */
+            NNSP_CUDA(cudaMemcpy2DAsync(dpcm + (size_t)s0 * dstride, dstride * sizeof(int16_t),
+                                        pcm + (size_t)s0 * stream_stride, stream_stride * sizeof(int16_t),
+                                        dstride * sizeof(int16_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, c->h2d_stream));
+            NNSP_CUDA(cudaEventRecord(c->ev_h2d[buf][k], c->h2d_stream));
+        }
     for (int k = 0; k < nsl; k++) {
-        const int s0 = (int)(((long long)c->S * k / nsl) & ~15LL);
-        const int s1 = (k == nsl - 1) ? c->S : (int)(((long long)c->S * (k + 1) / nsl) & ~15LL);
+        int s0, s1;
+        slice(k, &s0, &s1);
         if (s1 <= s0) continue;
         cudaStream_t st = c->xs[k % 3];
         if (c->host_fmt == NNSP_B200_HOST_AUDADC) {                 /* the application's ingest (main_nnsp.cc:58-65) on the device */
@@ -1438,13 +1470,13 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
             NNSP_CUDA(cudaMemcpy2DAsync(c->d_raw + (size_t)s0 * dstride, dstride * sizeof(uint32_t),
                                         raw + (size_t)s0 * stream_stride, stream_stride * sizeof(uint32_t),
                                         dstride * sizeof(uint32_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
-            if ((rc = launch_ingest(c->d_raw + (size_t)s0 * dstride, c->d_pcm + (size_t)s0 * dstride, (long long)(s1 - s0) * T, c->device, st))) return rc;
+            if ((rc = launch_ingest(c->d_raw + (size_t)s0 * dstride, dpcm + (size_t)s0 * dstride, (long long)(s1 - s0) * T, c->device, st))) return rc;
         } else
-        NNSP_CUDA(cudaMemcpy2DAsync(c->d_pcm + (size_t)s0 * dstride, dstride * sizeof(int16_t),
-                                    pcm + (size_t)s0 * stream_stride, stream_stride * sizeof(int16_t),
-                                    dstride * sizeof(int16_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, st));
-        rc = cascade_launch(c, c->d_pcm, dstride, T, s0, s1 - s0, results ? c->d_res : nullptr, nullptr, st, false, k);
+            NNSP_CUDA(cudaStreamWaitEvent(st, c->ev_h2d[buf][k], 0));
+        rc = cascade_launch(c, dpcm, dstride, T, s0, s1 - s0, results ? c->d_res : nullptr, nullptr, st, false, k);
         if (rc) return rc;
+        NNSP_CUDA(cudaEventRecord(c->ev_read[buf][k], st));         /* every reader of the slice's PCM has joined st by now */
+        c->read_valid[buf][k] = true;
         if (results)
             NNSP_CUDA(cudaMemcpyAsync(results + (size_t)s0 * T, c->d_res + (size_t)s0 * T,
                                       (size_t)(s1 - s0) * T * sizeof(nnsp_b200_cascade_result), cudaMemcpyDeviceToHost, st));
@@ -1491,6 +1523,7 @@ int nnsp_b200_cascade_sync(nnsp_b200_cascade *c)
     NNSP_CUDA(cudaSetDevice(c->device));
     NNSP_CUDA(cudaStreamSynchronize(c->stream));
     NNSP_CUDA(cudaStreamSynchronize(c->nn_stream));
+    NNSP_CUDA(cudaStreamSynchronize(c->h2d_stream));
     for (auto s : c->xs) NNSP_CUDA(cudaStreamSynchronize(s));
     c->host_inflight = false;
     return NNSP_B200_OK;
@@ -1565,6 +1598,9 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto s : c->xs) if (s) cudaStreamDestroy(s);
     for (auto &r : c->host_ev) for (auto e : r) if (e) cudaEventDestroy(e);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    for (auto &r : c->ev_h2d) for (auto e : r) if (e) cudaEventDestroy(e);
+    for (auto &r : c->ev_read) for (auto e : r) if (e) cudaEventDestroy(e);
     for (auto &row : c->tl) for (auto e : row) if (e) cudaEventDestroy(e);
     for (auto &row : c->gs) for (auto g : row) if (g) cudaStreamDestroy(g);
     for (auto e : c->ev_fork) if (e) cudaEventDestroy(e);
