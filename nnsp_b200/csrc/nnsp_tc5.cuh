@@ -18,12 +18,13 @@
  *   (odd, 16..31) and the tails (bytes 32..39 of frame 2 e | of frame 2 e + 1). The second 16-byte chunk of a K = 32
  *   instruction is either the NEXT entry of the same array (LBO = 16: frames f and f + 2) or the same entry of the
  *   next array (LBO = the array stride): 15 chunks -> 8 instructions per plane, 16 per tile.
- *   Roles (one persistent CTA per SM, 13 warps): 8 finish warps (TMEM lane quarter x share of the 16-unit blocks; TMEM -> registers
- *   -> bias, shift, tanh -> the tile's byte planes assembled in shared memory -> coalesced 16-byte stores), 4 conversion warps (TMA bulk copies of the raw int16 rows through
- *   a 4-deep ring -> byte planes in entry layout), 1 warp whose lane 0 issues the MMAs -- its own warp because the issue of
- *   a queued tcgen05.mma blocks, which would stall the conversion behind it. Three A buffers / TMEM stages in flight.
+ *   Roles (one persistent CTA per SM, 13 warps): 8 finish warps (TMEM lane quarter x share of the 16-unit blocks; TMEM ->
+ *   registers -> bias, shift, tanh -> the tile's byte planes assembled in shared memory -> coalesced 16-byte stores),
+ *   4 conversion warps (TMA bulk copies of the raw int16 rows through a 4-deep ring -> byte planes in entry layout), 1 warp
+ *   whose lane 0 issues the MMAs -- its own warp because the issue of a queued tcgen05.mma blocks, which would stall the
+ *   conversion behind it. Three A buffers / TMEM stages in flight.
  * Eligibility (launch_split_layers): a range selection (the batched NNSPClass; the cascade's rounds keep seg_kernel<2>),
- * layer 0 = fc 240 -> rows <= 80 with tanh and the exact 32-bit finish, followed by an LSTM, no activation tap.
+ * layer 0 = fc 240 -> rows <= 80 with tanh and the exact 32-bit finish, followed by an LSTM, no activation tap,
  * and at least 45 % of the tiles' inference slots in use (tc5_wanted, nnsp_split.cu). NNSP_B200_TC5=0 keeps the mma.sync
  * kernel, =2 takes this one whenever the layer qualifies. */
 #pragma once

@@ -6,7 +6,7 @@
  *   run  : tools/tc5_gemm_bench [streams] [units N: 72 S2I, 64 KWS, 28 VAD]
  *   SASS : cuobjdump -sass tools/tc5_gemm_bench | grep -E "UTCIMMA|UTCBAR|LDTM|IMMA"
  *
- * Both kernels take what feat_kernel writes -- standardised int16 feature rows [stream][frame][40] -- and produce the int16
+ * All kernels take what feat_kernel writes -- standardised int16 feature rows [stream][frame][40] -- and produce the int16
  * activations of layer 0 for every (stream, inference) row: row (s, i) reads frames 2i .. 2i+5 (240 values, the 6 x 40 context).
  * The int16 x int8 product is exact on int8 tensor cores through x = 256 hi + lo (hi signed, lo unsigned byte):
  *     acc = (acc_hi << 8) + acc_lo,   two MMAs per k-step, int32 accumulators.
@@ -15,9 +15,16 @@
  *                 two byte planes of the tile are laid out in shared memory as K-major core matrices (8 rows x 16 bytes, no
  *                 swizzle), one elected thread issues the 16 MMAs (8 k-steps x {s8 x s8, u8 x s8}) into two TMEM accumulators,
  *                 tcgen05.commit arrives on an mbarrier, and all 8 warps run the finish out of TMEM (tcgen05.ld 32x32b).
+ *   tc5p_kernel : the same contraction warp-specialised and pipelined: TMA bulk copies feed four producer warps that expand
+ *                 the windows into the core-matrix layout, two A buffers, two TMEM stages, eight finish warps.
+ *   tc5s_kernel : no window expansion -- the feature sequence stored once as 16-byte entries of even / odd frames, the A
+ *                 descriptor's start address does the sliding (the formulation of the product's seg0_tc5_kernel,
+ *                 nnsp_tc5.cuh): 2 streams x 64 inference slots per tile, 8 K = 32 instructions per byte plane, the MMA issue
+ *                 in its own warp, three stages. TC5_PROF=1 prints where the issuing and the conversion thread of CTA 0
+ *                 spend a tile's period.
  *   imma_kernel : mma.sync.m16n8k32 on the same planes (ldmatrix A fragments, B fragments pre-packed), the formulation of
  *                 seg_kernel<feat>.
- * Every output of both kernels is compared with a plain int64 reference kernel. */
+ * Every output of every kernel is compared with a plain int64 reference kernel. */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
