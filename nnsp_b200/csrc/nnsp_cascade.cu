@@ -1455,9 +1455,13 @@ static int cascade_enqueue_host(nnsp_b200_cascade *c, const int16_t *pcm, long l
             slice(k, &s0, &s1);
             if (s1 <= s0) continue;
             if (c->read_valid[buf][k]) NNSP_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_read[buf][k], 0));   /* the call before last has read this buffer */
-            NNSP_CUDA(cudaMemcpy2DAsync(dpcm + (size_t)s0 * dstride, dstride * sizeof(int16_t),
-                                        pcm + (size_t)s0 * stream_stride, stream_stride * sizeof(int16_t),
-                                        dstride * sizeof(int16_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, c->h2d_stream));
+            if (stream_stride == dstride)
+                NNSP_CUDA(cudaMemcpyAsync(dpcm + (size_t)s0 * dstride, pcm + (size_t)s0 * stream_stride,
+                                          (size_t)(s1 - s0) * dstride * sizeof(int16_t), cudaMemcpyHostToDevice, c->h2d_stream));
+            else
+                NNSP_CUDA(cudaMemcpy2DAsync(dpcm + (size_t)s0 * dstride, dstride * sizeof(int16_t),
+                                            pcm + (size_t)s0 * stream_stride, stream_stride * sizeof(int16_t),
+                                            dstride * sizeof(int16_t), (size_t)(s1 - s0), cudaMemcpyHostToDevice, c->h2d_stream));
             NNSP_CUDA(cudaEventRecord(c->ev_h2d[buf][k], c->h2d_stream));
         }
     for (int k = 0; k < nsl; k++) {
