@@ -981,6 +981,7 @@ struct nnsp_b200_cascade {
     RoundArrays ra{};
     int rounds = 3;                            /* stage-sorted rounds per call (1 .. CS_MAX_ROUNDS); NNSP_B200_CASCADE_ROUNDS */
     uint8_t *planes[2] = { nullptr, nullptr };
+    int16_t *vseq = nullptr; int vseq_rows = 0;   /* [S][vseq_rows][40]: the standardised window rows of round 1 (vseq_kernel), input of the tcgen05 layer-0 kernel */
     int32_t *dec = nullptr;
     long long split_cap_T = 0;
     cudaStream_t gs[4][3] = {};                /* per pipeline stream (3 host-call streams + the device-call stream): one per model group */
@@ -1012,16 +1013,31 @@ static bool cascade_use_split(const nnsp_b200_cascade *c, const nnsp_b200_taps *
     return true;
 }
 
+/* Layer 0 of the first round (which holds nearly all streams) on the tcgen05 kernel: vseq_kernel writes every stream's
+ * standardised window rows once, seg0_tc5_kernel contracts them (nnsp_split.cu, nnsp_tc5.cuh). Bit-exact and tested, but
+ * OFF unless NNSP_B200_TC5=2: its CTA needs a whole SM's shared memory, so unlike seg_kernel<2> it cannot share SMs with
+ * the next call's front end, and the call is no faster (8 192 streams x 100 frames: 1.441 vs 1.430 ms back to back). */
+static bool cascade_tc5_round()
+{
+    const char *e = getenv("NNSP_B200_TC5");
+    return e && e[0] == '2';
+}
+
 static int cascade_ensure_split(nnsp_b200_cascade *c, int T)
 {
     if (!c->split_ok || c->path == 1 || T <= c->split_cap_T) return NNSP_B200_OK;
     NNSP_CUDA(cudaDeviceSynchronize());
     for (auto &p : c->planes) { if (p) cudaFree(p); p = nullptr; }
     if (c->dec) { cudaFree(c->dec); c->dec = nullptr; }
+    if (c->vseq) { cudaFree(c->vseq); c->vseq = nullptr; }
     c->split_cap_T = 0;
     const size_t n_inf_max = (size_t)(T + 1) / 2, tiles = (size_t)c->S / 16 + (size_t)(CG_GROUPS + 1) * CS_MAX_SLICES + 2;
     for (auto &p : c->planes) NNSP_CUDA(cudaMalloc(&p, tiles * n_inf_max * 32 * c->pa_max));
     NNSP_CUDA(cudaMalloc(&c->dec, ((size_t)c->S + 16) * n_inf_max * sizeof(int32_t)));
+    if (cascade_tc5_round()) {
+        c->vseq_rows = (int)(2 * n_inf_max + 4);
+        NNSP_CUDA(cudaMalloc(&c->vseq, (size_t)c->S * c->vseq_rows * NNSP_B200_NMEL * sizeof(int16_t)));
+    }
     c->split_cap_T = T;
     return NNSP_B200_OK;
 }
@@ -1120,6 +1136,7 @@ static int cascade_launch(nnsp_b200_cascade *c, const int16_t *pcm, long long st
                 q.dec = c->dec; q.dec_stride = n_inf_max;
                 q.thresh_prob = 0; q.thr_prob = &c->thr->prob[id]; q.thr_stride = (int)(sizeof(CascThr) / sizeof(int16_t));   /* per stream: thr[s].prob[id] */
                 q.tstart = c->ra.tstart; q.tb = c->ra.tb; q.age0 = c->ra.age0; q.lmfix = c->ra.lmfix;
+                if (r == 0 && c->vseq) { q.vseq = c->vseq; q.vseq_rows = c->vseq_rows; }
                 cudaStream_t gs = c->gs[lane_set][k];
                 NNSP_CUDA(cudaStreamWaitEvent(gs, c->ev_fork[lane_set], 0));
                 if ((rc = launch_split_layers(c->mm[id], q, c->device, gs))) return rc;
@@ -1590,7 +1607,7 @@ void nnsp_b200_cascade_destroy(nnsp_b200_cascade *c)
     cudaDeviceSynchronize();
     for (int i = 0; i < 3; i++) if (c->have[i]) free_model(&c->dm[i]);
     cudaFree(c->st.ctx); cudaFree(c->st.h); cudaFree(c->st.c); cudaFree(c->st.scal); cudaFree(c->st.casc);
-    cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale); cudaFree(c->thr);
+    cudaFree(c->st.hist); cudaFree(c->st.lmhist); cudaFree(c->stale); cudaFree(c->thr); cudaFree(c->vseq);
     cudaFree(c->logmel); cudaFree(c->logmel2); cudaFree(c->hist2); cudaFree(c->d_pcm); cudaFree(c->d_res); cudaFree(c->d_raw);
     if (c->nn_stream) cudaStreamDestroy(c->nn_stream);
     for (auto e : c->ev_feat) if (e) cudaEventDestroy(e);

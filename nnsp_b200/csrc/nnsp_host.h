@@ -119,6 +119,9 @@ struct SplitGroup {
      * buffer is still partly zero (spectrogram_module.c:25-31) */
     const int *tstart = nullptr, *tb = nullptr, *age0 = nullptr;
     const int32_t *lmfix = nullptr;      /* [S][2][40] */
+    /* cascade, first round: scratch for the streams' standardised window rows, [S][vseq_rows][40] (vseq_kernel); with it
+     * layer 0 runs on the tcgen05 kernel. Null: seg_kernel<2> standardises while staging (later rounds, few streams) */
+    int16_t *vseq = nullptr; int vseq_rows = 0;
 };
 int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int device, cudaStream_t st);
 int split_supported(const MmaDeviceModel &mm);

@@ -1045,6 +1045,51 @@ static int launch_scan(const ScanArgs &a, int ntiles, size_t smem, int device, c
  * few of the slots (a 2-frame call: 1 of 64) and the mma.sync kernel, whose cost follows the rows, is faster -- measured
  * break-even near half-full tiles (4 096 streams x 2 frames: 59 vs 48 us per call; 100-frame calls: 240 vs 395 us).
  * NNSP_B200_TC5: 0 = never, 2 = whenever the layer qualifies (tests), otherwise by that rule. */
+/* The window rows of a cascade round, once per stream instead of once per 16-inference work item: row v of stream s is
+ * frame tstart[s] - 5 + v of the call, for v < 2 * (its inferences) + 4. Sources exactly as seg_kernel<2> stages them:
+ * frames before the instance's life in this call began are its stored context rows (already standardised); later ones are
+ * log-mel rows -- of the instance's first two frames (lmfix), of this call, or of the carried history, by the model's
+ * look-back (PcmBufClass_getData, PcmBufClass.c:38-85) -- standardised with the model's statistics
+ * (feature_module.c:67-73). One thread per (stream, row, 4 features). */
+struct VseqArgs {
+    const MmaModel *model;
+    const int *list, *count;
+    const int *tstart, *tb, *age0;
+    const int32_t *logmel, *lmhist, *lmfix;
+    const int16_t *ctx;
+    int T, dmax, dback, rows;
+    int16_t *vseq;
+};
+__global__ void __launch_bounds__(256) vseq_kernel(VseqArgs a)
+{
+    const int nsel = *a.count;
+    const long long total = (long long)nsel * a.rows * 10;
+    const MmaModel &M = *a.model;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(e / (a.rows * 10)), rem = (int)(e - (long long)p * a.rows * 10), v = rem / 10, x = rem - v * 10;
+        const long long s = a.list[p];
+        const int ts = a.tstart[s];
+        const int ninf = ts < a.T ? (a.T - ts + 1) >> 1 : 0;
+        if (v >= 2 * ninf + 4 || ninf == 0) continue;
+        const int f = ts - 5 + v, life = f - a.tb[s];
+        int16_t w[4] = { 0, 0, 0, 0 };
+        if (life < 0) {
+            const uint2 c = *reinterpret_cast<const uint2 *>(a.ctx + s * 240 + (6 + life) * 40 + x * 4);
+            *reinterpret_cast<uint2 *>(w) = c;
+        } else if (f < a.T) {
+            const int la = life + a.age0[s], fr = f - a.dback;
+            const int32_t *row = (la < 2) ? a.lmfix + (s * 2 + la) * NNSP_B200_NMEL
+                               : (fr >= 0) ? a.logmel + (s * a.T + fr) * NNSP_B200_NMEL
+                                           : a.lmhist + (s * a.dmax + a.dmax + fr) * NNSP_B200_NMEL;
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(row + x * 4));
+            const int32_t u[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int c = 0; c < 4; c++) w[c] = standardise(u[c], M.mean[4 * x + c], M.stdR[4 * x + c], M.feat_rshift);
+        }
+        *reinterpret_cast<uint2 *>(a.vseq + (s * a.rows + v) * NNSP_B200_NMEL + x * 4) = *reinterpret_cast<const uint2 *>(w);
+    }
+}
+
 static bool tc5_wanted(int n_inf)
 {
     const char *e = getenv("NNSP_B200_TC5");
@@ -1085,15 +1130,29 @@ int launch_split_layers(const MmaDeviceModel &mm, const SplitGroup &q, int devic
     while (li < D->numlayers) {
         int l1 = li;
         while (l1 < D->numlayers && D->layer[l1].type == LAYER_FC) l1++;
-        if (l1 > li && from_feat && l1 == 1 && q.mode == 1 && mm.tc5 && D->pa <= TC5_PAMAX && !q.list && !q.tstart && !tp.act && tc5_wanted(q.n_inf)) {
-            /* layer 0 of the batched path on the tcgen05 tensor cores (nnsp_tc5.cuh) */
+        const bool tc5_batch = q.mode == 1 && !q.list && !q.tstart;                       /* the batched NNSPClass */
+        const bool tc5_round = q.mode == 2 && q.list && q.tstart && q.vseq;                /* first round of the cascade */
+        if (l1 > li && from_feat && l1 == 1 && (tc5_batch || tc5_round) && mm.tc5 && D->pa <= TC5_PAMAX && !tp.act && tc5_wanted(q.n_inf)) {
+            /* layer 0 on the tcgen05 tensor cores (nnsp_tc5.cuh) */
+            if (tc5_round) {
+                VseqArgs v{};
+                v.model = mm.d; v.list = q.list; v.count = q.count; v.tstart = q.tstart; v.tb = q.tb; v.age0 = q.age0;
+                v.logmel = q.logmel; v.lmhist = q.lmhist; v.lmfix = q.lmfix; v.ctx = q.ctx;
+                v.T = q.T; v.dmax = q.dmax; v.dback = q.dback; v.rows = q.vseq_rows; v.vseq = q.vseq;
+                long long work = (long long)q.max_streams * q.vseq_rows * 10;
+                int grid = (int)((work + 255) / 256);
+                grid = grid < 1 ? 1 : (grid > 8 * sm_count(device) ? 8 * sm_count(device) : grid);
+                vseq_kernel<<<grid, 256, 0, st>>>(v);
+                NNSP_LAUNCH_CHECK();
+            }
             Tc5Args a{};
             a.img = mm.tc5; a.tables = q.tables; a.np = mm.tc5_np; a.rs = -D->layer[0].sh_out;
             a.s0 = q.s0; a.ns = q.ns; a.tile0 = q.tile0;
             a.T = q.T; a.first = q.first; a.n_inf = q.n_inf; a.nchunks = (q.n_inf + TC5_KC - 1) / TC5_KC;
             a.pa = D->pa; a.tile_bytes = tile_bytes;
             a.feat16 = q.feat16; a.ctx = q.ctx; a.out_planes = bufs[which];
-            const int nitems = ((q.ns + 1) / 2) * a.nchunks;
+            if (tc5_round) { a.list = q.list; a.count = q.count; a.tile_off = q.tile_off; a.tstart = q.tstart; a.vseq = q.vseq; a.vf = q.vseq_rows; }
+            const int nitems = (((tc5_round ? q.max_streams : q.ns) + 1) / 2) * a.nchunks;
             const int grid = nitems < sm_count(device) ? nitems : sm_count(device);
             seg0_tc5_kernel<<<grid, TC5_THREADS, sizeof(Tc5Smem) + 1024, st>>>(a);
             NNSP_LAUNCH_CHECK();

@@ -69,7 +69,23 @@ struct Tc5Args {
     const int16_t *feat16;          /* [S][T][40] */
     const int16_t *ctx;             /* [S][240] */
     uint8_t *out_planes;
+    /* cascade rounds (vseq != null): the selection is a device-side list (count, plane tile offset as in StreamSel), stream s
+     * has its own first inference frame tstart[s], hence (T - tstart[s] + 1) / 2 inferences, and its window rows were
+     * written by vseq_kernel: vseq[s][v] = row of frame tstart[s] - 5 + v, already standardised, context rows included */
+    const int *list, *count, *tile_off, *tstart;
+    const int16_t *vseq;
+    int vf;                         /* rows per stream in vseq */
 };
+__device__ __forceinline__ int tc5_nsel(const Tc5Args &a) { return a.list ? *a.count : a.ns; }
+__device__ __forceinline__ long long tc5_sid(const Tc5Args &a, int p) { return a.list ? a.list[p] : (long long)a.s0 + p; }
+/* inferences of stream position p that fall into the chunk starting at inference k0 */
+__device__ __forceinline__ int tc5_nk(const Tc5Args &a, int p, int nsel, int k0)
+{
+    if (p >= nsel) return 0;
+    int ninf = a.n_inf;
+    if (a.vseq) { const int ts = a.tstart[tc5_sid(a, p)]; ninf = ts < a.T ? (a.T - ts + 1) >> 1 : 0; }
+    return max(0, min(TC5_KC, ninf - k0));
+}
 
 __device__ __forceinline__ uint64_t tc5_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
 {   /* shared-memory matrix descriptor, no swizzle: address, leading / stride byte offsets in 16-byte units, version 1 */
@@ -109,7 +125,8 @@ seg0_tc5_kernel(Tc5Args a)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int np = a.np, T = a.T;
     const uint32_t st_cols = 2u * (uint32_t)np;                              /* TMEM columns of a stage: hi sums | lo sums */
-    const int npairs = (a.ns + 1) >> 1, nitems = npairs * a.nchunks;
+    const int nsel = tc5_nsel(a);
+    const int npairs = (nsel + 1) >> 1, nitems = npairs * a.nchunks;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem)), "r"(512u) : "memory");
@@ -169,17 +186,25 @@ seg0_tc5_kernel(Tc5Args a)
          * (feature_module.c:54-57: row 6 + f of the stored window for f = -5 .. -1) */
         auto fetch = [&](int item, int rb) {
             const int chunk = item / npairs, pair = item - chunk * npairs;
-            const int k0 = chunk * TC5_KC, nk = min(TC5_KC, a.n_inf - k0), nfr = 2 * nk + 4;
-            const int f_lo = a.first - 5 + 2 * k0, nctx = f_lo < 0 ? -f_lo : 0;
-            const int nstr = min(TC5_STREAMS, a.ns - 2 * pair);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&sm.raw_full[rb])), "r"((uint32_t)(nstr * nfr * 80)) : "memory");
-            for (int q = 0; q < nstr; q++) {
-                const long long s = a.s0 + 2 * pair + q;
+            const int k0 = chunk * TC5_KC;
+            const int f_lo = a.first - 5 + 2 * k0, nctx = (!a.vseq && f_lo < 0) ? -f_lo : 0;
+            int nfr[TC5_STREAMS];
+            uint32_t bytes = 0;
+            for (int q = 0; q < TC5_STREAMS; q++) {
+                const int nk = tc5_nk(a, 2 * pair + q, nsel, k0);
+                nfr[q] = nk > 0 ? 2 * nk + 4 : 0;
+                bytes += (uint32_t)(nfr[q] * 80);
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&sm.raw_full[rb])), "r"(bytes) : "memory");
+            for (int q = 0; q < TC5_STREAMS; q++) {
+                if (!nfr[q]) continue;
+                const long long s = tc5_sid(a, 2 * pair + q);
                 if (nctx)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  :: "r"(smem_u32(&sm.raw[rb][q][0])), "l"(a.ctx + s * 240 + (6 + f_lo) * 40), "r"((uint32_t)(nctx * 80)), "r"(smem_u32(&sm.raw_full[rb])) : "memory");
+                const int16_t *src = a.vseq ? a.vseq + (s * a.vf + 2 * k0) * 40 : a.feat16 + (s * T + f_lo + nctx) * 40;
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(smem_u32(&sm.raw[rb][q][nctx * 40])), "l"(a.feat16 + (s * T + f_lo + nctx) * 40), "r"((uint32_t)((nfr - nctx) * 80)), "r"(smem_u32(&sm.raw_full[rb])) : "memory");
+                             :: "r"(smem_u32(&sm.raw[rb][q][nctx * 40])), "l"(src), "r"((uint32_t)((nfr[q] - nctx) * 80)), "r"(smem_u32(&sm.raw_full[rb])) : "memory");
             }
         };
         if (ptid == 0)
@@ -192,8 +217,8 @@ seg0_tc5_kernel(Tc5Args a)
             if (ptid == 0 && item + (TC5_RING - 1) * (int)gridDim.x < nitems) fetch(item + (TC5_RING - 1) * gridDim.x, (n + TC5_RING - 1) % TC5_RING);
             if (use >= 1) tc5_wait(&sm.mma_done[b], (uint32_t)((use - 1) & 1));                  /* the MMAs that read a[b] are complete */
             tc5_wait(&sm.raw_full[rb], (uint32_t)((n / TC5_RING) & 1));
-            const int chunk = item / npairs;
-            const int nfr = 2 * min(TC5_KC, a.n_inf - chunk * TC5_KC) + 4;
+            const int chunk = item / npairs, pair = item - chunk * npairs;
+            const int nfr = 2 * max(tc5_nk(a, 2 * pair, nsel, chunk * TC5_KC), tc5_nk(a, 2 * pair + 1, nsel, chunk * TC5_KC)) + 4;   /* rows past a stream's own count are stale: their slots are dropped */
             for (int e = ptid; e < TC5_STREAMS * nfr; e += TC5_CONV_THREADS) {
                 const int q = e / nfr, fr = e - q * nfr;
                 const uint4 *src = reinterpret_cast<const uint4 *>(&sm.raw[rb][q][fr * 40]);
@@ -242,9 +267,10 @@ seg0_tc5_kernel(Tc5Args a)
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, n++) {
             const int b = n % TC5_STAGES, use = n / TC5_STAGES;
             const int chunk = item / npairs, pair = item - chunk * npairs;
-            const int k0 = chunk * TC5_KC, nk = min(TC5_KC, a.n_inf - k0);
-            const int nstr = min(TC5_STREAMS, a.ns - 2 * pair);
-            const bool live = slot < nk && q < nstr;
+            const int k0 = chunk * TC5_KC;
+            const int nk0 = tc5_nk(a, 2 * pair, nsel, k0), nk1 = tc5_nk(a, 2 * pair + 1, nsel, k0), nk = max(nk0, nk1);
+            const int nstr = min(TC5_STREAMS, nsel - 2 * pair);
+            const bool live = slot < (q ? nk1 : nk0);
             tc5_wait(&sm.mma_done[b], (uint32_t)(use & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem + st_cols * b + ((uint32_t)((warp & 3) * 32) << 16);
@@ -277,7 +303,8 @@ seg0_tc5_kernel(Tc5Args a)
             }
             asm volatile("bar.sync %0, 128;" :: "r"(2 + set) : "memory");        /* the set's 32 slots are assembled */
             {   /* copy out: the plane columns past the padded units leave as the zeros the staging buffer was cleared to */
-                uint8_t *gbase = a.out_planes + (size_t)(a.tile0 + ((2 * pair) >> 4)) * (size_t)a.tile_bytes + (size_t)((2 * pair) & 15) * pa + (size_t)piece * 16;
+                const size_t tile_abs = (size_t)a.tile0 + (a.list ? (size_t)*a.tile_off : 0) + (size_t)((2 * pair) >> 4);
+                uint8_t *gbase = a.out_planes + tile_abs * (size_t)a.tile_bytes + (size_t)((2 * pair) & 15) * pa + (size_t)piece * 16;
                 const int nrun = 2 * min(32, nk - 32 * set);                     /* (slot, plane) runs of this set; <= 0: nothing */
                 if (piece * 16 < nstr * pa)
                     for (int run = half; run < nrun; run += 8) {

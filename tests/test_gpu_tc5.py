@@ -131,3 +131,26 @@ def test_async_host_calls_of_bench_shape(nb, oracle, monkeypatch):
     for x in pin + pres:
         x.free()
     b.close()
+
+
+def test_cascade_first_round_on_the_tcgen05_kernel(nb, oracle):
+    """NNSP_B200_TC5=2 (the fixture) also sends layer 0 of the cascade's first round through vseq_kernel + the tcgen05 kernel
+    (device-side stream lists, per-stream first inference frames, context / look-back / fresh-instance rows): every field of
+    the result records against the oracle, over calls long enough for the kernel to be chosen and with stage changes inside."""
+    S, n, calls = 48, 150, 5
+    pcm = nb.synth_pcm(S, n * calls, first_stream=0)
+    models = [nb.Model.from_blob(nb.MODEL_DIR + "/" + MODEL_FILE[i]) for i in range(3)]
+    c = nb.Cascade(models, S, params=dict(thresh_timeout_s2i=45))
+    before = nb.tc5_launches()
+    got = np.concatenate([c.exec(pcm[:, k * n * 160:(k + 1) * n * 160]) for k in range(calls)], axis=1)
+    assert nb.tc5_launches() - before == 3 * calls          # one per model group of the first round
+    par = c.params_array()
+    c.close()
+    om = [oracle.model(i) for i in range(3)]
+    stages = np.zeros(3, np.int64)
+    for s in range(S):
+        r, _, _ = oracle.cascade_run(om, pcm[s], params=par, taps=False)
+        for f in r.dtype.names:
+            assert (got[s][f] == r[f]).all(), "stream %d field %s" % (s, f)
+        stages += np.bincount(r["stage_id"], minlength=3)
+    assert (stages > 0).all(), stages                        # all three models were live somewhere
